@@ -1,0 +1,187 @@
+/*
+ * psim.h — C ABI of libpsim, the B200 (sm_100a) replacement for PedigreeSim's meiosis and
+ * genotype-emission hot path.
+ *
+ * The reference (PedigreeSim 2.2, pure Java) has no FFI. The path sits behind two Java call seams
+ * (file:line relative to /root/reference/src/PedigreeSim/):
+ *
+ *   Seam A, meiosis:  Main.simulateIndividuals(popdata, maxfounderallele)      Main.java:1504-1520
+ *                     called from Main.simulate                                Main.java:358-361
+ *   Seam B, emission: Main.writeGenotypesFile / writeAlleledoseFile /
+ *                     writeAllAlleledoseFile                                   Main.java:903-1088
+ *                     called from Main.simulate                                Main.java:399-426
+ *
+ * A Java host binds these entry points with java.lang.foreign downcall handles or JNI
+ * (INTEGRATION.md shows the stub). Conventions:
+ *   - plain pointers and sizes; the caller owns every host buffer it passes, the library copies
+ *     in and owns all device memory; output buffers are caller-allocated (query sizes first);
+ *   - every call returns 0 on success, otherwise a PSIM_E* code with text in psim_last_error().
+ *     (The reference throws java.lang.Exception(message), Main.java:106-109,446-448; the Java
+ *     stub rethrows the text.)
+ *   - one context per host thread; results do not depend on thread or GPU count (counter-based
+ *     Philox streams keyed by seed, replicate, individual, chromosome, parent);
+ *   - positions are MORGAN, i.e. the host has already done the reference's `cM / 100.0`
+ *     (Main.java:619-620,678,1275) in fp64;
+ *   - homolog order in every haplostruct array is the .hsa file order
+ *     [individual][chromosome][homolog] (Main.java:1112-1131);
+ *   - there is no CPU fallback: without a CUDA device psim_create fails.
+ */
+#ifndef PSIM_H
+#define PSIM_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PSIM_ABI_VERSION 1
+
+typedef struct psim_ctx psim_ctx;
+
+enum {
+    PSIM_OK = 0,
+    PSIM_EINVAL = 1,    /* bad argument or call order */
+    PSIM_ECUDA = 2,     /* CUDA runtime error (no device, out of memory, launch failure) */
+    PSIM_ECAPACITY = 3, /* a device-side buffer limit was exceeded (e.g. chiasmata per bivalent) */
+    PSIM_ESTATE = 4     /* required input not set (pedigree, map, haplostructs ...) */
+};
+
+/* The model flags of PopulationData (PopulationData.java:187-222) plus the RNG identity. */
+typedef struct psim_config {
+    int32_t ploidy;                /* PLOIDY: positive, even, <= 16 */
+    int32_t chiasma_interference;  /* MAPFUNCTION: 0 = HALDANE, 1 = KOSAMBI */
+    int32_t natural_pairing;       /* NATURALPAIRING */
+    int32_t allow_no_recomb;       /* ALLOWNORECOMBINATION */
+    double parallel_multivalents;  /* PARALLELMULTIVALENTS in [0,1] */
+    double paired_centromeres;     /* PAIREDCENTROMERES in [0,1] */
+    int64_t seed;                  /* SEED (the reference parses an int32, Main.java:139) */
+    uint32_t replicate_first;      /* first replicate id; replicate r uses Philox key (seed, r) */
+    uint32_t replicate_count;      /* >= 1: independent replicate pedigrees simulated side by side */
+    int32_t device;                /* CUDA device ordinal */
+    int32_t reserved;
+} psim_config;
+
+int psim_abi_version(void);
+
+/* Lifetime. */
+int psim_create(const psim_config* cfg, psim_ctx** out);
+void psim_destroy(psim_ctx* ctx);
+const char* psim_last_error(const psim_ctx* ctx); /* ctx may be NULL: error of the last failed psim_create */
+
+/* Chromosome table (Chromosome.java:65-88, TetraploidChromosome.java:80-89; read by
+ * Main.readChromosomeFile, Main.java:581-634). pref_pairing / frac_quadrivalents may be NULL for
+ * ploidy 2. */
+int psim_set_chromosomes(psim_ctx* ctx, int32_t n_chrom, const double* length_morgan,
+                         const double* centromere_morgan, const double* pref_pairing,
+                         const double* frac_quadrivalents);
+
+/* Pedigree in parents-first order (PopulationData.sortPedigree guarantees it,
+ * PopulationData.java:309-430): parent0[i] = parent1[i] = -1 marks a founder, otherwise both are
+ * indices < i. Every replicate shares this pedigree. */
+int psim_set_pedigree(psim_ctx* ctx, int64_t n_ind, const int32_t* parent0, const int32_t* parent1);
+
+/* Preset haplostructs for individuals [first, first+count) of replicate `replicate` — the replay
+ * / extend modes (Main.readHaploStructFiles, Main.java:1166-1291). seg_off has
+ * count*n_chrom*ploidy+1 entries; pos_morgan[seg_off[h]] is the start of homolog h's first segment
+ * (the chromosome head, HaploStruct.java:38-48). */
+int psim_set_haplostructs(psim_ctx* ctx, uint32_t replicate, int64_t first, int64_t count,
+                          const int64_t* seg_off, const int32_t* founder, const double* pos_morgan);
+
+/* Seam A. Gives founders without a haplostruct their founder alleles
+ * (Individual.calcFounderHaplostruct, Individual.java:155-171: the k-th such founder gets
+ * max_founder_allele+1+k*ploidy ...) and runs conception() (Individual.java:255-261) for every
+ * other individual without one, one pedigree generation per kernel batch, in every replicate.
+ * max_founder_allele is what readHaploStructFiles returned (-1 for a fresh simulation). */
+int psim_simulate(psim_ctx* ctx, int32_t max_founder_allele);
+
+/* Read back haplostructs of individuals [first, first+count) of one replicate
+ * (what Main.writeHaploStructFiles serialises, Main.java:1100-1136). */
+int psim_segment_count(psim_ctx* ctx, uint32_t replicate, int64_t first, int64_t count, int64_t* n_segments);
+int psim_get_haplostructs(psim_ctx* ctx, uint32_t replicate, int64_t first, int64_t count,
+                          int64_t* seg_off, int32_t* founder, double* pos_morgan);
+
+/* Parental meiotic configurations (Individual.parconfig, Genotype.java:38-51; serialised by
+ * Main.writeMeioticConfigsFile, Main.java:1138-1164). quad[count][n_chrom][2],
+ * chromseq[count][n_chrom][2][ploidy] (0-based homolog numbers); -1 for individuals that were
+ * not simulated in this context (founders, preset). */
+int psim_get_meiotic_configs(psim_ctx* ctx, uint32_t replicate, int64_t first, int64_t count,
+                             int32_t* quad, int32_t* chromseq);
+
+/* Linkage map: locus_off[n_chrom+1], positions ascending within each chromosome exactly as
+ * Chromosome.addLocus leaves them (Chromosome.java:133-162; read by Main.readMapFile,
+ * Main.java:636-695). */
+int psim_set_map(psim_ctx* ctx, const int64_t* locus_off, const double* pos_morgan);
+
+/* Optional founder genotypes (Main.readFounderGenotypesFile, Main.java:783-891), as codes:
+ * code[l*n_alleles + a] = rank of founder allele a's name among the locus' sorted unique allele
+ * names (Locus.java:88-103), so the "MAX_ALLELE" of Main.java:407,991-992 is the largest code at
+ * the locus. n_alleles = founder allele count. Pass code = NULL to clear. */
+int psim_set_allele_codes(psim_ctx* ctx, int32_t n_alleles, const uint8_t* code);
+
+/* Seam B. One fused pass writes every requested table for individuals
+ * [ind_first, ind_first+ind_count) x all replicates of the context and loci
+ * [locus_first, locus_first+locus_count) (global locus index = map order).
+ * Tables are locus-major like the reference's files; a NULL pointer skips a table.
+ * Column of (replicate r, individual i, homolog h) in founder / allele tables:
+ *     ((r - replicate_first) * ind_count + (i - ind_first)) * ploidy + h
+ * and in the dose table ((r - replicate_first) * ind_count + (i - ind_first)). */
+#define PSIM_DOSE_MIN_ALLELE (-1) /* Main.MIN_ALLELE, Main.java:941 */
+#define PSIM_DOSE_MAX_ALLELE (-2) /* Main.MAX_ALLELE, Main.java:942 */
+#define PSIM_MEM_HOST 0
+#define PSIM_MEM_DEVICE 1
+
+typedef struct psim_emit_targets {
+    void* founder;         /* u8 (founder_bytes = 1) or u16 (= 2) founder allele per cell:   */
+    int64_t founder_pitch; /*   _founderalleles.dat, Main.writeGenotypesFile(founders=true)  */
+    int32_t founder_bytes;
+    int32_t memory;        /* PSIM_MEM_HOST or PSIM_MEM_DEVICE (all pointers of this call) */
+    void* allele;          /* u8 allele code per cell: _genotypes.dat, needs allele codes */
+    int64_t allele_pitch;
+    void* dose;            /* u8 dose per individual: _alleledose.dat, Main.writeAlleledoseFile */
+    int64_t dose_pitch;
+    int32_t dose_which;    /* with codes: MAX/MIN_ALLELE or the name of founder allele `which`; */
+    int32_t reserved;      /*   without codes: founder allele `which` (Main.java:402-418,987-1015) */
+} psim_emit_targets;
+
+int psim_emit(psim_ctx* ctx, int64_t ind_first, int64_t ind_count, int64_t locus_first,
+              int64_t locus_count, const psim_emit_targets* targets);
+
+/* _allAlleledose.dat (Main.writeAllAlleledoseFile, Main.java:1037-1088): one row per
+ * (locus, allele). Without codes the alleles are the founder alleles 0..A-1; with codes they are
+ * the codes 0..max at each locus. row_off[locus_count+1] receives the first row of each locus. */
+int psim_all_dose_rows(psim_ctx* ctx, int64_t locus_first, int64_t locus_count, int64_t* row_off);
+int psim_emit_all_dose(psim_ctx* ctx, int64_t ind_first, int64_t ind_count, int64_t locus_first,
+                       int64_t locus_count, void* out, int64_t pitch, int32_t memory);
+
+/* Introspection for benchmarks and sharded drivers. */
+typedef struct psim_stats {
+    int64_t n_meioses;          /* Individual.doMeiosis() equivalents run by psim_simulate */
+    int64_t n_units;            /* (meiosis, chromosome) units */
+    int64_t n_segments;         /* segments resident on the device */
+    int64_t kernel_launches;    /* libpsim kernels launched since create */
+    double  ms_simulate;        /* device time of the last psim_simulate (CUDA events) */
+    double  ms_emit_kernel;     /* device time of the emission kernels of the last psim_emit* */
+    double  ms_emit_total;      /* device time of the last psim_emit* including copies */
+    int64_t emit_kernel_launches; /* emission-kernel launches of the last psim_emit* */
+} psim_stats;
+int psim_get_stats(psim_ctx* ctx, psim_stats* out);
+
+/* Device-resident haplostruct exchange for a pedigree sharded over several GPUs (one context per
+ * rank; DESIGN.md "Multi-GPU"). export gives device pointers to a packed copy of the haplostructs
+ * of [first, first+count) (valid until the next call on the context); import appends them on the
+ * receiving context. The all-gather between the two is the caller's NCCL call. */
+typedef struct psim_device_hs {
+    int64_t n_homologs;   /* count * n_chrom * ploidy * replicate_count */
+    int64_t n_segments;
+    const int64_t* seg_off;  /* device, n_homologs+1 */
+    const int32_t* founder;  /* device, n_segments */
+    const double* pos;       /* device, n_segments */
+} psim_device_hs;
+int psim_export_haplostructs_device(psim_ctx* ctx, int64_t first, int64_t count, psim_device_hs* out);
+int psim_import_haplostructs_device(psim_ctx* ctx, int64_t first, int64_t count, const psim_device_hs* in);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PSIM_H */

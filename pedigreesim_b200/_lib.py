@@ -1,0 +1,265 @@
+"""ctypes binding of libpsim.so (include/psim.h).
+
+There is deliberately no fallback: if the CUDA library is missing or no device is present the
+calls raise. Nothing here imports the CPU oracle.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+PKG = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(PKG, "libpsim.so")
+
+PSIM_OK, PSIM_EINVAL, PSIM_ECUDA, PSIM_ECAPACITY, PSIM_ESTATE = 0, 1, 2, 3, 4
+DOSE_MIN_ALLELE, DOSE_MAX_ALLELE = -1, -2
+MEM_HOST, MEM_DEVICE = 0, 1
+
+
+class PsimError(RuntimeError):
+    def __init__(self, code, message):
+        super().__init__(message)
+        self.code = code
+
+
+class Config(C.Structure):
+    _fields_ = [
+        ("ploidy", C.c_int32), ("chiasma_interference", C.c_int32), ("natural_pairing", C.c_int32),
+        ("allow_no_recomb", C.c_int32), ("parallel_multivalents", C.c_double), ("paired_centromeres", C.c_double),
+        ("seed", C.c_int64), ("replicate_first", C.c_uint32), ("replicate_count", C.c_uint32),
+        ("device", C.c_int32), ("reserved", C.c_int32),
+    ]
+
+
+class EmitTargets(C.Structure):
+    _fields_ = [
+        ("founder", C.c_void_p), ("founder_pitch", C.c_int64), ("founder_bytes", C.c_int32), ("memory", C.c_int32),
+        ("allele", C.c_void_p), ("allele_pitch", C.c_int64),
+        ("dose", C.c_void_p), ("dose_pitch", C.c_int64), ("dose_which", C.c_int32), ("reserved", C.c_int32),
+    ]
+
+
+class Stats(C.Structure):
+    _fields_ = [
+        ("n_meioses", C.c_int64), ("n_units", C.c_int64), ("n_segments", C.c_int64), ("kernel_launches", C.c_int64),
+        ("ms_simulate", C.c_double), ("ms_emit_kernel", C.c_double), ("ms_emit_total", C.c_double),
+        ("emit_kernel_launches", C.c_int64),
+    ]
+
+
+class DeviceHS(C.Structure):
+    _fields_ = [("n_homologs", C.c_int64), ("n_segments", C.c_int64), ("seg_off", C.c_void_p),
+                ("founder", C.c_void_p), ("pos", C.c_void_p)]
+
+
+EXPORTS = [
+    "psim_abi_version", "psim_create", "psim_destroy", "psim_last_error", "psim_set_chromosomes", "psim_set_pedigree",
+    "psim_set_haplostructs", "psim_simulate", "psim_segment_count", "psim_get_haplostructs", "psim_get_meiotic_configs",
+    "psim_set_map", "psim_set_allele_codes", "psim_emit", "psim_all_dose_rows", "psim_emit_all_dose", "psim_get_stats",
+    "psim_export_haplostructs_device", "psim_import_haplostructs_device",
+]
+
+_lib = None
+
+
+def load():
+    """Load libpsim.so. Raises if it has not been built (python -m pedigreesim_b200.build)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise PsimError(PSIM_ESTATE, "libpsim.so is not built: run `python -m pedigreesim_b200.build` "
+                                     "(there is no CPU fallback)")
+    L = C.CDLL(LIB_PATH)
+    vp, i32, i64, u32 = C.c_void_p, C.c_int32, C.c_int64, C.c_uint32
+    L.psim_abi_version.restype = i32
+    L.psim_create.argtypes = [C.POINTER(Config), C.POINTER(vp)]
+    L.psim_destroy.argtypes = [vp]
+    L.psim_destroy.restype = None
+    L.psim_last_error.argtypes = [vp]
+    L.psim_last_error.restype = C.c_char_p
+    L.psim_set_chromosomes.argtypes = [vp, i32, vp, vp, vp, vp]
+    L.psim_set_pedigree.argtypes = [vp, i64, vp, vp]
+    L.psim_set_haplostructs.argtypes = [vp, u32, i64, i64, vp, vp, vp]
+    L.psim_simulate.argtypes = [vp, i32]
+    L.psim_segment_count.argtypes = [vp, u32, i64, i64, C.POINTER(i64)]
+    L.psim_get_haplostructs.argtypes = [vp, u32, i64, i64, vp, vp, vp]
+    L.psim_get_meiotic_configs.argtypes = [vp, u32, i64, i64, vp, vp]
+    L.psim_set_map.argtypes = [vp, vp, vp]
+    L.psim_set_allele_codes.argtypes = [vp, i32, vp]
+    L.psim_emit.argtypes = [vp, i64, i64, i64, i64, C.POINTER(EmitTargets)]
+    L.psim_all_dose_rows.argtypes = [vp, i64, i64, vp]
+    L.psim_emit_all_dose.argtypes = [vp, i64, i64, i64, i64, vp, i64, i32]
+    L.psim_get_stats.argtypes = [vp, C.POINTER(Stats)]
+    L.psim_export_haplostructs_device.argtypes = [vp, i64, i64, C.POINTER(DeviceHS)]
+    L.psim_import_haplostructs_device.argtypes = [vp, i64, i64, C.POINTER(DeviceHS)]
+    _lib = L
+    return L
+
+
+def _p(a):
+    return a.ctypes.data_as(C.c_void_p) if a is not None else None
+
+
+class PsimContext:
+    """One libpsim context = the device-resident population(s) of one host thread."""
+
+    def __init__(self, ploidy, kosambi=False, natural_pairing=True, allow_no_recomb=True, parallel_multivalents=0.0,
+                 paired_centromeres=0.0, seed=12345, replicate_first=0, replicate_count=1, device=0):
+        self.L = load()
+        self.P = ploidy
+        self.R = replicate_count
+        self.replicate_first = replicate_first
+        cfg = Config(ploidy, int(kosambi), int(natural_pairing), int(allow_no_recomb), parallel_multivalents,
+                     paired_centromeres, seed, replicate_first, replicate_count, device, 0)
+        h = C.c_void_p()
+        rc = self.L.psim_create(C.byref(cfg), C.byref(h))
+        if rc != 0:
+            raise PsimError(rc, self.L.psim_last_error(None).decode())
+        self.h = h
+        self.C = 0
+        self.N = 0
+        self.Ltot = 0
+        self.A = 0
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.L.psim_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    def _chk(self, rc):
+        if rc != 0:
+            raise PsimError(rc, self.L.psim_last_error(self.h).decode())
+
+    # --- inputs
+    def set_chromosomes(self, length_M, centromere_M, pref_pairing=None, frac_quad=None):
+        ln = np.ascontiguousarray(length_M, dtype=np.float64)
+        ce = np.ascontiguousarray(centromere_M, dtype=np.float64)
+        pp = None if pref_pairing is None else np.ascontiguousarray(pref_pairing, dtype=np.float64)
+        fq = None if frac_quad is None else np.ascontiguousarray(frac_quad, dtype=np.float64)
+        self.C = len(ln)
+        self._chk(self.L.psim_set_chromosomes(self.h, self.C, _p(ln), _p(ce), _p(pp), _p(fq)))
+
+    def set_pedigree(self, parent0, parent1):
+        p0 = np.ascontiguousarray(parent0, dtype=np.int32)
+        p1 = np.ascontiguousarray(parent1, dtype=np.int32)
+        self.N = len(p0)
+        self._chk(self.L.psim_set_pedigree(self.h, self.N, _p(p0), _p(p1)))
+
+    def set_haplostructs(self, first, seg_off, founder, pos, replicate=None):
+        so = np.ascontiguousarray(seg_off, dtype=np.int64)
+        fo = np.ascontiguousarray(founder, dtype=np.int32)
+        po = np.ascontiguousarray(pos, dtype=np.float64)
+        count = (len(so) - 1) // (self.C * self.P)
+        rep = self.replicate_first if replicate is None else replicate
+        self._chk(self.L.psim_set_haplostructs(self.h, rep, first, count, _p(so), _p(fo), _p(po)))
+
+    def set_map(self, locus_off, pos_M):
+        lo = np.ascontiguousarray(locus_off, dtype=np.int64)
+        po = np.ascontiguousarray(pos_M, dtype=np.float64)
+        self._chk(self.L.psim_set_map(self.h, _p(lo), _p(po)))
+        self.Ltot = int(lo[-1])
+        self.A = 0
+
+    def set_allele_codes(self, code):
+        if code is None:
+            self._chk(self.L.psim_set_allele_codes(self.h, 0, None))
+            self.A = 0
+            return
+        code = np.ascontiguousarray(code, dtype=np.uint8)
+        self.A = code.shape[1]
+        self._chk(self.L.psim_set_allele_codes(self.h, self.A, _p(code)))
+
+    # --- seam A
+    def simulate(self, maxfounderallele=-1):
+        self._chk(self.L.psim_simulate(self.h, maxfounderallele))
+
+    def get_haplostructs(self, first=0, count=None, replicate=None):
+        count = self.N - first if count is None else count
+        rep = self.replicate_first if replicate is None else replicate
+        n = C.c_int64()
+        self._chk(self.L.psim_segment_count(self.h, rep, first, count, C.byref(n)))
+        so = np.zeros(count * self.C * self.P + 1, dtype=np.int64)
+        fo = np.zeros(n.value, dtype=np.int32)
+        po = np.zeros(n.value, dtype=np.float64)
+        self._chk(self.L.psim_get_haplostructs(self.h, rep, first, count, _p(so), _p(fo), _p(po)))
+        return so, fo, po
+
+    def get_meiotic_configs(self, first=0, count=None, replicate=None):
+        count = self.N - first if count is None else count
+        rep = self.replicate_first if replicate is None else replicate
+        quad = np.zeros((count, self.C, 2), dtype=np.int32)
+        seq = np.zeros((count, self.C, 2, self.P), dtype=np.int32)
+        self._chk(self.L.psim_get_meiotic_configs(self.h, rep, first, count, _p(quad), _p(seq)))
+        return quad, seq
+
+    # --- seam B
+    def emit(self, founder=False, allele=False, dose=False, dose_which=0, ind_first=0, ind_count=None, loc_first=0,
+             loc_count=None, founder_bytes=1):
+        """Emit into fresh host arrays; returns a dict of the requested tables ([loci][columns])."""
+        ind_count = self.N - ind_first if ind_count is None else ind_count
+        loc_count = self.Ltot - loc_first if loc_count is None else loc_count
+        q = self.R * ind_count
+        out = {}
+        t = EmitTargets()
+        t.memory = MEM_HOST
+        t.dose_which = dose_which
+        t.founder_bytes = founder_bytes
+        if founder:
+            out["founder"] = np.zeros((loc_count, q * self.P), dtype=np.uint8 if founder_bytes == 1 else np.uint16)
+            t.founder = out["founder"].ctypes.data
+            t.founder_pitch = q * self.P * founder_bytes
+        if allele:
+            out["allele"] = np.zeros((loc_count, q * self.P), dtype=np.uint8)
+            t.allele = out["allele"].ctypes.data
+            t.allele_pitch = q * self.P
+        if dose:
+            out["dose"] = np.zeros((loc_count, q), dtype=np.uint8)
+            t.dose = out["dose"].ctypes.data
+            t.dose_pitch = q
+        self._chk(self.L.psim_emit(self.h, ind_first, ind_count, loc_first, loc_count, C.byref(t)))
+        return out
+
+    def emit_into(self, targets, ind_first, ind_count, loc_first, loc_count):
+        """Emit into caller-provided memory described by an EmitTargets (host or device pointers)."""
+        self._chk(self.L.psim_emit(self.h, ind_first, ind_count, loc_first, loc_count, C.byref(targets)))
+
+    def all_dose_rows(self, loc_first=0, loc_count=None):
+        loc_count = self.Ltot - loc_first if loc_count is None else loc_count
+        ro = np.zeros(loc_count + 1, dtype=np.int64)
+        self._chk(self.L.psim_all_dose_rows(self.h, loc_first, loc_count, _p(ro)))
+        return ro
+
+    def emit_all_dose(self, ind_first=0, ind_count=None, loc_first=0, loc_count=None):
+        ind_count = self.N - ind_first if ind_count is None else ind_count
+        loc_count = self.Ltot - loc_first if loc_count is None else loc_count
+        ro = self.all_dose_rows(loc_first, loc_count)
+        q = self.R * ind_count
+        out = np.zeros((int(ro[-1]), q), dtype=np.uint8)
+        self._chk(self.L.psim_emit_all_dose(self.h, ind_first, ind_count, loc_first, loc_count, _p(out), q, MEM_HOST))
+        return ro, out
+
+    def stats(self):
+        s = Stats()
+        self._chk(self.L.psim_get_stats(self.h, C.byref(s)))
+        return {k: getattr(s, k) for k, _ in Stats._fields_}
+
+    def export_device(self, first, count):
+        d = DeviceHS()
+        self._chk(self.L.psim_export_haplostructs_device(self.h, first, count, C.byref(d)))
+        return d
+
+    def import_device(self, first, count, d):
+        self._chk(self.L.psim_import_haplostructs_device(self.h, first, count, C.byref(d)))

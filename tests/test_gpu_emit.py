@@ -1,0 +1,163 @@
+"""Replay parity of the emission kernels (K0 + K2) through the C ABI: given HaploStructs, the
+founder-allele / genotype / dose tables must equal the CPU oracle's bit for bit
+(reference: Main.writeGenotypesFile / writeAlleledoseFile / writeAllAlleledoseFile,
+Main.java:903-1088, over HaploStruct.getFounderAt, HaploStruct.java:107-142)."""
+import numpy as np
+import pytest
+
+import _cases
+import _oracle
+
+pytestmark = pytest.mark.gpu
+
+
+def _both(ploidy, lengths, n_ind, n_alleles, loci, seed, codes=0, max_segments=6, grid_breaks=True):
+    rng = np.random.default_rng(seed)
+    off, pos = _cases.uniform_map(lengths, loci)
+    grid = pos[off[0]:off[1]] if grid_breaks and loci[0] > 2 else None
+    seg_off, founder, segpos = _cases.random_haplostructs(rng, n_ind, lengths, ploidy, n_alleles, max_segments, grid)
+    # pedigree: all founders (only emission is exercised)
+    p = -np.ones(n_ind, np.int32)
+    engines = []
+    for kind in ("oracle-philox", "gpu"):
+        e = _cases.make_engine(kind, ploidy)
+        e.set_chromosomes(lengths, [x * 0.4 for x in lengths])
+        e.set_pedigree(p, p)
+        e.set_haplostructs(0, seg_off, founder, segpos)
+        e.set_map(off, pos)
+        if codes:
+            e.set_allele_codes(_cases.hash_codes(int(off[-1]), n_alleles, codes, salt=seed))
+        engines.append(e)
+    return engines
+
+
+@pytest.mark.parametrize("ploidy,n_ind,loci", [
+    (2, 37, [50]), (2, 1200, [300, 7, 129]), (4, 700, [257, 64]), (6, 300, [130, 200]), (8, 90, [77]),
+    (10, 33, [40, 41]), (12, 20, [35]), (16, 9, [19]),
+])
+def test_founder_and_dose_tables_match_oracle(ploidy, n_ind, loci):
+    lengths = [1.0 + 0.25 * k for k in range(len(loci))]
+    n_alleles = min(255, ploidy * 5)
+    o, g = _both(ploidy, lengths, n_ind, n_alleles, loci, seed=ploidy * 1000 + n_ind)
+    for which in (0, 3, n_alleles - 1):
+        ref = _cases.oracle_emit_all(o, which=which)
+        got = g.emit(founder=True, dose=True, dose_which=which)
+        assert np.array_equal(got["founder"], ref["founder"])
+        assert np.array_equal(got["dose"], ref["dose"])
+
+
+@pytest.mark.parametrize("ploidy,codes", [(2, 2), (4, 2), (4, 5), (6, 3), (8, 2), (12, 4)])
+def test_genotype_codes_and_max_allele_dose_match_oracle(ploidy, codes):
+    lengths = [1.2, 0.8]
+    loci = [211, 97]
+    n_alleles = ploidy * 2
+    o, g = _both(ploidy, lengths, 260, n_alleles, loci, seed=77 + ploidy, codes=codes)
+    for which in (_oracle.MAX_ALLELE, _oracle.MIN_ALLELE, 1):
+        got = g.emit(founder=True, allele=True, dose=True, dose_which=which)
+        assert np.array_equal(got["founder"], o.emit(_oracle.EMIT_FOUNDER))
+        assert np.array_equal(got["allele"], o.emit(_oracle.EMIT_ALLELE))
+        assert np.array_equal(got["dose"], o.emit(_oracle.EMIT_DOSE, which=which))
+
+
+def test_sub_ranges_and_single_tables():
+    o, g = _both(4, [1.0, 1.5], 333, 8, [150, 260], seed=5)
+    full_f = o.emit(_oracle.EMIT_FOUNDER)
+    full_d = o.emit(_oracle.EMIT_DOSE, which=2)
+    for (i0, ni, l0, nl) in [(0, 333, 0, 410), (10, 100, 140, 30), (332, 1, 409, 1), (7, 129, 0, 1), (100, 233, 149, 2)]:
+        got = g.emit(founder=True, ind_first=i0, ind_count=ni, loc_first=l0, loc_count=nl)
+        assert np.array_equal(got["founder"], full_f[l0:l0 + nl, i0 * 4:(i0 + ni) * 4])
+        got = g.emit(dose=True, dose_which=2, ind_first=i0, ind_count=ni, loc_first=l0, loc_count=nl)
+        assert np.array_equal(got["dose"], full_d[l0:l0 + nl, i0:i0 + ni])
+
+
+def test_locus_on_breakpoint_belongs_to_the_segment_starting_there():
+    # HaploStruct.findSegment: a locus exactly on a breakpoint takes the founder of the new segment
+    lengths = [1.0]
+    off = np.array([0, 5], np.int64)
+    pos = np.array([0.0, 0.25, 0.25, 0.5, 1.0])
+    seg_off = np.array([0, 3, 4], np.int64)
+    founder = np.array([0, 1, 0, 1], np.int32)
+    segpos = np.array([0.0, 0.25, 0.5, 0.0])
+    p = -np.ones(1, np.int32)
+    res = []
+    for kind in ("oracle-philox", "gpu"):
+        e = _cases.make_engine(kind, 2)
+        e.set_chromosomes(lengths, [0.5])
+        e.set_pedigree(p, p)
+        e.set_haplostructs(0, seg_off, founder, segpos)
+        e.set_map(off, pos)
+        res.append(e)
+    ref = res[0].emit(_oracle.EMIT_FOUNDER)
+    assert ref[:, 0].tolist() == [0, 1, 1, 0, 0]
+    assert np.array_equal(res[1].emit(founder=True)["founder"], ref)
+
+
+def test_unsorted_and_redundant_breakpoints_follow_findsegment():
+    # hand-written .hsb files may hold equal-founder neighbours, zero-length and even unsorted
+    # segments; the answer is defined by the tail scan of findSegment
+    rng = np.random.default_rng(3)
+    lengths = [1.0]
+    off, pos = _cases.uniform_map(lengths, [64])
+    n_ind, P = 50, 2
+    seg_off, founder, segpos = [0], [], []
+    for _ in range(n_ind * P):
+        n = int(rng.integers(1, 7))
+        bp = rng.random(n - 1)  # NOT sorted
+        if n > 2 and rng.random() < 0.5:
+            bp[1] = bp[0]  # zero-length segment
+        segpos += [0.0] + bp.tolist()
+        founder += rng.integers(0, 4, n).tolist()
+        seg_off.append(seg_off[-1] + n)
+    p = -np.ones(n_ind, np.int32)
+    res = []
+    for kind in ("oracle-philox", "gpu"):
+        e = _cases.make_engine(kind, P)
+        e.set_chromosomes(lengths, [0.5])
+        e.set_pedigree(p, p)
+        e.set_haplostructs(0, np.array(seg_off), np.array(founder), np.array(segpos))
+        e.set_map(off, pos)
+        res.append(e)
+    assert np.array_equal(res[1].emit(founder=True)["founder"], res[0].emit(_oracle.EMIT_FOUNDER))
+
+
+def test_all_allele_dose_rows():
+    for codes in (0, 3):
+        o, g = _both(4, [1.0], 120, 8, [90], seed=11, codes=codes)
+        ro, out = g.emit_all_dose()
+        n_loci = 90
+        if codes == 0:
+            assert ro.tolist() == [8 * k for k in range(n_loci + 1)]
+            for a in range(8):
+                assert np.array_equal(out[a::8], o.emit(_oracle.EMIT_DOSE, which=a))
+        else:
+            al = o.emit(_oracle.EMIT_ALLELE).reshape(n_loci, 120, 4)
+            for l in range(n_loci):
+                for k in range(int(ro[l + 1] - ro[l])):
+                    assert np.array_equal(out[ro[l] + k], (al[l] == k).sum(axis=1))
+
+
+def test_u16_founder_table_for_many_founders():
+    ploidy, n_ind = 2, 40
+    rng = np.random.default_rng(9)
+    lengths = [1.0]
+    off, pos = _cases.uniform_map(lengths, [33])
+    seg_off, founder, segpos = _cases.random_haplostructs(rng, n_ind, lengths, ploidy, 1000, 4)
+    # 600 founders -> 1200 founder alleles: needs the u16 table
+    n_f = 600
+    p0 = np.concatenate([-np.ones(n_f, np.int32), np.zeros(n_ind, np.int32)])
+    p1 = np.concatenate([-np.ones(n_f, np.int32), np.ones(n_ind, np.int32)])
+    res = []
+    for kind in ("oracle-philox", "gpu"):
+        e = _cases.make_engine(kind, ploidy)
+        e.set_chromosomes(lengths, [0.5])
+        e.set_pedigree(p0, p1)
+        e.set_haplostructs(n_f, seg_off, founder, segpos)
+        e.simulate()  # founders only
+        e.set_map(off, pos)
+        res.append(e)
+    ref = res[0].emit(_oracle.EMIT_FOUNDER_U16)
+    got = res[1].emit(founder=True, founder_bytes=2)["founder"]
+    assert np.array_equal(got, ref)
+    import pedigreesim_b200
+    with pytest.raises(pedigreesim_b200.PsimError):
+        res[1].emit(founder=True, founder_bytes=1)

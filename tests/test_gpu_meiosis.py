@@ -1,0 +1,146 @@
+"""Parity of the meiosis kernels (K1) through the C ABI against the CPU oracle running on the same
+Philox streams: founder alleles per segment, segment counts and meiotic configurations must be
+bit-exact; breakpoints (fp64, computed with CUDA's log/exp/pow instead of libm's) must agree to
+1e-12 relative. Reference path: Individual.conception/doMeiosis/calcChromConfig
+(Individual.java:255-349,601-904), Multivalent.java:79-577, Quadrivalent.java:108-510."""
+import numpy as np
+import pytest
+
+import _cases
+
+pytestmark = pytest.mark.gpu
+
+POS_RTOL = 1e-12
+
+
+def run_pair(ploidy, p0, p1, lengths, centro, pref=None, fq=None, seed=12345, replicate=0, **model):
+    out = []
+    for kind in ("oracle-philox", "gpu"):
+        e = _cases.make_engine(kind, ploidy, seed=seed, replicate_first=replicate, **model)
+        e.set_chromosomes(lengths, centro, pref, fq)
+        e.set_pedigree(p0, p1)
+        e.simulate()
+        out.append(e)
+    return out
+
+
+def assert_same_population(o, g, replicate=None):
+    so, fo, po = o.get_haplostructs()
+    sg, fg, pg = g.get_haplostructs(replicate=replicate) if replicate is not None else g.get_haplostructs()
+    assert np.array_equal(so, sg), "segment counts differ"
+    assert np.array_equal(fo, fg), "founder alleles differ"
+    assert np.allclose(po, pg, rtol=POS_RTOL, atol=1e-15), "breakpoints differ beyond fp tolerance"
+    qo, sqo = o.get_meiotic_configs()
+    qg, sqg = g.get_meiotic_configs(replicate=replicate) if replicate is not None else g.get_meiotic_configs()
+    assert np.array_equal(qo, qg), "quadrivalent counts differ"
+    assert np.array_equal(sqo, sqg), "chromseq differs"
+
+
+@pytest.mark.parametrize("kosambi", [False, True])
+@pytest.mark.parametrize("poptype", ["F1", "F2", "BC", "S1"])
+def test_diploid_standard_populations(poptype, kosambi):
+    p0, p1 = _cases.std_pedigree(poptype, 200)
+    o, g = run_pair(2, p0, p1, [1.0, 0.6, 2.5], [0.5, 0.1, 2.5], kosambi=kosambi)
+    assert_same_population(o, g)
+
+
+@pytest.mark.parametrize("ploidy", [4, 6, 8, 10, 12])
+@pytest.mark.parametrize("natural", [True, False])
+def test_polyploid_pairing_and_quadrivalents(ploidy, natural):
+    p0, p1 = _cases.std_pedigree("F2", 150)  # F2: parents carry recombinant homologs
+    C = 4
+    o, g = run_pair(ploidy, p0, p1, [1.0, 1.3, 0.8, 2.0], [0.4, 0.65, 0.0, 1.0],
+                    pref=[0.0, 0.3, 0.7, 1.0], fq=[0.5, 1.0, 0.25, 0.0], natural_pairing=natural, seed=99 + ploidy)
+    assert_same_population(o, g)
+    quad, _ = g.get_meiotic_configs()
+    if ploidy >= 4:
+        assert quad[3:, :C - 1].max() >= 1  # quadrivalents do occur
+
+
+@pytest.mark.parametrize("kosambi", [False, True])
+@pytest.mark.parametrize("paral,paired", [(0.0, 0.0), (1.0, 0.0), (0.0, 1.0), (0.35, 0.6), (1.0, 1.0)])
+def test_tetraploid_model_switches(kosambi, paral, paired):
+    p0, p1 = _cases.std_pedigree("F2", 120)
+    o, g = run_pair(4, p0, p1, [1.0, 1.6], [0.3, 0.8], pref=[0.0, 0.5], fq=[1.0, 0.5], kosambi=kosambi,
+                    natural_pairing=False, parallel_multivalents=paral, paired_centromeres=paired, seed=4242)
+    assert_same_population(o, g)
+
+
+@pytest.mark.parametrize("ploidy", [2, 4])
+@pytest.mark.parametrize("kosambi", [False, True])
+def test_no_empty_bivalents(ploidy, kosambi):
+    p0, p1 = _cases.std_pedigree("F2", 80)
+    o, g = run_pair(ploidy, p0, p1, [0.8, 1.5], [0.4, 0.7], pref=[0.2, 0.2], fq=[0.5, 0.5], kosambi=kosambi,
+                    allow_no_recomb=False, seed=31)
+    assert_same_population(o, g)
+
+
+def test_random_deep_pedigree():
+    rng = np.random.default_rng(2)
+    p0, p1 = _cases.random_pedigree(rng, 6, 400)
+    o, g = run_pair(4, p0, p1, [1.0, 1.2], [0.5, 0.2], pref=[0.25, 0.0], fq=[0.0, 0.0], seed=8)
+    assert_same_population(o, g)
+
+
+def test_ril_selfing_chain():
+    p0, p1 = _cases.ril_pedigree(64, 8)
+    o, g = run_pair(2, p0, p1, [1.5] * 3, [0.75] * 3, seed=5)
+    assert_same_population(o, g)
+    so, _, _ = g.get_haplostructs()
+    assert np.diff(so).max() > 4  # F8 homologs carry many unmerged segments
+
+
+def test_replicates_use_their_own_streams():
+    p0, p1 = _cases.std_pedigree("F1", 60)
+    import pedigreesim_b200
+    g = pedigreesim_b200.PsimContext(4, seed=77, replicate_first=5, replicate_count=3)
+    g.set_chromosomes([1.0, 1.0], [0.5, 0.5], [0.25, 0.25], [0.0, 0.0])
+    g.set_pedigree(p0, p1)
+    g.simulate()
+    for r in (5, 6, 7):
+        o = _cases.make_engine("oracle-philox", 4, seed=77, replicate_first=r)
+        o.set_chromosomes([1.0, 1.0], [0.5, 0.5], [0.25, 0.25], [0.0, 0.0])
+        o.set_pedigree(p0, p1)
+        o.simulate()
+        assert_same_population(o, g, replicate=r)
+    a = g.get_haplostructs(replicate=5)
+    b = g.get_haplostructs(replicate=6)
+    assert not (len(a[1]) == len(b[1]) and np.array_equal(a[1], b[1]))
+
+
+def test_extend_population_mode3():
+    # Main.java:343-373: individuals with preset haplostructs are kept, the rest simulated, new
+    # founders continue the founder-allele numbering after maxfounderallele
+    p0, p1 = _cases.std_pedigree("F1", 30)
+    o1, g1 = run_pair(2, p0, p1, [1.0], [0.5], seed=3)
+    so, fo, po = o1.get_haplostructs()
+    # second cycle: a new founder (index 32) crossed with F1 individuals
+    p0b = np.concatenate([p0, [-1], np.arange(2, 12, dtype=np.int32)])
+    p1b = np.concatenate([p1, [-1], np.full(10, 32, np.int32)])
+    out = []
+    for kind in ("oracle-philox", "gpu"):
+        e = _cases.make_engine(kind, 2, seed=3)
+        e.set_chromosomes([1.0], [0.5])
+        e.set_pedigree(p0b, p1b)
+        e.set_haplostructs(0, so, fo, po)
+        e.simulate(maxfounderallele=int(fo.max()))
+        out.append(e)
+    assert_same_population(*out)
+    _, f2, _ = out[1].get_haplostructs(first=32, count=1)
+    assert f2.tolist() == [4, 5]
+
+
+def test_emission_after_simulation_matches_oracle():
+    import _oracle
+    p0, p1 = _cases.std_pedigree("F1", 300)
+    o, g = run_pair(4, p0, p1, [1.0, 0.9], [0.4, 0.3], pref=[0.3, 0.3], fq=[0.5, 0.5], natural_pairing=False, seed=12)
+    off, pos = _cases.uniform_map([1.0, 0.9], [400, 123])
+    codes = _cases.hash_codes(int(off[-1]), 8, 2)
+    for e in (o, g):
+        e.set_map(off, pos)
+        e.set_allele_codes(codes)
+    got = g.emit(founder=True, allele=True, dose=True, dose_which=_oracle.MAX_ALLELE)
+    # breakpoints may differ in the last ulp between libm and CUDA; no locus sits that close
+    assert np.array_equal(got["founder"], o.emit(_oracle.EMIT_FOUNDER))
+    assert np.array_equal(got["allele"], o.emit(_oracle.EMIT_ALLELE))
+    assert np.array_equal(got["dose"], o.emit(_oracle.EMIT_DOSE, which=_oracle.MAX_ALLELE))
