@@ -16,8 +16,10 @@ def _both(ploidy, lengths, n_ind, n_alleles, loci, seed, codes=0, max_segments=6
     off, pos = _cases.uniform_map(lengths, loci)
     grid = pos[off[0]:off[1]] if grid_breaks and loci[0] > 2 else None
     seg_off, founder, segpos = _cases.random_haplostructs(rng, n_ind, lengths, ploidy, n_alleles, max_segments, grid)
-    # pedigree: all founders (only emission is exercised)
-    p = -np.ones(n_ind, np.int32)
+    # only emission is exercised: every individual gets a preset haplostruct; enough founders to
+    # own n_alleles founder alleles, the rest nominally their offspring
+    nf = min(n_ind, -(-n_alleles // ploidy))
+    p = np.concatenate([-np.ones(nf, np.int32), np.zeros(n_ind - nf, np.int32)])
     engines = []
     for kind in ("oracle-philox", "gpu"):
         e = _cases.make_engine(kind, ploidy)
