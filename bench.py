@@ -1,0 +1,333 @@
+#!/usr/bin/env python
+"""Benchmark of the PedigreeSim hot path on B200: meioses/s and genotype calls/s.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+A step is one pass of the hot path over one batch of synthetic input: BASELINE.json configs[1]
+(autotetraploid F1 of 10 000, quadrivalent fraction 0.5, preferential pairing 0.3, 12 chromosomes
+x 2 000 loci, biallelic founder genotypes): all 20 000 meioses (K1), the breakpoint -> locus-run
+index (K0) and the dense emission of the founder-allele matrix plus the MAX-allele dose table (K2,
+the HBM-write-bound kernel; N*L*(P+1) algorithmic bytes). With N > 1 GPUs every rank simulates and
+emits its own replicate population of that size (weak scaling, no data-path collective).
+
+Prints ONE JSON line (rank 0). `value` is measured with inputs resident in HBM and outputs written
+to HBM; `e2e` is the same metric through the C ABI with host buffers (pedigree / map / allele-code
+uploads and the device->host copy of both tables inside the timed region).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+SEED = 12345
+
+
+# ------------------------------------------------------------------------------------ workload
+def workload(popsize=10000):
+    """BASELINE.json configs[1] as SURVEY.md §8(d) item 2 spells it out."""
+    P, C, loci = 4, 12, 2000
+    lengths = np.array([(80 + 10 * (c % 5)) / 100.0 for c in range(C)])
+    centro = 0.4 * lengths
+    pref = np.full(C, 0.3)
+    fq = np.full(C, 0.5)
+    p0 = np.array([-1, -1] + [0] * popsize, np.int32)  # POPTYPE=F1 (Main.java:1471-1476)
+    p1 = np.array([-1, -1] + [1] * popsize, np.int32)
+    off = np.arange(C + 1, dtype=np.int64) * loci
+    pos = np.concatenate([ln * (np.arange(loci) + 0.5) / loci for ln in lengths])
+    A = 2 * P
+    l = np.arange(C * loci, dtype=np.uint64)[:, None]
+    a = np.arange(A, dtype=np.uint64)[None, :]
+    with np.errstate(over="ignore"):
+        h = (l * np.uint64(0x9E3779B97F4A7C15) + a * np.uint64(0xC2B2AE3D27D4EB4F)) >> np.uint64(29)
+    code = (h & np.uint64(1)).astype(np.uint8)
+    code[code.max(axis=1) == 0, 0] = 1  # keep every locus biallelic so the codes are ranks 0/1
+    code[code.min(axis=1) == 1, 0] = 0
+    return dict(P=P, C=C, L=C * loci, N=len(p0), M=2 * popsize, lengths=lengths, centro=centro, pref=pref, fq=fq,
+                p0=p0, p1=p1, off=off, pos=pos, code=code, A=A,
+                model=dict(kosambi=False, natural_pairing=False, allow_no_recomb=True))
+
+
+WORKLOAD_NAME = ("configs[1]: autotetraploid F1 of 10000 (POPTYPE=F1), NATURALPAIRING=0, quadrivalents 0.5, "
+                 "prefPairing 0.3, 12 chromosomes (80-120 cM) x 2000 loci, biallelic .gen")
+
+
+# ------------------------------------------------------------------------------------ clocks
+class ClockSampler:
+    """nvidia-smi clocks and throttle reasons while the timed region runs (B200_PROFILING.md)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index = index
+        self.lines = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for k, nm in enumerate(names):
+                if f[5 + k].lower().startswith("active"):
+                    reasons.add(nm)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def measured_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs, copy read+write)"
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+# ------------------------------------------------------------------------------------ CPU arm
+def cpu_port_run(w, offspring, steps, warmup):
+    """The oracle (CPU restatement of the reference, java.util.Random draw order) on `offspring`
+    F1 individuals of the same workload: simulate + founder table + MAX-allele dose table."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import _oracle
+    ws = workload(offspring)
+    times = []
+    for s in range(warmup + steps):
+        t0 = time.perf_counter()
+        o = _oracle.Oracle(ws["P"], rng=_oracle.RNG_JAVA, seed=SEED + s, **ws["model"])
+        o.set_chromosomes(ws["lengths"], ws["centro"], ws["pref"], ws["fq"])
+        o.set_pedigree(ws["p0"], ws["p1"])
+        o.simulate()
+        o.set_map(ws["off"], ws["pos"])
+        o.set_allele_codes(ws["code"])
+        o.emit(_oracle.EMIT_FOUNDER)
+        o.emit(_oracle.EMIT_DOSE, which=_oracle.MAX_ALLELE)
+        o.close()
+        if s >= warmup:
+            times.append(time.perf_counter() - t0)
+    t = float(np.mean(times))
+    cells = ws["N"] * ws["L"] * ws["P"]
+    return cells / t / 1e9, t, ws
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    w = workload()
+    total = args.steps + args.warmup
+    # about 2 minutes for the whole run at ~0.013 G allele-loci/s on one core (measured at 10000
+    # offspring; smaller samples stay in cache and run up to 4x faster per cell)
+    offspring = int(max(100, min(10000, 120.0 / total * 0.013e9 / (w["L"] * w["P"]))))
+    v, t, ws = cpu_port_run(w, offspring, args.steps, args.warmup)
+    sample = "same workload with POPSIZE=%d of 10000 offspring per step (all 24000 loci)" % offspring
+    out = {
+        "impl": "reference", "metric": "genotype calls/sec (G allele-loci/s)", "value": v, "unit": "G allele-loci/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": t * 1e3,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+        "config": {"workload": WORKLOAD_NAME, "sample": sample},
+        "cpu_baseline": {"value": v, "unit": "G allele-loci/s", "cores": 1, "kind": "port", "sample": sample,
+                         "note": "no JVM in the image: the reference jar cannot run; this is the oracle restatement "
+                                 "(single-threaded like the jar), without the jar's text formatting"},
+        "e2e": {"value": v, "unit": "G allele-loci/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "meioses_per_s": ws["M"] / t,
+    }
+    print(json.dumps(out))
+
+
+# ------------------------------------------------------------------------------------ GPU arm
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    import pedigreesim_b200 as ps
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (libpsim has no CPU fallback)")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    w = workload()
+    P, L, N, M = w["P"], w["L"], w["N"], w["M"]
+    ctx = ps.PsimContext(P, seed=SEED, replicate_first=rank, device=local, **w["model"])
+    stream = torch.cuda.Stream()
+    ctx.set_stream(stream.cuda_stream)
+    ctx.set_chromosomes(w["lengths"], w["centro"], w["pref"], w["fq"])
+    ctx.set_pedigree(w["p0"], w["p1"])
+    ctx.set_map(w["off"], w["pos"])
+    ctx.set_allele_codes(w["code"])
+    fp = (N * P + 127) // 128 * 128
+    dp = (N + 127) // 128 * 128
+    d_founder = torch.empty((L, fp), dtype=torch.uint8, device="cuda")
+    d_dose = torch.empty((L, dp), dtype=torch.uint8, device="cuda")
+    tgt = ps.EmitTargets()
+    tgt.founder, tgt.founder_pitch, tgt.founder_bytes = d_founder.data_ptr(), fp, 1
+    tgt.dose, tgt.dose_pitch, tgt.dose_which = d_dose.data_ptr(), dp, ps.DOSE_MAX_ALLELE
+    tgt.memory = ps.MEM_DEVICE
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+
+    acc = {"sim": 0.0, "emit": 0.0, "launches": 0, "emit_launches": 0}
+
+    def step(k, timed):
+        ctx.reset(SEED, rank + world * (k + 1))  # a fresh replicate every step: nothing is cached
+        ctx.simulate()
+        ctx.emit_into(tgt, 0, N, 0, L)
+        if timed:
+            st = ctx.stats()
+            acc["sim"] += st["ms_simulate"]
+            acc["emit"] += st["ms_emit_kernel"]
+            acc["emit_launches"] += st["emit_kernel_launches"]
+
+    with torch.cuda.stream(stream):
+        for k in range(args.warmup):
+            step(k, False)
+        sampler = ClockSampler(local)
+        if rank == 0:
+            sampler.start()
+        l0 = ctx.stats()["kernel_launches"]
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        torch.cuda.synchronize()
+        e0.record(stream)
+        for k in range(args.steps):
+            step(args.warmup + k, True)
+        e1.record(stream)
+        torch.cuda.synchronize()
+        barrier()
+        ms = e0.elapsed_time(e1)
+        launches = ctx.stats()["kernel_launches"] - l0
+        clocks = sampler.stop() if rank == 0 else None
+
+        # end to end through the C ABI with host buffers
+        h_founder = torch.empty((L, N * P), dtype=torch.uint8, pin_memory=True)
+        h_dose = torch.empty((L, N), dtype=torch.uint8, pin_memory=True)
+        ht = ps.EmitTargets()
+        ht.founder, ht.founder_pitch, ht.founder_bytes = h_founder.data_ptr(), N * P, 1
+        ht.dose, ht.dose_pitch, ht.dose_which = h_dose.data_ptr(), N, ps.DOSE_MAX_ALLELE
+        ht.memory = ps.MEM_HOST
+
+        def e2e_step(k):
+            ctx.set_pedigree(w["p0"], w["p1"])  # drops the population and re-uploads the pedigree
+            ctx.reset(SEED, rank + world * (1000 + k))
+            ctx.set_map(w["off"], w["pos"])
+            ctx.set_allele_codes(w["code"])
+            ctx.simulate()
+            ctx.emit_into(ht, 0, N, 0, L)
+
+        e2e_steps = max(1, min(args.steps, 5))
+        e2e_step(-1)
+        barrier()
+        torch.cuda.synchronize()
+        e0.record(stream)
+        for k in range(e2e_steps):
+            e2e_step(k)
+        e1.record(stream)
+        torch.cuda.synchronize()
+        barrier()
+        ms_e2e = e0.elapsed_time(e1)
+
+    if world > 1:
+        t = torch.tensor([ms, ms_e2e], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms, ms_e2e = float(t[0]), float(t[1])
+    cells = N * L * P
+    value = world * cells * args.steps / (ms * 1e-3) / 1e9
+    e2e_value = world * cells * e2e_steps / (ms_e2e * 1e-3) / 1e9
+    peak, peak_src = measured_peak()
+    k2_ms = acc["emit"] / max(1, acc["emit_launches"])
+    algo_bytes = N * L * (P + 1)
+    achieved = algo_bytes / (k2_ms * 1e-3) / 1e9 if k2_ms > 0 else 0.0
+    if rank == 0:
+        out = {
+            "metric": "genotype calls/sec (G allele-loci/s)", "value": value, "unit": "G allele-loci/s",
+            "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+            "config": {"workload": WORKLOAD_NAME, "per_gpu": "one replicate population per rank, no collective",
+                       "tables": "founder-allele u8 [L][N*P] + MAX-allele dose u8 [L][N]",
+                       "l2": "1.2 GB of output per step exceeds the 126 MB L2; a new replicate is simulated every step",
+                       "positions": "fp64 Morgan"},
+            "meioses_per_s": world * M * args.steps / (ms * 1e-3),
+            "kernel_ms": {"simulate_per_step": acc["sim"] / args.steps, "emit_kernel_per_launch": k2_ms,
+                          "emit_kernel_share_of_step": acc["emit"] / ms if ms > 0 else None},
+            "roofline": {"bound": "hbm", "kernel": "k_emit_tiles<4,4>", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                         "frac": achieved / peak, "traffic": None, "algorithmic_bytes_per_launch": algo_bytes,
+                         "peak_source": peak_src},
+            "e2e": {"value": e2e_value, "unit": "G allele-loci/s", "steps": e2e_steps, "ms_per_step": ms_e2e / e2e_steps,
+                    "h2d_bytes_per_step": int(w["p0"].nbytes * 2 + w["off"].nbytes + w["pos"].nbytes + w["code"].nbytes),
+                    "d2h_bytes_per_step": int(L * N * P + L * N)},
+            "gpu_launches": int(launches),
+            "clocks": clocks,
+        }
+        if world == 1 and not args.no_cpu:
+            v, t, ws = cpu_port_run(w, 2500, 1, 0)
+            out["cpu_baseline"] = {"value": v, "unit": "G allele-loci/s", "cores": 1, "kind": "port",
+                                   "sample": "same workload with POPSIZE=2500 of 10000 offspring, all 24000 loci, "
+                                             "once: %.1f s" % t,
+                                   "meioses_per_s": ws["M"] / t}
+        prof = os.path.join(ROOT, "profiles", "k2_traffic.json")
+        if os.path.exists(prof):
+            try:
+                out["roofline"]["traffic"] = json.load(open(prof)).get("dram_bytes_per_launch")
+            except Exception:
+                pass
+        print(json.dumps(out))
+    ctx.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 0)
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        if args.warmup < 3:
+            args.warmup = 3
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -154,6 +154,16 @@ int psim_all_dose_rows(psim_ctx* ctx, int64_t locus_first, int64_t locus_count, 
 int psim_emit_all_dose(psim_ctx* ctx, int64_t ind_first, int64_t ind_count, int64_t locus_first,
                        int64_t locus_count, void* out, int64_t pitch, int32_t memory);
 
+/* Drop every haplostruct and meiotic configuration (pedigree, chromosomes, map and allele codes
+ * stay resident) and give the context a new RNG identity: the next psim_simulate is an
+ * independent draw. Used by Monte Carlo drivers that re-simulate the same pedigree. */
+int psim_reset(psim_ctx* ctx, int64_t seed, uint32_t replicate_first);
+
+/* Run all device work of this context on the caller's CUDA stream (a cudaStream_t passed as a
+ * pointer-sized integer; 0 restores the context's own stream). Lets a host that owns streams
+ * order and time libpsim's work with its own events. */
+int psim_set_stream(psim_ctx* ctx, uint64_t cuda_stream);
+
 /* Introspection for benchmarks and sharded drivers. */
 typedef struct psim_stats {
     int64_t n_meioses;          /* Individual.doMeiosis() equivalents run by psim_simulate */

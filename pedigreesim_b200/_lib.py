@@ -56,7 +56,7 @@ EXPORTS = [
     "psim_abi_version", "psim_create", "psim_destroy", "psim_last_error", "psim_set_chromosomes", "psim_set_pedigree",
     "psim_set_haplostructs", "psim_simulate", "psim_segment_count", "psim_get_haplostructs", "psim_get_meiotic_configs",
     "psim_set_map", "psim_set_allele_codes", "psim_emit", "psim_all_dose_rows", "psim_emit_all_dose", "psim_get_stats",
-    "psim_export_haplostructs_device", "psim_import_haplostructs_device",
+    "psim_export_haplostructs_device", "psim_import_haplostructs_device", "psim_reset", "psim_set_stream",
 ]
 
 _lib = None
@@ -90,6 +90,8 @@ def load():
     L.psim_emit.argtypes = [vp, i64, i64, i64, i64, C.POINTER(EmitTargets)]
     L.psim_all_dose_rows.argtypes = [vp, i64, i64, vp]
     L.psim_emit_all_dose.argtypes = [vp, i64, i64, i64, i64, vp, i64, i32]
+    L.psim_reset.argtypes = [vp, i64, u32]
+    L.psim_set_stream.argtypes = [vp, C.c_uint64]
     L.psim_get_stats.argtypes = [vp, C.POINTER(Stats)]
     L.psim_export_haplostructs_device.argtypes = [vp, i64, i64, C.POINTER(DeviceHS)]
     L.psim_import_haplostructs_device.argtypes = [vp, i64, i64, C.POINTER(DeviceHS)]
@@ -250,6 +252,13 @@ class PsimContext:
         out = np.zeros((int(ro[-1]), q), dtype=np.uint8)
         self._chk(self.L.psim_emit_all_dose(self.h, ind_first, ind_count, loc_first, loc_count, _p(out), q, MEM_HOST))
         return ro, out
+
+    def reset(self, seed, replicate_first=0):
+        self.replicate_first = replicate_first
+        self._chk(self.L.psim_reset(self.h, seed, replicate_first))
+
+    def set_stream(self, cuda_stream):
+        self._chk(self.L.psim_set_stream(self.h, int(cuda_stream)))
 
     def stats(self):
         s = Stats()

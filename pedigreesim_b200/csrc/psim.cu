@@ -665,7 +665,7 @@ struct psim_ctx_impl {
     std::string err;
     int C = 0, P = 0, R = 1;
     int64_t N = 0;
-    cudaStream_t stream = nullptr, copy_stream = nullptr;
+    cudaStream_t stream = nullptr, own_stream = nullptr, copy_stream = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev2 = nullptr, ev3 = nullptr;
     ModelParams model{};
     std::vector<ChromParams> chrom_h;
@@ -842,13 +842,14 @@ int psim_create(const psim_config* cfg, psim_ctx** out) {
     c->model.seed = (uint32_t)cfg->seed;
     cudaDeviceProp prop;
     if (cudaGetDeviceProperties(&prop, cfg->device) == cudaSuccess) c->sm_count = prop.multiProcessorCount;
-    bool ok = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) == cudaSuccess &&
+    bool ok = cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking) == cudaSuccess &&
               cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking) == cudaSuccess &&
               cudaEventCreate(&c->ev0) == cudaSuccess && cudaEventCreate(&c->ev1) == cudaSuccess &&
               cudaEventCreate(&c->ev2) == cudaSuccess && cudaEventCreate(&c->ev3) == cudaSuccess &&
               cudaMalloc((void**)&c->error_flag_d, sizeof(int)) == cudaSuccess &&
               cudaMalloc((void**)&c->tile_counter_d, sizeof(int)) == cudaSuccess;
     if (!ok) { g_create_error = std::string("CUDA setup failed: ") + cudaGetErrorString(cudaGetLastError()); delete c; return PSIM_ECUDA; }
+    c->stream = c->own_stream;
     cudaMemset(c->error_flag_d, 0, sizeof(int));
     *out = (psim_ctx*)c;
     return PSIM_OK;
@@ -869,7 +870,7 @@ void psim_destroy(psim_ctx* ctx) {
     if (c->ev1) cudaEventDestroy(c->ev1);
     if (c->ev2) cudaEventDestroy(c->ev2);
     if (c->ev3) cudaEventDestroy(c->ev3);
-    if (c->stream) cudaStreamDestroy(c->stream);
+    if (c->own_stream) cudaStreamDestroy(c->own_stream);
     if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
     delete c;
 }
@@ -1512,6 +1513,34 @@ int psim_emit_all_dose(psim_ctx* ctx, int64_t ind_first, int64_t ind_count, int6
     cudaEventElapsedTime(&ms, c->ev0, c->ev1);
     c->stats.ms_emit_total = ms;
     c->stats.ms_emit_kernel = ms;
+    return PSIM_OK;
+}
+
+int psim_reset(psim_ctx* ctx, int64_t seed, uint32_t replicate_first) {
+    psim_ctx_impl* c = CTX;
+    if (!c) return PSIM_EINVAL;
+    if (c->N == 0) return fail(c, PSIM_ESTATE, "psim_set_pedigree must be called first");
+    cudaSetDevice(c->cfg.device);
+    c->cfg.seed = seed;
+    c->cfg.replicate_first = replicate_first;
+    c->model.seed = (uint32_t)seed;
+    CUDA_TRY(cudaMemsetAsync(c->desc_d, 0, c->n_hom * sizeof(uint64_t), c->stream));
+    const int64_t ncfg = (int64_t)c->R * c->N * c->C * 2;
+    CUDA_TRY(cudaMemsetAsync(c->cfg_quad_d, 0xFF, ncfg, c->stream));
+    CUDA_TRY(cudaMemsetAsync(c->cfg_seq_d, 0xFF, ncfg * c->P, c->stream));
+    std::fill(c->hs_reps.begin(), c->hs_reps.end(), 0);
+    c->slab_used = 0;
+    c->stats.n_segments = 0;
+    c->runs_valid = false;
+    return PSIM_OK;
+}
+
+int psim_set_stream(psim_ctx* ctx, uint64_t cuda_stream) {
+    psim_ctx_impl* c = CTX;
+    if (!c) return PSIM_EINVAL;
+    cudaSetDevice(c->cfg.device);
+    cudaStreamSynchronize(c->stream);
+    c->stream = cuda_stream ? (cudaStream_t)(uintptr_t)cuda_stream : c->own_stream;
     return PSIM_OK;
 }
 
