@@ -171,9 +171,11 @@ typedef struct psim_stats {
     int64_t n_segments;         /* segments resident on the device */
     int64_t kernel_launches;    /* libpsim kernels launched since create */
     double  ms_simulate;        /* device time of the last psim_simulate (CUDA events) */
-    double  ms_emit_kernel;     /* device time of the emission kernels of the last psim_emit* */
-    double  ms_emit_total;      /* device time of the last psim_emit* including copies */
-    int64_t emit_kernel_launches; /* emission-kernel launches of the last psim_emit* */
+    double  ms_emit_kernel;     /* device time of the streaming emission kernel (k_emit_tiles / k_emit_generic)
+                                   launches of the last psim_emit*, CUDA events on the launching stream */
+    double  ms_emit_total;      /* device time of the last psim_emit* including plan kernels and copies */
+    int64_t emit_kernel_launches; /* streaming-kernel launches of the last psim_emit* */
+    double  ms_emit_plan;       /* device time of the tile-plan / dense helper kernels of the last psim_emit* */
 } psim_stats;
 int psim_get_stats(psim_ctx* ctx, psim_stats* out);
 

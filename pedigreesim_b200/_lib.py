@@ -9,7 +9,7 @@ import os
 import numpy as np
 
 PKG = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(PKG, "libpsim.so")
+LIB_PATH = os.environ.get("PSIM_LIB", os.path.join(PKG, "libpsim.so"))  # PSIM_LIB: tuning builds only
 
 PSIM_OK, PSIM_EINVAL, PSIM_ECUDA, PSIM_ECAPACITY, PSIM_ESTATE = 0, 1, 2, 3, 4
 DOSE_MIN_ALLELE, DOSE_MAX_ALLELE = -1, -2
@@ -43,7 +43,7 @@ class Stats(C.Structure):
     _fields_ = [
         ("n_meioses", C.c_int64), ("n_units", C.c_int64), ("n_segments", C.c_int64), ("kernel_launches", C.c_int64),
         ("ms_simulate", C.c_double), ("ms_emit_kernel", C.c_double), ("ms_emit_total", C.c_double),
-        ("emit_kernel_launches", C.c_int64),
+        ("emit_kernel_launches", C.c_int64), ("ms_emit_plan", C.c_double),
     ]
 
 

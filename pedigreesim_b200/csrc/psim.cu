@@ -14,8 +14,10 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
+#include <type_traits>
 #include <vector>
 
 #include <cub/device/device_scan.cuh>
@@ -309,6 +311,11 @@ __global__ void __launch_bounds__(128) k_index_runs(int64_t n_hom, int64_t hom_p
 // bytes) and walks the tile's loci in map order; the cells only change where one of its homologs
 // starts a new run, so the steady state is "re-store the same registers on the next row":
 // 128-bit coalesced stores, 32*NC contiguous bytes per warp and row.
+// With founder genotypes (allele codes) the per-locus work is kept off the cells:
+//   dose   = horizontal nibble sum of (multiplicity-of-each-founder-allele & per-locus nibble mask)
+//   allele = PRMT byte lookup of 4 cells at a time in the locus' code table
+// both tables are staged per tile in shared memory. MODE 0: no codes, 1: A <= 8, 2: A <= 16,
+// 3: any A (per-cell lookup).
 struct EmitArgs {
     int C, R, P;
     int64_t N;
@@ -328,184 +335,434 @@ struct EmitArgs {
     int n_col_tiles;
     int n_tiles;
     int* tile_counter;
+    // tile plan written by k_emit_plan, read by k_emit_tiles: one contiguous block per tile
+    //   uint4 [0]                     run starts inside the tile per warp (4 counters)
+    //   uint4 [1]                     tile coordinates: l0, l1 (chromosome-local rows), column tile, row of l0 in the output
+    //   uint4 [2 .. NG*128+1]         founder bytes of the tile's first row: [cg][slot], 16 cells each
+    //   uint4 [2 + NG*128 .. ]        the run starts: [warp][EMIT_EV] words row_rel << 22 | lane << 15 | column << 8 | founder
+    uint4* plan_blk;
+    int plan_blk_size;            // uint4 per tile: 2 + NG * 128 + EMIT_EV
+    int* dense_list;              // [1 + n_units] count, then (tile, warp) units with more than EMIT_EV run starts
     uint8_t* founder; int64_t founder_pitch;
     uint8_t* allele;  int64_t allele_pitch;
     uint8_t* dose;    int64_t dose_pitch;
-    int dose_mode;                // 0: founder == which, 1: code == per-locus match code
-    int dose_which;
-    const uint8_t* code;          // [L][A] or null
-    const uint8_t* match_code;    // [L] per-locus code to count (dose_mode 1)
+    int dose_which;               // MODE 0: founder allele to count
+    const uint32_t* code16;       // [L][4] allele codes of founder alleles 0..15, one byte each (MODE 1, 2)
+    const uint32_t* nibmask;      // [L][2] nibble a = 0xF iff founder allele a carries the counted allele (MODE 1, 2)
+    const uint8_t* code;          // [L][A] (MODE 3)
+    const uint8_t* match_code;    // [L] code to count (MODE 3)
     int A;
 };
 
+#ifndef PSIM_EMIT_MINB
+#define PSIM_EMIT_MINB 6
+#endif
 constexpr int EMIT_THREADS = 128;
+constexpr int EMIT_MAX_TILE_LOCI = 256;   // row index inside a tile must fit 16 bits
+constexpr int EMIT_EV = 64;           // run starts a warp may have inside a tile on the fast path (two per lane)
 constexpr uint32_t NO_EVENT = 0xFFFFFFFFu;
 
+struct TileCoord {
+    int c, ct;
+    int64_t gl0, gl1, c_off;
+    uint32_t l0, l1;
+};
+__device__ __forceinline__ TileCoord decode_tile(const EmitArgs& a, int tile) {
+    TileCoord t;
+    int k = 0;
+    while (tile >= a.chunk_tile_base[k + 1]) k++;
+    t.c = a.chunk_chrom[k];
+    const int t_in = tile - a.chunk_tile_base[k];
+    const int lt = t_in / a.n_col_tiles;
+    t.ct = t_in % a.n_col_tiles;
+    t.gl0 = a.chunk_l0[k] + (int64_t)lt * a.tile_loci;
+    t.gl1 = min(t.gl0 + a.tile_loci, a.chunk_l1[k]);
+    t.c_off = a.locus_off[t.c];
+    t.l0 = (uint32_t)(t.gl0 - t.c_off);
+    t.l1 = (uint32_t)(t.gl1 - t.c_off);
+    return t;
+}
 template <int P, int G>
-__global__ void __launch_bounds__(EMIT_THREADS) k_emit_tiles(const EmitArgs a) {
+__device__ __forceinline__ void thread_homologs(const EmitArgs& a, int c, int64_t q0, int64_t (&hid0)[G]) {
+#pragma unroll
+    for (int g = 0; g < G; g++) {
+        const int64_t q = q0 + g;
+        if (q < a.n_cols_ind) {
+            const int64_t r = q / a.ind_count, i = a.ind_first + q % a.ind_count;
+            hid0[g] = (((int64_t)c * a.R + r) * a.N + i) * P;
+        } else hid0[g] = -1;
+    }
+}
+
+// K2a — tile plan, homolog-major. One thread per (chromosome chunk, emitted column) walks that
+// homolog's run list once over the chunk's loci and leaves, for every tile it crosses, the founder
+// byte at the tile's first row (coalesced byte stores into the owning thread slot's 16-byte
+// vectors) and the run starts inside the tile, appended to the list of the warp that owns the
+// column (atomic ticket; the streaming warp sorts its list). Reads cost the streaming kernel
+// about 3.4x their byte share of DRAM time (profiles/write_ceiling_r1.txt), so the plan is kept
+// as small as it can be: 1 byte per cell and tile plus 4 bytes per run start.
+__global__ void __launch_bounds__(256) k_emit_plan(const EmitArgs a, int NC) {
+    const int k = blockIdx.y;
+    const int64_t col = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    const int P = a.P;
+    if (col >= a.n_cols_ind * P) return;
+    const int c = a.chunk_chrom[k];
+    const int64_t q = col / P;
+    const int h = (int)(col % P);
+    const int64_t r = q / a.ind_count, i = a.ind_first + q % a.ind_count;
+    const int64_t hid = (((int64_t)c * a.R + r) * a.N + i) * P + h;
+    const int slot = (int)((col / NC) % EMIT_THREADS);
+    const int ct = (int)(col / ((int64_t)NC * EMIT_THREADS));
+    const int jcol = (int)(col % NC);
+    const int ncg = NC / 16;
+    const uint64_t d = __ldg(a.run_desc + hid);
+    const uint32_t b = (uint32_t)desc_begin(d), n = desc_count(d);
+    const int64_t c_off = a.locus_off[c];
+    const uint32_t l_begin = (uint32_t)(a.chunk_l0[k] - c_off), l_end = (uint32_t)(a.chunk_l1[k] - c_off);
+    uint32_t lo = 0, hi = n;   // last run with lb <= l_begin
+    while (hi - lo > 1) { const uint32_t mid = (lo + hi) >> 1; if (__ldg(a.run_lb + b + mid) <= l_begin) lo = mid; else hi = mid; }
+    uint32_t f = n ? __ldg(a.run_founder + b + lo) : 0;
+    uint32_t kx = lo + 1;
+    uint32_t nxt = kx < n ? __ldg(a.run_lb + b + kx) : NO_EVENT;
+    const int n_lt = (int)((l_end - l_begin + a.tile_loci - 1) / a.tile_loci);
+    const uint32_t ev_lo = ((uint32_t)(slot & 31) << 15) | ((uint32_t)jcol << 8);
+    for (int lt = 0; lt < n_lt; lt++) {
+        const int tile = a.chunk_tile_base[k] + lt * a.n_col_tiles + ct;
+        const uint32_t tl0 = l_begin + (uint32_t)lt * a.tile_loci;
+        const uint32_t tl1 = min(tl0 + (uint32_t)a.tile_loci, l_end);
+        uint4* blk = a.plan_blk + (int64_t)tile * a.plan_blk_size;
+        while (nxt <= tl0) {   // a run starting exactly on the tile's first row is its start state
+            f = __ldg(a.run_founder + b + kx);
+            kx++;
+            nxt = kx < n ? __ldg(a.run_lb + b + kx) : NO_EVENT;
+        }
+        if (slot == 0 && jcol == 0)   // one thread per tile leaves the coordinates the streaming kernel needs
+            blk[1] = make_uint4(tl0, tl1, (uint32_t)ct, (uint32_t)(c_off + tl0 - a.locus_first));
+        reinterpret_cast<uint8_t*>(blk + 2 + (jcol >> 4) * EMIT_THREADS + slot)[jcol & 15] = (uint8_t)f;
+        while (nxt < tl1) {
+            f = __ldg(a.run_founder + b + kx);
+            uint32_t* cnt = reinterpret_cast<uint32_t*>(blk) + (slot >> 5);
+            const uint32_t idx = atomicAdd(cnt, 1u);
+            if (idx < EMIT_EV)
+                reinterpret_cast<uint32_t*>(blk + 2 + ncg * EMIT_THREADS)[(slot >> 5) * EMIT_EV + idx] = ((nxt - tl0) << 22) | ev_lo | f;
+            kx++;
+            nxt = kx < n ? __ldg(a.run_lb + b + kx) : NO_EVENT;
+        }
+    }
+}
+
+template <int NW>
+__device__ __forceinline__ void store_cells(uint8_t* p, const uint32_t (&v)[NW], bool full, int64_t col0, int64_t n_cols) {
+    if (full) {
+#pragma unroll
+        for (int q = 0; q < NW / 4; q++) reinterpret_cast<uint4*>(p)[q] = make_uint4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+    } else {
+#pragma unroll
+        for (int j = 0; j < NW * 4; j++) if (col0 + j < n_cols) p[j] = (uint8_t)(v[j / 4] >> (8 * (j % 4)));
+    }
+}
+
+__device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(smem)), "l"(gmem));
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+
+// K2b — streaming. A block's four warps take the same tile (2 KB contiguous per row written at the
+// same time), tiles are handed out in row-band order by an atomic ticket requested a tile early;
+// the plan block of the next tile is copied into shared memory with cp.async while the current
+// one streams, so no global round trip is ever waited for (under a saturated write stream each
+// costs thousands of cycles). Each warp sorts its run starts once (bitonic, one entry per lane)
+// and then walks them with warp-uniform control flow: write rows without any per-row checks up to
+// the next run start, let the owning lane patch its registers, go on.
+template <int P, int G, int MODE>
+__global__ void __launch_bounds__(EMIT_THREADS, PSIM_EMIT_MINB) k_emit_tiles(const EmitArgs a) {
     constexpr int NC = G * P;
     static_assert(NC % 16 == 0, "a thread's cells must be whole 16-byte vectors");
-    constexpr int NV = NC / 16;
-    extern __shared__ __align__(16) uint32_t s_dyn[];
-    uint32_t (*s_next)[EMIT_THREADS] = reinterpret_cast<uint32_t (*)[EMIT_THREADS]>(s_dyn);
-    uint32_t (*s_idx)[EMIT_THREADS] = reinterpret_cast<uint32_t (*)[EMIT_THREADS]>(s_dyn + NC * EMIT_THREADS);
-    int& s_tile = *reinterpret_cast<int*>(s_dyn + 2 * NC * EMIT_THREADS);
-    const int tid = threadIdx.x;
+    constexpr int NW = NC / 4;          // 32-bit words of packed cells
+    constexpr int NG = NC / 16;         // 16-byte vectors of packed cells
+    constexpr int DW = (G + 3) / 4;     // 32-bit words of packed doses
+    constexpr int W = MODE == 2 ? 2 : 1;  // nibble words per individual (8 founder alleles each)
+    constexpr int SW = MODE == 0 ? DW : MODE == 3 ? 1 : G * W;   // words of derived per-thread state
+    constexpr int PB = 2 + NG * EMIT_THREADS + EMIT_EV;          // uint4 per plan block
+    __shared__ uint4 s_blk[2][PB];
+    __shared__ int s_ticket[2];
+    const int tid = threadIdx.x, lane = tid & 31, wq = tid >> 5;
     const bool want_f = a.founder != nullptr, want_a = a.allele != nullptr, want_d = a.dose != nullptr;
+    const int64_t n_cols = a.n_cols_ind * P;
 
-    for (;;) {
-        if (tid == 0) s_tile = atomicAdd(a.tile_counter, 1);
-        __syncthreads();
-        const int tile = s_tile;
-        __syncthreads();
-        if (tile >= a.n_tiles) break;
-        int k = 0;
-        while (tile >= a.chunk_tile_base[k + 1]) k++;
-        const int c = a.chunk_chrom[k];
-        const int t_in = tile - a.chunk_tile_base[k];
-        const int lt = t_in / a.n_col_tiles, ct = t_in % a.n_col_tiles;
-        const int64_t gl0 = a.chunk_l0[k] + (int64_t)lt * a.tile_loci;                 // global loci of the tile
-        const int64_t gl1 = min(gl0 + a.tile_loci, a.chunk_l1[k]);
-        const int64_t c_off = a.locus_off[c];
-        const uint32_t l0 = (uint32_t)(gl0 - c_off), l1 = (uint32_t)(gl1 - c_off);     // chromosome-local
+    auto prefetch_plan = [&](int tile, int buf) {
+        const uint4* src = a.plan_blk + (int64_t)tile * PB;
+        for (int i = tid; i < PB; i += EMIT_THREADS) cp_async16(&s_blk[buf][i], src + i);
+        cp_async_commit();
+    };
+    int ticket = 0;     // thread 0: the outstanding atomic result
+    int tile = blockIdx.x, tile_next = 0;
+    if (tid == 0) { s_ticket[0] = gridDim.x + atomicAdd(a.tile_counter, 1); ticket = atomicAdd(a.tile_counter, 1); }
+    __syncthreads();
+    tile_next = s_ticket[0];
+    int par = 1, buf = 0;
+    if (tile < a.n_tiles) prefetch_plan(tile, 0);
+    for (; tile < a.n_tiles;) {
+        cp_async_wait_all();
+        if (tid == 0) { s_ticket[par] = gridDim.x + ticket; ticket = atomicAdd(a.tile_counter, 1); }
+        __syncthreads();   // plan block of `tile` complete and visible; next ticket published
+        const int cb = buf;
+        buf ^= 1;
+        const int tile_cur = tile;
+        tile = tile_next;
+        tile_next = s_ticket[par];
+        par ^= 1;
+        if (tile < a.n_tiles) prefetch_plan(tile, buf);
 
-        const int64_t q0 = ((int64_t)ct * EMIT_THREADS + tid) * G;  // first emitted individual of this thread
-        int64_t hid0[G];
-#pragma unroll
-        for (int g = 0; g < G; g++) {
-            const int64_t q = q0 + g;
-            if (q < a.n_cols_ind) {
-                const int64_t r = q / a.ind_count, i = a.ind_first + q % a.ind_count;
-                hid0[g] = (((int64_t)c * a.R + r) * a.N + i) * P;
-            } else hid0[g] = -1;
+        const uint32_t n_ev = reinterpret_cast<const uint32_t*>(&s_blk[cb][0])[wq];
+        if (n_ev > (uint32_t)EMIT_EV) {   // sparse map: this (tile, warp) unit goes to k_emit_dense
+            if (lane == 0) a.dense_list[1 + atomicAdd(a.dense_list, 1)] = tile_cur * (EMIT_THREADS / 32) + wq;
+            continue;
         }
-        uint32_t pk[NC / 4];
+        const uint4 tc = s_blk[cb][1];     // tile coordinates left by k_emit_plan
+        const uint32_t l0 = tc.x, l1 = tc.y;
+        const int64_t row0 = (int64_t)tc.w;
+        const int64_t c_off = row0 + a.locus_first - l0;
+        const int64_t q0 = ((int64_t)tc.z * EMIT_THREADS + tid) * G;   // first emitted individual of this lane
+        const int64_t colf = q0 * P;                                    // first founder/allele column
+        const bool full = colf + NC <= n_cols;
+
+        // ---- the warp's run starts, sorted by row: element i = lane + 32 r lives in ev[r] of the
+        // lane, bitonic network over the 64 slots (unused ones hold NO_EVENT and sort to the end)
+        uint32_t ev[2];
+        {
+            const uint32_t* src = reinterpret_cast<const uint32_t*>(&s_blk[cb][2 + NG * EMIT_THREADS]) + wq * EMIT_EV;
+            ev[0] = (uint32_t)lane < n_ev ? src[lane] : NO_EVENT;
+            ev[1] = (uint32_t)lane + 32 < n_ev ? src[lane + 32] : NO_EVENT;
+        }
+        if (n_ev > 1) {
 #pragma unroll
-        for (int w = 0; w < NC / 4; w++) pk[w] = 0;
-        uint32_t next_ev = NO_EVENT;
-        // tile entry: locate the run that contains l0 for each of the NC homologs
+            for (int k2 = 2; k2 <= 64; k2 <<= 1) {
+#pragma unroll
+                for (int j = k2 >> 1; j > 0; j >>= 1) {
+                    if (j == 32) {   // partner is the lane's other register
+                        const uint32_t lo_v = min(ev[0], ev[1]), hi_v = max(ev[0], ev[1]);
+                        ev[0] = lo_v; ev[1] = hi_v;     // k2 == 64: the whole array ascends
+                    } else {
+#pragma unroll
+                        for (int r = 0; r < 2; r++) {
+                            const int i = lane + 32 * r;
+                            const uint32_t other = __shfl_xor_sync(0xFFFFFFFFu, ev[r], j);
+                            const bool keep_min = ((i & k2) == 0) == ((i & j) == 0);
+                            ev[r] = keep_min ? min(ev[r], other) : max(ev[r], other);
+                        }
+                    }
+                }
+            }
+        }
+        // ---- state of this lane at the tile's first row
+        uint32_t pk[NW];
+#pragma unroll
+        for (int cg = 0; cg < NG; cg++) {
+            const uint4 v = s_blk[cb][2 + cg * EMIT_THREADS + tid];
+            pk[4 * cg] = v.x; pk[4 * cg + 1] = v.y; pk[4 * cg + 2] = v.z; pk[4 * cg + 3] = v.w;
+        }
+        uint32_t st[SW];           // MODE 0: packed doses; MODE 1/2: nibble multiplicities [g][w]
+        uint32_t sel[NW];          // MODE 1/2 with allele table: PRMT selectors
+        uint32_t him[NW];          // MODE 2: 0xFF per cell whose founder allele is >= 8
+#pragma unroll
+        for (int w = 0; w < SW; w++) st[w] = 0;
 #pragma unroll
         for (int j = 0; j < NC; j++) {
-            const int g = j / P, h = j % P;
-            uint32_t nxt = NO_EVENT, idx = 0, f = 0;
-            if (hid0[g] >= 0) {
-                const uint64_t d = a.run_desc[hid0[g] + h];
-                const uint32_t b = (uint32_t)desc_begin(d), n = desc_count(d);
-                uint32_t lo = 0, hi = n;  // last run with lb <= l0
-                while (hi - lo > 1) { const uint32_t mid = (lo + hi) >> 1; if (a.run_lb[b + mid] <= l0) lo = mid; else hi = mid; }
-                f = a.run_founder[b + lo];
-                idx = b + lo + 1;
-                nxt = lo + 1 < n ? a.run_lb[b + lo + 1] : NO_EVENT;
-            }
-            s_next[j][tid] = nxt;
-            s_idx[j][tid] = idx;
-            next_ev = min(next_ev, nxt);
-            pk[j / 4] |= f << (8 * (j % 4));
+            const uint32_t f = (pk[j / 4] >> (8 * (j % 4))) & 0xFF;
+            if (MODE == 0) { if (f == (uint32_t)a.dose_which) st[(j / P) / 4] += 1u << (8 * ((j / P) % 4)); }
+            else if (MODE == 1) st[j / P] += 1u << (4 * (f & 7));
+            else if (MODE == 2) st[(j / P) * W + (f >> 3 & 1)] += 1u << (4 * (f & 7));
         }
-        uint32_t dose_pk[(G + 3) / 4];
-        auto recompute_dose = [&]() {
+        if (MODE == 1 || MODE == 2) {
 #pragma unroll
-            for (int w = 0; w < (G + 3) / 4; w++) dose_pk[w] = 0;
+            for (int w = 0; w < NW; w++) {
+                const uint32_t v = pk[w];
+                sel[w] = (v & 0x7) | ((v >> 4) & 0x70) | ((v >> 8) & 0x700) | ((v >> 12) & 0x7000);
+                him[w] = ((v >> 3) & 0x01010101u) * 0xFFu;
+            }
+        }
+
+        // ---- stream the rows
+        uint32_t l = l0;
+        uint8_t* pf = a.founder + row0 * a.founder_pitch + colf;
+        uint8_t* pa = a.allele + row0 * a.allele_pitch + colf;
+        uint8_t* pd = a.dose + row0 * a.dose_pitch + q0;
+        const uint4* code16 = reinterpret_cast<const uint4*>(a.code16) + c_off;    // per-locus tables: warp-uniform
+        const uint2* nibmask = reinterpret_cast<const uint2*>(a.nibmask) + c_off;  // loads through L1
+        // compiled once per combination of requested tables so that the hot loop carries no
+        // predicated-off work (WF / WA / WD shadow the runtime flags)
+        auto emit_rows_t = [&](auto full_tag, auto wf_tag, auto wa_tag, auto wd_tag, uint32_t stop) {
+            constexpr bool FULL = decltype(full_tag)::value;
+            constexpr bool want_f = decltype(wf_tag)::value, want_a = decltype(wa_tag)::value, want_d = decltype(wd_tag)::value;
+#pragma unroll 4
+            for (; l < stop; l++) {
+                uint32_t dose_pk[DW];
+                if (want_f) { store_cells<NW>(pf, pk, FULL, colf, n_cols); pf += a.founder_pitch; }
+                if (MODE == 0) {
 #pragma unroll
-            for (int j = 0; j < NC; j++) {
-                const uint32_t f = (pk[j / 4] >> (8 * (j % 4))) & 0xFF;
-                if (f == (uint32_t)a.dose_which) dose_pk[(j / P) / 4] += 1u << (8 * ((j / P) % 4));
+                    for (int w = 0; w < DW; w++) dose_pk[w] = st[w];
+                } else if (MODE == 1 || MODE == 2) {
+                    if (want_a) {
+                        const uint4 tb = __ldg(code16 + l);
+                        uint32_t ak[NW];
+#pragma unroll
+                        for (int w = 0; w < NW; w++) {
+                            const uint32_t lov = __byte_perm(tb.x, tb.y, sel[w]);
+                            if (MODE == 2) { const uint32_t hiv = __byte_perm(tb.z, tb.w, sel[w]); ak[w] = (lov & ~him[w]) | (hiv & him[w]); }
+                            else ak[w] = lov;
+                        }
+                        store_cells<NW>(pa, ak, FULL, colf, n_cols);
+                        pa += a.allele_pitch;
+                    }
+                    if (want_d) {
+                        uint2 m;
+                        if (W == 2) m = __ldg(nibmask + l);
+                        else { m.x = __ldg(reinterpret_cast<const uint32_t*>(nibmask + l)); m.y = 0; }
+#pragma unroll
+                        for (int w = 0; w < DW; w++) dose_pk[w] = 0;
+#pragma unroll
+                        for (int g = 0; g < G; g++) {
+                            uint32_t d = ((st[g * W] & m.x) * 0x11111111u) >> 28;
+                            if (W == 2) d += ((st[g * W + W - 1] & m.y) * 0x11111111u) >> 28;
+                            dose_pk[g / 4] |= d << (8 * (g % 4));
+                        }
+                    }
+                } else {
+                    const uint8_t* codes = a.code + (c_off + l) * a.A;
+                    const uint32_t match = a.match_code[c_off + l];
+                    uint32_t ak[NW];
+#pragma unroll
+                    for (int w = 0; w < DW; w++) dose_pk[w] = 0;
+#pragma unroll
+                    for (int w = 0; w < NW; w++) ak[w] = 0;
+#pragma unroll
+                    for (int j = 0; j < NC; j++) {
+                        const uint32_t f = (pk[j / 4] >> (8 * (j % 4))) & 0xFF;
+                        const uint32_t al = __ldg(codes + f);
+                        ak[j / 4] |= al << (8 * (j % 4));
+                        if (al == match) dose_pk[(j / P) / 4] += 1u << (8 * ((j / P) % 4));
+                    }
+                    if (want_a) { store_cells<NW>(pa, ak, FULL, colf, n_cols); pa += a.allele_pitch; }
+                }
+                if (want_d) {
+                    if (FULL) {
+                        if (G % 16 == 0) {
+#pragma unroll
+                            for (int v = 0; v < G / 16; v++)
+                                reinterpret_cast<uint4*>(pd)[v] = make_uint4(dose_pk[(4 * v) % DW], dose_pk[(4 * v + 1) % DW], dose_pk[(4 * v + 2) % DW], dose_pk[(4 * v + 3) % DW]);
+                        } else if (G == 8) {
+                            *reinterpret_cast<uint2*>(pd) = make_uint2(dose_pk[0], dose_pk[DW - 1]);
+                        } else if (G == 4) {
+                            *reinterpret_cast<uint32_t*>(pd) = dose_pk[0];
+                        } else if (G == 2) {
+                            *reinterpret_cast<uint16_t*>(pd) = (uint16_t)dose_pk[0];
+                        } else {
+#pragma unroll
+                            for (int g = 0; g < G; g++) pd[g] = (uint8_t)(dose_pk[g / 4] >> (8 * (g % 4)));
+                        }
+                    } else {
+#pragma unroll
+                        for (int g = 0; g < G; g++) if (q0 + g < a.n_cols_ind) pd[g] = (uint8_t)(dose_pk[g / 4] >> (8 * (g % 4)));
+                    }
+                    pd += a.dose_pitch;
+                }
             }
         };
-        if (want_d && a.dose_mode == 0) recompute_dose();
+        auto emit_rows = [&](auto full_tag, uint32_t stop) {
+            using T = std::true_type;
+            using F = std::false_type;
+            if (MODE == 0) {   // no allele table without codes
+                if (want_f) { if (want_d) emit_rows_t(full_tag, T{}, F{}, T{}, stop); else emit_rows_t(full_tag, T{}, F{}, F{}, stop); }
+                else emit_rows_t(full_tag, F{}, F{}, T{}, stop);
+            } else if (want_f) {
+                if (want_a) { if (want_d) emit_rows_t(full_tag, T{}, T{}, T{}, stop); else emit_rows_t(full_tag, T{}, T{}, F{}, stop); }
+                else { if (want_d) emit_rows_t(full_tag, T{}, F{}, T{}, stop); else emit_rows_t(full_tag, T{}, F{}, F{}, stop); }
+            } else {
+                if (want_a) { if (want_d) emit_rows_t(full_tag, F{}, T{}, T{}, stop); else emit_rows_t(full_tag, F{}, T{}, F{}, stop); }
+                else emit_rows_t(full_tag, F{}, F{}, T{}, stop);
+            }
+        };
+        for (uint32_t k = 0;; k++) {   // warp-uniform walk over the sorted run starts
+            const uint32_t e = k < n_ev ? __shfl_sync(0xFFFFFFFFu, k < 32 ? ev[0] : ev[1], k & 31) : NO_EVENT;
+            const uint32_t wstop = min(l0 + (e >> 22), l1);
+            if (full) emit_rows(std::true_type{}, wstop);
+            else if (colf < n_cols) emit_rows(std::false_type{}, wstop);
+            else l = wstop;
+            if (e == NO_EVENT) break;
+            if (((e >> 15) & 31) == (uint32_t)lane) {      // this lane's run starts here: patch the registers
+                const uint32_t col = (e >> 8) & 0x7F, f = e & 0xFF;
+                const uint32_t cw = col >> 2, sh = (col & 3) * 8, g = col / P;
+                uint32_t old = 0;
+#pragma unroll
+                for (int w = 0; w < NW; w++) {
+                    const bool hit = (uint32_t)w == cw;
+                    const uint32_t msk = hit ? 0xFFu << sh : 0u;
+                    old |= pk[w] & msk;
+                    pk[w] = (pk[w] & ~msk) | ((f << sh) & msk);
+                    if (MODE == 1 || MODE == 2) {
+                        const uint32_t nsh = sh >> 1, nmsk = hit ? 0xFu << nsh : 0u;
+                        sel[w] = (sel[w] & ~nmsk) | (((f & 7) << nsh) & nmsk);
+                        if (MODE == 2) him[w] = (him[w] & ~msk) | (f & 8 ? msk : 0u);
+                    }
+                }
+                old >>= sh;
+                if (MODE == 0) {
+                    const uint32_t delta = ((f == (uint32_t)a.dose_which) - (old == (uint32_t)a.dose_which)) << (8 * (g & 3));
+#pragma unroll
+                    for (int w = 0; w < DW; w++) st[w] += (uint32_t)w == (g >> 2) ? delta : 0u;
+                } else if (MODE == 1) {
+                    const uint32_t delta = (1u << (4 * (f & 7))) - (1u << (4 * (old & 7)));
+#pragma unroll
+                    for (int gg = 0; gg < G; gg++) st[gg] += (uint32_t)gg == g ? delta : 0u;
+                } else if (MODE == 2) {
+                    const uint32_t dec = 1u << (4 * (old & 7)), inc = 1u << (4 * (f & 7));
+                    const uint32_t wi_old = g * W + (old >> 3 & 1), wi_new = g * W + (f >> 3 & 1);
+#pragma unroll
+                    for (int w = 0; w < SW; w++) st[w] += ((uint32_t)w == wi_new ? inc : 0u) - ((uint32_t)w == wi_old ? dec : 0u);
+                }
+            }
+        }
+    }
+}
 
-        const int64_t colf = ((int64_t)ct * EMIT_THREADS + tid) * NC;   // first founder/allele column
-        const int64_t n_cols = a.n_cols_ind * P;
-        const bool full = colf + NC <= n_cols;
-        const bool any = colf < n_cols;
-        int64_t row = gl0 - a.locus_first;
-        for (uint32_t l = l0; l < l1; l++, row++) {
-            if (l == next_ev) {
-                next_ev = NO_EVENT;
-#pragma unroll
-                for (int j = 0; j < NC; j++) {
-                    uint32_t nxt = s_next[j][tid];
-                    if (nxt == l) {
-                        const int g = j / P, h = j % P;
-                        const uint32_t idx = s_idx[j][tid];
-                        const uint32_t f = a.run_founder[idx];
-                        pk[j / 4] = (pk[j / 4] & ~(0xFFu << (8 * (j % 4)))) | (f << (8 * (j % 4)));
-                        const uint64_t d = a.run_desc[hid0[g] + h];
-                        const uint32_t end = (uint32_t)desc_begin(d) + desc_count(d);
-                        nxt = idx + 1 < end ? a.run_lb[idx + 1] : NO_EVENT;
-                        s_next[j][tid] = nxt;
-                        s_idx[j][tid] = idx + 1;
-                    }
-                    next_ev = min(next_ev, nxt);
-                }
-                if (want_d && a.dose_mode == 0) recompute_dose();
+// Dense units (a warp has more than EMIT_EV run starts inside the tile — sparse maps, where the
+// tables are tiny): every cell is searched. One warp per unit listed by k_emit_tiles.
+template <int P, int G>
+__global__ void __launch_bounds__(EMIT_THREADS) k_emit_dense(const EmitArgs a) {
+    const int n_dense = a.dense_list[0];
+    const bool want_f = a.founder != nullptr, want_a = a.allele != nullptr, want_d = a.dose != nullptr;
+    const bool coded = a.code != nullptr;
+    for (int di = blockIdx.x; di < n_dense; di += gridDim.x) {
+        const int u = a.dense_list[1 + di];
+        const TileCoord t = decode_tile(a, u >> 2);
+        const int n_rows = (int)(t.l1 - t.l0);
+        // work items: (row, lane of the unit, individual of the lane)
+        for (int it = threadIdx.x; it < n_rows * 32 * G; it += EMIT_THREADS) {
+            const int g = it % G, lane = (it / G) % 32;
+            const uint32_t l = t.l0 + it / (G * 32);
+            const int64_t q = ((int64_t)t.ct * EMIT_THREADS + (u & 3) * 32 + lane) * G + g;
+            if (q >= a.n_cols_ind) continue;
+            const int64_t r = q / a.ind_count, i = a.ind_first + q % a.ind_count;
+            const int64_t hid0 = (((int64_t)t.c * a.R + r) * a.N + i) * P;
+            const int64_t row = t.gl0 - a.locus_first + (l - t.l0);
+            const uint8_t* codes = coded ? a.code + (t.c_off + l) * a.A : nullptr;
+            const uint32_t match = coded ? (uint32_t)a.match_code[t.c_off + l] : (uint32_t)a.dose_which;
+            uint32_t dose = 0;
+#pragma unroll 1
+            for (int h = 0; h < P; h++) {
+                const uint64_t d = a.run_desc[hid0 + h];
+                const uint32_t b = (uint32_t)desc_begin(d), n = desc_count(d);
+                uint32_t lo = 0, hi = n;
+                while (hi - lo > 1) { const uint32_t mid = (lo + hi) >> 1; if (a.run_lb[b + mid] <= l) lo = mid; else hi = mid; }
+                const uint32_t f = a.run_founder[b + lo];
+                const uint32_t al = coded ? (uint32_t)codes[f] : f;
+                if (want_f) a.founder[row * a.founder_pitch + q * P + h] = (uint8_t)f;
+                if (want_a) a.allele[row * a.allele_pitch + q * P + h] = (uint8_t)al;
+                dose += al == match;
             }
-            if (!any) continue;
-            if (want_f) {
-                uint8_t* p = a.founder + row * a.founder_pitch + colf;
-                if (full) {
-#pragma unroll
-                    for (int v = 0; v < NV; v++)
-                        reinterpret_cast<uint4*>(p)[v] = make_uint4(pk[4 * v], pk[4 * v + 1], pk[4 * v + 2], pk[4 * v + 3]);
-                } else {
-#pragma unroll
-                    for (int j = 0; j < NC; j++) if (colf + j < n_cols) p[j] = (uint8_t)(pk[j / 4] >> (8 * (j % 4)));
-                }
-            }
-            if (want_a || (want_d && a.dose_mode == 1)) {
-                const uint8_t* codes = a.code + (c_off + l) * a.A;
-                const uint32_t match = want_d && a.dose_mode == 1 ? a.match_code[c_off + l] : 0;
-                uint32_t ak[NC / 4];
-                uint32_t dk[(G + 3) / 4];
-#pragma unroll
-                for (int w = 0; w < (G + 3) / 4; w++) dk[w] = 0;
-#pragma unroll
-                for (int w = 0; w < NC / 4; w++) ak[w] = 0;
-#pragma unroll
-                for (int j = 0; j < NC; j++) {
-                    const uint32_t f = (pk[j / 4] >> (8 * (j % 4))) & 0xFF;
-                    const uint32_t al = __ldg(codes + f);
-                    ak[j / 4] |= al << (8 * (j % 4));
-                    if (al == match) dk[(j / P) / 4] += 1u << (8 * ((j / P) % 4));
-                }
-                if (want_a) {
-                    uint8_t* p = a.allele + row * a.allele_pitch + colf;
-                    if (full) {
-#pragma unroll
-                        for (int v = 0; v < NV; v++)
-                            reinterpret_cast<uint4*>(p)[v] = make_uint4(ak[4 * v], ak[4 * v + 1], ak[4 * v + 2], ak[4 * v + 3]);
-                    } else {
-#pragma unroll
-                        for (int j = 0; j < NC; j++) if (colf + j < n_cols) p[j] = (uint8_t)(ak[j / 4] >> (8 * (j % 4)));
-                    }
-                }
-                if (want_d && a.dose_mode == 1) {
-#pragma unroll
-                    for (int w = 0; w < (G + 3) / 4; w++) dose_pk[w] = dk[w];
-                }
-            }
-            if (want_d) {
-                uint8_t* p = a.dose + row * a.dose_pitch + q0;
-                if (full) {
-                    if (G % 16 == 0) {
-#pragma unroll
-                        for (int v = 0; v < G / 16; v++)
-                            reinterpret_cast<uint4*>(p)[v] = make_uint4(dose_pk[4 * v], dose_pk[4 * v + 1], dose_pk[4 * v + 2], dose_pk[4 * v + 3]);
-                    } else if (G == 8) {
-                        *reinterpret_cast<uint2*>(p) = make_uint2(dose_pk[0], dose_pk[1]);
-                    } else if (G == 4) {
-                        *reinterpret_cast<uint32_t*>(p) = dose_pk[0];
-                    } else if (G == 2) {
-                        *reinterpret_cast<uint16_t*>(p) = (uint16_t)dose_pk[0];
-                    } else {
-#pragma unroll
-                        for (int g = 0; g < G; g++) p[g] = (uint8_t)(dose_pk[g / 4] >> (8 * (g % 4)));
-                    }
-                } else {
-#pragma unroll
-                    for (int g = 0; g < G; g++) if (q0 + g < a.n_cols_ind) p[g] = (uint8_t)(dose_pk[g / 4] >> (8 * (g % 4)));
-                }
-            }
+            if (want_d) a.dose[row * a.dose_pitch + q] = (uint8_t)dose;
         }
     }
 }
@@ -639,7 +896,11 @@ __global__ void k_gather_segments(int64_t n, int64_t first, int r, int C, int R,
     int64_t w = off[t];
     for (int s = 0; s < cn; s++, w++) { out_pos[w] = seg_pos[b + s]; out_founder[w] = seg_founder[b + s]; }
 }
-__global__ void k_match_codes(int64_t L, int A, int which, const uint8_t* __restrict__ code, uint8_t* __restrict__ match) {
+// Per-locus tables for the coded emission: the code to count for the dose table (Main.java:987-1000:
+// MAX / MIN allele name or the name of founder allele `which`), the padded 16-entry code table and
+// the nibble mask of founder alleles that carry the counted code.
+__global__ void k_match_codes(int64_t L, int A, int which, const uint8_t* __restrict__ code, uint8_t* __restrict__ match,
+                              uint32_t* __restrict__ code16, uint32_t* __restrict__ nibmask) {
     const int64_t l = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (l >= L) return;
     const uint8_t* cd = code + l * A;
@@ -648,6 +909,16 @@ __global__ void k_match_codes(int64_t L, int A, int which, const uint8_t* __rest
     else if (which == PSIM_DOSE_MIN_ALLELE) { m = 255; for (int k = 0; k < A; k++) m = min(m, (int)cd[k]); }
     else m = cd[(which < 0 || which >= A) ? 0 : which];
     match[l] = (uint8_t)m;
+    if (A <= 16) {
+        uint32_t t[4] = {0, 0, 0, 0}, nm[2] = {0, 0};
+        for (int k = 0; k < A; k++) {
+            t[k >> 2] |= (uint32_t)cd[k] << (8 * (k & 3));
+            if (cd[k] == m) nm[k >> 3] |= 0xFu << (4 * (k & 7));
+        }
+        for (int q = 0; q < 4; q++) code16[l * 4 + q] = t[q];
+        nibmask[l * 2] = nm[0];
+        nibmask[l * 2 + 1] = nm[1];
+    }
 }
 
 }  // namespace psim
@@ -667,6 +938,8 @@ struct psim_ctx_impl {
     int64_t N = 0;
     cudaStream_t stream = nullptr, own_stream = nullptr, copy_stream = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev2 = nullptr, ev3 = nullptr;
+    std::vector<cudaEvent_t> kev;   // event pool: triples (before plan, before stream, after stream) per launch
+    int kev_used = 0;
     ModelParams model{};
     std::vector<ChromParams> chrom_h;
     ChromParams* chrom_d = nullptr;
@@ -699,6 +972,8 @@ struct psim_ctx_impl {
     uint8_t* code_d = nullptr;
     std::vector<uint8_t> code_h;
     uint8_t* match_d = nullptr;
+    uint32_t* code16_d = nullptr;   // [L][4]
+    uint32_t* nibmask_d = nullptr;  // [L][2]
     int match_which = 12345678;
     int founder_allele_count = 0;
     // scratch
@@ -708,6 +983,10 @@ struct psim_ctx_impl {
     size_t cub_tmp_bytes = 0;
     void* staging = nullptr;
     size_t staging_bytes = 0;
+    // grow-only scratch of psim_simulate (no allocation in the steady state of a Monte Carlo loop)
+    struct Buf { void* p = nullptr; size_t cap = 0; };
+    Buf b_lev, b_np, b_cnt, b_off, b_ppos, b_phom, b_find, b_fal;
+    Buf b_plan, b_dense_list;
     // export buffers
     int64_t* exp_off_d = nullptr; int32_t* exp_founder_d = nullptr; double* exp_pos_d = nullptr;
     int64_t exp_off_cap = 0, exp_seg_cap = 0;
@@ -751,7 +1030,9 @@ double calc_recomb_dist(double len) {
 
 int ensure_slab(psim_ctx_impl* c, int64_t need) {
     if (need <= c->slab_cap) return 0;
-    int64_t cap = std::max<int64_t>(need, c->slab_cap + c->slab_cap / 2);
+    // grow generously: a Monte Carlo loop re-simulates populations whose segment totals vary by a
+    // few percent, and a reallocation (cudaMalloc + copy + cudaFree) costs far more than the memory
+    int64_t cap = std::max<int64_t>(need + need / 4, 2 * c->slab_cap);
     cap = std::max<int64_t>(cap, 1 << 16);
     double* np = nullptr; int32_t* nf = nullptr;
     CUDA_TRY(dev_alloc(&np, cap));
@@ -763,6 +1044,14 @@ int ensure_slab(psim_ctx_impl* c, int64_t need) {
     }
     cudaFree(c->seg_pos_d); cudaFree(c->seg_founder_d);
     c->seg_pos_d = np; c->seg_founder_d = nf; c->slab_cap = cap;
+    return 0;
+}
+int ensure_buf(psim_ctx_impl* c, psim_ctx_impl::Buf& b, size_t bytes) {
+    if (bytes <= b.cap) return 0;
+    cudaFree(b.p);
+    b.p = nullptr; b.cap = 0;
+    CUDA_TRY(cudaMalloc(&b.p, bytes));
+    b.cap = bytes;
     return 0;
 }
 int ensure_cub(psim_ctx_impl* c, size_t bytes) {
@@ -792,17 +1081,26 @@ void free_population(psim_ctx_impl* c) {
     c->runs_valid = false;
 }
 
-template <int P, int G>
-void launch_tiles(psim_ctx_impl* c, const EmitArgs& ea, int blocks) {
-    constexpr size_t smem = (size_t)2 * G * P * EMIT_THREADS * sizeof(uint32_t) + 16;
-    static bool configured = false;
-    if (!configured) {
-        cudaFuncSetAttribute(k_emit_tiles<P, G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        configured = true;
-    }
-    k_emit_tiles<P, G><<<blocks, EMIT_THREADS, smem, c->stream>>>(ea);
+template <int P, int G, int MODE>
+void launch_tiles_mode(psim_ctx_impl* c, const EmitArgs& ea, int blocks) {
+    k_emit_tiles<P, G, MODE><<<blocks, EMIT_THREADS, 0, c->stream>>>(ea);
 }
-
+cudaEvent_t next_kev(psim_ctx_impl* c) {
+    if (c->kev_used == (int)c->kev.size()) { cudaEvent_t e; cudaEventCreate(&e); c->kev.push_back(e); }
+    return c->kev[c->kev_used++];
+}
+template <int P, int G>
+void launch_tiles(psim_ctx_impl* c, const EmitArgs& ea, int blocks, int mode) {
+    const int64_t n_cols = ea.n_cols_ind * P;
+    k_emit_plan<<<dim3((unsigned)((n_cols + 255) / 256), (unsigned)ea.n_chunks), 256, 0, c->stream>>>(ea, G * P);
+    cudaEventRecord(next_kev(c), c->stream);
+    if (mode == 0) launch_tiles_mode<P, G, 0>(c, ea, blocks);
+    else if (mode == 1) launch_tiles_mode<P, G, 1>(c, ea, blocks);
+    else if (mode == 2) launch_tiles_mode<P, G, 2>(c, ea, blocks);
+    else launch_tiles_mode<P, G, 3>(c, ea, blocks);
+    cudaEventRecord(next_kev(c), c->stream);
+    k_emit_dense<P, G><<<c->sm_count * 4, EMIT_THREADS, 0, c->stream>>>(ea);
+}
 }  // namespace
 
 extern "C" {
@@ -864,8 +1162,12 @@ void psim_destroy(psim_ctx* ctx) {
     cudaFree(c->chrom_d); cudaFree(c->seg_pos_d); cudaFree(c->seg_founder_d);
     cudaFree(c->run_lb_d); cudaFree(c->run_founder_d);
     cudaFree(c->locus_off_d); cudaFree(c->locus_pos_d); cudaFree(c->code_d); cudaFree(c->match_d);
+    cudaFree(c->code16_d); cudaFree(c->nibmask_d);
     cudaFree(c->error_flag_d); cudaFree(c->tile_counter_d); cudaFree(c->cub_tmp); cudaFree(c->staging);
     cudaFree(c->exp_off_d); cudaFree(c->exp_founder_d); cudaFree(c->exp_pos_d);
+    for (cudaEvent_t e : c->kev) cudaEventDestroy(e);
+    for (psim_ctx_impl::Buf* b : {&c->b_lev, &c->b_np, &c->b_cnt, &c->b_off, &c->b_ppos, &c->b_phom, &c->b_find, &c->b_fal,
+                                 &c->b_plan, &c->b_dense_list}) cudaFree(b->p);
     if (c->ev0) cudaEventDestroy(c->ev0);
     if (c->ev1) cudaEventDestroy(c->ev1);
     if (c->ev2) cudaEventDestroy(c->ev2);
@@ -1022,17 +1324,16 @@ int psim_simulate(psim_ctx* ctx, int32_t max_founder_allele) {
         const int n_new = (int)f_ind.size();
         const int64_t nseg = (int64_t)n_new * R * C * P;
         if (int rc = ensure_slab(c, c->slab_used + nseg)) return rc;
-        int32_t *ind_d = nullptr, *al_d = nullptr;
-        CUDA_TRY(dev_alloc(&ind_d, (size_t)n_new));
-        CUDA_TRY(dev_alloc(&al_d, (size_t)n_new));
+        if (int rc = ensure_buf(c, c->b_find, n_new * sizeof(int32_t))) return rc;
+        if (int rc = ensure_buf(c, c->b_fal, n_new * sizeof(int32_t))) return rc;
+        int32_t *ind_d = (int32_t*)c->b_find.p, *al_d = (int32_t*)c->b_fal.p;
         CUDA_TRY(cudaMemcpyAsync(ind_d, f_ind.data(), n_new * sizeof(int32_t), cudaMemcpyHostToDevice, c->stream));
         CUDA_TRY(cudaMemcpyAsync(al_d, f_allele.data(), n_new * sizeof(int32_t), cudaMemcpyHostToDevice, c->stream));
         k_init_founders<<<grid_for(nseg, 256), 256, 0, c->stream>>>(n_new * R, n_new, ind_d, al_d, C, R, N, P, c->chrom_d, c->desc_d,
                                                                     c->seg_pos_d, c->seg_founder_d, c->slab_used);
         c->stats.kernel_launches++;
         CUDA_TRY(cudaGetLastError());
-        CUDA_TRY(cudaStreamSynchronize(c->stream));
-        cudaFree(ind_d); cudaFree(al_d);
+        CUDA_TRY(cudaStreamSynchronize(c->stream));  // f_ind / f_allele are stack-owned host buffers
         c->slab_used += nseg;
         for (int32_t i : f_ind) c->hs_reps[i] = R;
     }
@@ -1054,13 +1355,15 @@ int psim_simulate(psim_ctx* ctx, int32_t max_founder_allele) {
     int32_t* lev_d = nullptr; int32_t* plan_np = nullptr; int64_t* plan_cnt = nullptr; int64_t* plan_off = nullptr;
     double* plan_pos = nullptr; uint8_t* plan_hom = nullptr;
     if (scratch_ind > 0) {
-        const int64_t nu = scratch_ind * C * R * P;
-        CUDA_TRY(dev_alloc(&lev_d, (size_t)scratch_ind));
-        CUDA_TRY(dev_alloc(&plan_np, (size_t)nu));
-        CUDA_TRY(dev_alloc(&plan_cnt, (size_t)nu + 1));
-        CUDA_TRY(dev_alloc(&plan_off, (size_t)nu + 1));
-        CUDA_TRY(dev_alloc(&plan_pos, (size_t)nu * c->piece_cap));
-        CUDA_TRY(dev_alloc(&plan_hom, (size_t)nu * c->piece_cap));
+        const size_t nu = (size_t)scratch_ind * C * R * P;
+        if (int rc = ensure_buf(c, c->b_lev, scratch_ind * sizeof(int32_t))) return rc;
+        if (int rc = ensure_buf(c, c->b_np, nu * sizeof(int32_t))) return rc;
+        if (int rc = ensure_buf(c, c->b_cnt, (nu + 1) * sizeof(int64_t))) return rc;
+        if (int rc = ensure_buf(c, c->b_off, (nu + 1) * sizeof(int64_t))) return rc;
+        if (int rc = ensure_buf(c, c->b_ppos, nu * c->piece_cap * sizeof(double))) return rc;
+        if (int rc = ensure_buf(c, c->b_phom, nu * c->piece_cap)) return rc;
+        lev_d = (int32_t*)c->b_lev.p; plan_np = (int32_t*)c->b_np.p; plan_cnt = (int64_t*)c->b_cnt.p;
+        plan_off = (int64_t*)c->b_off.p; plan_pos = (double*)c->b_ppos.p; plan_hom = (uint8_t*)c->b_phom.p;
     }
     int rc_out = PSIM_OK;
     for (int lv = 1; lv <= max_level && rc_out == PSIM_OK; lv++) {
@@ -1109,7 +1412,6 @@ int psim_simulate(psim_ctx* ctx, int32_t max_founder_allele) {
     }
     CUDA_TRY(cudaEventRecord(c->ev1, c->stream));
     CUDA_TRY(cudaStreamSynchronize(c->stream));
-    cudaFree(lev_d); cudaFree(plan_np); cudaFree(plan_cnt); cudaFree(plan_off); cudaFree(plan_pos); cudaFree(plan_hom);
     float ms = 0.f;
     cudaEventElapsedTime(&ms, c->ev0, c->ev1);
     c->stats.ms_simulate = ms;
@@ -1222,7 +1524,9 @@ int psim_set_map(psim_ctx* ctx, const int64_t* locus_off, const double* pos) {
     c->L = locus_off[c->C];
     c->locus_off_h.assign(locus_off, locus_off + c->C + 1);
     cudaFree(c->locus_off_d); cudaFree(c->locus_pos_d); cudaFree(c->code_d); cudaFree(c->match_d);
+    cudaFree(c->code16_d); cudaFree(c->nibmask_d);
     c->locus_off_d = nullptr; c->locus_pos_d = nullptr; c->code_d = nullptr; c->match_d = nullptr;
+    c->code16_d = nullptr; c->nibmask_d = nullptr;
     c->A = 0; c->code_h.clear();
     CUDA_TRY(dev_alloc(&c->locus_off_d, (size_t)c->C + 1));
     CUDA_TRY(dev_alloc(&c->locus_pos_d, (size_t)c->L));
@@ -1237,14 +1541,17 @@ int psim_set_allele_codes(psim_ctx* ctx, int32_t n_alleles, const uint8_t* code)
     if (!c) return PSIM_EINVAL;
     if (c->L == 0) return fail(c, PSIM_ESTATE, "psim_set_map must be called first");
     cudaSetDevice(c->cfg.device);
-    cudaFree(c->code_d); cudaFree(c->match_d);
-    c->code_d = nullptr; c->match_d = nullptr; c->A = 0; c->code_h.clear(); c->match_which = 12345678;
+    cudaFree(c->code_d); cudaFree(c->match_d); cudaFree(c->code16_d); cudaFree(c->nibmask_d);
+    c->code_d = nullptr; c->match_d = nullptr; c->code16_d = nullptr; c->nibmask_d = nullptr;
+    c->A = 0; c->code_h.clear(); c->match_which = 12345678;
     if (!code) return PSIM_OK;
     if (n_alleles <= 0 || n_alleles > 256) return fail(c, PSIM_EINVAL, "allele codes need 1..256 founder alleles");
     c->A = n_alleles;
     c->code_h.assign(code, code + (size_t)c->L * n_alleles);
     CUDA_TRY(dev_alloc(&c->code_d, (size_t)c->L * n_alleles));
     CUDA_TRY(dev_alloc(&c->match_d, (size_t)c->L));
+    CUDA_TRY(dev_alloc(&c->code16_d, (size_t)c->L * 4));
+    CUDA_TRY(dev_alloc(&c->nibmask_d, (size_t)c->L * 2));
     CUDA_TRY(cudaMemcpy(c->code_d, code, (size_t)c->L * n_alleles, cudaMemcpyHostToDevice));
     return PSIM_OK;
 }
@@ -1295,13 +1602,25 @@ static int emit_device(psim_ctx_impl* c, int64_t ind_first, int64_t ind_count, i
         ea.locus_off = c->locus_off_d;
         ea.ind_first = ind_first; ea.ind_count = ind_count; ea.n_cols_ind = n_cols_ind;
         ea.locus_first = row0_locus;
-        ea.tile_loci = 128;
+        static const int env_tile = getenv("PSIM_TILE_LOCI") ? atoi(getenv("PSIM_TILE_LOCI")) : 0;       // tuning knobs
+        static const int env_bps = getenv("PSIM_BLOCKS_PER_SM") ? atoi(getenv("PSIM_BLOCKS_PER_SM")) : 0;
+        {   // rows per tile: as tall as possible (the plan is read once per tile) while a warp's expected
+            // number of run starts per tile stays far below EMIT_EV
+            const double seg_per_hom = c->n_hom > 0 ? (double)c->slab_used / (double)c->n_hom : 1.0;
+            const double loci_per_chrom = std::max(1.0, (double)c->L / c->C);
+            const double starts_per_cell = std::max(0.0, seg_per_hom - 1.0) / loci_per_chrom;
+            int rows = 64;
+            while (rows > 8 && 32.0 * G * P * rows * starts_per_cell > 24.0) rows >>= 1;
+            ea.tile_loci = env_tile > 0 ? std::min(env_tile, EMIT_MAX_TILE_LOCI) : rows;
+        }
         ea.n_col_tiles = (int)((n_cols_ind + (int64_t)EMIT_THREADS * G - 1) / ((int64_t)EMIT_THREADS * G));
         ea.founder = (uint8_t*)founder; ea.founder_pitch = founder_pitch;
         ea.allele = allele; ea.allele_pitch = allele_pitch;
         ea.dose = dose; ea.dose_pitch = dose_pitch;
-        ea.dose_mode = dose_mode; ea.dose_which = dose_which;
+        ea.dose_which = dose_which;
         ea.code = c->code_d; ea.match_code = c->match_d; ea.A = c->A;
+        ea.code16 = c->code16_d; ea.nibmask = c->nibmask_d;
+        const int mode = !c->code_d ? 0 : c->A <= 8 ? 1 : c->A <= 16 ? 2 : 3;
         ea.tile_counter = c->tile_counter_d;
         // chromosomes touched by [l_begin, l_end), at most 64 per launch
         int k0 = 0;
@@ -1321,13 +1640,23 @@ static int emit_device(psim_ctx_impl* c, int64_t ind_first, int64_t ind_count, i
             }
             if (ea.n_chunks == 0) break;
             ea.n_tiles = ea.chunk_tile_base[ea.n_chunks];
+            {
+                const size_t nt = (size_t)ea.n_tiles;
+                ea.plan_blk_size = 2 + (G * P / 16) * EMIT_THREADS + EMIT_EV;
+                if (int rc = ensure_buf(c, c->b_plan, nt * ea.plan_blk_size * sizeof(uint4))) return rc;
+                if (int rc = ensure_buf(c, c->b_dense_list, (nt * (EMIT_THREADS / 32) + 1) * sizeof(int))) return rc;
+                ea.plan_blk = (uint4*)c->b_plan.p;
+                ea.dense_list = (int*)c->b_dense_list.p;
+                CUDA_TRY(cudaMemsetAsync(ea.plan_blk, 0, nt * ea.plan_blk_size * sizeof(uint4), c->stream));
+                CUDA_TRY(cudaMemsetAsync(ea.dense_list, 0, sizeof(int), c->stream));
+            }
             CUDA_TRY(cudaMemsetAsync(c->tile_counter_d, 0, sizeof(int), c->stream));
-            const int blocks = std::min(ea.n_tiles, c->sm_count * 8);
-            if (P == 2) launch_tiles<2, 8>(c, ea, blocks);
-            else if (P == 4) launch_tiles<4, 4>(c, ea, blocks);
-            else if (P == 6) launch_tiles<6, 8>(c, ea, blocks);
-            else launch_tiles<8, 2>(c, ea, blocks);
-            c->stats.kernel_launches++;
+            const int blocks = std::min(ea.n_tiles, c->sm_count * (env_bps > 0 ? env_bps : 4));
+            if (P == 2) launch_tiles<2, 8>(c, ea, blocks, mode);
+            else if (P == 4) launch_tiles<4, 4>(c, ea, blocks, mode);
+            else if (P == 6) launch_tiles<6, 8>(c, ea, blocks, mode);
+            else launch_tiles<8, 2>(c, ea, blocks, mode);
+            c->stats.kernel_launches += 3;
             c->stats.emit_kernel_launches++;
             CUDA_TRY(cudaGetLastError());
         }
@@ -1343,7 +1672,9 @@ static int emit_device(psim_ctx_impl* c, int64_t ind_first, int64_t ind_count, i
         ga.dose_mode = dose_mode; ga.dose_which = dose_which;
         ga.code = c->code_d; ga.match_code = c->match_d; ga.A = c->A;
         const int64_t nt = ga.l_count * n_cols_ind;
+        cudaEventRecord(next_kev(c), c->stream);
         k_emit_generic<<<grid_for(nt, 256), 256, 0, c->stream>>>(ga);
+        cudaEventRecord(next_kev(c), c->stream);
         c->stats.kernel_launches++;
         c->stats.emit_kernel_launches++;
         CUDA_TRY(cudaGetLastError());
@@ -1378,67 +1709,102 @@ int psim_emit(psim_ctx* ctx, int64_t ind_first, int64_t ind_count, int64_t locus
     if (t->allele && t->allele_pitch < n_cols) return fail(c, PSIM_EINVAL, "allele_pitch too small");
     if (t->dose && t->dose_pitch < n_cols_ind) return fail(c, PSIM_EINVAL, "dose_pitch too small");
     int dose_mode = 0, dose_which = t->dose_which;
-    if (t->dose) {
-        if (c->code_d) {
-            dose_mode = 1;
-            if (c->match_which != t->dose_which) {
-                k_match_codes<<<grid_for(c->L, 256), 256, 0, c->stream>>>(c->L, c->A, t->dose_which, c->code_d, c->match_d);
-                c->stats.kernel_launches++;
-                c->match_which = t->dose_which;
-            }
-        } else if (dose_which < 0) {
-            dose_which = 0x7FFFFFFF;  // Main.java:1010-1014: no founder allele equals a negative index -> all zero
+    if (c->code_d) {
+        dose_mode = 1;
+        if (c->match_which != t->dose_which) {
+            k_match_codes<<<grid_for(c->L, 256), 256, 0, c->stream>>>(c->L, c->A, t->dose_which, c->code_d, c->match_d,
+                                                                       c->code16_d, c->nibmask_d);
+            c->stats.kernel_launches++;
+            CUDA_TRY(cudaGetLastError());
+            c->match_which = t->dose_which;
         }
+    } else if (dose_which < 0) {
+        dose_which = 0x7FFFFFFF;  // Main.java:1010-1014: no founder allele equals a negative index -> all zero
     }
     c->stats.emit_kernel_launches = 0;
+    c->kev_used = 0;
     CUDA_TRY(cudaEventRecord(c->ev0, c->stream));
-    float ms_kernel = 0.f;
     if (t->memory == PSIM_MEM_DEVICE) {
-        CUDA_TRY(cudaEventRecord(c->ev2, c->stream));
         if (int rc = emit_device(c, ind_first, ind_count, locus_first, locus_first + locus_count, locus_first, t->founder,
                                  t->founder_pitch, fb, (uint8_t*)t->allele, t->allele_pitch, (uint8_t*)t->dose, t->dose_pitch,
                                  dose_mode, dose_which)) return rc;
-        CUDA_TRY(cudaEventRecord(c->ev3, c->stream));
         CUDA_TRY(cudaEventRecord(c->ev1, c->stream));
         CUDA_TRY(cudaStreamSynchronize(c->stream));
-        cudaEventElapsedTime(&ms_kernel, c->ev2, c->ev3);
     } else {
-        // host targets: stage locus chunks on the device, copy out with 2-D copies into the caller's pitch
+        // Host targets: locus chunks are emitted into one of two device slots and copied out on a
+        // second stream while the next chunk is computed. A table whose host pitch is not 16-byte
+        // aligned is written with an aligned pitch and repacked on the device (2-D device copy),
+        // so that the PCIe transfer is always one large contiguous copy.
+        // direct: dense and aligned host rows, the kernel writes the host layout; repack: dense but
+        // unaligned; strided: padded host rows (a view into a wider table) are copied row by row
+        struct Tab { void* host; int64_t hpitch, width; bool direct; int64_t spitch; bool strided; };
         auto up = [](int64_t x, int64_t m) { return (x + m - 1) / m * m; };
-        const int64_t fp = t->founder ? up(n_cols * fb, 2048) : 0;
-        const int64_t ap = t->allele ? up(n_cols, 2048) : 0;
-        const int64_t dp = t->dose ? up(n_cols_ind, 2048) : 0;
-        const int64_t row_bytes = fp + ap + dp;
-        int64_t rows = std::max<int64_t>(1, std::min<int64_t>(locus_count, (int64_t)(1LL << 30) / row_bytes));
-        if (int rc = ensure_staging(c, (size_t)(rows * row_bytes))) return rc;
-        uint8_t* sf = (uint8_t*)c->staging;
-        uint8_t* sa = sf + rows * fp;
-        uint8_t* sd = sa + rows * ap;
-        for (int64_t l0 = locus_first; l0 < locus_first + locus_count; l0 += rows) {
-            const int64_t l1 = std::min(l0 + rows, locus_first + locus_count);
-            CUDA_TRY(cudaEventRecord(c->ev2, c->stream));
-            if (int rc = emit_device(c, ind_first, ind_count, l0, l1, l0, t->founder ? sf : nullptr, fp, fb, t->allele ? sa : nullptr, ap,
-                                     t->dose ? sd : nullptr, dp, dose_mode, dose_which)) return rc;
-            CUDA_TRY(cudaEventRecord(c->ev3, c->stream));
-            const int64_t nr = l1 - l0, r0 = l0 - locus_first;
-            if (t->founder)
-                CUDA_TRY(cudaMemcpy2DAsync((uint8_t*)t->founder + r0 * t->founder_pitch, t->founder_pitch, sf, fp, n_cols * fb, nr, cudaMemcpyDeviceToHost, c->stream));
-            if (t->allele)
-                CUDA_TRY(cudaMemcpy2DAsync((uint8_t*)t->allele + r0 * t->allele_pitch, t->allele_pitch, sa, ap, n_cols, nr, cudaMemcpyDeviceToHost, c->stream));
-            if (t->dose)
-                CUDA_TRY(cudaMemcpy2DAsync((uint8_t*)t->dose + r0 * t->dose_pitch, t->dose_pitch, sd, dp, n_cols_ind, nr, cudaMemcpyDeviceToHost, c->stream));
-            CUDA_TRY(cudaStreamSynchronize(c->stream));
-            float ms = 0.f;
-            cudaEventElapsedTime(&ms, c->ev2, c->ev3);
-            ms_kernel += ms;
+        Tab tab[3] = {{t->founder, t->founder_pitch, n_cols * fb, false, 0, false},
+                      {t->allele, t->allele_pitch, n_cols, false, 0, false},
+                      {t->dose, t->dose_pitch, n_cols_ind, false, 0, false}};
+        int64_t row_bytes = 0;
+        for (Tab& x : tab) {
+            if (!x.host) continue;
+            x.strided = x.hpitch != x.width;
+            x.direct = !x.strided && x.width % 16 == 0;
+            x.spitch = x.direct ? x.hpitch : up(x.width, 128);
+            row_bytes += x.spitch + (x.direct || x.strided ? 0 : x.hpitch);
         }
+        const int64_t slot_budget = 96LL << 20;
+        const int64_t rows = std::max<int64_t>(1, std::min<int64_t>(locus_count, slot_budget / row_bytes));
+        const int64_t slot_bytes = up(rows * row_bytes, 256);
+        if (int rc = ensure_staging(c, (size_t)(2 * slot_bytes))) return rc;
+        cudaEvent_t ready[2] = {c->ev2, c->ev3};
+        cudaEvent_t freed[2] = {next_kev(c), next_kev(c)};
+        int k = 0;
+        for (int64_t l0 = locus_first; l0 < locus_first + locus_count; l0 += rows, k++) {
+            const int64_t l1 = std::min(l0 + rows, locus_first + locus_count);
+            const int64_t nr = l1 - l0, r0 = l0 - locus_first;
+            const int sl = k & 1;
+            uint8_t* base = (uint8_t*)c->staging + sl * slot_bytes;
+            uint8_t* sp[3]; uint8_t* dn[3];
+            {
+                uint8_t* p = base;
+                for (int q = 0; q < 3; q++) {
+                    sp[q] = dn[q] = nullptr;
+                    if (!tab[q].host) continue;
+                    sp[q] = p; p += rows * tab[q].spitch;
+                    if (!tab[q].direct && !tab[q].strided) { dn[q] = p; p += rows * tab[q].hpitch; }
+                }
+            }
+            if (k >= 2) CUDA_TRY(cudaStreamWaitEvent(c->stream, freed[sl], 0));   // slot copied out
+            if (int rc = emit_device(c, ind_first, ind_count, l0, l1, l0, sp[0], tab[0].spitch, fb, sp[1], tab[1].spitch,
+                                     sp[2], tab[2].spitch, dose_mode, dose_which)) return rc;
+            for (int q = 0; q < 3; q++)
+                if (dn[q])
+                    CUDA_TRY(cudaMemcpy2DAsync(dn[q], tab[q].hpitch, sp[q], tab[q].spitch, tab[q].width, nr, cudaMemcpyDeviceToDevice, c->stream));
+            CUDA_TRY(cudaEventRecord(ready[sl], c->stream));
+            CUDA_TRY(cudaStreamWaitEvent(c->copy_stream, ready[sl], 0));
+            for (int q = 0; q < 3; q++) {
+                if (!tab[q].host) continue;
+                uint8_t* dst = (uint8_t*)tab[q].host + r0 * tab[q].hpitch;
+                if (tab[q].strided)
+                    CUDA_TRY(cudaMemcpy2DAsync(dst, tab[q].hpitch, sp[q], tab[q].spitch, tab[q].width, nr, cudaMemcpyDeviceToHost, c->copy_stream));
+                else
+                    CUDA_TRY(cudaMemcpyAsync(dst, tab[q].direct ? sp[q] : dn[q], (size_t)(nr * tab[q].width), cudaMemcpyDeviceToHost, c->copy_stream));
+            }
+            CUDA_TRY(cudaEventRecord(freed[sl], c->copy_stream));
+        }
+        CUDA_TRY(cudaStreamSynchronize(c->copy_stream));
         CUDA_TRY(cudaEventRecord(c->ev1, c->stream));
         CUDA_TRY(cudaStreamSynchronize(c->stream));
     }
-    float ms_total = 0.f;
+    float ms_total = 0.f, ms_kernel = 0.f;
     cudaEventElapsedTime(&ms_total, c->ev0, c->ev1);
+    const int first_pair = t->memory == PSIM_MEM_DEVICE ? 0 : 2;
+    for (int i = first_pair; i + 1 < c->kev_used; i += 2) {
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, c->kev[i], c->kev[i + 1]);
+        ms_kernel += ms;
+    }
     c->stats.ms_emit_kernel = ms_kernel;
     c->stats.ms_emit_total = ms_total;
+    c->stats.ms_emit_plan = 0.0;
     return PSIM_OK;
 }
 
