@@ -95,6 +95,11 @@ int psim_set_haplostructs(psim_ctx* ctx, uint32_t replicate, int64_t first, int6
  * max_founder_allele is what readHaploStructFiles returned (-1 for a fresh simulation). */
 int psim_simulate(psim_ctx* ctx, int32_t max_founder_allele);
 
+/* Same, but only the listed non-founders are simulated (their parents must already have a
+ * haplostruct or be listed too). For drivers that shard the individuals of a generation over
+ * several GPUs; founders without a haplostruct are initialised on every call. */
+int psim_simulate_subset(psim_ctx* ctx, int32_t max_founder_allele, const int32_t* individuals, int64_t count);
+
 /* Read back haplostructs of individuals [first, first+count) of one replicate
  * (what Main.writeHaploStructFiles serialises, Main.java:1100-1136). */
 int psim_segment_count(psim_ctx* ctx, uint32_t replicate, int64_t first, int64_t count, int64_t* n_segments);

@@ -56,7 +56,7 @@ EXPORTS = [
     "psim_abi_version", "psim_create", "psim_destroy", "psim_last_error", "psim_set_chromosomes", "psim_set_pedigree",
     "psim_set_haplostructs", "psim_simulate", "psim_segment_count", "psim_get_haplostructs", "psim_get_meiotic_configs",
     "psim_set_map", "psim_set_allele_codes", "psim_emit", "psim_all_dose_rows", "psim_emit_all_dose", "psim_get_stats",
-    "psim_export_haplostructs_device", "psim_import_haplostructs_device", "psim_reset", "psim_set_stream",
+    "psim_export_haplostructs_device", "psim_import_haplostructs_device", "psim_reset", "psim_set_stream", "psim_simulate_subset",
 ]
 
 _lib = None
@@ -82,6 +82,7 @@ def load():
     L.psim_set_pedigree.argtypes = [vp, i64, vp, vp]
     L.psim_set_haplostructs.argtypes = [vp, u32, i64, i64, vp, vp, vp]
     L.psim_simulate.argtypes = [vp, i32]
+    L.psim_simulate_subset.argtypes = [vp, i32, vp, i64]
     L.psim_segment_count.argtypes = [vp, u32, i64, i64, C.POINTER(i64)]
     L.psim_get_haplostructs.argtypes = [vp, u32, i64, i64, vp, vp, vp]
     L.psim_get_meiotic_configs.argtypes = [vp, u32, i64, i64, vp, vp]
@@ -187,6 +188,10 @@ class PsimContext:
     # --- seam A
     def simulate(self, maxfounderallele=-1):
         self._chk(self.L.psim_simulate(self.h, maxfounderallele))
+
+    def simulate_subset(self, individuals, maxfounderallele=-1):
+        ind = np.ascontiguousarray(individuals, dtype=np.int32)
+        self._chk(self.L.psim_simulate_subset(self.h, maxfounderallele, _p(ind), len(ind)))
 
     def get_haplostructs(self, first=0, count=None, replicate=None):
         count = self.N - first if count is None else count

@@ -1301,9 +1301,10 @@ int psim_set_haplostructs(psim_ctx* ctx, uint32_t replicate, int64_t first, int6
     return PSIM_OK;
 }
 
-int psim_simulate(psim_ctx* ctx, int32_t max_founder_allele) {
-    psim_ctx_impl* c = CTX;
-    if (!c) return PSIM_EINVAL;
+// subset == nullptr: every individual without a haplostruct; otherwise only the listed non-founders
+// (founders without a haplostruct are always initialised: it is cheap and every rank of a sharded
+// pedigree needs them).
+static int simulate_impl(psim_ctx_impl* c, int32_t max_founder_allele, const int32_t* subset, int64_t n_subset) {
     if (c->N == 0) return fail(c, PSIM_ESTATE, "psim_set_pedigree must be called first");
     cudaSetDevice(c->cfg.device);
     const int C = c->C, P = c->P, R = c->R;
@@ -1340,9 +1341,20 @@ int psim_simulate(psim_ctx* ctx, int32_t max_founder_allele) {
     // --- generations: level = 1 + max(level of parents) over individuals still to simulate
     std::vector<int32_t> level(N, 0);
     int32_t max_level = 0;
+    std::vector<uint8_t> wanted;
+    if (subset) {
+        wanted.assign(N, 0);
+        for (int64_t k = 0; k < n_subset; k++) {
+            if (subset[k] < 0 || subset[k] >= N) return fail(c, PSIM_EINVAL, "individual index out of bounds");
+            wanted[subset[k]] = 1;
+        }
+    }
     for (int64_t i = 0; i < N; i++) {
         if (c->hs_reps[i]) continue;
-        level[i] = 1 + std::max(level[c->par0_h[i]], level[c->par1_h[i]]);
+        if (subset && !wanted[i]) { level[i] = -1; continue; }   // left for another rank / a later call
+        const int32_t l0 = level[c->par0_h[i]], l1 = level[c->par1_h[i]];
+        if (l0 < 0 || l1 < 0) return fail(c, PSIM_ESTATE, "a parent of individual " + std::to_string(i) + " has no haplostruct yet");
+        level[i] = 1 + std::max(l0, l1);
         max_level = std::max(max_level, level[i]);
     }
     std::vector<std::vector<int32_t>> by_level(max_level + 1);
@@ -1418,6 +1430,20 @@ int psim_simulate(psim_ctx* ctx, int32_t max_founder_allele) {
     c->stats.n_segments = c->slab_used;
     c->runs_valid = false;
     return rc_out;
+}
+
+int psim_simulate(psim_ctx* ctx, int32_t max_founder_allele) {
+    psim_ctx_impl* c = CTX;
+    if (!c) return PSIM_EINVAL;
+    return simulate_impl(c, max_founder_allele, nullptr, 0);
+}
+
+int psim_simulate_subset(psim_ctx* ctx, int32_t max_founder_allele, const int32_t* individuals, int64_t count) {
+    psim_ctx_impl* c = CTX;
+    if (!c) return PSIM_EINVAL;
+    if (count > 0 && !individuals) return fail(c, PSIM_EINVAL, "null individual list");
+    static const int32_t none = 0;
+    return simulate_impl(c, max_founder_allele, individuals ? individuals : &none, count);
 }
 
 static int check_range(psim_ctx_impl* c, uint32_t replicate, int64_t first, int64_t count, int& r) {

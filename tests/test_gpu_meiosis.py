@@ -144,3 +144,41 @@ def test_emission_after_simulation_matches_oracle():
     assert np.array_equal(got["founder"], o.emit(_oracle.EMIT_FOUNDER))
     assert np.array_equal(got["allele"], o.emit(_oracle.EMIT_ALLELE))
     assert np.array_equal(got["dose"], o.emit(_oracle.EMIT_DOSE, which=_oracle.MAX_ALLELE))
+
+
+def test_sharded_generations_on_one_gpu_match_oracle():
+    """The large-pedigree path without NCCL: two contexts on one GPU play the two ranks; each
+    simulates its block of every generation (psim_simulate_subset) and receives the other's block
+    through the device export / import calls the NCCL all-gather uses. Philox streams are keyed by
+    individual, so both must equal the unsharded oracle."""
+    import torch
+    from pedigreesim_b200 import sharded
+    p0, p1 = _cases.ril_pedigree(21, 4)
+    lengths, centro = [1.0, 1.4], [0.5, 0.2]
+    ranks = []
+    for _ in range(2):
+        g = _cases.make_engine("gpu", 2, seed=77)
+        g.set_chromosomes(lengths, centro)
+        g.set_pedigree(p0, p1)
+        ranks.append(sharded.PsimShard(g))
+    for sh in ranks:
+        sh.simulate_subset(np.zeros(0, np.int32))      # founders everywhere
+    for inds in sharded.levelize(p0, p1):
+        blocks = sharded.block_partition(inds, 2)
+        for r, sh in enumerate(ranks):
+            if len(blocks[r]):
+                sh.simulate_subset(blocks[r])
+        for r, sh in enumerate(ranks):
+            for first, count in sharded.contiguous_runs(blocks[r]):
+                off, fo, po = sh.export_range(first, count)
+                ranks[1 - r].import_range(first, count, off, fo, po)
+        torch.cuda.synchronize()
+    o = _cases.make_engine("oracle-philox", 2, seed=77)
+    o.set_chromosomes(lengths, centro)
+    o.set_pedigree(p0, p1)
+    o.simulate()
+    so, fo, po = o.get_haplostructs()
+    for sh in ranks:
+        sg, fg, pg = sh.ctx.get_haplostructs()
+        assert np.array_equal(so, sg) and np.array_equal(fo, fg)
+        assert np.allclose(po, pg, rtol=POS_RTOL, atol=1e-15)
