@@ -22,16 +22,22 @@ def levelize(parent0, parent1, has_hs=None):
     individuals that already have a haplostruct are level 0. Returns a list of index arrays
     (level 1, 2, ...). The reference walks the individuals strictly in order
     (Main.simulateIndividuals, Main.java:1504-1520); levels are the units that can run in parallel."""
-    p0 = np.asarray(parent0)
-    p1 = np.asarray(parent1)
+    p0 = np.asarray(parent0).astype(np.int64)
+    p1 = np.asarray(parent1).astype(np.int64)
     n = len(p0)
+    idx = np.arange(n)
+    todo = p0 >= 0
+    if has_hs is not None:
+        todo &= ~np.asarray(has_hs, bool)
+    if np.any(todo & ((p0 >= idx) | (p1 >= idx) | (p1 < 0))):
+        raise ValueError("pedigree is not in parents-first order")
     level = np.zeros(n, np.int32)
-    for i in range(n):
-        if p0[i] < 0 or (has_hs is not None and has_hs[i]):
-            continue
-        if p0[i] >= i or p1[i] >= i or p1[i] < 0:
-            raise ValueError("pedigree is not in parents-first order")
-        level[i] = 1 + max(level[p0[i]], level[p1[i]])
+    t = np.nonzero(todo)[0]
+    while True:   # one relaxation per generation (vectorised; parents-first order bounds the depth)
+        new = 1 + np.maximum(level[p0[t]], level[p1[t]])
+        if np.array_equal(new, level[t]):
+            break
+        level[t] = new
     return [np.nonzero(level == l)[0].astype(np.int32) for l in range(1, int(level.max()) + 1)]
 
 
@@ -113,6 +119,9 @@ class PsimShard:
     def import_range(self, first, count, off, fo, po):
         from ._lib import DeviceHS
         off, fo, po = off.contiguous(), fo.contiguous(), po.contiguous()
+        # libpsim copies on its own stream: the collective that filled these tensors (enqueued on
+        # torch's stream) must have finished first
+        torch.cuda.current_stream().synchronize()
         d = DeviceHS(off.numel() - 1, fo.numel(), C.c_void_p(off.data_ptr()), C.c_void_p(fo.data_ptr()), C.c_void_p(po.data_ptr()))
         self.ctx.import_device(first, count, d)
 

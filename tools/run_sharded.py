@@ -76,11 +76,18 @@ def main():
             ref.simulate()
             s2, f2, x2 = ref.get_haplostructs(first=last, count=args.lines)
             ok = bool(np.array_equal(so, s2) and np.array_equal(fo, f2) and np.array_equal(po, x2))
+            if not ok:
+                print("mismatch vs unsharded: seg_off %s founder %s pos %s (sizes %d / %d)" % (
+                    np.array_equal(so, s2), len(fo) == len(f2) and np.array_equal(fo, f2),
+                    len(po) == len(x2) and np.array_equal(po, x2), len(fo), len(f2)), flush=True)
             ref.close()
         digest = torch.tensor([float(fo.sum() % 1000003), float(len(fo))], device="cuda", dtype=torch.float64)
         all_d = [torch.zeros_like(digest) for _ in range(world)]
         dist.all_gather(all_d, digest)
-        ok = ok and all(bool(torch.equal(all_d[0], d)) for d in all_d)
+        same = all(bool(torch.equal(all_d[0], d)) for d in all_d)
+        if not same and rank == 0:
+            print("rank digests differ:", [d.tolist() for d in all_d], flush=True)
+        ok = ok and same
     if rank == 0:
         meioses = 2 * (n - 2)
         print(json.dumps({"n_gpus": world, "individuals": n, "meioses": meioses, "seconds": dt, "meioses_per_s": meioses / dt,
