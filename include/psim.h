@@ -29,6 +29,7 @@
 #ifndef PSIM_H
 #define PSIM_H
 
+#include <stddef.h>
 #include <stdint.h>
 
 #ifdef __cplusplus
@@ -168,6 +169,13 @@ int psim_reset(psim_ctx* ctx, int64_t seed, uint32_t replicate_first);
  * pointer-sized integer; 0 restores the context's own stream). Lets a host that owns streams
  * order and time libpsim's work with its own events. */
 int psim_set_stream(psim_ctx* ctx, uint64_t cuda_stream);
+
+/* Page-locked host memory for emission targets and haplostruct buffers: a table emitted into
+ * memory from psim_alloc_host leaves the GPU as one DMA at PCIe rate instead of being staged
+ * through the driver's bounce buffer (what the reference's `PrintWriter` sink becomes on the
+ * host side, Main.java:903-1088). Any other host pointer still works, only slower. */
+int psim_alloc_host(psim_ctx* ctx, size_t bytes, void** out);
+int psim_free_host(psim_ctx* ctx, void* p);
 
 /* Introspection for benchmarks and sharded drivers. */
 typedef struct psim_stats {

@@ -654,13 +654,14 @@ inline void write_meiotic_configs_file(const std::string& path, const Population
         }
 }
 // Main.java:903-939
-inline void write_genotypes_file(const std::string& path, bool founders, Population& pop) {
+inline void write_genotypes_file(const std::string& path, bool founders, Population& pop, std::string* log = nullptr) {
     OutFile out(path);
     out.str("marker");
     for (size_t i = 0; i < pop.ind.size(); i++)
         for (int h = 0; h < pop.P(); h++) out.tab_str(pop.ind_name[i] + "_" + std::to_string(h + 1));
     out.nl();
-    for (int c = 0; c < pop.C(); c++)
+    for (int c = 0; c < pop.C(); c++) {
+        if (log) *log += "chrom " + pop.model.chrom[c].name + "\n";  // System.out.println("chrom "+...)
         for (auto& l : pop.locus[c]) {
             out.str(l.name);
             for (size_t i = 0; i < pop.ind.size(); i++)
@@ -670,15 +671,17 @@ inline void write_genotypes_file(const std::string& path, bool founders, Populat
                 }
             out.nl();
         }
+    }
 }
 constexpr int MIN_ALLELE = -1, MAX_ALLELE = -2;  // Main.java:941-942
 // Main.java:969-1022
-inline void write_alleledose_file(const std::string& path, int which, bool actual, Population& pop) {
+inline void write_alleledose_file(const std::string& path, int which, bool actual, Population& pop, std::string* log = nullptr) {
     OutFile out(path);
     out.str("marker");
     for (auto& n : pop.ind_name) out.tab_str(n);
     out.nl();
-    for (int c = 0; c < pop.C(); c++)
+    for (int c = 0; c < pop.C(); c++) {
+        if (log) *log += "chrom " + pop.model.chrom[c].name + "\n";  // System.out.println("chrom "+...)
         for (auto& l : pop.locus[c]) {
             out.str(l.name);
             std::string match;
@@ -697,14 +700,16 @@ inline void write_alleledose_file(const std::string& path, int which, bool actua
             }
             out.nl();
         }
+    }
 }
 // Main.java:1037-1088
-inline void write_all_alleledose_file(const std::string& path, bool actual, Population& pop) {
+inline void write_all_alleledose_file(const std::string& path, bool actual, Population& pop, std::string* log = nullptr) {
     OutFile out(path);
     out.str("marker\tallele");
     for (auto& n : pop.ind_name) out.tab_str(n);
     out.nl();
-    for (int c = 0; c < pop.C(); c++)
+    for (int c = 0; c < pop.C(); c++) {
+        if (log) *log += "chrom " + pop.model.chrom[c].name + "\n";  // System.out.println("chrom "+...)
         for (auto& l : pop.locus[c]) {
             const int rows = actual ? (int)l.uniques().size() : pop.founder_allele_count;
             for (int a = 0; a < rows; a++) {
@@ -721,6 +726,7 @@ inline void write_all_alleledose_file(const std::string& path, bool actual, Popu
                 out.nl();
             }
         }
+    }
 }
 
 // ---------------------------------------------------------------- Main.simulate (normal mode)
@@ -751,12 +757,33 @@ inline int run_parameter_file(const std::string& par_path, int rng_mode, std::st
     if (par.count("NATURALPAIRING")) m.natural_pairing = to_boolean(par["NATURALPAIRING"]);
     if (par.count("MISSING")) pop.missing = par["MISSING"];
     int32_t seed = par.count("SEED") ? (int32_t)std::atoi(par["SEED"].c_str()) : 12345;
-    if (!par.count("CHROMFILE")) { say(base_name + ": no CHROMFILE specified"); return 0; }
-    if (!par.count("OUTPUT")) { say(base_name + ": no OUTPUT specified"); return 0; }
+    auto check_infile = [&](const std::string& descr, const std::string& p) {  // Main.java:58-71
+        std::ifstream f(resolve(p));
+        if (f.good()) return true;
+        say(descr + " " + p + " not found or not readable");
+        return false;
+    };
+    auto can_create = [&](const std::string& p) {  // Main.java:1449-1462
+        std::remove(p.c_str());
+        std::ofstream f(p);
+        if (!f.good()) return false;
+        f.close();
+        return std::remove(p.c_str()) == 0;
+    };
+    {   // Main.java:142-160: a later message overwrites an earlier one
+        std::string e;
+        if (!par.count("CHROMFILE")) e = base_name + ": no CHROMFILE specified";
+        if (!par.count("OUTPUT")) e = base_name + ": no OUTPUT specified";
+        else if (!can_create(resolve(par["OUTPUT"]) + ".hsa") || !can_create(resolve(par["OUTPUT"]) + ".hsb") ||
+                 !can_create(resolve(par["OUTPUT"]) + "_meioticconfigs.dat"))
+            e = base_name + ": cannot create " + par["OUTPUT"] + ".*";
+        if (!e.empty()) { say(e); return 0; }
+    }
     const std::string output = resolve(par["OUTPUT"]);
     if (rng_mode == 0) pop.rng_holder.reset(new JavaRandom((int64_t)seed));
     else pop.rng_holder.reset(new PhiloxStream((uint32_t)seed, 0));
     m.rng = pop.rng_holder.get();
+    if (!check_infile("CHROMFILE", par["CHROMFILE"])) return 0;
     try {
         read_chromosome_file(resolve(par["CHROMFILE"]), pop);
         if (pop.C() == 0) throw std::runtime_error("CHROMFILE: no chromosomes");
@@ -770,14 +797,19 @@ inline int run_parameter_file(const std::string& par_path, int rng_mode, std::st
     }
     std::string err;
     if (par.count("PEDFILE")) {
+        if (!check_infile("PEDFILE", par["PEDFILE"])) return 0;
         auto orig = read_pedigree_file(resolve(par["PEDFILE"]), err);
         if (!err.empty()) { say("Error reading PEDFILE " + par["PEDFILE"] + ": " + err); return 0; }
         try {
             auto sorted = sort_pedigree(orig, pop.missing);
-            create_population(pop, sorted);
+            // PopulationData.createPopulation returns its failure as a string (PopulationData.java:432-464):
+            // the (partial) pedigree is still written and the bare message is printed last (Main.java:244-258,444)
+            std::string create_err;
+            try { create_population(pop, sorted); } catch (std::exception& ex) { create_err = ex.what(); }
             bool changed = false;
             for (size_t i = 0; i < sorted.size(); i++) if (sorted[i][0] != orig[i][0]) changed = true;
             if (changed) { say("write file " + par["OUTPUT"] + ".ped"); write_pedigree_file(output + ".ped", pop); }
+            if (!create_err.empty()) { say(create_err); return 0; }
         } catch (std::exception& ex) { say(std::string("Error in pedigree: ") + ex.what()); return 0; }
     } else {
         if (!par.count("POPTYPE") || !par.count("POPSIZE")) {
@@ -793,6 +825,8 @@ inline int run_parameter_file(const std::string& par_path, int rng_mode, std::st
     int maxfounderallele = -1;
     size_t hapstruct_read = 0;
     if (par.count("HAPLOSTRUCT")) {
+        if (!check_infile("HAPLOSTRUCT file", par["HAPLOSTRUCT"] + ".hsa") ||
+            !check_infile("HAPLOSTRUCT file", par["HAPLOSTRUCT"] + ".hsb")) return 0;
         try { maxfounderallele = read_haplostruct_files(resolve(par["HAPLOSTRUCT"]), pop); }
         catch (std::exception& ex) { say(std::string("Error reading HAPLOSTRUCT file ") + ex.what()); return 0; }
     }
@@ -815,10 +849,12 @@ inline int run_parameter_file(const std::string& par_path, int rng_mode, std::st
         }
     } catch (std::exception& ex) { say(ex.what()); return 0; }
     if (par.count("MAPFILE")) {
+        if (!check_infile("MAPFILE", par["MAPFILE"])) return 0;
         try { read_map_file(resolve(par["MAPFILE"]), pop); }
         catch (std::exception& ex) { say("Error reading MAPFILE " + par["MAPFILE"] + ": " + ex.what()); return 0; }
         bool founder_genotypes = false;
         if (par.count("FOUNDERFILE")) {
+            if (!check_infile("FOUNDERFILE", par["FOUNDERFILE"])) return 0;
             try { read_founder_genotypes_file(resolve(par["FOUNDERFILE"]), pop); founder_genotypes = true; }
             catch (std::exception& ex) { say("Error reading FOUNDERFILE " + par["FOUNDERFILE"] + ": " + ex.what()); return 0; }
         }
@@ -826,16 +862,16 @@ inline int run_parameter_file(const std::string& par_path, int rng_mode, std::st
             int which = 0;
             if (founder_genotypes) {
                 say("write file " + par["OUTPUT"] + "_genotypes.dat");
-                write_genotypes_file(output + "_genotypes.dat", false, pop);
+                write_genotypes_file(output + "_genotypes.dat", false, pop, &log);
                 which = MAX_ALLELE;
             }
             say("write file " + par["OUTPUT"] + "_founderalleles.dat");
-            write_genotypes_file(output + "_founderalleles.dat", true, pop);
+            write_genotypes_file(output + "_founderalleles.dat", true, pop, &log);
             say("write file " + par["OUTPUT"] + "_alleledose.dat");
-            write_alleledose_file(output + "_alleledose.dat", which, founder_genotypes, pop);
+            write_alleledose_file(output + "_alleledose.dat", which, founder_genotypes, pop, &log);
             if (!founder_genotypes || pop.max_allele_count() > 2) {
                 say("write file " + par["OUTPUT"] + "_allAlleledose.dat");
-                write_all_alleledose_file(output + "_allAlleledose.dat", founder_genotypes, pop);
+                write_all_alleledose_file(output + "_allAlleledose.dat", founder_genotypes, pop, &log);
             }
         } catch (std::exception& ex) { say(std::string("Error writing files: ") + ex.what()); return 0; }
     } else if (par.count("HAPLOSTRUCT") && hapstruct_read == pop.ind.size()) {

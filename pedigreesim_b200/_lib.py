@@ -57,6 +57,7 @@ EXPORTS = [
     "psim_set_haplostructs", "psim_simulate", "psim_segment_count", "psim_get_haplostructs", "psim_get_meiotic_configs",
     "psim_set_map", "psim_set_allele_codes", "psim_emit", "psim_all_dose_rows", "psim_emit_all_dose", "psim_get_stats",
     "psim_export_haplostructs_device", "psim_import_haplostructs_device", "psim_reset", "psim_set_stream", "psim_simulate_subset",
+    "psim_alloc_host", "psim_free_host",
 ]
 
 _lib = None
@@ -93,6 +94,8 @@ def load():
     L.psim_emit_all_dose.argtypes = [vp, i64, i64, i64, i64, vp, i64, i32]
     L.psim_reset.argtypes = [vp, i64, u32]
     L.psim_set_stream.argtypes = [vp, C.c_uint64]
+    L.psim_alloc_host.argtypes = [vp, C.c_size_t, C.POINTER(vp)]
+    L.psim_free_host.argtypes = [vp, vp]
     L.psim_get_stats.argtypes = [vp, C.POINTER(Stats)]
     L.psim_export_haplostructs_device.argtypes = [vp, i64, i64, C.POINTER(DeviceHS)]
     L.psim_import_haplostructs_device.argtypes = [vp, i64, i64, C.POINTER(DeviceHS)]

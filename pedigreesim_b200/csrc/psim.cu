@@ -1936,6 +1936,24 @@ int psim_set_stream(psim_ctx* ctx, uint64_t cuda_stream) {
     return PSIM_OK;
 }
 
+int psim_alloc_host(psim_ctx* ctx, size_t bytes, void** out) {
+    psim_ctx_impl* c = CTX;
+    if (!c || !out) return PSIM_EINVAL;
+    cudaSetDevice(c->cfg.device);
+    *out = nullptr;
+    CUDA_TRY(cudaHostAlloc(out, bytes ? bytes : 1, cudaHostAllocPortable));
+    return PSIM_OK;
+}
+
+int psim_free_host(psim_ctx* ctx, void* p) {
+    psim_ctx_impl* c = CTX;
+    if (!c) return PSIM_EINVAL;
+    if (!p) return PSIM_OK;
+    cudaSetDevice(c->cfg.device);
+    CUDA_TRY(cudaFreeHost(p));
+    return PSIM_OK;
+}
+
 int psim_get_stats(psim_ctx* ctx, psim_stats* out) {
     psim_ctx_impl* c = CTX;
     if (!c || !out) return PSIM_EINVAL;
