@@ -349,17 +349,25 @@ struct EmitArgs {
     int dose_which;               // MODE 0: founder allele to count
     const uint32_t* code16;       // [L][4] allele codes of founder alleles 0..15, one byte each (MODE 1, 2)
     const uint32_t* nibmask;      // [L][2] nibble a = 0xF iff founder allele a carries the counted allele (MODE 1, 2)
+    const uint4* mtab;            // [L] bytes 0..7: 1 iff founder allele a carries the counted allele; bytes 8..15: the same << 4
     const uint8_t* code;          // [L][A] (MODE 3)
     const uint8_t* match_code;    // [L] code to count (MODE 3)
     int A;
 };
 
 #ifndef PSIM_EMIT_MINB
-#define PSIM_EMIT_MINB 6
+#define PSIM_EMIT_MINB 4
 #endif
 constexpr int EMIT_THREADS = 128;
-constexpr int EMIT_MAX_TILE_LOCI = 256;   // row index inside a tile must fit 16 bits
-constexpr int EMIT_EV = 64;           // run starts a warp may have inside a tile on the fast path (two per lane)
+constexpr int EMIT_MAX_TILE_LOCI = 64;    // rows of a tile (its per-row dose tables are staged in shared memory)
+constexpr int EMIT_EV = 32;           // run starts a warp may have inside a tile on the fast path (one per lane)
+constexpr int EMIT_K = 6;             // ... and a single lane (kept sorted in registers)
+#ifndef PSIM_EMIT_SYNC_ROWS
+#define PSIM_EMIT_SYNC_ROWS 8
+#endif
+// The four warps of a block re-align every EMIT_SYNC rows so that the 2 KB row pieces of a tile
+// reach L2 (and later DRAM) together; without it they drift apart by up to a tile (0 = off).
+constexpr int EMIT_SYNC = PSIM_EMIT_SYNC_ROWS;
 constexpr uint32_t NO_EVENT = 0xFFFFFFFFu;
 
 struct TileCoord {
@@ -462,6 +470,12 @@ __device__ __forceinline__ void store_cells(uint8_t* p, const uint32_t (&v)[NW],
     }
 }
 
+// PRMT with the selector taken as is (nibbles 0..7 pick a byte; __byte_perm would first mask it)
+__device__ __forceinline__ uint32_t prmt(uint32_t lo, uint32_t hi, uint32_t sel) {
+    uint32_t r;
+    asm("prmt.b32 %0, %1, %2, %3;" : "=r"(r) : "r"(lo), "r"(hi), "r"(sel));
+    return r;
+}
 __device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(smem)), "l"(gmem));
 }
@@ -470,11 +484,13 @@ __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wai
 
 // K2b — streaming. A block's four warps take the same tile (2 KB contiguous per row written at the
 // same time), tiles are handed out in row-band order by an atomic ticket requested a tile early;
-// the plan block of the next tile is copied into shared memory with cp.async while the current
-// one streams, so no global round trip is ever waited for (under a saturated write stream each
-// costs thousands of cycles). Each warp sorts its run starts once (bitonic, one entry per lane)
-// and then walks them with warp-uniform control flow: write rows without any per-row checks up to
-// the next run start, let the owning lane patch its registers, go on.
+// the plan block of the next tile (and, with founder genotypes, its per-locus tables) is copied
+// into shared memory with cp.async while the current one streams, so no global round trip is ever
+// waited for (under a saturated write stream each costs thousands of cycles).
+// Run starts: the warp's unsorted list (one per lane) is routed to the owning lanes with six
+// ballots and a few shuffles; every lane keeps its own (at most EMIT_K) in registers, sorted by
+// row. The row loop then has a fixed trip count and no warp-wide breaks: a lane compares the row
+// with its next run start and patches its registers in a short divergent branch.
 template <int P, int G, int MODE>
 __global__ void __launch_bounds__(EMIT_THREADS, PSIM_EMIT_MINB) k_emit_tiles(const EmitArgs a) {
     constexpr int NC = G * P;
@@ -483,9 +499,13 @@ __global__ void __launch_bounds__(EMIT_THREADS, PSIM_EMIT_MINB) k_emit_tiles(con
     constexpr int NG = NC / 16;         // 16-byte vectors of packed cells
     constexpr int DW = (G + 3) / 4;     // 32-bit words of packed doses
     constexpr int W = MODE == 2 ? 2 : 1;  // nibble words per individual (8 founder alleles each)
-    constexpr int SW = MODE == 0 ? DW : MODE == 3 ? 1 : G * W;   // words of derived per-thread state
+    // A <= 8 and 2 or 4 homologs: the dose is a byte-table lookup of the PRMT selectors (no extra state)
+    constexpr bool FASTD = MODE == 1 && (P == 4 || P == 2);
+    constexpr int SW = MODE == 0 ? DW : (MODE == 3 || FASTD) ? 1 : G * W;   // words of derived per-thread state
     constexpr int PB = 2 + NG * EMIT_THREADS + EMIT_EV;          // uint4 per plan block
+    constexpr int K = EMIT_K;
     __shared__ uint4 s_blk[2][PB];
+    __shared__ uint4 s_tab[2][FASTD ? EMIT_MAX_TILE_LOCI + 1 : 1];   // per-row dose tables of the tile (+1: read-ahead)
     __shared__ int s_ticket[2];
     const int tid = threadIdx.x, lane = tid & 31, wq = tid >> 5;
     const bool want_f = a.founder != nullptr, want_a = a.allele != nullptr, want_d = a.dose != nullptr;
@@ -494,6 +514,14 @@ __global__ void __launch_bounds__(EMIT_THREADS, PSIM_EMIT_MINB) k_emit_tiles(con
     auto prefetch_plan = [&](int tile, int buf) {
         const uint4* src = a.plan_blk + (int64_t)tile * PB;
         for (int i = tid; i < PB; i += EMIT_THREADS) cp_async16(&s_blk[buf][i], src + i);
+        if (FASTD && want_d) {   // tile coordinates from the launch arguments: no dependent global load
+            int k = 0;
+            while (tile >= a.chunk_tile_base[k + 1]) k++;
+            const int lt = (tile - a.chunk_tile_base[k]) / a.n_col_tiles;
+            const int64_t g0 = a.chunk_l0[k] + (int64_t)lt * a.tile_loci;
+            const int64_t g1 = min(g0 + a.tile_loci, a.chunk_l1[k]);
+            if (tid < (int)(g1 - g0)) cp_async16(&s_tab[buf][tid], a.mtab + g0 + tid);
+        }
         cp_async_commit();
     };
     int ticket = 0;     // thread 0: the outstanding atomic result
@@ -516,46 +544,45 @@ __global__ void __launch_bounds__(EMIT_THREADS, PSIM_EMIT_MINB) k_emit_tiles(con
         if (tile < a.n_tiles) prefetch_plan(tile, buf);
 
         const uint32_t n_ev = reinterpret_cast<const uint32_t*>(&s_blk[cb][0])[wq];
-        if (n_ev > (uint32_t)EMIT_EV) {   // sparse map: this (tile, warp) unit goes to k_emit_dense
-            if (lane == 0) a.dense_list[1 + atomicAdd(a.dense_list, 1)] = tile_cur * (EMIT_THREADS / 32) + wq;
-            continue;
+        // ---- route the warp's run starts to the lanes that own them
+        uint32_t q[K];
+        bool dense = n_ev > (uint32_t)EMIT_EV;
+        if (!dense) {
+            const uint32_t* src = reinterpret_cast<const uint32_t*>(&s_blk[cb][2 + NG * EMIT_THREADS]) + wq * EMIT_EV;
+            const uint32_t evr = (uint32_t)lane < n_ev ? src[lane] : NO_EVENT;
+            const uint32_t tgt = (evr >> 15) & 31;
+            uint32_t hm = __ballot_sync(0xFFFFFFFFu, evr != NO_EVENT);   // lanes holding a run start of mine
+#pragma unroll
+            for (int b = 0; b < 5; b++) {
+                const uint32_t B = __ballot_sync(0xFFFFFFFFu, (tgt >> b) & 1);
+                hm &= ((lane >> b) & 1) ? B : ~B;
+            }
+#pragma unroll
+            for (int i = 0; i < K; i++) {
+                const uint32_t e = __shfl_sync(0xFFFFFFFFu, evr, (__ffs(hm) - 1) & 31);
+                q[i] = hm ? e : NO_EVENT;
+                hm &= hm - 1;
+            }
+            dense = __any_sync(0xFFFFFFFFu, hm != 0);   // a lane with more than K: rare, searched per cell
+            // sort by row (the top bits): 12-comparator network for 6 inputs
+            auto ce = [&](int x, int y) { const uint32_t lo = min(q[x], q[y]), hi = max(q[x], q[y]); q[x] = lo; q[y] = hi; };
+            static_assert(K == 6, "the sorting network below is for 6 entries");
+            ce(0, 5); ce(1, 3); ce(2, 4); ce(1, 2); ce(3, 4); ce(0, 3); ce(2, 5); ce(0, 1); ce(2, 3); ce(4, 5); ce(1, 2); ce(3, 4);
         }
         const uint4 tc = s_blk[cb][1];     // tile coordinates left by k_emit_plan
-        const uint32_t l0 = tc.x, l1 = tc.y;
+        const uint32_t l0 = tc.x, n_rows = tc.y - tc.x;
+        if (dense) {   // sparse map: this (tile, warp) unit goes to k_emit_dense
+            if (lane == 0) a.dense_list[1 + atomicAdd(a.dense_list, 1)] = tile_cur * (EMIT_THREADS / 32) + wq;
+            if (EMIT_SYNC > 0)   // keep the block's barrier schedule
+                for (uint32_t r = EMIT_SYNC > 0 ? EMIT_SYNC - 1 : 0; r < n_rows; r += EMIT_SYNC > 0 ? EMIT_SYNC : 1) __syncthreads();
+            continue;
+        }
         const int64_t row0 = (int64_t)tc.w;
         const int64_t c_off = row0 + a.locus_first - l0;
         const int64_t q0 = ((int64_t)tc.z * EMIT_THREADS + tid) * G;   // first emitted individual of this lane
         const int64_t colf = q0 * P;                                    // first founder/allele column
-        const bool full = colf + NC <= n_cols;
+        const bool full = colf + NC <= n_cols;   // lanes beyond the last column run along with every store masked off
 
-        // ---- the warp's run starts, sorted by row: element i = lane + 32 r lives in ev[r] of the
-        // lane, bitonic network over the 64 slots (unused ones hold NO_EVENT and sort to the end)
-        uint32_t ev[2];
-        {
-            const uint32_t* src = reinterpret_cast<const uint32_t*>(&s_blk[cb][2 + NG * EMIT_THREADS]) + wq * EMIT_EV;
-            ev[0] = (uint32_t)lane < n_ev ? src[lane] : NO_EVENT;
-            ev[1] = (uint32_t)lane + 32 < n_ev ? src[lane + 32] : NO_EVENT;
-        }
-        if (n_ev > 1) {
-#pragma unroll
-            for (int k2 = 2; k2 <= 64; k2 <<= 1) {
-#pragma unroll
-                for (int j = k2 >> 1; j > 0; j >>= 1) {
-                    if (j == 32) {   // partner is the lane's other register
-                        const uint32_t lo_v = min(ev[0], ev[1]), hi_v = max(ev[0], ev[1]);
-                        ev[0] = lo_v; ev[1] = hi_v;     // k2 == 64: the whole array ascends
-                    } else {
-#pragma unroll
-                        for (int r = 0; r < 2; r++) {
-                            const int i = lane + 32 * r;
-                            const uint32_t other = __shfl_xor_sync(0xFFFFFFFFu, ev[r], j);
-                            const bool keep_min = ((i & k2) == 0) == ((i & j) == 0);
-                            ev[r] = keep_min ? min(ev[r], other) : max(ev[r], other);
-                        }
-                    }
-                }
-            }
-        }
         // ---- state of this lane at the tile's first row
         uint32_t pk[NW];
 #pragma unroll
@@ -563,17 +590,19 @@ __global__ void __launch_bounds__(EMIT_THREADS, PSIM_EMIT_MINB) k_emit_tiles(con
             const uint4 v = s_blk[cb][2 + cg * EMIT_THREADS + tid];
             pk[4 * cg] = v.x; pk[4 * cg + 1] = v.y; pk[4 * cg + 2] = v.z; pk[4 * cg + 3] = v.w;
         }
-        uint32_t st[SW];           // MODE 0: packed doses; MODE 1/2: nibble multiplicities [g][w]
-        uint32_t sel[NW];          // MODE 1/2 with allele table: PRMT selectors
+        uint32_t st[SW];           // MODE 0: packed doses; MODE 1/2 (not FASTD): nibble multiplicities [g][w]
+        uint32_t sel[NW];          // MODE 1/2: PRMT selectors (low 3 bits of every cell)
         uint32_t him[NW];          // MODE 2: 0xFF per cell whose founder allele is >= 8
 #pragma unroll
         for (int w = 0; w < SW; w++) st[w] = 0;
+        if (!FASTD) {
 #pragma unroll
-        for (int j = 0; j < NC; j++) {
-            const uint32_t f = (pk[j / 4] >> (8 * (j % 4))) & 0xFF;
-            if (MODE == 0) { if (f == (uint32_t)a.dose_which) st[(j / P) / 4] += 1u << (8 * ((j / P) % 4)); }
-            else if (MODE == 1) st[j / P] += 1u << (4 * (f & 7));
-            else if (MODE == 2) st[(j / P) * W + (f >> 3 & 1)] += 1u << (4 * (f & 7));
+            for (int j = 0; j < NC; j++) {
+                const uint32_t f = (pk[j / 4] >> (8 * (j % 4))) & 0xFF;
+                if (MODE == 0) { if (f == (uint32_t)a.dose_which) st[(j / P) / 4] += 1u << (8 * ((j / P) % 4)); }
+                else if (MODE == 1) st[j / P] += 1u << (4 * (f & 7));
+                else if (MODE == 2) st[(j / P) * W + (f >> 3 & 1)] += 1u << (4 * (f & 7));
+            }
         }
         if (MODE == 1 || MODE == 2) {
 #pragma unroll
@@ -584,28 +613,77 @@ __global__ void __launch_bounds__(EMIT_THREADS, PSIM_EMIT_MINB) k_emit_tiles(con
             }
         }
 
+        // one of this lane's homologs starts a new run on row `nxt`: patch the registers
+        uint32_t nxt = q[0] >> 22;
+        auto take_run_starts = [&](uint32_t r) {
+            do {
+                const uint32_t e = q[0];
+                const uint32_t col = (e >> 8) & 0x7F, f = e & 0xFF;
+                const uint32_t cw = col >> 2, sh = (col & 3) * 8, g = col / P;
+                uint32_t old = 0;
+#pragma unroll
+                for (int w = 0; w < NW; w++) {
+                    const bool hit = (uint32_t)w == cw;
+                    const uint32_t msk = hit ? 0xFFu << sh : 0u;
+                    old |= pk[w] & msk;
+                    pk[w] = (pk[w] & ~msk) | ((f << sh) & msk);
+                    if (MODE == 1 || MODE == 2) {
+                        const uint32_t nsh = sh >> 1, nmsk = hit ? 0xFu << nsh : 0u;
+                        sel[w] = (sel[w] & ~nmsk) | (((f & 7) << nsh) & nmsk);
+                        if (MODE == 2) him[w] = (him[w] & ~msk) | (f & 8 ? msk : 0u);
+                    }
+                }
+                old >>= sh;
+                if (MODE == 0) {
+                    const uint32_t delta = ((f == (uint32_t)a.dose_which) - (old == (uint32_t)a.dose_which)) << (8 * (g & 3));
+#pragma unroll
+                    for (int w = 0; w < DW; w++) st[w] += (uint32_t)w == (g >> 2) ? delta : 0u;
+                } else if (MODE == 1 && !FASTD) {
+                    const uint32_t delta = (1u << (4 * (f & 7))) - (1u << (4 * (old & 7)));
+#pragma unroll
+                    for (int gg = 0; gg < G; gg++) st[gg] += (uint32_t)gg == g ? delta : 0u;
+                } else if (MODE == 2) {
+                    const uint32_t dec = 1u << (4 * (old & 7)), inc = 1u << (4 * (f & 7));
+                    const uint32_t wi_old = g * W + (old >> 3 & 1), wi_new = g * W + (f >> 3 & 1);
+#pragma unroll
+                    for (int w = 0; w < SW; w++) st[w] += ((uint32_t)w == wi_new ? inc : 0u) - ((uint32_t)w == wi_old ? dec : 0u);
+                }
+#pragma unroll
+                for (int i = 0; i + 1 < K; i++) q[i] = q[i + 1];
+                q[K - 1] = NO_EVENT;
+                nxt = q[0] >> 22;
+            } while (nxt == r);
+        };
+
         // ---- stream the rows
-        uint32_t l = l0;
-        uint8_t* pf = a.founder + row0 * a.founder_pitch + colf;
-        uint8_t* pa = a.allele + row0 * a.allele_pitch + colf;
-        uint8_t* pd = a.dose + row0 * a.dose_pitch + q0;
-        const uint4* code16 = reinterpret_cast<const uint4*>(a.code16) + c_off;    // per-locus tables: warp-uniform
-        const uint2* nibmask = reinterpret_cast<const uint2*>(a.nibmask) + c_off;  // loads through L1
+        uint8_t* const pf0 = a.founder + row0 * a.founder_pitch + colf;
+        uint8_t* const pa0 = a.allele + row0 * a.allele_pitch + colf;
+        uint8_t* const pd0 = a.dose + row0 * a.dose_pitch + q0;
+        const uint32_t fpitch32 = (uint32_t)a.founder_pitch, apitch32 = (uint32_t)a.allele_pitch, dpitch32 = (uint32_t)a.dose_pitch;
+        const uint4* code16 = reinterpret_cast<const uint4*>(a.code16) + c_off + l0;    // per-locus tables: warp-uniform
+        const uint2* nibmask = reinterpret_cast<const uint2*>(a.nibmask) + c_off + l0;  // loads through L1
         // compiled once per combination of requested tables so that the hot loop carries no
         // predicated-off work (WF / WA / WD shadow the runtime flags)
-        auto emit_rows_t = [&](auto full_tag, auto wf_tag, auto wa_tag, auto wd_tag, uint32_t stop) {
-            constexpr bool FULL = decltype(full_tag)::value;
+        // (`full` stays a per-lane runtime flag: the loop holds block barriers, so the lanes of a warp
+        // must not split into differently compiled copies of it)
+        auto emit_rows_t = [&](auto wf_tag, auto wa_tag, auto wd_tag) {
+            const bool FULL = full;
             constexpr bool want_f = decltype(wf_tag)::value, want_a = decltype(wa_tag)::value, want_d = decltype(wd_tag)::value;
+            uint4 Tn = s_tab[cb][0];
 #pragma unroll 4
-            for (; l < stop; l++) {
+            for (uint32_t r = 0; r < n_rows; r++) {
+                if (r == nxt) take_run_starts(r);
                 uint32_t dose_pk[DW];
-                if (want_f) { store_cells<NW>(pf, pk, FULL, colf, n_cols); pf += a.founder_pitch; }
+                uint8_t* const pf = pf0 + (uint64_t)(r * fpitch32);   // a tile spans far less than 4 GB
+                uint8_t* const pa = pa0 + (uint64_t)(r * apitch32);
+                uint8_t* const pd = pd0 + (uint64_t)(r * dpitch32);
+                if (want_f) store_cells<NW>(pf, pk, FULL, colf, n_cols);
                 if (MODE == 0) {
 #pragma unroll
                     for (int w = 0; w < DW; w++) dose_pk[w] = st[w];
                 } else if (MODE == 1 || MODE == 2) {
                     if (want_a) {
-                        const uint4 tb = __ldg(code16 + l);
+                        const uint4 tb = __ldg(code16 + r);
                         uint32_t ak[NW];
 #pragma unroll
                         for (int w = 0; w < NW; w++) {
@@ -614,24 +692,39 @@ __global__ void __launch_bounds__(EMIT_THREADS, PSIM_EMIT_MINB) k_emit_tiles(con
                             else ak[w] = lov;
                         }
                         store_cells<NW>(pa, ak, FULL, colf, n_cols);
-                        pa += a.allele_pitch;
                     }
-                    if (want_d) {
+                    if (want_d && FASTD) {
+                        // T = {1 per founder allele that carries the counted allele (bytes 0..7), the same << 4}
+                        const uint4 T = Tn;
+                        Tn = s_tab[cb][r + 1];   // next row's table: its latency hides behind this row's stores
+                        if (P == 4) {          // one word = one individual
+                            const uint32_t y01 = prmt(T.x, T.y, sel[0]) + prmt(T.z, T.w, sel[1]);
+                            const uint32_t y23 = prmt(T.x, T.y, sel[2]) + prmt(T.z, T.w, sel[3]);
+                            const uint32_t v = __dp4a(y01, 0x01010101u, 0u) | (__dp4a(y23, 0x01010101u, 0u) << 8);
+                            dose_pk[0] = prmt(0x03020100u, 0x07060504u, v);   // dose nibbles (<= 4) to bytes
+                        } else {               // P == 2: one word = two individuals
+                            uint32_t s2[NW];
+#pragma unroll
+                            for (int w = 0; w < NW; w++) { const uint32_t x = prmt(T.x, T.y, sel[w]); s2[w] = x + (x >> 8); }
+#pragma unroll
+                            for (int w = 0; w < DW; w++) dose_pk[w] = prmt(s2[2 * w], s2[2 * w + 1], 0x6420u);
+                        }
+                    } else if (want_d) {
                         uint2 m;
-                        if (W == 2) m = __ldg(nibmask + l);
-                        else { m.x = __ldg(reinterpret_cast<const uint32_t*>(nibmask + l)); m.y = 0; }
+                        if (W == 2) m = __ldg(nibmask + r);
+                        else { m.x = __ldg(reinterpret_cast<const uint32_t*>(nibmask + r)); m.y = 0; }
 #pragma unroll
                         for (int w = 0; w < DW; w++) dose_pk[w] = 0;
 #pragma unroll
                         for (int g = 0; g < G; g++) {
-                            uint32_t d = ((st[g * W] & m.x) * 0x11111111u) >> 28;
-                            if (W == 2) d += ((st[g * W + W - 1] & m.y) * 0x11111111u) >> 28;
+                            uint32_t d = ((st[(g * W) % SW] & m.x) * 0x11111111u) >> 28;
+                            if (W == 2) d += ((st[(g * W + W - 1) % SW] & m.y) * 0x11111111u) >> 28;
                             dose_pk[g / 4] |= d << (8 * (g % 4));
                         }
                     }
                 } else {
-                    const uint8_t* codes = a.code + (c_off + l) * a.A;
-                    const uint32_t match = a.match_code[c_off + l];
+                    const uint8_t* codes = a.code + (c_off + l0 + r) * a.A;
+                    const uint32_t match = a.match_code[c_off + l0 + r];
                     uint32_t ak[NW];
 #pragma unroll
                     for (int w = 0; w < DW; w++) dose_pk[w] = 0;
@@ -644,7 +737,7 @@ __global__ void __launch_bounds__(EMIT_THREADS, PSIM_EMIT_MINB) k_emit_tiles(con
                         ak[j / 4] |= al << (8 * (j % 4));
                         if (al == match) dose_pk[(j / P) / 4] += 1u << (8 * ((j / P) % 4));
                     }
-                    if (want_a) { store_cells<NW>(pa, ak, FULL, colf, n_cols); pa += a.allele_pitch; }
+                    if (want_a) store_cells<NW>(pa, ak, FULL, colf, n_cols);
                 }
                 if (want_d) {
                     if (FULL) {
@@ -666,62 +759,22 @@ __global__ void __launch_bounds__(EMIT_THREADS, PSIM_EMIT_MINB) k_emit_tiles(con
 #pragma unroll
                         for (int g = 0; g < G; g++) if (q0 + g < a.n_cols_ind) pd[g] = (uint8_t)(dose_pk[g / 4] >> (8 * (g % 4)));
                     }
-                    pd += a.dose_pitch;
                 }
+                if (EMIT_SYNC > 0 && (r % (EMIT_SYNC > 0 ? EMIT_SYNC : 1)) == EMIT_SYNC - 1) __syncthreads();
             }
         };
-        auto emit_rows = [&](auto full_tag, uint32_t stop) {
+        {
             using T = std::true_type;
             using F = std::false_type;
             if (MODE == 0) {   // no allele table without codes
-                if (want_f) { if (want_d) emit_rows_t(full_tag, T{}, F{}, T{}, stop); else emit_rows_t(full_tag, T{}, F{}, F{}, stop); }
-                else emit_rows_t(full_tag, F{}, F{}, T{}, stop);
+                if (want_f) { if (want_d) emit_rows_t(T{}, F{}, T{}); else emit_rows_t(T{}, F{}, F{}); }
+                else emit_rows_t(F{}, F{}, T{});
             } else if (want_f) {
-                if (want_a) { if (want_d) emit_rows_t(full_tag, T{}, T{}, T{}, stop); else emit_rows_t(full_tag, T{}, T{}, F{}, stop); }
-                else { if (want_d) emit_rows_t(full_tag, T{}, F{}, T{}, stop); else emit_rows_t(full_tag, T{}, F{}, F{}, stop); }
+                if (want_a) { if (want_d) emit_rows_t(T{}, T{}, T{}); else emit_rows_t(T{}, T{}, F{}); }
+                else { if (want_d) emit_rows_t(T{}, F{}, T{}); else emit_rows_t(T{}, F{}, F{}); }
             } else {
-                if (want_a) { if (want_d) emit_rows_t(full_tag, F{}, T{}, T{}, stop); else emit_rows_t(full_tag, F{}, T{}, F{}, stop); }
-                else emit_rows_t(full_tag, F{}, F{}, T{}, stop);
-            }
-        };
-        for (uint32_t k = 0;; k++) {   // warp-uniform walk over the sorted run starts
-            const uint32_t e = k < n_ev ? __shfl_sync(0xFFFFFFFFu, k < 32 ? ev[0] : ev[1], k & 31) : NO_EVENT;
-            const uint32_t wstop = min(l0 + (e >> 22), l1);
-            if (full) emit_rows(std::true_type{}, wstop);
-            else if (colf < n_cols) emit_rows(std::false_type{}, wstop);
-            else l = wstop;
-            if (e == NO_EVENT) break;
-            if (((e >> 15) & 31) == (uint32_t)lane) {      // this lane's run starts here: patch the registers
-                const uint32_t col = (e >> 8) & 0x7F, f = e & 0xFF;
-                const uint32_t cw = col >> 2, sh = (col & 3) * 8, g = col / P;
-                uint32_t old = 0;
-#pragma unroll
-                for (int w = 0; w < NW; w++) {
-                    const bool hit = (uint32_t)w == cw;
-                    const uint32_t msk = hit ? 0xFFu << sh : 0u;
-                    old |= pk[w] & msk;
-                    pk[w] = (pk[w] & ~msk) | ((f << sh) & msk);
-                    if (MODE == 1 || MODE == 2) {
-                        const uint32_t nsh = sh >> 1, nmsk = hit ? 0xFu << nsh : 0u;
-                        sel[w] = (sel[w] & ~nmsk) | (((f & 7) << nsh) & nmsk);
-                        if (MODE == 2) him[w] = (him[w] & ~msk) | (f & 8 ? msk : 0u);
-                    }
-                }
-                old >>= sh;
-                if (MODE == 0) {
-                    const uint32_t delta = ((f == (uint32_t)a.dose_which) - (old == (uint32_t)a.dose_which)) << (8 * (g & 3));
-#pragma unroll
-                    for (int w = 0; w < DW; w++) st[w] += (uint32_t)w == (g >> 2) ? delta : 0u;
-                } else if (MODE == 1) {
-                    const uint32_t delta = (1u << (4 * (f & 7))) - (1u << (4 * (old & 7)));
-#pragma unroll
-                    for (int gg = 0; gg < G; gg++) st[gg] += (uint32_t)gg == g ? delta : 0u;
-                } else if (MODE == 2) {
-                    const uint32_t dec = 1u << (4 * (old & 7)), inc = 1u << (4 * (f & 7));
-                    const uint32_t wi_old = g * W + (old >> 3 & 1), wi_new = g * W + (f >> 3 & 1);
-#pragma unroll
-                    for (int w = 0; w < SW; w++) st[w] += ((uint32_t)w == wi_new ? inc : 0u) - ((uint32_t)w == wi_old ? dec : 0u);
-                }
+                if (want_a) { if (want_d) emit_rows_t(F{}, T{}, T{}); else emit_rows_t(F{}, T{}, F{}); }
+                else emit_rows_t(F{}, F{}, T{});
             }
         }
     }
@@ -767,6 +820,267 @@ __global__ void __launch_bounds__(EMIT_THREADS) k_emit_dense(const EmitArgs a) {
     }
 }
 
+// ------------------------------------------------------------------------------------------
+// K2 "row image" path — the roofline kernel for founder + dose tables.
+// A block owns a band of consecutive locus rows of one chromosome and a segment of at most ~46 KB of
+// the founder row. It keeps the CURRENT ROW of that segment in shared memory (1 byte per cell; with
+// founder genotypes also a 4-bit copy used as PRMT selectors), patches the few cells whose homolog
+// starts a new run on the row, and sends the row to global memory as ONE contiguous TMA bulk store
+// (cp.async.bulk shared -> global): every table row leaves the SM as 40 KB + 10 KB of consecutive
+// bytes, which is the write pattern HBM likes (tools/write_rowimage.cu, profiles/README.md), and it
+// stays that way however the blocks drift against each other. The dose row is recomputed per locus
+// from the 4-bit image (A <= 8, ploidy 2 or 4) or patched like the founder row (no genotypes).
+// The plan (k_band_plan) holds, per (band, segment) unit, the founder byte of every cell on the
+// band's first row and the unordered list of run starts inside the band: 1 byte per cell and BAND,
+// bands being ~80 rows, so plan reads are ~1 % of the bytes written.
+struct RowsArgs {
+    int C, R, P;
+    int64_t N;
+    const uint64_t* run_desc;
+    const uint32_t* run_lb;
+    const uint16_t* run_founder;
+    int64_t ind_first, ind_count, n_cols_ind;
+    int64_t locus_first;          // global locus of output row 0
+    int n_chunks;                 // chromosome pieces of this launch (<= 64)
+    int chunk_chrom[64];
+    int64_t chunk_l0[64], chunk_l1[64], chunk_coff[64];
+    int chunk_bands[64];          // bands the piece is cut into (equal row counts, +-1)
+    int chunk_unit_base[65];
+    int n_seg, seg_cells;         // segments per row; cells per segment (a multiple of 16 * P)
+    int n_units, cap;             // units = sum(bands) * n_seg; run starts a unit's list can hold
+    uint8_t* plan;                // per unit: [count u32, 12 bytes pad][seg_cells state bytes][cap run starts]
+    int64_t plan_stride;
+    int* unit_counter;            // ticket
+    int* overflow;                // [0] = number of units whose list overflowed, then their ids
+    uint8_t* founder; int64_t founder_pitch;
+    uint8_t* dose;    int64_t dose_pitch;
+    int dose_which;               // without genotypes: founder allele to count
+    const uint4* mtab;            // with genotypes: per-locus byte tables of the counted allele (k_match_codes)
+};
+
+__device__ __forceinline__ void band_rows(const RowsArgs& a, int k, int j, int64_t& g0, int64_t& g1) {
+    const int64_t len = a.chunk_l1[k] - a.chunk_l0[k];
+    g0 = a.chunk_l0[k] + len * j / a.chunk_bands[k];
+    g1 = a.chunk_l0[k] + len * (j + 1) / a.chunk_bands[k];
+}
+
+// One thread per (chromosome piece, emitted cell column): walks the homolog's runs once down the
+// piece and leaves the state byte of every band plus the run starts inside it.
+__global__ void __launch_bounds__(256) k_band_plan(const RowsArgs a) {
+    const int k = blockIdx.y;
+    const int64_t col = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    const int P = a.P;
+    if (col >= a.n_cols_ind * P) return;
+    const int c = a.chunk_chrom[k];
+    const int64_t q = col / P;
+    const int h = (int)(col % P);
+    const int64_t r = q / a.ind_count, i = a.ind_first + q % a.ind_count;
+    const int64_t hid = (((int64_t)c * a.R + r) * a.N + i) * P + h;
+    const int s = (int)(col / a.seg_cells);
+    const uint32_t cs = (uint32_t)(col % a.seg_cells);
+    const uint64_t d = __ldg(a.run_desc + hid);
+    const uint32_t b = (uint32_t)desc_begin(d), n = desc_count(d);
+    const int64_t c_off = a.chunk_coff[k];
+    const uint32_t l_begin = (uint32_t)(a.chunk_l0[k] - c_off);
+    uint32_t lo = 0, hi = n;   // last run with lb <= l_begin
+    while (hi - lo > 1) { const uint32_t mid = (lo + hi) >> 1; if (__ldg(a.run_lb + b + mid) <= l_begin) lo = mid; else hi = mid; }
+    uint32_t f = n ? __ldg(a.run_founder + b + lo) : 0;
+    uint32_t kx = lo + 1;
+    uint32_t nxt = kx < n ? __ldg(a.run_lb + b + kx) : NO_EVENT;
+    for (int j = 0; j < a.chunk_bands[k]; j++) {
+        int64_t g0, g1;
+        band_rows(a, k, j, g0, g1);
+        const uint32_t tl0 = (uint32_t)(g0 - c_off), tl1 = (uint32_t)(g1 - c_off);
+        uint8_t* pu = a.plan + (int64_t)(a.chunk_unit_base[k] + j * a.n_seg + s) * a.plan_stride;
+        while (nxt <= tl0) {   // a run starting exactly on the band's first row is its start state
+            f = __ldg(a.run_founder + b + kx);
+            kx++;
+            nxt = kx < n ? __ldg(a.run_lb + b + kx) : NO_EVENT;
+        }
+        pu[16 + cs] = (uint8_t)f;
+        while (nxt < tl1) {
+            f = __ldg(a.run_founder + b + kx);
+            const uint32_t idx = atomicAdd(reinterpret_cast<uint32_t*>(pu), 1u);
+            if (idx < (uint32_t)a.cap)
+                reinterpret_cast<uint32_t*>(pu + 16 + a.seg_cells)[idx] = ((nxt - tl0) << 24) | (cs << 8) | f;
+            kx++;
+            nxt = kx < n ? __ldg(a.run_lb + b + kx) : NO_EVENT;
+        }
+    }
+}
+
+constexpr int ROWS_THREADS = 512;
+constexpr int ROWS_MAX_BAND = 255;     // the row of a run start inside its band is 8 bits
+constexpr int ROWS_SMEM = 200 * 1024;  // one block per SM
+
+__device__ __forceinline__ void bulk_store(void* gdst, const void* ssrc, uint32_t bytes) {
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst),
+                 "r"((uint32_t)__cvta_generic_to_shared(ssrc)), "r"(bytes) : "memory");
+}
+
+// DK: how the dose row is made. 0 = no dose table, 1 = no genotypes (count of one founder allele:
+// patched like the founder row), 2 = genotypes, A <= 8, ploidy 4, 3 = genotypes, A <= 8, ploidy 2.
+// Founder and dose rows are double-buffered: while the bulk engine streams row r-1 out of one
+// buffer, row r is made in the other (copy + patch, or recomputed), so the engine always has a
+// row queued and the block never waits for the row it has just issued.
+template <int DK>
+__global__ void __launch_bounds__(ROWS_THREADS, 1) k_emit_rows(const RowsArgs a) {
+    extern __shared__ __align__(128) uint8_t smem[];
+    const int tid = threadIdx.x;
+    const int P = a.P;
+    const int seg_cells = a.seg_cells, seg_ind = seg_cells / P;
+    uint8_t* const img0 = smem;                                              // founder byte of every cell on the current row (x2)
+    uint8_t* const img1 = img0 + seg_cells;
+    uint32_t* const nib = reinterpret_cast<uint32_t*>(img1 + seg_cells);     // DK >= 2: the same, 4 bits per cell
+    uint8_t* const dose0 = reinterpret_cast<uint8_t*>(nib) + (DK >= 2 ? seg_cells / 2 : 0);
+    uint8_t* const dose1 = dose0 + (DK >= 1 ? seg_ind : 0);
+    uint32_t* const evs = reinterpret_cast<uint32_t*>(dose1 + (DK >= 1 ? seg_ind : 0));   // the unit's run starts sorted by row
+    uint32_t* const start = evs + a.cap;                                     // [band rows + 1] first run start of each row
+    uint32_t* const cursor = start + ROWS_MAX_BAND + 2;
+    __shared__ int s_unit;
+    const int64_t n_cols = a.n_cols_ind * P;
+    const bool count_ok = a.dose_which >= 0 && a.dose_which < 256;           // DK 1: a founder allele that exists
+
+    for (;;) {
+        __syncthreads();
+        if (tid == 0) s_unit = atomicAdd(a.unit_counter, 1);
+        __syncthreads();
+        const int u = s_unit;
+        if (u >= a.n_units) break;
+        int k = 0;
+        while (u >= a.chunk_unit_base[k + 1]) k++;
+        const int j = (u - a.chunk_unit_base[k]) / a.n_seg, s = (u - a.chunk_unit_base[k]) % a.n_seg;
+        int64_t g0, g1;
+        band_rows(a, k, j, g0, g1);
+        const int n_rows = (int)(g1 - g0);
+        const int64_t out_row0 = g0 - a.locus_first;
+        const int64_t c0 = (int64_t)s * seg_cells;                            // first cell column of the segment
+        const int n_cell = (int)min((int64_t)seg_cells, n_cols - c0);         // a multiple of P
+        const int n_ind = n_cell / P;
+        const uint8_t* pu = a.plan + (int64_t)u * a.plan_stride;
+        const uint32_t n_ev = *reinterpret_cast<const uint32_t*>(pu);
+        if (n_ev > (uint32_t)a.cap) {   // sparse map: searched per cell afterwards (k_emit_generic)
+            if (tid == 0) a.overflow[1 + atomicAdd(a.overflow, 1)] = u;
+            continue;
+        }
+        // the bulk engine must be done reading the previous unit's rows out of shared memory
+        if (tid == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+        __syncthreads();
+
+        // ---- start state of the band, run starts bucketed by row
+        for (int i = tid * 16; i < seg_cells; i += ROWS_THREADS * 16)
+            *reinterpret_cast<uint4*>(img0 + i) = __ldg(reinterpret_cast<const uint4*>(pu + 16 + i));
+        for (int i = tid; i <= n_rows; i += ROWS_THREADS) start[i] = 0;
+        __syncthreads();
+        const uint32_t* ev_g = reinterpret_cast<const uint32_t*>(pu + 16 + seg_cells);
+        for (uint32_t e = tid; e < n_ev; e += ROWS_THREADS) atomicAdd(&start[__ldg(ev_g + e) >> 24], 1u);
+        __syncthreads();
+        if (tid < 32) {   // exclusive scan of the row histogram (<= 256 bins) by one warp
+            uint32_t carry = 0;
+            for (int base = 0; base <= n_rows; base += 32) {
+                const int i = base + tid;
+                const uint32_t v = i <= n_rows ? start[i] : 0;
+                uint32_t x = v;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) { const uint32_t y = __shfl_up_sync(0xFFFFFFFFu, x, o); if (tid >= o) x += y; }
+                if (i <= n_rows) { start[i] = carry + x - v; cursor[i] = carry + x - v; }
+                carry += __shfl_sync(0xFFFFFFFFu, x, 31);
+            }
+        }
+        __syncthreads();
+        for (uint32_t e = tid; e < n_ev; e += ROWS_THREADS) {
+            const uint32_t w = __ldg(ev_g + e);
+            evs[atomicAdd(&cursor[w >> 24], 1u)] = w;
+        }
+        if (DK >= 2) {   // 4-bit image: low 3 bits of every cell, the PRMT selectors of the dose lookup
+            for (int i = tid; i < seg_cells / 16; i += ROWS_THREADS) {
+                const uint4 v = reinterpret_cast<const uint4*>(img0)[i];
+                auto pack = [](uint32_t x) { return (x & 0x7) | ((x >> 4) & 0x70) | ((x >> 8) & 0x700) | ((x >> 12) & 0x7000); };
+                reinterpret_cast<uint2*>(nib)[i] = make_uint2(pack(v.x) | (pack(v.y) << 16), pack(v.z) | (pack(v.w) << 16));
+            }
+        }
+        if (DK == 1) {   // dose of one founder allele on the band's first row
+            for (int i = tid; i < seg_ind; i += ROWS_THREADS) {
+                int dsum = 0;
+                for (int h = 0; h < P; h++) dsum += img0[i * P + h] == (uint8_t)a.dose_which;
+                dose0[i] = (uint8_t)(count_ok ? dsum : 0);
+            }
+        }
+        uint4 Tn = make_uint4(0, 0, 0, 0);
+        if (DK >= 2) Tn = __ldg(a.mtab + g0);
+        __syncthreads();
+        // the second buffer starts from the same state (it becomes row 1)
+        for (int i = tid; i < seg_cells / 16; i += ROWS_THREADS) reinterpret_cast<uint4*>(img1)[i] = reinterpret_cast<const uint4*>(img0)[i];
+        if (DK == 1)
+            for (int i = tid; i < seg_ind / 16; i += ROWS_THREADS) reinterpret_cast<uint4*>(dose1)[i] = reinterpret_cast<const uint4*>(dose0)[i];
+
+        // ---- the rows. Buffer r & 1 holds row r-2 when row r begins: it takes the run starts of rows r-1 and r.
+        auto patch = [&](uint8_t* img, uint8_t* drow, uint32_t e0, uint32_t e1) {
+            for (uint32_t e = e0 + tid; e < e1; e += ROWS_THREADS) {
+                const uint32_t w = evs[e], cs = (w >> 8) & 0xFFFF, f = w & 0xFF;
+                if (DK == 1) {
+                    const int delta = (int)(f == (uint32_t)a.dose_which) - (int)(count_ok && img[cs] == (uint8_t)a.dose_which);
+                    const uint32_t ind = cs / P;
+                    if (delta) atomicAdd(reinterpret_cast<uint32_t*>(drow) + (ind >> 2), (uint32_t)delta << (8 * (ind & 3)));
+                }
+                img[cs] = (uint8_t)f;
+            }
+        };
+        for (int r = 0; r < n_rows; r++) {
+            const uint32_t e0 = start[r], e1 = start[r + 1];   // this row's run starts (row 0 has none: they are the state)
+            uint8_t* const img = (r & 1) ? img1 : img0;
+            uint8_t* const drow = (r & 1) ? dose1 : dose0;
+            // buffers of row r were last read by the bulk stores of row r-2
+            if (r > 1 && tid == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+            if (DK >= 2) {
+                for (uint32_t e = e0 + tid; e < e1; e += ROWS_THREADS) {
+                    const uint32_t w = evs[e], cs = (w >> 8) & 0xFFFF, sh = (cs & 7) * 4;
+                    atomicAnd(&nib[cs >> 3], ~(0xFu << sh));
+                    atomicOr(&nib[cs >> 3], (w & 7) << sh);
+                }
+            }
+            __syncthreads();
+            if (r > 0) patch(img, drow, start[r - 1], e0);   // catch up with row r-1
+            if (DK >= 2) {
+                const uint4 T = Tn;
+                if (r + 1 < n_rows) Tn = __ldg(a.mtab + g0 + r + 1);
+                if (DK == 2) {   // 8 individuals per step: 4 words of the 4-bit image in, 8 dose bytes out
+                    for (int i = tid; i < seg_ind / 8; i += ROWS_THREADS) {
+                        const uint4 v = reinterpret_cast<const uint4*>(nib)[i];
+                        auto two = [&](uint32_t w) { return __dp4a(prmt(T.x, T.y, w) + prmt(T.z, T.w, w >> 16), 0x01010101u, 0u); };
+                        const uint32_t lo = two(v.x) | (two(v.y) << 8), hi = two(v.z) | (two(v.w) << 8);   // dose nibbles
+                        reinterpret_cast<uint2*>(drow)[i] = make_uint2(prmt(0x03020100u, 0x07060504u, lo), prmt(0x03020100u, 0x07060504u, hi));
+                    }
+                } else {         // ploidy 2: 16 individuals per step
+                    for (int i = tid; i < seg_ind / 16; i += ROWS_THREADS) {
+                        const uint4 v = reinterpret_cast<const uint4*>(nib)[i];
+                        auto four = [&](uint32_t w) {
+                            const uint32_t xl = prmt(T.x, T.y, w), xh = prmt(T.x, T.y, w >> 16);
+                            return prmt(xl + (xl >> 8), xh + (xh >> 8), 0x6420u);
+                        };
+                        reinterpret_cast<uint4*>(drow)[i] = make_uint4(four(v.x), four(v.y), four(v.z), four(v.w));
+                    }
+                }
+            }
+            __syncthreads();
+            patch(img, drow, e0, e1);
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            __syncthreads();
+            uint8_t* const gf = a.founder ? a.founder + (out_row0 + r) * a.founder_pitch + c0 : nullptr;
+            uint8_t* const gd = a.dose ? a.dose + (out_row0 + r) * a.dose_pitch + c0 / P : nullptr;
+            if (tid == 0) {
+                if (gf && (n_cell & ~15)) bulk_store(gf, img, (uint32_t)(n_cell & ~15));
+                if (DK >= 1 && gd && (n_ind & ~15)) bulk_store(gd, drow, (uint32_t)(n_ind & ~15));
+                asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+            }
+            // ragged ends (a bulk store moves multiples of 16 bytes)
+            if (gf && tid < (n_cell & 15)) gf[(n_cell & ~15) + tid] = img[(n_cell & ~15) + tid];
+            if (DK >= 1 && gd && tid >= 32 && tid - 32 < (n_ind & 15)) gd[(n_ind & ~15) + tid - 32] = drow[(n_ind & ~15) + tid - 32];
+        }
+    }
+    if (tid == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+}
+
 // Generic emission: one thread per (locus row, emitted individual); any ploidy, u8 or u16 founders,
 // any pitch. Used for ploidies without a tiled instantiation and for unaligned device targets.
 struct EmitGenericArgs {
@@ -779,6 +1093,7 @@ struct EmitGenericArgs {
     int64_t ind_first, ind_count, n_cols_ind;
     int64_t locus_first;          // row 0 of the outputs
     int64_t l_begin, l_count;     // global loci of this launch
+    int64_t q_first, q_count;     // emitted individuals (columns) of this launch
     void* founder; int64_t founder_pitch; int founder_bytes;
     uint8_t* allele; int64_t allele_pitch;
     uint8_t* dose; int64_t dose_pitch;
@@ -788,9 +1103,9 @@ struct EmitGenericArgs {
 
 __global__ void __launch_bounds__(256) k_emit_generic(const EmitGenericArgs a) {
     const int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-    if (t >= a.l_count * a.n_cols_ind) return;
-    const int64_t q = t % a.n_cols_ind;
-    const int64_t gl = a.l_begin + t / a.n_cols_ind;
+    if (t >= a.l_count * a.q_count) return;
+    const int64_t q = a.q_first + t % a.q_count;
+    const int64_t gl = a.l_begin + t / a.q_count;
     int c = 0;
     while (gl >= a.locus_off[c + 1]) c++;
     const uint32_t l = (uint32_t)(gl - a.locus_off[c]);
@@ -900,7 +1215,7 @@ __global__ void k_gather_segments(int64_t n, int64_t first, int r, int C, int R,
 // MAX / MIN allele name or the name of founder allele `which`), the padded 16-entry code table and
 // the nibble mask of founder alleles that carry the counted code.
 __global__ void k_match_codes(int64_t L, int A, int which, const uint8_t* __restrict__ code, uint8_t* __restrict__ match,
-                              uint32_t* __restrict__ code16, uint32_t* __restrict__ nibmask) {
+                              uint32_t* __restrict__ code16, uint32_t* __restrict__ nibmask, uint4* __restrict__ mtab) {
     const int64_t l = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (l >= L) return;
     const uint8_t* cd = code + l * A;
@@ -918,6 +1233,10 @@ __global__ void k_match_codes(int64_t L, int A, int which, const uint8_t* __rest
         for (int q = 0; q < 4; q++) code16[l * 4 + q] = t[q];
         nibmask[l * 2] = nm[0];
         nibmask[l * 2 + 1] = nm[1];
+        uint32_t mt[2] = {0, 0};   // byte table for the PRMT dose lookup (A <= 8 paths)
+        for (int k = 0; k < A && k < 8; k++)
+            if (cd[k] == m) mt[k >> 2] |= 1u << (8 * (k & 3));
+        mtab[l] = make_uint4(mt[0], mt[1], mt[0] << 4, mt[1] << 4);
     }
 }
 
@@ -974,6 +1293,7 @@ struct psim_ctx_impl {
     uint8_t* match_d = nullptr;
     uint32_t* code16_d = nullptr;   // [L][4]
     uint32_t* nibmask_d = nullptr;  // [L][2]
+    uint4* mtab_d = nullptr;        // [L]
     int match_which = 12345678;
     int founder_allele_count = 0;
     // scratch
@@ -1101,6 +1421,132 @@ void launch_tiles(psim_ctx_impl* c, const EmitArgs& ea, int blocks, int mode) {
     cudaEventRecord(next_kev(c), c->stream);
     k_emit_dense<P, G><<<c->sm_count * 4, EMIT_THREADS, 0, c->stream>>>(ea);
 }
+// Row-image emission (k_band_plan + k_emit_rows) of loci [l_begin, l_end). Returns PSIM_OK and sets
+// `done` when the request fits the path; otherwise leaves `done` false for the tiled / generic paths.
+template <int DK>
+static void launch_rows(psim_ctx_impl* c, const RowsArgs& ra, int blocks, size_t smem) {
+    cudaFuncSetAttribute(k_emit_rows<DK>, cudaFuncAttributeMaxDynamicSharedMemorySize, ROWS_SMEM);
+    k_emit_rows<DK><<<blocks, ROWS_THREADS, smem, c->stream>>>(ra);
+}
+
+static int emit_rows_path(psim_ctx_impl* c, int64_t ind_first, int64_t ind_count, int64_t l_begin, int64_t l_end, int64_t row0_locus,
+                          uint8_t* founder, int64_t founder_pitch, uint8_t* dose, int64_t dose_pitch, int dose_which, int mode,
+                          bool& done) {
+    done = false;
+    static const bool disabled = getenv("PSIM_NO_ROWS") != nullptr;
+    const int P = c->P;
+    if (disabled || !(mode == 0 || (mode == 1 && (P == 2 || P == 4)))) return PSIM_OK;
+    const int DK = !dose ? 0 : mode == 0 ? 1 : P == 4 ? 2 : 3;
+    const int64_t n_cols_ind = (int64_t)c->R * ind_count, n_cols = n_cols_ind * P;
+    const int cap = 8192;
+    const double per_cell = 2.0 + (DK >= 2 ? 0.5 : 0.0) + (DK >= 1 ? 2.0 : 0.0) / P;
+    const int64_t budget = ROWS_SMEM - 2 * (ROWS_MAX_BAND + 2) * 4 - cap * 4;
+    const int64_t quantum = 16 * P;
+    int64_t seg_max = (int64_t)(budget / per_cell) / quantum * quantum;
+    seg_max = std::min<int64_t>(seg_max, 65535 / quantum * quantum);
+    const int n_seg = (int)((n_cols + seg_max - 1) / seg_max);
+    const int64_t seg_cells = ((n_cols + n_seg - 1) / n_seg + quantum - 1) / quantum * quantum;
+    // run starts per cell and row, from the resident haplostructs (as in the tiled path)
+    const double seg_per_hom = c->n_hom > 0 ? (double)c->slab_used / (double)c->n_hom : 1.0;
+    const double loci_per_chrom = std::max(1.0, (double)c->L / c->C);
+    const double starts_per_cell = std::max(0.0, seg_per_hom - 1.0) / loci_per_chrom;
+    static const int env_band = getenv("PSIM_BAND_ROWS") ? atoi(getenv("PSIM_BAND_ROWS")) : 0;
+    static const int env_bps = getenv("PSIM_ROWS_BLOCKS_PER_SM") ? atoi(getenv("PSIM_ROWS_BLOCKS_PER_SM")) : 0;
+    const int n_blocks = c->sm_count * (env_bps > 0 ? env_bps : 1);
+    // band height: one unit per resident block when the request is large, never so tall that a unit's
+    // expected run starts come near the list capacity
+    int64_t band = ((l_end - l_begin) * n_seg + n_blocks - 1) / n_blocks;
+    band = std::max<int64_t>(32, std::min<int64_t>(band, ROWS_MAX_BAND));
+    while (band > 8 && starts_per_cell * (double)seg_cells * (double)band > cap / 2) band = band * 3 / 4;
+    if (starts_per_cell * (double)seg_cells * (double)band > cap / 2) return PSIM_OK;   // sparse map: tiled / dense path
+    if (env_band > 0) band = std::min(env_band, ROWS_MAX_BAND);
+
+    RowsArgs ra{};
+    ra.C = c->C; ra.R = c->R; ra.P = P; ra.N = c->N;
+    ra.run_desc = c->run_desc_d; ra.run_lb = c->run_lb_d; ra.run_founder = c->run_founder_d;
+    ra.ind_first = ind_first; ra.ind_count = ind_count; ra.n_cols_ind = n_cols_ind;
+    ra.locus_first = row0_locus;
+    ra.n_seg = n_seg; ra.seg_cells = (int)seg_cells; ra.cap = cap;
+    ra.plan_stride = (16 + seg_cells + (int64_t)cap * 4 + 127) / 128 * 128;
+    ra.founder = founder; ra.founder_pitch = founder_pitch;
+    ra.dose = dose; ra.dose_pitch = dose_pitch;
+    ra.dose_which = dose_which; ra.mtab = c->mtab_d;
+    ra.unit_counter = c->tile_counter_d;
+    const size_t smem = 2 * (size_t)seg_cells + (DK >= 2 ? seg_cells / 2 : 0) + (size_t)(DK >= 1 ? 2 : 0) * (seg_cells / P) +
+                        (size_t)cap * 4 + 2 * (ROWS_MAX_BAND + 2) * 4;
+    int k0 = 0;
+    while (k0 < c->C && c->locus_off_h[k0 + 1] <= l_begin) k0++;
+    while (k0 < c->C && c->locus_off_h[k0] < l_end) {
+        ra.n_chunks = 0;
+        ra.chunk_unit_base[0] = 0;
+        while (k0 < c->C && c->locus_off_h[k0] < l_end && ra.n_chunks < 64) {
+            const int64_t a0 = std::max(l_begin, c->locus_off_h[k0]), a1 = std::min(l_end, c->locus_off_h[k0 + 1]);
+            if (a1 > a0) {
+                const int q = ra.n_chunks++;
+                ra.chunk_chrom[q] = k0; ra.chunk_l0[q] = a0; ra.chunk_l1[q] = a1; ra.chunk_coff[q] = c->locus_off_h[k0];
+                const int64_t len = a1 - a0;
+                int64_t nb = std::max<int64_t>(1, (len + band / 2) / band);
+                nb = std::max(nb, (len + ROWS_MAX_BAND - 1) / ROWS_MAX_BAND);
+                ra.chunk_bands[q] = (int)nb;
+                ra.chunk_unit_base[q + 1] = ra.chunk_unit_base[q] + (int)nb * n_seg;
+            }
+            k0++;
+        }
+        if (ra.n_chunks == 0) break;
+        ra.n_units = ra.chunk_unit_base[ra.n_chunks];
+        if (int rc = ensure_buf(c, c->b_plan, (size_t)ra.n_units * ra.plan_stride)) return rc;
+        if (int rc = ensure_buf(c, c->b_dense_list, ((size_t)ra.n_units + 1) * sizeof(int))) return rc;
+        ra.plan = (uint8_t*)c->b_plan.p;
+        ra.overflow = (int*)c->b_dense_list.p;
+        CUDA_TRY(cudaMemset2DAsync(ra.plan, (size_t)ra.plan_stride, 0, 16, (size_t)ra.n_units, c->stream));   // list counters
+        CUDA_TRY(cudaMemsetAsync(ra.overflow, 0, sizeof(int), c->stream));
+        CUDA_TRY(cudaMemsetAsync(c->tile_counter_d, 0, sizeof(int), c->stream));
+        k_band_plan<<<dim3((unsigned)((n_cols + 255) / 256), (unsigned)ra.n_chunks), 256, 0, c->stream>>>(ra);
+        cudaEventRecord(next_kev(c), c->stream);
+        const int blocks = std::min(ra.n_units, n_blocks);
+        if (DK == 0) launch_rows<0>(c, ra, blocks, smem);
+        else if (DK == 1) launch_rows<1>(c, ra, blocks, smem);
+        else if (DK == 2) launch_rows<2>(c, ra, blocks, smem);
+        else launch_rows<3>(c, ra, blocks, smem);
+        cudaEventRecord(next_kev(c), c->stream);
+        c->stats.kernel_launches += 2;
+        c->stats.emit_kernel_launches++;
+        CUDA_TRY(cudaGetLastError());
+        // units whose run-start list overflowed (not expected with the band heuristic): searched per cell
+        int n_over = 0;
+        CUDA_TRY(cudaMemcpyAsync(&n_over, ra.overflow, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+        CUDA_TRY(cudaStreamSynchronize(c->stream));
+        if (n_over > 0) {
+            std::vector<int> units((size_t)n_over);
+            CUDA_TRY(cudaMemcpy(units.data(), ra.overflow + 1, (size_t)n_over * sizeof(int), cudaMemcpyDeviceToHost));
+            for (int u : units) {
+                int k = 0;
+                while (u >= ra.chunk_unit_base[k + 1]) k++;
+                const int j = (u - ra.chunk_unit_base[k]) / n_seg, sg = (u - ra.chunk_unit_base[k]) % n_seg;
+                const int64_t len = ra.chunk_l1[k] - ra.chunk_l0[k];
+                const int64_t g0 = ra.chunk_l0[k] + len * j / ra.chunk_bands[k], g1 = ra.chunk_l0[k] + len * (j + 1) / ra.chunk_bands[k];
+                EmitGenericArgs ga{};
+                ga.C = c->C; ga.R = c->R; ga.P = P; ga.N = c->N;
+                ga.run_desc = c->run_desc_d; ga.run_lb = c->run_lb_d; ga.run_founder = c->run_founder_d;
+                ga.locus_off = c->locus_off_d;
+                ga.ind_first = ind_first; ga.ind_count = ind_count; ga.n_cols_ind = n_cols_ind;
+                ga.locus_first = row0_locus; ga.l_begin = g0; ga.l_count = g1 - g0;
+                ga.q_first = (int64_t)sg * (seg_cells / P);
+                ga.q_count = std::min<int64_t>(seg_cells / P, n_cols_ind - ga.q_first);
+                ga.founder = founder; ga.founder_pitch = founder_pitch; ga.founder_bytes = 1;
+                ga.dose = dose; ga.dose_pitch = dose_pitch;
+                ga.dose_mode = mode == 0 ? 0 : 1; ga.dose_which = dose_which;
+                ga.code = c->code_d; ga.match_code = c->match_d; ga.A = c->A;
+                k_emit_generic<<<grid_for(ga.l_count * ga.q_count, 256), 256, 0, c->stream>>>(ga);
+                c->stats.kernel_launches++;
+                CUDA_TRY(cudaGetLastError());
+            }
+        }
+    }
+    done = true;
+    return PSIM_OK;
+}
+
 }  // namespace
 
 extern "C" {
@@ -1162,7 +1608,7 @@ void psim_destroy(psim_ctx* ctx) {
     cudaFree(c->chrom_d); cudaFree(c->seg_pos_d); cudaFree(c->seg_founder_d);
     cudaFree(c->run_lb_d); cudaFree(c->run_founder_d);
     cudaFree(c->locus_off_d); cudaFree(c->locus_pos_d); cudaFree(c->code_d); cudaFree(c->match_d);
-    cudaFree(c->code16_d); cudaFree(c->nibmask_d);
+    cudaFree(c->code16_d); cudaFree(c->nibmask_d); cudaFree(c->mtab_d);
     cudaFree(c->error_flag_d); cudaFree(c->tile_counter_d); cudaFree(c->cub_tmp); cudaFree(c->staging);
     cudaFree(c->exp_off_d); cudaFree(c->exp_founder_d); cudaFree(c->exp_pos_d);
     for (cudaEvent_t e : c->kev) cudaEventDestroy(e);
@@ -1550,9 +1996,9 @@ int psim_set_map(psim_ctx* ctx, const int64_t* locus_off, const double* pos) {
     c->L = locus_off[c->C];
     c->locus_off_h.assign(locus_off, locus_off + c->C + 1);
     cudaFree(c->locus_off_d); cudaFree(c->locus_pos_d); cudaFree(c->code_d); cudaFree(c->match_d);
-    cudaFree(c->code16_d); cudaFree(c->nibmask_d);
+    cudaFree(c->code16_d); cudaFree(c->nibmask_d); cudaFree(c->mtab_d);
     c->locus_off_d = nullptr; c->locus_pos_d = nullptr; c->code_d = nullptr; c->match_d = nullptr;
-    c->code16_d = nullptr; c->nibmask_d = nullptr;
+    c->code16_d = nullptr; c->nibmask_d = nullptr; c->mtab_d = nullptr;
     c->A = 0; c->code_h.clear();
     CUDA_TRY(dev_alloc(&c->locus_off_d, (size_t)c->C + 1));
     CUDA_TRY(dev_alloc(&c->locus_pos_d, (size_t)c->L));
@@ -1567,8 +2013,8 @@ int psim_set_allele_codes(psim_ctx* ctx, int32_t n_alleles, const uint8_t* code)
     if (!c) return PSIM_EINVAL;
     if (c->L == 0) return fail(c, PSIM_ESTATE, "psim_set_map must be called first");
     cudaSetDevice(c->cfg.device);
-    cudaFree(c->code_d); cudaFree(c->match_d); cudaFree(c->code16_d); cudaFree(c->nibmask_d);
-    c->code_d = nullptr; c->match_d = nullptr; c->code16_d = nullptr; c->nibmask_d = nullptr;
+    cudaFree(c->code_d); cudaFree(c->match_d); cudaFree(c->code16_d); cudaFree(c->nibmask_d); cudaFree(c->mtab_d);
+    c->code_d = nullptr; c->match_d = nullptr; c->code16_d = nullptr; c->nibmask_d = nullptr; c->mtab_d = nullptr;
     c->A = 0; c->code_h.clear(); c->match_which = 12345678;
     if (!code) return PSIM_OK;
     if (n_alleles <= 0 || n_alleles > 256) return fail(c, PSIM_EINVAL, "allele codes need 1..256 founder alleles");
@@ -1578,6 +2024,7 @@ int psim_set_allele_codes(psim_ctx* ctx, int32_t n_alleles, const uint8_t* code)
     CUDA_TRY(dev_alloc(&c->match_d, (size_t)c->L));
     CUDA_TRY(dev_alloc(&c->code16_d, (size_t)c->L * 4));
     CUDA_TRY(dev_alloc(&c->nibmask_d, (size_t)c->L * 2));
+    CUDA_TRY(dev_alloc(&c->mtab_d, (size_t)c->L));
     CUDA_TRY(cudaMemcpy(c->code_d, code, (size_t)c->L * n_alleles, cudaMemcpyHostToDevice));
     return PSIM_OK;
 }
@@ -1619,8 +2066,17 @@ static int emit_device(psim_ctx_impl* c, int64_t ind_first, int64_t ind_count, i
     const bool aligned = (!founder || ((uintptr_t)founder % 16 == 0 && founder_pitch % 16 == 0)) &&
                          (!allele || ((uintptr_t)allele % 16 == 0 && allele_pitch % 16 == 0)) &&
                          (!dose || ((uintptr_t)dose % 16 == 0 && dose_pitch % 16 == 0));
-    const bool tiled = G != 0 && aligned && founder_bytes == 1 && c->founder_allele_count <= 256 &&
+    const int64_t max_pitch = (int64_t)1 << 25;   // row offsets inside a tile are 32-bit (64 rows)
+    const bool small_pitch = founder_pitch < max_pitch && allele_pitch < max_pitch && dose_pitch < max_pitch;
+    const bool tiled = G != 0 && aligned && small_pitch && founder_bytes == 1 && c->founder_allele_count <= 256 &&
                        c->run_cap < (int64_t)0xFFFFFFFF;
+    if (tiled && !allele && (founder || dose)) {
+        bool done = false;
+        const int mode0 = !c->code_d ? 0 : c->A <= 8 ? 1 : c->A <= 16 ? 2 : 3;
+        if (int rc = emit_rows_path(c, ind_first, ind_count, l_begin, l_end, row0_locus, (uint8_t*)founder, founder_pitch, dose, dose_pitch,
+                                    dose_which, mode0, done)) return rc;
+        if (done) return PSIM_OK;
+    }
     if (tiled) {
         EmitArgs ea{};
         ea.C = c->C; ea.R = c->R; ea.P = P; ea.N = c->N;
@@ -1636,7 +2092,7 @@ static int emit_device(psim_ctx_impl* c, int64_t ind_first, int64_t ind_count, i
             const double loci_per_chrom = std::max(1.0, (double)c->L / c->C);
             const double starts_per_cell = std::max(0.0, seg_per_hom - 1.0) / loci_per_chrom;
             int rows = 64;
-            while (rows > 8 && 32.0 * G * P * rows * starts_per_cell > 24.0) rows >>= 1;
+            while (rows > 8 && 32.0 * G * P * rows * starts_per_cell > 18.0) rows >>= 1;
             ea.tile_loci = env_tile > 0 ? std::min(env_tile, EMIT_MAX_TILE_LOCI) : rows;
         }
         ea.n_col_tiles = (int)((n_cols_ind + (int64_t)EMIT_THREADS * G - 1) / ((int64_t)EMIT_THREADS * G));
@@ -1645,7 +2101,7 @@ static int emit_device(psim_ctx_impl* c, int64_t ind_first, int64_t ind_count, i
         ea.dose = dose; ea.dose_pitch = dose_pitch;
         ea.dose_which = dose_which;
         ea.code = c->code_d; ea.match_code = c->match_d; ea.A = c->A;
-        ea.code16 = c->code16_d; ea.nibmask = c->nibmask_d;
+        ea.code16 = c->code16_d; ea.nibmask = c->nibmask_d; ea.mtab = c->mtab_d;
         const int mode = !c->code_d ? 0 : c->A <= 8 ? 1 : c->A <= 16 ? 2 : 3;
         ea.tile_counter = c->tile_counter_d;
         // chromosomes touched by [l_begin, l_end), at most 64 per launch
@@ -1693,6 +2149,7 @@ static int emit_device(psim_ctx_impl* c, int64_t ind_first, int64_t ind_count, i
         ga.locus_off = c->locus_off_d;
         ga.ind_first = ind_first; ga.ind_count = ind_count; ga.n_cols_ind = n_cols_ind;
         ga.locus_first = row0_locus; ga.l_begin = l_begin; ga.l_count = l_end - l_begin;
+        ga.q_first = 0; ga.q_count = n_cols_ind;
         ga.founder = founder; ga.founder_pitch = founder_pitch; ga.founder_bytes = founder_bytes;
         ga.allele = allele; ga.allele_pitch = allele_pitch; ga.dose = dose; ga.dose_pitch = dose_pitch;
         ga.dose_mode = dose_mode; ga.dose_which = dose_which;
@@ -1739,7 +2196,7 @@ int psim_emit(psim_ctx* ctx, int64_t ind_first, int64_t ind_count, int64_t locus
         dose_mode = 1;
         if (c->match_which != t->dose_which) {
             k_match_codes<<<grid_for(c->L, 256), 256, 0, c->stream>>>(c->L, c->A, t->dose_which, c->code_d, c->match_d,
-                                                                       c->code16_d, c->nibmask_d);
+                                                                       c->code16_d, c->nibmask_d, c->mtab_d);
             c->stats.kernel_launches++;
             CUDA_TRY(cudaGetLastError());
             c->match_which = t->dose_which;
