@@ -1484,15 +1484,38 @@ static int emit_rows_path(psim_ctx_impl* c, int64_t ind_first, int64_t ind_count
             if (a1 > a0) {
                 const int q = ra.n_chunks++;
                 ra.chunk_chrom[q] = k0; ra.chunk_l0[q] = a0; ra.chunk_l1[q] = a1; ra.chunk_coff[q] = c->locus_off_h[k0];
-                const int64_t len = a1 - a0;
-                int64_t nb = std::max<int64_t>(1, (len + band / 2) / band);
-                nb = std::max(nb, (len + ROWS_MAX_BAND - 1) / ROWS_MAX_BAND);
-                ra.chunk_bands[q] = (int)nb;
-                ra.chunk_unit_base[q + 1] = ra.chunk_unit_base[q] + (int)nb * n_seg;
             }
             k0++;
         }
         if (ra.n_chunks == 0) break;
+        {   // bands per chromosome piece: proportional to its rows, rounded so that the total is the
+            // target (one unit per resident block) — largest remainders get the extra band
+            int64_t total = 0;
+            for (int q = 0; q < ra.n_chunks; q++) total += ra.chunk_l1[q] - ra.chunk_l0[q];
+            const int64_t target = std::max<int64_t>(1, (total + band - 1) / band);
+            int64_t given = 0;
+            double rem[64];
+            for (int q = 0; q < ra.n_chunks; q++) {
+                const int64_t len = ra.chunk_l1[q] - ra.chunk_l0[q];
+                const double ideal = (double)len * (double)target / (double)total;
+                int64_t nb = std::max<int64_t>(1, (int64_t)ideal);
+                nb = std::max(nb, (len + ROWS_MAX_BAND - 1) / ROWS_MAX_BAND);
+                nb = std::min(nb, len);
+                ra.chunk_bands[q] = (int)nb;
+                rem[q] = ideal - (double)nb;
+                given += nb;
+            }
+            while (given < target) {
+                int best = -1;
+                for (int q = 0; q < ra.n_chunks; q++)
+                    if (ra.chunk_bands[q] < ra.chunk_l1[q] - ra.chunk_l0[q] && (best < 0 || rem[q] > rem[best])) best = q;
+                if (best < 0) break;
+                ra.chunk_bands[best]++;
+                rem[best] -= 1.0;
+                given++;
+            }
+            for (int q = 0; q < ra.n_chunks; q++) ra.chunk_unit_base[q + 1] = ra.chunk_unit_base[q] + ra.chunk_bands[q] * n_seg;
+        }
         ra.n_units = ra.chunk_unit_base[ra.n_chunks];
         if (int rc = ensure_buf(c, c->b_plan, (size_t)ra.n_units * ra.plan_stride)) return rc;
         if (int rc = ensure_buf(c, c->b_dense_list, ((size_t)ra.n_units + 1) * sizeof(int))) return rc;
