@@ -7,7 +7,7 @@
 //   seg_pos[] f64 Morgan / seg_founder[] i32              HaploStruct.recombPos / founder, unmerged
 //   run_desc / run_lb[] u32 / run_founder[] u16           K0 output: per homolog the runs of loci
 //                                                         that carry one founder (locus-index space)
-// Kernels: k_init_founders, k_meiosis_plan (K1a), k_meiosis_assemble (K1b), k_index_runs (K0),
+// Kernels: k_init_founders, k_meiosis_config + k_meiosis_mv (K1a), k_meiosis_assemble (K1b), k_index_runs (K0),
 //          k_emit_tiles<P,G> (K2, HBM-write-bound), k_emit_generic, gather/scatter helpers.
 #include <cuda_runtime.h>
 
@@ -79,49 +79,98 @@ struct PlanArgs {
     int8_t* cfg_quad;            // [R*N][C][2]
     int8_t* cfg_seq;             // [R*N][C][2][P]
     int* error_flag;
+    int64_t* task_bi;            // bivalents of the batch: (thread id of the unit) * 8 + multivalent number
+    int64_t* task_quad;          // quadrivalents
+    int* task_count;             // [0] bivalents, [1] quadrivalents
 };
 
-__global__ void __launch_bounds__(128) k_meiosis_plan(PlanArgs a) {
+// K1a is split in two so that the warps of the heavy part run one code path:
+//   k_meiosis_config  one thread per (child, chromosome, parent): pairing configuration only
+//                     (Individual.calcChromConfig); it also files every multivalent of the unit as a
+//                     task in the bivalent or the quadrivalent list (one atomic per warp and list)
+//   k_meiosis_mv<Q>   one thread per task of one kind: crossing-over, centromere order, choice of
+//                     the transmitted chromatids and their trace into the plan
+// Every multivalent has its own Philox stream (stage 1 + v), so the split changes no draw.
+__device__ __forceinline__ void plan_decode(const PlanArgs& a, int64_t t, int& par, int& j, int& r, int& c) {
+    par = (int)(t & 1);
+    const int64_t unit = t >> 1;
+    j = (int)(unit % a.n_lev);
+    r = (int)((unit / a.n_lev) % a.R);
+    c = (int)(unit / ((int64_t)a.n_lev * a.R));
+}
+
+__global__ void __launch_bounds__(128) k_meiosis_config(PlanArgs a) {
     const int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     const int64_t total = (int64_t)a.C * a.R * a.n_lev * 2;
-    if (t >= total) return;
-    const int par = (int)(t & 1);
-    const int64_t unit = t >> 1;
-    const int j = (int)(unit % a.n_lev);
-    const int r = (int)((unit / a.n_lev) % a.R);
-    const int c = (int)(unit / ((int64_t)a.n_lev * a.R));
+    int n_quad = 0, n_bi = 0;
+    if (t < total) {
+        int par, j, r, c;
+        plan_decode(a, t, par, j, r, c);
+        const int P = a.P;
+        const int32_t child = a.lev_ind[j];
+        const int32_t parent = par == 0 ? a.par0[child] : a.par1[child];
+        const ChromParams ch = a.chrom[c];
+        HomologView hv[MAXP];
+        const int64_t phid0 = (((int64_t)c * a.R + r) * a.N + parent) * P;
+        for (int h = 0; h < P; h++) {
+            const uint64_t d = a.desc[phid0 + h];
+            hv[h].pos = a.seg_pos + desc_begin(d);
+            hv[h].founder = a.seg_founder + desc_begin(d);
+            hv[h].n = (int)desc_count(d);
+        }
+        PhiloxStream rng;
+        rng.init(a.model.seed, a.replicate_first + (uint32_t)r);
+        PairingState ps;
+        rng.seek((uint32_t)child, (uint32_t)c, (uint32_t)par, STAGE_CONFIG);
+        calc_chrom_config(ps, rng, a.model, ch, hv);
+        const int64_t q = (((int64_t)r * a.N + child) * a.C + c) * 2 + par;
+        a.cfg_quad[q] = (int8_t)ps.quad;
+        for (int h = 0; h < P; h++) a.cfg_seq[q * P + h] = ps.chromseq[h];
+        n_quad = ps.quad;
+        n_bi = (P - 4 * ps.quad) / 2;
+    }
+    // file the tasks: exclusive prefix inside the warp, one atomic per warp and list
+    const int lane = threadIdx.x & 31;
+    int sq = n_quad, sb = n_bi;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const int yq = __shfl_up_sync(0xFFFFFFFFu, sq, o), yb = __shfl_up_sync(0xFFFFFFFFu, sb, o);
+        if (lane >= o) { sq += yq; sb += yb; }
+    }
+    int base_q = 0, base_b = 0;
+    if (lane == 31) {
+        if (sq) base_q = atomicAdd(a.task_count + 1, sq);
+        if (sb) base_b = atomicAdd(a.task_count, sb);
+    }
+    base_q = __shfl_sync(0xFFFFFFFFu, base_q, 31) + sq - n_quad;
+    base_b = __shfl_sync(0xFFFFFFFFu, base_b, 31) + sb - n_bi;
+    for (int v = 0; v < n_quad; v++) a.task_quad[base_q + v] = t * 8 + v;
+    for (int v = 0; v < n_bi; v++) a.task_bi[base_b + v] = t * 8 + n_quad + v;
+}
+
+template <bool QUAD>
+__global__ void __launch_bounds__(128) k_meiosis_mv(PlanArgs a) {
+    const int64_t ti = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (ti >= (int64_t)a.task_count[QUAD ? 1 : 0]) return;
+    const int64_t code = (QUAD ? a.task_quad : a.task_bi)[ti];
+    const int v = (int)(code & 7);
+    int par, j, r, c;
+    plan_decode(a, code >> 3, par, j, r, c);
     const int P = a.P, p2 = P / 2;
     const int32_t child = a.lev_ind[j];
     const int32_t parent = par == 0 ? a.par0[child] : a.par1[child];
     const ChromParams ch = a.chrom[c];
     const ModelParams& m = a.model;
-
-    HomologView hv[MAXP];
     const int64_t phid0 = (((int64_t)c * a.R + r) * a.N + parent) * P;
-    for (int h = 0; h < P; h++) {
-        const uint64_t d = a.desc[phid0 + h];
-        hv[h].pos = a.seg_pos + desc_begin(d);
-        hv[h].founder = a.seg_founder + desc_begin(d);
-        hv[h].n = (int)desc_count(d);
-    }
+    const int64_t q = (((int64_t)r * a.N + child) * a.C + c) * 2 + par;
+    const int quad = a.cfg_quad[q];
+    const int8_t* chromseq = a.cfg_seq + q * P;
     PhiloxStream rng;
     rng.init(m.seed, a.replicate_first + (uint32_t)r);
-    PairingState ps;
-    rng.seek((uint32_t)child, (uint32_t)c, (uint32_t)par, STAGE_CONFIG);
-    calc_chrom_config(ps, rng, m, ch, hv);
-    {
-        const int64_t q = (((int64_t)r * a.N + child) * a.C + c) * 2 + par;
-        a.cfg_quad[q] = (int8_t)ps.quad;
-        for (int h = 0; h < P; h++) a.cfg_seq[q * P + h] = ps.chromseq[h];
-    }
-    // gamete 0 before the homolog shuffle: slot -> (multivalent base in chromseq, starting chromatid slot, stage)
-    Chiasmata x;
-    x.overflow = false;
-    // Multivalents are processed one at a time; each transmitted chromatid is traced straight into
-    // the plan entry of the child homolog it will occupy after the gamete's homolog shuffle.
+    // Each transmitted chromatid is traced straight into the plan entry of the child homolog it
+    // will occupy after the gamete's homolog shuffle. The shuffle draws come from their own stream:
+    // slot h of the transmitted gamete receives pre-shuffle slot shuf[h] (Individual.java:325-335).
     const int64_t u0 = (((int64_t)c * a.R + r) * a.n_lev + j) * P + (int64_t)par * p2;
-    // The shuffle draws come from their own stream, so take them first: slot h of the transmitted
-    // gamete receives pre-shuffle slot shuf[h] (Individual.java:325-335).
     int8_t shuf[MAXP / 2];
     for (int s = 0; s < p2; s++) shuf[s] = (int8_t)s;
     rng.seek((uint32_t)child, (uint32_t)c, (uint32_t)par, STAGE_SHUFFLE);
@@ -129,67 +178,72 @@ __global__ void __launch_bounds__(128) k_meiosis_plan(PlanArgs a) {
     int8_t dest_of_slot[MAXP / 2];  // pre-shuffle slot -> final homolog position
     for (int h = 0; h < p2; h++) dest_of_slot[shuf[h]] = (int8_t)h;
 
-    uint32_t stage = 1;
-    const int firstbi = ps.quad * 4;
-    const int n_mv = ps.quad + (P - firstbi) / 2;
-    for (int v = 0; v < n_mv; v++) {
-        const bool is_quad = v < ps.quad;
-        const int k = is_quad ? 4 : 2;
-        const int base = is_quad ? 4 * v : firstbi + 2 * (v - ps.quad);
-        rng.seek((uint32_t)child, (uint32_t)c, (uint32_t)par, stage++);
-        double exchange_lim1 = 0.0;
-        if (is_quad) exchange_lim1 = quadrivalent_crossing_over(x, rng, m, ch);
-        else parallel_crossing_over(x, rng, m, ch, 2);
-        if (x.overflow) { atomicExch(a.error_flag, PSIM_ECAPACITY); return; }
-        int8_t centro[8];
-        if (is_quad) quadrivalent_centromere_order(rng, m, ch, exchange_lim1, centro);
-        else multivalent_centromere_order(rng, 2, centro);
-        int start_slots[2];
-        select_gamete0(x, rng, k, ch, centro, start_slots);
-        const int n_out = is_quad ? 2 : 1;
-        for (int o = 0; o < n_out; o++) {
-            // Individual.java:297-321: quadrivalent v fills gamete slots 2v, 2v+1; bivalent v' fills firstbi/2 + v'
-            const int pre_slot = is_quad ? 2 * v + o : firstbi / 2 + (v - ps.quad);
-            const int64_t u = u0 + dest_of_slot[pre_slot];
-            double* ppos = a.plan_pos + u * a.piece_cap;
-            uint8_t* phom = a.plan_hom + u * a.piece_cap;
-            // Multivalent.slotsToPatterns (:332-357) for the selected chromatid
-            int cur = start_slots[o];
-            int np = 0;
-            ppos[0] = ch.head;
-            phom[0] = (uint8_t)ps.chromseq[base + (cur >> 1)];
-            np = 1;
-            bool over = false;
-            for (int e = 0; e < x.n; e++) {
-                int nxt = -1;
-                if (x.a[e] == cur) nxt = x.b[e];
-                else if (x.b[e] == cur) nxt = x.a[e];
-                if (nxt >= 0) {
-                    if (np >= a.piece_cap) { over = true; break; }
-                    ppos[np] = x.pos[e];
-                    phom[np] = (uint8_t)ps.chromseq[base + (nxt >> 1)];
-                    np++;
-                    cur = nxt;
-                }
+    const int firstbi = quad * 4;
+    constexpr int k = QUAD ? 4 : 2;
+    const int base = QUAD ? 4 * v : firstbi + 2 * (v - quad);
+    Chiasmata x;
+    x.overflow = false;
+    rng.seek((uint32_t)child, (uint32_t)c, (uint32_t)par, 1u + (uint32_t)v);
+    double exchange_lim1 = 0.0;
+    if (QUAD) exchange_lim1 = quadrivalent_crossing_over(x, rng, m, ch);
+    else parallel_crossing_over(x, rng, m, ch, 2);
+    if (x.overflow) { atomicExch(a.error_flag, PSIM_ECAPACITY); return; }
+    int8_t centro[8];
+    if (QUAD) quadrivalent_centromere_order(rng, m, ch, exchange_lim1, centro);
+    else multivalent_centromere_order(rng, 2, centro);
+    int start_slots[2];
+    select_gamete0(x, rng, k, ch, centro, start_slots);
+    constexpr int n_out = QUAD ? 2 : 1;
+    for (int o = 0; o < n_out; o++) {
+        // Individual.java:297-321: quadrivalent v fills gamete slots 2v, 2v+1; bivalent v' fills firstbi/2 + v'
+        const int pre_slot = QUAD ? 2 * v + o : firstbi / 2 + (v - quad);
+        const int64_t u = u0 + dest_of_slot[pre_slot];
+        double* ppos = a.plan_pos + u * a.piece_cap;
+        uint8_t* phom = a.plan_hom + u * a.piece_cap;
+        // Multivalent.slotsToPatterns (:332-357) for the selected chromatid
+        int cur = start_slots[o];
+        int np = 0;
+        ppos[0] = ch.head;
+        phom[0] = (uint8_t)chromseq[base + (cur >> 1)];
+        np = 1;
+        bool over = false;
+        for (int e = 0; e < x.n; e++) {
+            int nxt = -1;
+            if (x.a[e] == cur) nxt = x.b[e];
+            else if (x.b[e] == cur) nxt = x.a[e];
+            if (nxt >= 0) {
+                if (np >= a.piece_cap) { over = true; break; }
+                ppos[np] = x.pos[e];
+                phom[np] = (uint8_t)chromseq[base + (nxt >> 1)];
+                np++;
+                cur = nxt;
             }
-            if (over) { atomicExch(a.error_flag, PSIM_ECAPACITY); return; }
-            a.plan_np[u] = np;
-            // Multivalent.fillGamete (:539-577): number of segments the chromatid will have
-            int64_t cnt = 0;
-            if (np == 1) {
-                cnt = hv[phom[0]].n;
-            } else {
-                for (int q = 0; q < np; q++) {
-                    const HomologView& h = hv[phom[q]];
-                    const double patstart = ppos[q];
-                    const double patend = q < np - 1 ? ppos[q + 1] : ch.tail;
-                    int seg = h.find_segment(patstart) + 1;
-                    cnt++;
-                    while (seg < h.n && h.pos[seg] < patend) { cnt++; seg++; }
-                }
-            }
-            a.plan_cnt[u] = cnt;
         }
+        if (over) { atomicExch(a.error_flag, PSIM_ECAPACITY); return; }
+        a.plan_np[u] = np;
+        // Multivalent.fillGamete (:539-577): number of segments the chromatid will have
+        auto view = [&](int hom) {
+            const uint64_t d = a.desc[phid0 + hom];
+            HomologView hvw;
+            hvw.pos = a.seg_pos + desc_begin(d);
+            hvw.founder = a.seg_founder + desc_begin(d);
+            hvw.n = (int)desc_count(d);
+            return hvw;
+        };
+        int64_t cnt = 0;
+        if (np == 1) {
+            cnt = view(phom[0]).n;
+        } else {
+            for (int qq = 0; qq < np; qq++) {
+                const HomologView h = view(phom[qq]);
+                const double patstart = ppos[qq];
+                const double patend = qq < np - 1 ? ppos[qq + 1] : ch.tail;
+                int seg = h.find_segment(patstart) + 1;
+                cnt++;
+                while (seg < h.n && h.pos[seg] < patend) { cnt++; seg++; }
+            }
+        }
+        a.plan_cnt[u] = cnt;
     }
 }
 
@@ -1306,7 +1360,7 @@ struct psim_ctx_impl {
     // grow-only scratch of psim_simulate (no allocation in the steady state of a Monte Carlo loop)
     struct Buf { void* p = nullptr; size_t cap = 0; };
     Buf b_lev, b_np, b_cnt, b_off, b_ppos, b_phom, b_find, b_fal;
-    Buf b_plan, b_dense_list;
+    Buf b_plan, b_dense_list, b_task;
     // export buffers
     int64_t* exp_off_d = nullptr; int32_t* exp_founder_d = nullptr; double* exp_pos_d = nullptr;
     int64_t exp_off_cap = 0, exp_seg_cap = 0;
@@ -1636,7 +1690,7 @@ void psim_destroy(psim_ctx* ctx) {
     cudaFree(c->exp_off_d); cudaFree(c->exp_founder_d); cudaFree(c->exp_pos_d);
     for (cudaEvent_t e : c->kev) cudaEventDestroy(e);
     for (psim_ctx_impl::Buf* b : {&c->b_lev, &c->b_np, &c->b_cnt, &c->b_off, &c->b_ppos, &c->b_phom, &c->b_find, &c->b_fal,
-                                 &c->b_plan, &c->b_dense_list}) cudaFree(b->p);
+                                 &c->b_plan, &c->b_dense_list, &c->b_task}) cudaFree(b->p);
     if (c->ev0) cudaEventDestroy(c->ev0);
     if (c->ev1) cudaEventDestroy(c->ev1);
     if (c->ev2) cudaEventDestroy(c->ev2);
@@ -1862,8 +1916,19 @@ static int simulate_impl(psim_ctx_impl* c, int32_t max_founder_allele, const int
             pa.plan_pos = plan_pos; pa.plan_hom = plan_hom;
             pa.cfg_quad = c->cfg_quad_d; pa.cfg_seq = c->cfg_seq_d; pa.error_flag = c->error_flag_d;
             const int64_t n_half = (int64_t)n_lev * C * R * 2;
-            k_meiosis_plan<<<grid_for(n_half, 128), 128, 0, c->stream>>>(pa);
-            c->stats.kernel_launches++;
+            const int64_t cap_bi = n_half * (P / 2), cap_quad = n_half * (P / 4);
+            if (int rc = ensure_buf(c, c->b_task, (size_t)(cap_bi + cap_quad) * sizeof(int64_t) + 16)) { rc_out = rc; break; }
+            pa.task_count = (int*)c->b_task.p;
+            pa.task_bi = (int64_t*)((uint8_t*)c->b_task.p + 16);
+            pa.task_quad = pa.task_bi + cap_bi;
+            CUDA_TRY(cudaMemsetAsync(pa.task_count, 0, 16, c->stream));
+            k_meiosis_config<<<grid_for(n_half, 128), 128, 0, c->stream>>>(pa);
+            k_meiosis_mv<false><<<grid_for(cap_bi, 128), 128, 0, c->stream>>>(pa);
+            c->stats.kernel_launches += 2;
+            if (cap_quad > 0) {
+                k_meiosis_mv<true><<<grid_for(cap_quad, 128), 128, 0, c->stream>>>(pa);
+                c->stats.kernel_launches++;
+            }
             CUDA_TRY(cudaGetLastError());
             CUDA_TRY(cudaMemsetAsync(plan_cnt + nu, 0, sizeof(int64_t), c->stream));
             if (int rc = exclusive_scan_i64(c, plan_cnt, plan_off, nu + 1)) { rc_out = rc; break; }
