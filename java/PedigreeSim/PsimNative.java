@@ -58,6 +58,9 @@ final class PsimNative implements AutoCloseable {
     private static final MethodHandle SET_MAP = fn("psim_set_map", FunctionDescriptor.of(JAVA_INT, ADDRESS, ADDRESS, ADDRESS));
     private static final MethodHandle SET_CODES = fn("psim_set_allele_codes",
             FunctionDescriptor.of(JAVA_INT, ADDRESS, JAVA_INT, ADDRESS));
+    // page-locked target tables: int psim_alloc_host(psim_ctx*, size_t, void**), int psim_free_host(psim_ctx*, void*)
+    private static final MethodHandle ALLOC_HOST = fn("psim_alloc_host", FunctionDescriptor.of(JAVA_INT, ADDRESS, JAVA_LONG, ADDRESS));
+    private static final MethodHandle FREE_HOST = fn("psim_free_host", FunctionDescriptor.of(JAVA_INT, ADDRESS, ADDRESS));
     private static final MethodHandle EMIT = fn("psim_emit",
             FunctionDescriptor.of(JAVA_INT, ADDRESS, JAVA_LONG, JAVA_LONG, JAVA_LONG, JAVA_LONG, ADDRESS));
 
