@@ -160,6 +160,33 @@ int psim_all_dose_rows(psim_ctx* ctx, int64_t locus_first, int64_t locus_count, 
 int psim_emit_all_dose(psim_ctx* ctx, int64_t ind_first, int64_t ind_count, int64_t locus_first,
                        int64_t locus_count, void* out, int64_t pitch, int32_t memory);
 
+/* Seam B as TEXT: the lines of _founderalleles.dat / _genotypes.dat / _alleledose.dat for loci
+ * [locus_first, locus_first+locus_count), formatted on the device — what the reference produces
+ * with one PrintWriter.print per cell (Main.writeGenotypesFile Main.java:903-939,
+ * writeAlleledoseFile :969-1022). Every line is
+ *     <locus name> { '\t' <token> } '\n'
+ * with one token per cell in psim_emit's column order: the founder allele number, the allele NAME
+ * of the cell's founder allele at the locus, or the dose. The host appends the bytes to its files
+ * (header lines stay with the host). Locus names come from psim_set_locus_names (map order);
+ * allele names from psim_set_allele_names: for every locus its sorted unique allele names
+ * (Locus.getUniqueAlleleNames, Locus.java:88-103), name k belonging to code k of
+ * psim_set_allele_codes. Offsets are into the concatenated characters (no terminators). */
+int psim_set_locus_names(psim_ctx* ctx, const int64_t* name_off /* [L+1] */, const char* chars);
+int psim_set_allele_names(psim_ctx* ctx, const int64_t* locus_first_name /* [L+1] */, const int64_t* name_off /* [names+1] */,
+                          const char* chars);
+typedef struct psim_text_targets {
+    char* founder; int64_t founder_capacity; int64_t founder_bytes;   /* bytes = out: length of the text written */
+    char* allele;  int64_t allele_capacity;  int64_t allele_bytes;
+    char* dose;    int64_t dose_capacity;    int64_t dose_bytes;
+    int32_t dose_which;    /* as in psim_emit_targets */
+    int32_t reserved;
+} psim_text_targets;
+/* Host buffers (page-locked ones from psim_alloc_host are fastest); a NULL pointer skips a table.
+ * Fails with PSIM_ECAPACITY (and the bytes needed in *_bytes) when a buffer is too small: an upper
+ * bound per line is name + cells * (1 + longest token) + 1. */
+int psim_emit_text(psim_ctx* ctx, int64_t ind_first, int64_t ind_count, int64_t locus_first, int64_t locus_count,
+                   psim_text_targets* targets);
+
 /* Drop every haplostruct and meiotic configuration (pedigree, chromosomes, map and allele codes
  * stay resident) and give the context a new RNG identity: the next psim_simulate is an
  * independent draw. Used by Monte Carlo drivers that re-simulate the same pedigree. */

@@ -58,6 +58,12 @@ final class PsimNative implements AutoCloseable {
     private static final MethodHandle SET_MAP = fn("psim_set_map", FunctionDescriptor.of(JAVA_INT, ADDRESS, ADDRESS, ADDRESS));
     private static final MethodHandle SET_CODES = fn("psim_set_allele_codes",
             FunctionDescriptor.of(JAVA_INT, ADDRESS, JAVA_INT, ADDRESS));
+    // finished text lines of the table files: int psim_set_locus_names(ctx, int64_t* off, char* chars),
+    // int psim_set_allele_names(ctx, int64_t* first, int64_t* off, char* chars), int psim_emit_text(ctx, i0, ni, l0, nl, psim_text_targets*)
+    private static final MethodHandle SET_LOCUS_NAMES = fn("psim_set_locus_names", FunctionDescriptor.of(JAVA_INT, ADDRESS, ADDRESS, ADDRESS));
+    private static final MethodHandle SET_ALLELE_NAMES = fn("psim_set_allele_names", FunctionDescriptor.of(JAVA_INT, ADDRESS, ADDRESS, ADDRESS, ADDRESS));
+    private static final MethodHandle EMIT_TEXT = fn("psim_emit_text",
+            FunctionDescriptor.of(JAVA_INT, ADDRESS, JAVA_LONG, JAVA_LONG, JAVA_LONG, JAVA_LONG, ADDRESS));
     // page-locked target tables: int psim_alloc_host(psim_ctx*, size_t, void**), int psim_free_host(psim_ctx*, void*)
     private static final MethodHandle ALLOC_HOST = fn("psim_alloc_host", FunctionDescriptor.of(JAVA_INT, ADDRESS, JAVA_LONG, ADDRESS));
     private static final MethodHandle FREE_HOST = fn("psim_free_host", FunctionDescriptor.of(JAVA_INT, ADDRESS, ADDRESS));

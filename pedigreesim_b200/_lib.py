@@ -47,6 +47,13 @@ class Stats(C.Structure):
     ]
 
 
+class TextTargets(C.Structure):
+    _fields_ = [("founder", C.c_void_p), ("founder_capacity", C.c_int64), ("founder_bytes", C.c_int64),
+                ("allele", C.c_void_p), ("allele_capacity", C.c_int64), ("allele_bytes", C.c_int64),
+                ("dose", C.c_void_p), ("dose_capacity", C.c_int64), ("dose_bytes", C.c_int64),
+                ("dose_which", C.c_int32), ("reserved", C.c_int32)]
+
+
 class DeviceHS(C.Structure):
     _fields_ = [("n_homologs", C.c_int64), ("n_segments", C.c_int64), ("seg_off", C.c_void_p),
                 ("founder", C.c_void_p), ("pos", C.c_void_p)]
@@ -57,7 +64,7 @@ EXPORTS = [
     "psim_set_haplostructs", "psim_simulate", "psim_segment_count", "psim_get_haplostructs", "psim_get_meiotic_configs",
     "psim_set_map", "psim_set_allele_codes", "psim_emit", "psim_all_dose_rows", "psim_emit_all_dose", "psim_get_stats",
     "psim_export_haplostructs_device", "psim_import_haplostructs_device", "psim_reset", "psim_set_stream", "psim_simulate_subset",
-    "psim_alloc_host", "psim_free_host",
+    "psim_alloc_host", "psim_free_host", "psim_set_locus_names", "psim_set_allele_names", "psim_emit_text",
 ]
 
 _lib = None
@@ -94,6 +101,9 @@ def load():
     L.psim_emit_all_dose.argtypes = [vp, i64, i64, i64, i64, vp, i64, i32]
     L.psim_reset.argtypes = [vp, i64, u32]
     L.psim_set_stream.argtypes = [vp, C.c_uint64]
+    L.psim_set_locus_names.argtypes = [vp, vp, vp]
+    L.psim_set_allele_names.argtypes = [vp, vp, vp, vp]
+    L.psim_emit_text.argtypes = [vp, i64, i64, i64, i64, C.POINTER(TextTargets)]
     L.psim_alloc_host.argtypes = [vp, C.c_size_t, C.POINTER(vp)]
     L.psim_free_host.argtypes = [vp, vp]
     L.psim_get_stats.argtypes = [vp, C.POINTER(Stats)]
@@ -260,6 +270,42 @@ class PsimContext:
         out = np.zeros((int(ro[-1]), q), dtype=np.uint8)
         self._chk(self.L.psim_emit_all_dose(self.h, ind_first, ind_count, loc_first, loc_count, _p(out), q, MEM_HOST))
         return ro, out
+
+    @staticmethod
+    def _csr(strings):
+        b = [x.encode() if isinstance(x, str) else bytes(x) for x in strings]
+        off = np.zeros(len(b) + 1, dtype=np.int64)
+        np.cumsum([len(x) for x in b], out=off[1:])
+        return off, np.frombuffer(b"".join(b) + b"\0", dtype=np.uint8).copy()
+
+    def set_locus_names(self, names):
+        off, chars = self._csr(names)
+        self._chk(self.L.psim_set_locus_names(self.h, _p(off), _p(chars)))
+
+    def set_allele_names(self, names_per_locus):
+        """names_per_locus[l] = the locus' sorted unique allele names (name k <-> code k)."""
+        first = np.zeros(len(names_per_locus) + 1, dtype=np.int64)
+        np.cumsum([len(x) for x in names_per_locus], out=first[1:])
+        off, chars = self._csr([n for x in names_per_locus for n in x])
+        self._chk(self.L.psim_set_allele_names(self.h, _p(first), _p(off), _p(chars)))
+
+    def emit_text(self, founder=False, allele=False, dose=False, dose_which=0, ind_first=0, ind_count=None, loc_first=0,
+                  loc_count=None, capacity=None):
+        """Text lines of the requested tables (bytes objects); capacity defaults to a safe upper bound."""
+        ind_count = self.N - ind_first if ind_count is None else ind_count
+        loc_count = self.Ltot - loc_first if loc_count is None else loc_count
+        q = self.R * ind_count
+        cap = capacity if capacity is not None else loc_count * (q * self.P * 8 + 4096)
+        t = TextTargets()
+        t.dose_which = dose_which
+        bufs = {}
+        for name, want in (("founder", founder), ("allele", allele), ("dose", dose)):
+            if want:
+                bufs[name] = np.zeros(cap, dtype=np.uint8)
+                setattr(t, name, bufs[name].ctypes.data)
+                setattr(t, name + "_capacity", cap)
+        self._chk(self.L.psim_emit_text(self.h, ind_first, ind_count, loc_first, loc_count, C.byref(t)))
+        return {k: bytes(v[:getattr(t, k + "_bytes")]) for k, v in bufs.items()}
 
     def reset(self, seed, replicate_first=0):
         self.replicate_first = replicate_first

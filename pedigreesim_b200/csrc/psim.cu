@@ -1187,6 +1187,133 @@ __global__ void __launch_bounds__(256) k_emit_generic(const EmitGenericArgs a) {
     if (a.dose) a.dose[row * a.dose_pitch + q] = (uint8_t)dose;
 }
 
+// ------------------------------------------------------------------------------------------
+// K3 — the reference's table files as text, formatted on the device (Main.writeGenotypesFile /
+// writeAlleledoseFile, Main.java:903-1022: `label { '\t' token } '\n'` per locus, one
+// PrintWriter.print per cell in the reference). One block per table row: the row's cells are read
+// into shared memory a chunk at a time, every thread sizes (pass 1) or writes (pass 2) the tokens of
+// its run of consecutive cells at the offset a block scan gives it, and the chunk's text leaves
+// shared memory with coalesced stores. Pass 1 only measures; a device scan of the row lengths
+// places the rows back to back.
+constexpr int TEXT_THREADS = 256;
+
+struct TextArgs {
+    const uint8_t* cells; int64_t pitch; int cell_bytes;   // device table [rows][pitch], u8 or u16 cells
+    int64_t n_cells;               // tokens per row
+    int64_t row0_locus;            // global locus of table row 0
+    int n_rows;
+    const int64_t* label_off;      // [L+1] locus names (psim_set_locus_names)
+    const char* labels;
+    int kind;                      // 0 = decimal numbers, 1 = the locus' allele names by code
+    const int64_t* code_off;       // kind 1: [L+1] first name of each locus
+    const int64_t* name_off;       //         [names+1]
+    const char* names;
+    int max_tok;                   // longest token including its tab
+    int chunk;                     // cells per chunk, a multiple of TEXT_THREADS
+    int64_t* row_len;              // pass 1 out [n_rows]
+    const int64_t* row_off;        // pass 2 in  [n_rows+1]
+    char* text;                    // pass 2 out
+};
+
+template <bool WRITE>
+__global__ void __launch_bounds__(TEXT_THREADS) k_text_rows(const TextArgs a) {
+    extern __shared__ __align__(16) uint8_t smem[];
+    __shared__ uint32_t s_warp[TEXT_THREADS / 32];
+    __shared__ uint32_t s_nlen[256], s_nbeg[256];
+    const int tid = threadIdx.x, lane = tid & 31, wq = tid >> 5;
+    uint8_t* const s_cells = smem;                                   // chunk * cell_bytes
+    char* const s_text = reinterpret_cast<char*>(smem + (size_t)a.chunk * a.cell_bytes);   // chunk * max_tok (pass 2)
+    const int cpt = a.chunk / TEXT_THREADS;
+    for (int r = blockIdx.x; r < a.n_rows; r += gridDim.x) {
+        const int64_t gl = a.row0_locus + r;
+        const uint8_t* row = a.cells + (int64_t)r * a.pitch;
+        const int64_t lab0 = a.label_off[gl];
+        const int lab_n = (int)(a.label_off[gl + 1] - lab0);
+        char* out = WRITE ? a.text + a.row_off[r] : nullptr;
+        if (WRITE)
+            for (int i = tid; i < lab_n; i += TEXT_THREADS) out[i] = a.labels[lab0 + i];
+        int64_t base = 0;   // first name of the locus
+        if (a.kind == 1) {
+            base = a.code_off[gl];
+            const int k = (int)(a.code_off[gl + 1] - base);
+            __syncthreads();
+            for (int i = tid; i < k && i < 256; i += TEXT_THREADS) {
+                s_nbeg[i] = (uint32_t)(a.name_off[base + i] - a.name_off[base]);
+                s_nlen[i] = (uint32_t)(a.name_off[base + i + 1] - a.name_off[base + i]);
+            }
+        }
+        int64_t running = lab_n;
+        for (int64_t c0 = 0; c0 < a.n_cells; c0 += a.chunk) {
+            const int n = (int)min((int64_t)a.chunk, a.n_cells - c0);
+            __syncthreads();   // previous chunk's text has been copied out; name table loaded
+            {   // the chunk's cells, coalesced (rows start 4-byte aligned: staging pitches are multiples of 128)
+                const int nbytes = n * a.cell_bytes;
+                const uint8_t* src = row + c0 * a.cell_bytes;
+                for (int i = tid * 4; i < (nbytes & ~3); i += TEXT_THREADS * 4)
+                    *reinterpret_cast<uint32_t*>(s_cells + i) = *reinterpret_cast<const uint32_t*>(src + i);
+                if (tid < (nbytes & 3)) s_cells[(nbytes & ~3) + tid] = src[(nbytes & ~3) + tid];
+            }
+            __syncthreads();
+            const int i0 = tid * cpt, i1 = min(i0 + cpt, n);
+            auto cell = [&](int i) -> uint32_t {
+                return a.cell_bytes == 1 ? (uint32_t)s_cells[i] : (uint32_t)reinterpret_cast<const uint16_t*>(s_cells)[i];
+            };
+            auto tok_len = [&](uint32_t v) -> uint32_t {
+                if (a.kind == 1) return 1 + s_nlen[v & 255];
+                return v < 10 ? 2 : v < 100 ? 3 : v < 1000 ? 4 : v < 10000 ? 5 : 6;
+            };
+            uint32_t len = 0;
+            for (int i = i0; i < i1; i++) len += tok_len(cell(i));
+            // block exclusive scan of the per-thread lengths
+            uint32_t x = len;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) { const uint32_t y = __shfl_up_sync(0xFFFFFFFFu, x, o); if (lane >= o) x += y; }
+            if (lane == 31) s_warp[wq] = x;
+            __syncthreads();
+            uint32_t wbase = 0, total = 0;
+#pragma unroll
+            for (int w = 0; w < TEXT_THREADS / 32; w++) { const uint32_t v = s_warp[w]; if (w < wq) wbase += v; total += v; }
+            if (WRITE) {
+                char* p = s_text + wbase + x - len;
+                for (int i = i0; i < i1; i++) {
+                    const uint32_t v = cell(i);
+                    *p++ = '\t';
+                    if (a.kind == 1) {
+                        const char* nm = a.names + a.name_off[base] + s_nbeg[v & 255];
+                        const uint32_t nl = s_nlen[v & 255];
+                        for (uint32_t q = 0; q < nl; q++) *p++ = nm[q];
+                    } else {
+                        if (v >= 10000) *p++ = (char)('0' + v / 10000);
+                        if (v >= 1000) *p++ = (char)('0' + v / 1000 % 10);
+                        if (v >= 100) *p++ = (char)('0' + v / 100 % 10);
+                        if (v >= 10) *p++ = (char)('0' + v / 10 % 10);
+                        *p++ = (char)('0' + v % 10);
+                    }
+                }
+                __syncthreads();
+                char* dst = out + running;
+                // coalesced copy: head bytes up to 4-byte alignment of the destination, then words
+                const uint32_t mis = (uint32_t)((4 - ((uintptr_t)dst & 3)) & 3);
+                const uint32_t head = min(mis, total);
+                if (tid < head) dst[tid] = s_text[tid];
+                const uint32_t words = (total - head) >> 2;
+                for (uint32_t i = tid; i < words; i += TEXT_THREADS) {
+                    const char* s = s_text + head + 4 * i;   // shared memory side may be misaligned: assemble bytes
+                    const uint32_t w = (uint32_t)(uint8_t)s[0] | ((uint32_t)(uint8_t)s[1] << 8) | ((uint32_t)(uint8_t)s[2] << 16) | ((uint32_t)(uint8_t)s[3] << 24);
+                    *reinterpret_cast<uint32_t*>(dst + head + 4 * i) = w;
+                }
+                const uint32_t done = head + 4 * words;
+                if (tid < total - done) dst[done + tid] = s_text[done + tid];
+            }
+            running += total;
+        }
+        if (tid == 0) {
+            if (WRITE) out[running] = '\n';
+            else a.row_len[r] = running + 1;
+        }
+    }
+}
+
 // _allAlleledose rows: one thread per (row, emitted individual)
 struct AllDoseArgs {
     int C, R, P;
@@ -1348,6 +1475,10 @@ struct psim_ctx_impl {
     uint32_t* code16_d = nullptr;   // [L][4]
     uint32_t* nibmask_d = nullptr;  // [L][2]
     uint4* mtab_d = nullptr;        // [L]
+    // text emission (psim_set_locus_names / psim_set_allele_names)
+    int64_t* label_off_d = nullptr; char* labels_d = nullptr; int64_t label_max = 0;
+    int64_t* code_off_d = nullptr; int64_t* aname_off_d = nullptr; char* anames_d = nullptr; int64_t aname_max = 0;
+    std::vector<int64_t> code_off_h;
     int match_which = 12345678;
     int founder_allele_count = 0;
     // scratch
@@ -1360,7 +1491,7 @@ struct psim_ctx_impl {
     // grow-only scratch of psim_simulate (no allocation in the steady state of a Monte Carlo loop)
     struct Buf { void* p = nullptr; size_t cap = 0; };
     Buf b_lev, b_np, b_cnt, b_off, b_ppos, b_phom, b_find, b_fal;
-    Buf b_plan, b_dense_list, b_task;
+    Buf b_plan, b_dense_list, b_task, b_text, b_rowlen, b_rowoff;
     // export buffers
     int64_t* exp_off_d = nullptr; int32_t* exp_founder_d = nullptr; double* exp_pos_d = nullptr;
     int64_t exp_off_cap = 0, exp_seg_cap = 0;
@@ -1690,7 +1821,8 @@ void psim_destroy(psim_ctx* ctx) {
     cudaFree(c->exp_off_d); cudaFree(c->exp_founder_d); cudaFree(c->exp_pos_d);
     for (cudaEvent_t e : c->kev) cudaEventDestroy(e);
     for (psim_ctx_impl::Buf* b : {&c->b_lev, &c->b_np, &c->b_cnt, &c->b_off, &c->b_ppos, &c->b_phom, &c->b_find, &c->b_fal,
-                                 &c->b_plan, &c->b_dense_list, &c->b_task}) cudaFree(b->p);
+                                 &c->b_plan, &c->b_dense_list, &c->b_task, &c->b_text, &c->b_rowlen, &c->b_rowoff}) cudaFree(b->p);
+    cudaFree(c->label_off_d); cudaFree(c->labels_d); cudaFree(c->code_off_d); cudaFree(c->aname_off_d); cudaFree(c->anames_d);
     if (c->ev0) cudaEventDestroy(c->ev0);
     if (c->ev1) cudaEventDestroy(c->ev1);
     if (c->ev2) cudaEventDestroy(c->ev2);
@@ -2376,6 +2508,160 @@ int psim_emit(psim_ctx* ctx, int64_t ind_first, int64_t ind_count, int64_t locus
     c->stats.ms_emit_kernel = ms_kernel;
     c->stats.ms_emit_total = ms_total;
     c->stats.ms_emit_plan = 0.0;
+    return PSIM_OK;
+}
+
+int psim_set_locus_names(psim_ctx* ctx, const int64_t* name_off, const char* chars) {
+    psim_ctx_impl* c = CTX;
+    if (!c || !name_off || !chars) return PSIM_EINVAL;
+    if (c->L == 0) return fail(c, PSIM_ESTATE, "psim_set_map must be called first");
+    cudaSetDevice(c->cfg.device);
+    if (name_off[0] != 0) return fail(c, PSIM_EINVAL, "name_off[0] must be 0");
+    c->label_max = 0;
+    for (int64_t l = 0; l < c->L; l++) {
+        if (name_off[l + 1] < name_off[l]) return fail(c, PSIM_EINVAL, "name_off must not decrease");
+        c->label_max = std::max(c->label_max, name_off[l + 1] - name_off[l]);
+    }
+    cudaFree(c->label_off_d); cudaFree(c->labels_d);
+    c->label_off_d = nullptr; c->labels_d = nullptr;
+    CUDA_TRY(dev_alloc(&c->label_off_d, (size_t)c->L + 1));
+    CUDA_TRY(dev_alloc(&c->labels_d, (size_t)name_off[c->L]));
+    CUDA_TRY(cudaMemcpy(c->label_off_d, name_off, ((size_t)c->L + 1) * sizeof(int64_t), cudaMemcpyHostToDevice));
+    CUDA_TRY(cudaMemcpy(c->labels_d, chars, (size_t)name_off[c->L], cudaMemcpyHostToDevice));
+    return PSIM_OK;
+}
+
+int psim_set_allele_names(psim_ctx* ctx, const int64_t* locus_first_name, const int64_t* name_off, const char* chars) {
+    psim_ctx_impl* c = CTX;
+    if (!c || !locus_first_name || !name_off || !chars) return PSIM_EINVAL;
+    if (c->code_h.empty()) return fail(c, PSIM_ESTATE, "psim_set_allele_codes must be called first");
+    cudaSetDevice(c->cfg.device);
+    if (locus_first_name[0] != 0 || name_off[0] != 0) return fail(c, PSIM_EINVAL, "offsets must start at 0");
+    const int64_t n_names = locus_first_name[c->L];
+    c->aname_max = 0;
+    for (int64_t l = 0; l < c->L; l++) {
+        int mx = 0;
+        const uint8_t* cd = &c->code_h[(size_t)l * c->A];
+        for (int a = 0; a < c->A; a++) mx = std::max(mx, (int)cd[a]);
+        if (locus_first_name[l + 1] - locus_first_name[l] != mx + 1)
+            return fail(c, PSIM_EINVAL, "locus " + std::to_string(l) + " needs one name per allele code");
+    }
+    for (int64_t k = 0; k < n_names; k++) {
+        if (name_off[k + 1] < name_off[k]) return fail(c, PSIM_EINVAL, "name_off must not decrease");
+        c->aname_max = std::max(c->aname_max, name_off[k + 1] - name_off[k]);
+    }
+    cudaFree(c->code_off_d); cudaFree(c->aname_off_d); cudaFree(c->anames_d);
+    c->code_off_d = nullptr; c->aname_off_d = nullptr; c->anames_d = nullptr;
+    CUDA_TRY(dev_alloc(&c->code_off_d, (size_t)c->L + 1));
+    CUDA_TRY(dev_alloc(&c->aname_off_d, (size_t)n_names + 1));
+    CUDA_TRY(dev_alloc(&c->anames_d, (size_t)name_off[n_names]));
+    CUDA_TRY(cudaMemcpy(c->code_off_d, locus_first_name, ((size_t)c->L + 1) * sizeof(int64_t), cudaMemcpyHostToDevice));
+    CUDA_TRY(cudaMemcpy(c->aname_off_d, name_off, ((size_t)n_names + 1) * sizeof(int64_t), cudaMemcpyHostToDevice));
+    CUDA_TRY(cudaMemcpy(c->anames_d, chars, (size_t)name_off[n_names], cudaMemcpyHostToDevice));
+    return PSIM_OK;
+}
+
+int psim_emit_text(psim_ctx* ctx, int64_t ind_first, int64_t ind_count, int64_t locus_first, int64_t locus_count,
+                   psim_text_targets* t) {
+    psim_ctx_impl* c = CTX;
+    if (!c || !t) return PSIM_EINVAL;
+    cudaSetDevice(c->cfg.device);
+    if (int rc = emit_prepare(c, ind_first, ind_count, locus_first, locus_count)) return rc;
+    if (!t->founder && !t->allele && !t->dose) return fail(c, PSIM_EINVAL, "no output table requested");
+    if (!c->label_off_d) return fail(c, PSIM_ESTATE, "psim_set_locus_names must be called first");
+    if (t->allele && !c->code_d) return fail(c, PSIM_ESTATE, "allele table requested but no allele codes set");
+    if (t->allele && !c->code_off_d) return fail(c, PSIM_ESTATE, "allele table requested but no allele names set");
+    const int fb = c->founder_allele_count > 256 ? 2 : 1;
+    const int64_t n_cols_ind = (int64_t)c->R * ind_count, n_cols = n_cols_ind * c->P;
+    int dose_mode = 0, dose_which = t->dose_which;
+    if (c->code_d) {
+        dose_mode = 1;
+        if (c->match_which != t->dose_which) {
+            k_match_codes<<<grid_for(c->L, 256), 256, 0, c->stream>>>(c->L, c->A, t->dose_which, c->code_d, c->match_d,
+                                                                       c->code16_d, c->nibmask_d, c->mtab_d);
+            c->stats.kernel_launches++;
+            CUDA_TRY(cudaGetLastError());
+            c->match_which = t->dose_which;
+        }
+    } else if (dose_which < 0) {
+        dose_which = 0x7FFFFFFF;
+    }
+    c->stats.emit_kernel_launches = 0;
+    c->kev_used = 0;
+    CUDA_TRY(cudaEventRecord(c->ev0, c->stream));
+    auto up = [](int64_t x, int64_t m) { return (x + m - 1) / m * m; };
+    struct Tab { char* host; int64_t cap; int64_t* bytes; int64_t pitch; int cell_bytes; int kind; int max_tok; int64_t n_cells; };
+    Tab tab[3] = {{t->founder, t->founder_capacity, &t->founder_bytes, up(n_cols * fb, 128), fb, 0, fb == 1 ? 4 : 6, n_cols},
+                  {t->allele, t->allele_capacity, &t->allele_bytes, up(n_cols, 128), 1, 1, (int)(1 + c->aname_max), n_cols},
+                  {t->dose, t->dose_capacity, &t->dose_bytes, up(n_cols_ind, 128), 1, 0, 3, n_cols_ind}};
+    int64_t row_bytes = 0;
+    for (Tab& x : tab) { if (x.host) row_bytes += x.pitch; *x.bytes = 0; }
+    const int64_t rows = std::max<int64_t>(1, std::min<int64_t>(locus_count, (64LL << 20) / row_bytes));
+    if (int rc = ensure_staging(c, (size_t)(rows * row_bytes))) return rc;
+    if (int rc = ensure_buf(c, c->b_rowlen, ((size_t)rows + 1) * sizeof(int64_t))) return rc;
+    if (int rc = ensure_buf(c, c->b_rowoff, ((size_t)rows + 1) * sizeof(int64_t))) return rc;
+    bool too_small = false;
+    for (int64_t l0 = locus_first; l0 < locus_first + locus_count; l0 += rows) {
+        const int64_t l1 = std::min(l0 + rows, locus_first + locus_count), nr = l1 - l0;
+        uint8_t* sp[3];
+        {
+            uint8_t* p = (uint8_t*)c->staging;
+            for (int q = 0; q < 3; q++) { sp[q] = nullptr; if (tab[q].host) { sp[q] = p; p += rows * tab[q].pitch; } }
+        }
+        CUDA_TRY(cudaStreamSynchronize(c->copy_stream));   // the text of the previous block has left b_text
+        if (int rc = emit_device(c, ind_first, ind_count, l0, l1, l0, sp[0], tab[0].pitch, fb, sp[1], tab[1].pitch, sp[2], tab[2].pitch,
+                                 dose_mode, dose_which)) return rc;
+        for (int q = 0; q < 3; q++) {
+            if (!tab[q].host) continue;
+            TextArgs ta{};
+            ta.cells = sp[q]; ta.pitch = tab[q].pitch; ta.cell_bytes = tab[q].cell_bytes;
+            ta.n_cells = tab[q].n_cells; ta.row0_locus = l0; ta.n_rows = (int)nr;
+            ta.label_off = c->label_off_d; ta.labels = c->labels_d;
+            ta.kind = tab[q].kind; ta.code_off = c->code_off_d; ta.name_off = c->aname_off_d; ta.names = c->anames_d;
+            ta.max_tok = tab[q].max_tok;
+            int chunk = (int)(40960 / (tab[q].cell_bytes + tab[q].max_tok)) / TEXT_THREADS * TEXT_THREADS;
+            chunk = std::max(TEXT_THREADS, std::min(chunk, 8192));
+            ta.chunk = chunk;
+            const size_t smem = (size_t)chunk * (tab[q].cell_bytes + tab[q].max_tok) + 16;
+            if (smem > 200 * 1024) return fail(c, PSIM_ECAPACITY, "allele names longer than 700 characters are not supported in text emission");
+            ta.row_len = (int64_t*)c->b_rowlen.p;
+            const int blocks = (int)std::min<int64_t>(nr, (int64_t)c->sm_count * 8);
+            cudaFuncSetAttribute(k_text_rows<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            cudaFuncSetAttribute(k_text_rows<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            CUDA_TRY(cudaMemsetAsync(ta.row_len + nr, 0, sizeof(int64_t), c->stream));
+            k_text_rows<false><<<blocks, TEXT_THREADS, smem, c->stream>>>(ta);
+            c->stats.kernel_launches++;
+            CUDA_TRY(cudaGetLastError());
+            if (int rc = exclusive_scan_i64(c, (int64_t*)c->b_rowlen.p, (int64_t*)c->b_rowoff.p, nr + 1)) return rc;
+            int64_t total = 0;
+            CUDA_TRY(cudaMemcpyAsync(&total, (int64_t*)c->b_rowoff.p + nr, sizeof(int64_t), cudaMemcpyDeviceToHost, c->stream));
+            CUDA_TRY(cudaStreamSynchronize(c->stream));
+            if (*tab[q].bytes + total > tab[q].cap) too_small = true;
+            if (!too_small) {
+                CUDA_TRY(cudaStreamSynchronize(c->copy_stream));   // b_text may grow: nothing may be in flight from it
+                if (int rc = ensure_buf(c, c->b_text, (size_t)total)) return rc;
+                ta.row_off = (int64_t*)c->b_rowoff.p;
+                ta.text = (char*)c->b_text.p;
+                k_text_rows<true><<<blocks, TEXT_THREADS, smem, c->stream>>>(ta);
+                c->stats.kernel_launches++;
+                CUDA_TRY(cudaGetLastError());
+                CUDA_TRY(cudaEventRecord(c->ev2, c->stream));
+                CUDA_TRY(cudaStreamWaitEvent(c->copy_stream, c->ev2, 0));
+                CUDA_TRY(cudaMemcpyAsync(tab[q].host + *tab[q].bytes, c->b_text.p, (size_t)total, cudaMemcpyDeviceToHost, c->copy_stream));
+                // the next table reuses b_text: its write kernel must wait for this copy
+                CUDA_TRY(cudaEventRecord(c->ev3, c->copy_stream));
+                CUDA_TRY(cudaStreamWaitEvent(c->stream, c->ev3, 0));
+            }
+            *tab[q].bytes += total;
+        }
+    }
+    CUDA_TRY(cudaStreamSynchronize(c->copy_stream));
+    CUDA_TRY(cudaEventRecord(c->ev1, c->stream));
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    float ms_total = 0.f;
+    cudaEventElapsedTime(&ms_total, c->ev0, c->ev1);
+    c->stats.ms_emit_total = ms_total;
+    if (too_small) return fail(c, PSIM_ECAPACITY, "a text buffer is too small (the bytes needed are in the *_bytes fields)");
     return PSIM_OK;
 }
 

@@ -7,7 +7,7 @@
 // makes through FFM/JNI. There is no CPU path: without libpsim and a GPU the
 // simulation and emission steps fail with the library's message.
 //
-//   pedigreesim x.par [--parse-only] [--device N] [--block-mib M] [--quiet-chrom]
+//   pedigreesim x.par [--parse-only] [--device N] [--block-mib M]
 //
 // --parse-only stops before the first libpsim call (reads and validates every input, writes the
 // sorted/generated .ped) — used by the CPU-only tests of the host logic.
@@ -409,7 +409,6 @@ int run(const Options& opt) {
     try {
         if (L == 0) throw HostError("no loci on the map");
         const int A = pd.founder_allele_count;
-        const int fb = A > 256 ? 2 : 1;
         lib.chk(psim_set_map(lib.ctx, mp.locus_off.data(), mp.flat_pos.data()));
         if (founder_genotypes) lib.chk(psim_set_allele_codes(lib.ctx, A, mp.code.data()));
         const bool all_dose = !founder_genotypes || mp.max_allele_count > 2;
@@ -436,50 +435,81 @@ int run(const Options& opt) {
             write_table_header(*f_all, pd, 0, true);
         }
 
-        // one fused psim_emit per block of loci fills every table; rows are then formatted in parallel
+        // The three big tables leave the GPU as finished text (psim_emit_text): one fused call per
+        // block of loci formats every requested table on the device into page-locked buffers; a
+        // writer thread appends block k to the files while block k+1 is produced.
+        {
+            std::vector<int64_t> off((size_t)L + 1, 0);
+            std::string chars;
+            for (int64_t l = 0; l < L; l++) {
+                chars += *mp.flat_name[(size_t)l];
+                off[(size_t)l + 1] = (int64_t)chars.size();
+            }
+            chars.push_back('\0');
+            lib.chk(psim_set_locus_names(lib.ctx, off.data(), chars.data()));
+        }
+        int64_t label_max = 0, name_max = 0;
+        for (int64_t l = 0; l < L; l++) label_max = std::max<int64_t>(label_max, (int64_t)mp.flat_name[(size_t)l]->size());
+        if (founder_genotypes) {
+            std::vector<int64_t> first((size_t)L + 1, 0), noff(1, 0);
+            std::string chars;
+            for (int64_t l = 0; l < L; l++) {
+                for (const std::string& nm : mp.unique_names[(size_t)l]) {
+                    chars += nm;
+                    noff.push_back((int64_t)chars.size());
+                    name_max = std::max<int64_t>(name_max, (int64_t)nm.size());
+                }
+                first[(size_t)l + 1] = (int64_t)noff.size() - 1;
+            }
+            chars.push_back('\0');
+            lib.chk(psim_set_allele_names(lib.ctx, first.data(), noff.data(), chars.data()));
+        }
         const int64_t cols = N * P;
-        const int64_t row_bytes = cols * fb + (founder_genotypes ? cols : 0) + N;
-        const int64_t rows_blk = std::max<int64_t>(1, std::min<int64_t>(L, opt.block_bytes / row_bytes));
-        void *b_fnd = nullptr, *b_gen = nullptr, *b_dose = nullptr;
-        lib.chk(psim_alloc_host(lib.ctx, (size_t)(rows_blk * cols * fb), &b_fnd));
-        if (founder_genotypes) lib.chk(psim_alloc_host(lib.ctx, (size_t)(rows_blk * cols), &b_gen));
-        lib.chk(psim_alloc_host(lib.ctx, (size_t)(rows_blk * N), &b_dose));
-        for (int64_t l0 = 0; l0 < L; l0 += rows_blk) {
-            const int64_t nr = std::min(rows_blk, L - l0);
-            psim_emit_targets t{};
-            t.memory = PSIM_MEM_HOST;
-            t.founder = b_fnd;
-            t.founder_pitch = cols * fb;
-            t.founder_bytes = fb;
-            t.allele = b_gen;
-            t.allele_pitch = cols;
-            t.dose = b_dose;
-            t.dose_pitch = N;
-            t.dose_which = founder_genotypes ? PSIM_DOSE_MAX_ALLELE : 0;  // Main.java:402-418
-            lib.chk(psim_emit(lib.ctx, 0, N, l0, nr, &t));
-            auto label = [&](int64_t r, std::string& o) { o += *mp.flat_name[(size_t)(l0 + r)]; };
-            if (founder_genotypes) {
-                append_rows(*f_gen, nr, label, [&](int64_t r, std::string& o) {
-                    const uint8_t* row = (const uint8_t*)b_gen + r * cols;
-                    const auto& names = mp.unique_names[(size_t)(l0 + r)];
-                    for (int64_t k = 0; k < cols; k++) {
-                        o.push_back('\t');
-                        o += names[row[k]];
-                    }
+        auto digits = [](int64_t v) { int d = 1; while (v >= 10) { v /= 10; d++; } return d; };
+        const int64_t line_fnd = label_max + cols * (1 + digits(std::max(0, A - 1))) + 1;
+        const int64_t line_gen = founder_genotypes ? label_max + cols * (1 + name_max) + 1 : 0;
+        const int64_t line_dose = label_max + N * (1 + digits(P)) + 1;
+        const int64_t rows_blk = std::max<int64_t>(1, std::min<int64_t>(L, opt.block_bytes / (line_fnd + line_gen + line_dose)));
+        struct TextBufs { void *fnd = nullptr, *gen = nullptr, *dose = nullptr; psim_text_targets t{}; };
+        TextBufs tb[2];
+        for (TextBufs& x : tb) {
+            lib.chk(psim_alloc_host(lib.ctx, (size_t)(rows_blk * line_fnd), &x.fnd));
+            if (founder_genotypes) lib.chk(psim_alloc_host(lib.ctx, (size_t)(rows_blk * line_gen), &x.gen));
+            lib.chk(psim_alloc_host(lib.ctx, (size_t)(rows_blk * line_dose), &x.dose));
+        }
+        std::thread writer;
+        int cur = 0;
+        try {
+            for (int64_t l0 = 0; l0 < L; l0 += rows_blk, cur ^= 1) {
+                const int64_t nr = std::min(rows_blk, L - l0);
+                TextBufs& x = tb[cur];
+                x.t = psim_text_targets{};
+                x.t.founder = (char*)x.fnd;
+                x.t.founder_capacity = rows_blk * line_fnd;
+                x.t.allele = (char*)x.gen;
+                x.t.allele_capacity = rows_blk * line_gen;
+                x.t.dose = (char*)x.dose;
+                x.t.dose_capacity = rows_blk * line_dose;
+                x.t.dose_which = founder_genotypes ? PSIM_DOSE_MAX_ALLELE : 0;  // Main.java:402-418
+                lib.chk(psim_emit_text(lib.ctx, 0, N, l0, nr, &x.t));
+                if (writer.joinable()) writer.join();
+                writer = std::thread([&, cur] {
+                    const TextBufs& y = tb[cur];
+                    if (f_gen) f_gen->write(y.t.allele, (size_t)y.t.allele_bytes);
+                    f_fnd->write(y.t.founder, (size_t)y.t.founder_bytes);
+                    f_dose->write(y.t.dose, (size_t)y.t.dose_bytes);
                 });
             }
-            append_rows(*f_fnd, nr, label, [&](int64_t r, std::string& o) {
-                if (fb == 1)
-                    format_u8_row((const uint8_t*)b_fnd + r * cols, cols, o);
-                else
-                    format_u16_row((const uint16_t*)b_fnd + r * cols, cols, o);
-            });
-            append_rows(*f_dose, nr, label,
-                        [&](int64_t r, std::string& o) { format_u8_row((const uint8_t*)b_dose + r * N, N, o); });
+        } catch (...) {
+            if (writer.joinable()) writer.join();
+            throw;
         }
-        psim_free_host(lib.ctx, b_fnd);
-        if (b_gen) psim_free_host(lib.ctx, b_gen);
-        psim_free_host(lib.ctx, b_dose);
+        if (writer.joinable()) writer.join();
+        for (TextBufs& x : tb) {
+            psim_free_host(lib.ctx, x.fnd);
+            if (x.gen) psim_free_host(lib.ctx, x.gen);
+            psim_free_host(lib.ctx, x.dose);
+        }
 
         if (all_dose) {
             // rows per locus: founder alleles 0..A-1, or the locus' unique allele names in sorted order
