@@ -167,6 +167,24 @@ def run_reference(args):
 
 
 # ------------------------------------------------------------------------------------ GPU arm
+def bind_to_gpu_numa_node(index):
+    """Run this rank on the CPU cores next to its GPU (NVML's affinity mask), so that the page-locked
+    host tables of the end-to-end leg are first touched on the NUMA node the GPU's PCIe link hangs
+    off. Best effort: silently skipped when NVML or sched_setaffinity is not available."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(index)
+        n_cpu = os.cpu_count() or 1
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (n_cpu + 63) // 64)
+        cpus = {64 * w + b for w, mask in enumerate(words) for b in range(64) if (mask >> b) & 1}
+        cpus &= os.sched_getaffinity(0)
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+    except Exception:
+        pass
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
@@ -178,6 +196,7 @@ def run_ours(args):
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device (libpsim has no CPU fallback)")
     torch.cuda.set_device(local)
+    bind_to_gpu_numa_node(local)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     w = workload()

@@ -187,6 +187,24 @@ typedef struct psim_text_targets {
 int psim_emit_text(psim_ctx* ctx, int64_t ind_first, int64_t ind_count, int64_t locus_first, int64_t locus_count,
                    psim_text_targets* targets);
 
+/* TEST-mode statistics (the counters of Main.testMeiosis, Main.java:1660-1721) as device
+ * reductions over the GAMETES that made individuals [ind_first, ind_first+ind_count) of every
+ * replicate: homologs [0, P/2) of an individual are the gamete of parent 0's meiosis, [P/2, P) that
+ * of parent 1's (Gamete.fertilization, Gamete.java:95-116). One chromosome per call, Lc = its loci,
+ * A = founder alleles of the pedigree. Host pointers; NULL skips an output. With an S1 population
+ * of one founder this is the reference's TEST setting (one parent, POPSIZE meioses). */
+typedef struct psim_gamete_stats {
+    int64_t n_gametes;            /* out: 2 * ind_count * replicate_count */
+    uint32_t* allele_count;       /* [A][Lc]        gamete homologs with founder allele f at the locus (founderAlleleCountSel) */
+    uint32_t* dose_count;         /* [A][Lc][P/2+1] gametes by their dose of founder allele f (founderAlleleDoseSel) */
+    uint32_t* homozygous_count;   /* [Lc]           gametes holding a founder allele twice or more (founderHomSel) */
+    uint32_t* recomb_count;       /* [Lc][Lc]       entry [loc][loc2], loc2 < loc: gamete homologs whose founder alleles
+                                                    at the two loci differ (recombCountSel); other entries are 0 */
+    uint32_t* segments_hist;      /* [64]           gamete homologs by segment count - 1 (recombPoints; last bin: >= 63) */
+    uint32_t* quadrivalent_hist;  /* [P/4+1]        meioses by number of quadrivalents on the chromosome */
+} psim_gamete_stats;
+int psim_gamete_stats_run(psim_ctx* ctx, int64_t ind_first, int64_t ind_count, int32_t chrom, psim_gamete_stats* out);
+
 /* Drop every haplostruct and meiotic configuration (pedigree, chromosomes, map and allele codes
  * stay resident) and give the context a new RNG identity: the next psim_simulate is an
  * independent draw. Used by Monte Carlo drivers that re-simulate the same pedigree. */

@@ -54,6 +54,12 @@ class TextTargets(C.Structure):
                 ("dose_which", C.c_int32), ("reserved", C.c_int32)]
 
 
+class GameteStats(C.Structure):
+    _fields_ = [("n_gametes", C.c_int64), ("allele_count", C.c_void_p), ("dose_count", C.c_void_p),
+                ("homozygous_count", C.c_void_p), ("recomb_count", C.c_void_p), ("segments_hist", C.c_void_p),
+                ("quadrivalent_hist", C.c_void_p)]
+
+
 class DeviceHS(C.Structure):
     _fields_ = [("n_homologs", C.c_int64), ("n_segments", C.c_int64), ("seg_off", C.c_void_p),
                 ("founder", C.c_void_p), ("pos", C.c_void_p)]
@@ -65,6 +71,7 @@ EXPORTS = [
     "psim_set_map", "psim_set_allele_codes", "psim_emit", "psim_all_dose_rows", "psim_emit_all_dose", "psim_get_stats",
     "psim_export_haplostructs_device", "psim_import_haplostructs_device", "psim_reset", "psim_set_stream", "psim_simulate_subset",
     "psim_alloc_host", "psim_free_host", "psim_set_locus_names", "psim_set_allele_names", "psim_emit_text",
+    "psim_gamete_stats_run",
 ]
 
 _lib = None
@@ -104,6 +111,7 @@ def load():
     L.psim_set_locus_names.argtypes = [vp, vp, vp]
     L.psim_set_allele_names.argtypes = [vp, vp, vp, vp]
     L.psim_emit_text.argtypes = [vp, i64, i64, i64, i64, C.POINTER(TextTargets)]
+    L.psim_gamete_stats_run.argtypes = [vp, i64, i64, i32, C.POINTER(GameteStats)]
     L.psim_alloc_host.argtypes = [vp, C.c_size_t, C.POINTER(vp)]
     L.psim_free_host.argtypes = [vp, vp]
     L.psim_get_stats.argtypes = [vp, C.POINTER(Stats)]
@@ -306,6 +314,22 @@ class PsimContext:
                 setattr(t, name + "_capacity", cap)
         self._chk(self.L.psim_emit_text(self.h, ind_first, ind_count, loc_first, loc_count, C.byref(t)))
         return {k: bytes(v[:getattr(t, k + "_bytes")]) for k, v in bufs.items()}
+
+    def gamete_stats(self, chrom, n_loci, n_alleles, ind_first=0, ind_count=None, recomb=True):
+        """TEST-mode counters of one chromosome over the gametes of the given individuals (dict of arrays)."""
+        ind_count = self.N - ind_first if ind_count is None else ind_count
+        nd = self.P // 2 + 1
+        out = {"allele_count": np.zeros((n_alleles, n_loci), np.uint32), "dose_count": np.zeros((n_alleles, n_loci, nd), np.uint32),
+               "homozygous_count": np.zeros(n_loci, np.uint32), "segments_hist": np.zeros(64, np.uint32),
+               "quadrivalent_hist": np.zeros(self.P // 4 + 1, np.uint32)}
+        if recomb:
+            out["recomb_count"] = np.zeros((n_loci, n_loci), np.uint32)
+        gs = GameteStats()
+        for k, v in out.items():
+            setattr(gs, k, v.ctypes.data)
+        self._chk(self.L.psim_gamete_stats_run(self.h, ind_first, ind_count, chrom, C.byref(gs)))
+        out["n_gametes"] = gs.n_gametes
+        return out
 
     def reset(self, seed, replicate_first=0):
         self.replicate_first = replicate_first

@@ -182,3 +182,89 @@ def test_full_size_configs1_emission_properties():
     # every 1 Morgan-ish chromosome shows about one breakpoint per offspring homolog
     mean_bp = (nseg[2:] - 1).mean()
     assert 0.7 < mean_bp < 1.3
+
+
+# ------------------------------------------------------------------ device reductions
+def _numpy_gamete_stats(F, P, A):
+    """Main.testMeiosis counters (Main.java:1660-1721) from the founder table F [L][n_ind][P]."""
+    L, n, _ = F.shape
+    p2 = P // 2
+    G = F.reshape(L, n * 2, p2)                      # gametes: the two halves of every individual
+    allele = np.stack([(G == f).sum(axis=(1, 2)) for f in range(A)])                       # [A][L]
+    dose = np.stack([np.stack([((G == f).sum(axis=2) == d).sum(axis=1) for d in range(p2 + 1)], axis=1) for f in range(A)])
+    srt = np.sort(G, axis=2)
+    homoz = (srt[:, :, 1:] == srt[:, :, :-1]).any(axis=2).sum(axis=1) if p2 > 1 else np.zeros(L, int)
+    H = F.reshape(L, n * P)
+    rec = np.zeros((L, L), np.int64)
+    for a in range(L):
+        for b in range(a):
+            rec[a, b] = (H[a] != H[b]).sum()
+    return allele, dose, homoz, rec
+
+
+@pytest.mark.parametrize("ploidy,poptype,kw", [
+    (2, "F2", {}), (4, "S1", dict(natural_pairing=False)), (4, "F1", dict(natural_pairing=True, kosambi=True)),
+    (6, "F1", {}),
+])
+def test_device_gamete_statistics_match_counts_from_the_tables(ploidy, poptype, kw):
+    n = 3000
+    p0, p1 = _cases.std_pedigree(poptype, n)
+    lengths, centro = [1.1, 0.6], [0.4, 0.3]
+    pref, fq = ([0.4, 0.1], [0.6, 0.3]) if ploidy > 2 else (None, None)
+    g = _gpu(ploidy, p0, p1, lengths, centro, pref, fq, **kw)
+    loci = [37, 21]
+    off, pos = _cases.uniform_map(lengths, loci)
+    g.set_map(off, pos)
+    first = len(p0) - n
+    A = ploidy * (p0 < 0).sum()
+    F = g.emit(founder=True, ind_first=first)["founder"].reshape(sum(loci), n, ploidy)
+    so, fo, po = g.get_haplostructs(first)
+    quad, _ = g.get_meiotic_configs(first)
+    for c in range(2):
+        st = g.gamete_stats(c, loci[c], A, ind_first=first)
+        allele, dose, homoz, rec = _numpy_gamete_stats(F[off[c]:off[c + 1]], ploidy, A)
+        assert st["n_gametes"] == 2 * n
+        assert np.array_equal(st["allele_count"], allele)
+        assert np.array_equal(st["dose_count"], dose)
+        assert np.array_equal(st["homozygous_count"], homoz)
+        assert np.array_equal(st["recomb_count"], rec)
+        nseg = np.diff(so).reshape(n, 2, ploidy)[:, c, :].ravel()
+        assert np.array_equal(st["segments_hist"], np.bincount(np.minimum(nseg - 1, 63), minlength=64))
+        assert np.array_equal(st["quadrivalent_hist"], np.bincount(quad[:, c, :].ravel(), minlength=ploidy // 4 + 1))
+
+
+def test_test_mode_setting_double_reduction_and_recombination_on_device():
+    """The reference's TEST setting: one tetraploid parent, many meioses (an S1 population is two
+    gametes of the parent per individual). Quadrivalents allow double reduction: the homozygous
+    fraction must match the Java-LCG oracle's; recombination between the chromosome ends must match
+    the Haldane value for bivalent pairing."""
+    n = 60000
+    p0, p1 = _cases.std_pedigree("S1", n)
+    lengths, centro = [1.0], [0.3]
+    pos = np.array([0.0, 0.25, 0.5, 0.75, 1.0])
+    # all quadrivalents
+    g = _gpu(4, p0, p1, lengths, centro, [0.0], [1.0], natural_pairing=False)
+    g.set_map([0, 5], pos)
+    st = g.gamete_stats(0, 5, 4, ind_first=1)
+    n_o = 6000
+    q0, q1 = _cases.std_pedigree("S1", n_o)
+    o = _java_oracle(4, q0, q1, lengths, centro, [0.0], [1.0], natural_pairing=False)
+    o.set_map([0, 5], pos)
+    Fo = o.emit(_oracle.EMIT_FOUNDER, ind_first=1).reshape(5, n_o * 2, 2)
+    ho = (Fo[:, :, 0] == Fo[:, :, 1]).sum(axis=1)
+    for l in range(5):
+        tab = np.array([[st["homozygous_count"][l], st["n_gametes"] - st["homozygous_count"][l]], [ho[l], 2 * n_o - ho[l]]])
+        if tab[:, 0].sum() > 20:
+            assert stats.chi2_contingency(tab)[1] > P_FLOOR, (l, tab)
+    assert st["homozygous_count"][4] > 0 and st["quadrivalent_hist"].tolist() == [0, 2 * n]
+    # all bivalents, no preferential pairing: Haldane between the ends of a 1 M chromosome
+    g = _gpu(4, p0, p1, lengths, centro, [0.0], [0.0], natural_pairing=False)
+    g.set_map([0, 5], pos)
+    st = g.gamete_stats(0, 5, 4, ind_first=1)
+    assert st["homozygous_count"].sum() == 0 and st["quadrivalent_hist"].tolist() == [2 * n, 0]
+    r = st["recomb_count"][4, 0] / (st["n_gametes"] * 2)
+    expect = 0.5 * (1 - np.exp(-2.0))
+    # with 4 homologs a crossover partner carries a different founder allele with certainty, and
+    # returning to the same founder needs an even number of exchanges with the SAME partner
+    se = np.sqrt(0.25 / (st["n_gametes"] * 2))
+    assert abs(r - expect) < stats.norm.isf(P_FLOOR / 2) * se
