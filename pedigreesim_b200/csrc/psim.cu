@@ -965,7 +965,11 @@ __global__ void __launch_bounds__(256) k_band_plan(const RowsArgs a) {
 
 constexpr int ROWS_THREADS = 512;
 constexpr int ROWS_MAX_BAND = 255;     // the row of a run start inside its band is 8 bits
-constexpr int ROWS_SMEM = 200 * 1024;  // one block per SM
+constexpr int ROWS_SMEM = 220 * 1024;  // one block per SM
+#ifndef PSIM_ROWS_NBUF
+#define PSIM_ROWS_NBUF 2
+#endif
+constexpr int ROWS_NBUF = PSIM_ROWS_NBUF;   // row buffers: NBUF-1 rows can be queued at the bulk engine while the next is made
 
 __device__ __forceinline__ void bulk_store(void* gdst, const void* ssrc, uint32_t bytes) {
     asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst),
@@ -983,12 +987,11 @@ __global__ void __launch_bounds__(ROWS_THREADS, 1) k_emit_rows(const RowsArgs a)
     const int tid = threadIdx.x;
     const int P = a.P;
     const int seg_cells = a.seg_cells, seg_ind = seg_cells / P;
-    uint8_t* const img0 = smem;                                              // founder byte of every cell on the current row (x2)
-    uint8_t* const img1 = img0 + seg_cells;
-    uint32_t* const nib = reinterpret_cast<uint32_t*>(img1 + seg_cells);     // DK >= 2: the same, 4 bits per cell
+    constexpr int NB = ROWS_NBUF;
+    uint8_t* const img0 = smem;                                              // founder byte of every cell on the current row (x NB)
+    uint32_t* const nib = reinterpret_cast<uint32_t*>(img0 + (size_t)NB * seg_cells);   // DK >= 2: the same, 4 bits per cell
     uint8_t* const dose0 = reinterpret_cast<uint8_t*>(nib) + (DK >= 2 ? seg_cells / 2 : 0);
-    uint8_t* const dose1 = dose0 + (DK >= 1 ? seg_ind : 0);
-    uint32_t* const evs = reinterpret_cast<uint32_t*>(dose1 + (DK >= 1 ? seg_ind : 0));   // the unit's run starts sorted by row
+    uint32_t* const evs = reinterpret_cast<uint32_t*>(dose0 + (DK >= 1 ? (size_t)NB * seg_ind : 0));   // the unit's run starts sorted by row
     uint32_t* const start = evs + a.cap;                                     // [band rows + 1] first run start of each row
     uint32_t* const cursor = start + ROWS_MAX_BAND + 2;
     __shared__ int s_unit;
@@ -1063,12 +1066,16 @@ __global__ void __launch_bounds__(ROWS_THREADS, 1) k_emit_rows(const RowsArgs a)
         uint4 Tn = make_uint4(0, 0, 0, 0);
         if (DK >= 2) Tn = __ldg(a.mtab + g0);
         __syncthreads();
-        // the second buffer starts from the same state (it becomes row 1)
-        for (int i = tid; i < seg_cells / 16; i += ROWS_THREADS) reinterpret_cast<uint4*>(img1)[i] = reinterpret_cast<const uint4*>(img0)[i];
-        if (DK == 1)
-            for (int i = tid; i < seg_ind / 16; i += ROWS_THREADS) reinterpret_cast<uint4*>(dose1)[i] = reinterpret_cast<const uint4*>(dose0)[i];
+        // the other buffers start from the same state (they become rows 1 .. NB-1)
+        for (int b = 1; b < NB; b++) {
+            for (int i = tid; i < seg_cells / 16; i += ROWS_THREADS)
+                reinterpret_cast<uint4*>(img0 + (size_t)b * seg_cells)[i] = reinterpret_cast<const uint4*>(img0)[i];
+            if (DK == 1)
+                for (int i = tid; i < seg_ind / 16; i += ROWS_THREADS)
+                    reinterpret_cast<uint4*>(dose0 + (size_t)b * seg_ind)[i] = reinterpret_cast<const uint4*>(dose0)[i];
+        }
 
-        // ---- the rows. Buffer r & 1 holds row r-2 when row r begins: it takes the run starts of rows r-1 and r.
+        // ---- the rows. Buffer r % NB holds row r-NB when row r begins: it takes the run starts of rows r-NB+1 .. r.
         auto patch = [&](uint8_t* img, uint8_t* drow, uint32_t e0, uint32_t e1) {
             for (uint32_t e = e0 + tid; e < e1; e += ROWS_THREADS) {
                 const uint32_t w = evs[e], cs = (w >> 8) & 0xFFFF, f = w & 0xFF;
@@ -1082,10 +1089,10 @@ __global__ void __launch_bounds__(ROWS_THREADS, 1) k_emit_rows(const RowsArgs a)
         };
         for (int r = 0; r < n_rows; r++) {
             const uint32_t e0 = start[r], e1 = start[r + 1];   // this row's run starts (row 0 has none: they are the state)
-            uint8_t* const img = (r & 1) ? img1 : img0;
-            uint8_t* const drow = (r & 1) ? dose1 : dose0;
-            // buffers of row r were last read by the bulk stores of row r-2
-            if (r > 1 && tid == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+            uint8_t* const img = img0 + (size_t)(r % NB) * seg_cells;
+            uint8_t* const drow = dose0 + (size_t)(r % NB) * seg_ind;
+            // buffers of row r were last read by the bulk stores of row r-NB
+            if (r >= NB && tid == 0) asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(NB - 1) : "memory");
             if (DK >= 2) {
                 for (uint32_t e = e0 + tid; e < e1; e += ROWS_THREADS) {
                     const uint32_t w = evs[e], cs = (w >> 8) & 0xFFFF, sh = (cs & 7) * 4;
@@ -1094,7 +1101,11 @@ __global__ void __launch_bounds__(ROWS_THREADS, 1) k_emit_rows(const RowsArgs a)
                 }
             }
             __syncthreads();
-            if (r > 0) patch(img, drow, start[r - 1], e0);   // catch up with row r-1
+            // catch up with the rows this buffer missed, oldest first (a cell may change on two of them)
+            for (int m = NB - 1; m >= 1; m--) {
+                if (r - m >= 1) patch(img, drow, start[r - m], start[r - m + 1]);
+                if (m > 1) __syncthreads();
+            }
             if (DK >= 2) {
                 const uint4 T = Tn;
                 if (r + 1 < n_rows) Tn = __ldg(a.mtab + g0 + r + 1);
@@ -1217,7 +1228,7 @@ struct TextArgs {
 
 template <bool WRITE>
 __global__ void __launch_bounds__(TEXT_THREADS) k_text_rows(const TextArgs a) {
-    extern __shared__ __align__(16) uint8_t smem[];
+    extern __shared__ __align__(128) uint8_t smem[];
     __shared__ uint32_t s_warp[TEXT_THREADS / 32];
     __shared__ uint32_t s_nlen[256], s_nbeg[256];
     const int tid = threadIdx.x, lane = tid & 31, wq = tid >> 5;
@@ -1754,7 +1765,7 @@ static int emit_rows_path(psim_ctx_impl* c, int64_t ind_first, int64_t ind_count
     const int DK = !dose ? 0 : mode == 0 ? 1 : P == 4 ? 2 : 3;
     const int64_t n_cols_ind = (int64_t)c->R * ind_count, n_cols = n_cols_ind * P;
     const int cap = 8192;
-    const double per_cell = 2.0 + (DK >= 2 ? 0.5 : 0.0) + (DK >= 1 ? 2.0 : 0.0) / P;
+    const double per_cell = (double)ROWS_NBUF + (DK >= 2 ? 0.5 : 0.0) + (DK >= 1 ? (double)ROWS_NBUF : 0.0) / P;
     const int64_t budget = ROWS_SMEM - 2 * (ROWS_MAX_BAND + 2) * 4 - cap * 4;
     const int64_t quantum = 16 * P;
     int64_t seg_max = (int64_t)(budget / per_cell) / quantum * quantum;
@@ -1773,7 +1784,8 @@ static int emit_rows_path(psim_ctx_impl* c, int64_t ind_first, int64_t ind_count
     int64_t band = ((l_end - l_begin) * n_seg + n_blocks - 1) / n_blocks;
     band = std::max<int64_t>(32, std::min<int64_t>(band, ROWS_MAX_BAND));
     while (band > 8 && starts_per_cell * (double)seg_cells * (double)band > cap / 2) band = band * 3 / 4;
-    if (starts_per_cell * (double)seg_cells * (double)band > cap / 2) return PSIM_OK;   // sparse map: tiled / dense path
+    const bool forced = getenv("PSIM_ROWS_FORCE") != nullptr;   // test knob: take this path even if lists will overflow
+    if (!forced && starts_per_cell * (double)seg_cells * (double)band > cap / 2) return PSIM_OK;   // sparse map: tiled / dense path
     if (env_band > 0) band = std::min(env_band, ROWS_MAX_BAND);
 
     RowsArgs ra{};
@@ -1787,7 +1799,7 @@ static int emit_rows_path(psim_ctx_impl* c, int64_t ind_first, int64_t ind_count
     ra.dose = dose; ra.dose_pitch = dose_pitch;
     ra.dose_which = dose_which; ra.mtab = c->mtab_d;
     ra.unit_counter = c->tile_counter_d;
-    const size_t smem = 2 * (size_t)seg_cells + (DK >= 2 ? seg_cells / 2 : 0) + (size_t)(DK >= 1 ? 2 : 0) * (seg_cells / P) +
+    const size_t smem = ROWS_NBUF * (size_t)seg_cells + (DK >= 2 ? seg_cells / 2 : 0) + (size_t)(DK >= 1 ? ROWS_NBUF : 0) * (seg_cells / P) +
                         (size_t)cap * 4 + 2 * (ROWS_MAX_BAND + 2) * 4;
     int k0 = 0;
     while (k0 < c->C && c->locus_off_h[k0 + 1] <= l_begin) k0++;

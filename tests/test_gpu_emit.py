@@ -163,3 +163,43 @@ def test_u16_founder_table_for_many_founders():
     import pedigreesim_b200
     with pytest.raises(pedigreesim_b200.PsimError):
         res[1].emit(founder=True, founder_bytes=1)
+
+
+@pytest.mark.parametrize("ploidy,n_ind,codes", [(2, 41000, 2), (2, 33000, 0), (4, 15011, 2), (6, 12000, 0), (4, 30001, 0)])
+def test_rows_wider_than_one_shared_memory_segment(ploidy, n_ind, codes):
+    """More than ~56 K cells per locus row: the row-image kernel cuts the row into segments, each
+    with its own bulk stores (ragged last segment, dose tails that are not multiples of 16)."""
+    lengths = [1.0, 0.6]
+    loci = [70, 45]
+    n_alleles = ploidy * 2
+    o, g = _both(ploidy, lengths, n_ind, n_alleles, loci, seed=n_ind, codes=codes, max_segments=4)
+    which = _oracle.MAX_ALLELE if codes else 1
+    got = g.emit(founder=True, dose=True, dose_which=which)
+    assert np.array_equal(got["founder"], o.emit(_oracle.EMIT_FOUNDER))
+    assert np.array_equal(got["dose"], o.emit(_oracle.EMIT_DOSE, which=which))
+    # a window of individuals and loci that starts inside a segment
+    i0, ni, l0, nl = 1234, n_ind - 2000, 30, 60
+    sub = g.emit(founder=True, dose=True, dose_which=which, ind_first=i0, ind_count=ni, loc_first=l0, loc_count=nl)
+    assert np.array_equal(sub["founder"], got["founder"][l0:l0 + nl, i0 * ploidy:(i0 + ni) * ploidy])
+    assert np.array_equal(sub["dose"], got["dose"][l0:l0 + nl, i0:i0 + ni])
+
+
+def test_many_run_starts_per_row_fall_back_cleanly():
+    """A sparse map (few loci, long chromosomes): nearly every cell changes from one locus to the
+    next; the row-image path must hand over (or redo overflowing units) without a wrong byte."""
+    o, g = _both(4, [6.0], 3000, 8, [24], seed=8, max_segments=40, grid_breaks=False)
+    got = g.emit(founder=True, dose=True, dose_which=2)
+    assert np.array_equal(got["founder"], o.emit(_oracle.EMIT_FOUNDER))
+    assert np.array_equal(got["dose"], o.emit(_oracle.EMIT_DOSE, which=2))
+
+
+def test_overflowing_units_are_redone_per_cell(monkeypatch):
+    """Force the row-image path onto a map where the run-start lists overflow: those units go to
+    the overflow list and are redone by the per-cell kernel; the tables must still be exact."""
+    monkeypatch.setenv("PSIM_ROWS_FORCE", "1")
+    for ploidy, codes in ((4, 0), (4, 2), (2, 2)):
+        o, g = _both(ploidy, [6.0, 1.0], 3000, ploidy * 2, [24, 40], seed=21 + ploidy, codes=codes, max_segments=40, grid_breaks=False)
+        which = _oracle.MAX_ALLELE if codes else 3
+        got = g.emit(founder=True, dose=True, dose_which=which)
+        assert np.array_equal(got["founder"], o.emit(_oracle.EMIT_FOUNDER))
+        assert np.array_equal(got["dose"], o.emit(_oracle.EMIT_DOSE, which=which))

@@ -19,8 +19,8 @@ __device__ __forceinline__ uint32_t spin(uint32_t x, int n) {
 }
 
 // mode 0: one bulk store per table and row; mode 1: the row is cut into `pieces` bulk stores issued by different threads
-__global__ void __launch_bounds__(256) k_rowimage(uint8_t* f, uint32_t fpitch, uint8_t* d, uint32_t dpitch, int rows_total,
-                                                  int rows_per_band, int* counter, int delay, int jitter, int pieces, int nbuf) {
+__global__ void __launch_bounds__(512) k_rowimage(uint8_t* f, uint32_t fpitch, uint8_t* d, uint32_t dpitch, int rows_total,
+                                                  int rows_per_band, int* counter, int delay, int jitter, int pieces, int nbuf, int G) {
     extern __shared__ __align__(128) uint8_t smem[];
     __shared__ int s_band;
     const uint32_t img = fpitch + dpitch;   // bytes of one row image (both multiples of 128)
@@ -31,10 +31,14 @@ __global__ void __launch_bounds__(256) k_rowimage(uint8_t* f, uint32_t fpitch, u
         const int band = s_band;
         __syncthreads();
         if (band >= n_bands) break;
-        const int r0 = band * rows_per_band, r1 = min(r0 + rows_per_band, rows_total);
+        // G > 1: the G bands of a group deal their rows round-robin (concurrently written rows are neighbours)
+        const int grp = band / G, mem = band % G;
+        const int r0 = G == 1 ? band * rows_per_band : grp * G * rows_per_band + mem;
+        const int r1 = G == 1 ? min(r0 + rows_per_band, rows_total) : min((grp + 1) * G * rows_per_band, rows_total);
+        const int rstep = G;
         uint32_t x = spin(band * 977u + threadIdx.x, jitter ? (band * 37 % 11) * jitter : 0);
         int buf = 0;
-        for (int r = r0; r < r1; r++) {
+        for (int r = r0; r < r1; r += rstep) {
             // the buffer we are about to touch must have been read by the bulk engine
             if (threadIdx.x < pieces) {
                 if (nbuf == 2) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
@@ -97,22 +101,18 @@ int main() {
         printf("%-64s best %7.1f us %7.1f GB/s   mean %7.1f us\n", name, best * 1e3, bytes / best / 1e6, sum / 8 * 1e3);
     };
     CK(cudaFuncSetAttribute(k_rowimage, cudaFuncAttributeMaxDynamicSharedMemorySize, 3 * (fpitch + dpitch)));
-    for (int nbuf : {2, 3})
-        for (int threads : {128, 256})
-            for (int band : {20, 41, 82})
-                for (int pieces : {1, 4})
-                    for (int delay : {0, 200, 800})
-                        for (int jitter : {0, 400}) {
-                            if (jitter && delay != 200) continue;
-                            const int bps = nbuf == 2 ? 2 : 1;
-                            char nm[128];
-                            snprintf(nm, 128, "rowimage nbuf %d thr %d band %2d pieces %d delay %3d jitter %3d", nbuf, threads, band, pieces, delay, jitter);
-                            time(nm, [&] {
-                                CK(cudaMemsetAsync(counter, 0, 4));
-                                k_rowimage<<<148 * bps, threads, (size_t)nbuf * (fpitch + dpitch)>>>(f, fpitch, d, dpitch, rows, band, counter, delay, jitter, pieces, nbuf);
-                                CK(cudaGetLastError());
-                            });
-                        }
+    for (int rep = 0; rep < 2; rep++)
+    for (int G : {1, 4, 8, 16, 37, 148})
+        for (int delay : {0, 200}) {
+            const int nbuf = 3, threads = 512, band = 163, pieces = 1, jitter = delay ? 400 : 0;
+            char nm[128];
+            snprintf(nm, 128, "rowimage nbuf 3 thr 512 band 163 interleave %3d delay %3d jitter %3d", G, delay, jitter);
+            time(nm, [&] {
+                CK(cudaMemsetAsync(counter, 0, 4));
+                k_rowimage<<<148, threads, (size_t)nbuf * (fpitch + dpitch)>>>(f, fpitch, d, dpitch, rows, band, counter, delay, jitter, pieces, nbuf, G);
+                CK(cudaGetLastError());
+            });
+        }
     CK(cudaDeviceSynchronize());
     return 0;
 }
