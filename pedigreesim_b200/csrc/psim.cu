@@ -1781,8 +1781,21 @@ static int emit_rows_path(psim_ctx_impl* c, int64_t ind_first, int64_t ind_count
     const int n_blocks = c->sm_count * (env_bps > 0 ? env_bps : 1);
     // band height: one unit per resident block when the request is large, never so tall that a unit's
     // expected run starts come near the list capacity
-    int64_t band = ((l_end - l_begin) * n_seg + n_blocks - 1) / n_blocks;
-    band = std::max<int64_t>(32, std::min<int64_t>(band, ROWS_MAX_BAND));
+    int64_t band;
+    {   // number of bands: the fewest (tallest bands) for which the units fill whole waves of resident blocks
+        const int64_t rows_total = l_end - l_begin;
+        const int64_t b_min = (rows_total + ROWS_MAX_BAND - 1) / ROWS_MAX_BAND, b_max = std::max(b_min, rows_total / 32);
+        int64_t best = b_min;
+        double best_eff = 0.0;
+        for (int64_t b = b_min; b <= b_max && b < b_min + 4 * n_blocks; b++) {
+            const int64_t units = b * n_seg;
+            const double eff = (double)units / (double)((units + n_blocks - 1) / n_blocks * n_blocks);
+            if (eff > best_eff + 1e-9) { best_eff = eff; best = b; }
+            if (eff >= 0.97) break;
+        }
+        band = std::max<int64_t>(1, (rows_total + best - 1) / best);
+    }
+    band = std::max<int64_t>(8, std::min<int64_t>(band, ROWS_MAX_BAND));
     while (band > 8 && starts_per_cell * (double)seg_cells * (double)band > cap / 2) band = band * 3 / 4;
     const bool forced = getenv("PSIM_ROWS_FORCE") != nullptr;   // test knob: take this path even if lists will overflow
     if (!forced && starts_per_cell * (double)seg_cells * (double)band > cap / 2) return PSIM_OK;   // sparse map: tiled / dense path
