@@ -1784,14 +1784,17 @@ static int emit_rows_path(psim_ctx_impl* c, int64_t ind_first, int64_t ind_count
     int64_t band;
     {   // number of bands: the fewest (tallest bands) for which the units fill whole waves of resident blocks
         const int64_t rows_total = l_end - l_begin;
-        const int64_t b_min = (rows_total + ROWS_MAX_BAND - 1) / ROWS_MAX_BAND, b_max = std::max(b_min, rows_total / 32);
+        // tallest band whose expected run starts stay within half the list capacity
+        const double per_row = starts_per_cell * (double)seg_cells;
+        const int64_t band_cap = std::max<int64_t>(8, std::min<int64_t>(ROWS_MAX_BAND, per_row > 0 ? (int64_t)((cap / 2) / per_row) : ROWS_MAX_BAND));
+        const int64_t b_min = (rows_total + band_cap - 1) / band_cap, b_max = std::max(b_min, rows_total / 32);
         int64_t best = b_min;
         double best_eff = 0.0;
         for (int64_t b = b_min; b <= b_max && b < b_min + 4 * n_blocks; b++) {
             const int64_t units = b * n_seg;
             const double eff = (double)units / (double)((units + n_blocks - 1) / n_blocks * n_blocks);
             if (eff > best_eff + 1e-9) { best_eff = eff; best = b; }
-            if (eff >= 0.97) break;
+            if (best_eff >= 0.97 && b >= best + 8) break;   // good enough: look a little further for a full wave
         }
         band = std::max<int64_t>(1, (rows_total + best - 1) / best);
     }
