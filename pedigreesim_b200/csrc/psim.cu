@@ -1781,28 +1781,12 @@ static int emit_rows_path(psim_ctx_impl* c, int64_t ind_first, int64_t ind_count
     const int n_blocks = c->sm_count * (env_bps > 0 ? env_bps : 1);
     // band height: one unit per resident block when the request is large, never so tall that a unit's
     // expected run starts come near the list capacity
-    int64_t band;
-    {   // number of bands: the fewest (tallest bands) for which the units fill whole waves of resident blocks
-        const int64_t rows_total = l_end - l_begin;
-        // tallest band whose expected run starts stay within half the list capacity
-        const double per_row = starts_per_cell * (double)seg_cells;
-        const int64_t band_cap = std::max<int64_t>(8, std::min<int64_t>(ROWS_MAX_BAND, per_row > 0 ? (int64_t)((cap / 2) / per_row) : ROWS_MAX_BAND));
-        const int64_t b_min = (rows_total + band_cap - 1) / band_cap, b_max = std::max(b_min, rows_total / 32);
-        int64_t best = b_min;
-        double best_eff = 0.0;
-        for (int64_t b = b_min; b <= b_max && b < b_min + 4 * n_blocks; b++) {
-            const int64_t units = b * n_seg;
-            const double eff = (double)units / (double)((units + n_blocks - 1) / n_blocks * n_blocks);
-            if (eff > best_eff + 1e-9) { best_eff = eff; best = b; }
-            if (best_eff >= 0.97 && b >= best + 8) break;   // good enough: look a little further for a full wave
-        }
-        band = std::max<int64_t>(1, (rows_total + best - 1) / best);
-    }
-    band = std::max<int64_t>(8, std::min<int64_t>(band, ROWS_MAX_BAND));
-    while (band > 8 && starts_per_cell * (double)seg_cells * (double)band > cap / 2) band = band * 3 / 4;
+    // tallest band whose expected run starts stay within half the list capacity
+    const double per_row = starts_per_cell * (double)seg_cells;
     const bool forced = getenv("PSIM_ROWS_FORCE") != nullptr;   // test knob: take this path even if lists will overflow
-    if (!forced && starts_per_cell * (double)seg_cells * (double)band > cap / 2) return PSIM_OK;   // sparse map: tiled / dense path
-    if (env_band > 0) band = std::min(env_band, ROWS_MAX_BAND);
+    if (!forced && per_row * 8.0 > cap / 2) return PSIM_OK;      // sparse map: tiled / dense path
+    const int64_t band_cap = env_band > 0 ? std::min(env_band, ROWS_MAX_BAND)
+                           : std::max<int64_t>(8, std::min<int64_t>(ROWS_MAX_BAND, per_row > 0 ? (int64_t)((cap / 2) / per_row) : ROWS_MAX_BAND));
 
     RowsArgs ra{};
     ra.C = c->C; ra.R = c->R; ra.P = P; ra.N = c->N;
@@ -1831,32 +1815,45 @@ static int emit_rows_path(psim_ctx_impl* c, int64_t ind_first, int64_t ind_count
             k0++;
         }
         if (ra.n_chunks == 0) break;
-        {   // bands per chromosome piece: proportional to its rows, rounded so that the total is the
-            // target (one unit per resident block) — largest remainders get the extra band
+        {   // Bands per chromosome piece: proportional to its rows, largest remainders get the extra
+            // band. The total is the smallest one (tallest bands) whose units fill whole waves of
+            // resident blocks; no band is taller than band_cap.
             int64_t total = 0;
             for (int q = 0; q < ra.n_chunks; q++) total += ra.chunk_l1[q] - ra.chunk_l0[q];
-            const int64_t target = std::max<int64_t>(1, (total + band - 1) / band);
-            int64_t given = 0;
-            double rem[64];
-            for (int q = 0; q < ra.n_chunks; q++) {
-                const int64_t len = ra.chunk_l1[q] - ra.chunk_l0[q];
-                const double ideal = (double)len * (double)target / (double)total;
-                int64_t nb = std::max<int64_t>(1, (int64_t)ideal);
-                nb = std::max(nb, (len + ROWS_MAX_BAND - 1) / ROWS_MAX_BAND);
-                nb = std::min(nb, len);
-                ra.chunk_bands[q] = (int)nb;
-                rem[q] = ideal - (double)nb;
-                given += nb;
+            auto allocate = [&](int64_t target) -> int64_t {
+                int64_t given = 0;
+                double rem[64];
+                for (int q = 0; q < ra.n_chunks; q++) {
+                    const int64_t len = ra.chunk_l1[q] - ra.chunk_l0[q];
+                    const double ideal = (double)len * (double)target / (double)total;
+                    int64_t nb = std::max<int64_t>(1, (int64_t)ideal);
+                    nb = std::max(nb, (len + band_cap - 1) / band_cap);
+                    nb = std::min(nb, len);
+                    ra.chunk_bands[q] = (int)nb;
+                    rem[q] = ideal - (double)nb;
+                    given += nb;
+                }
+                while (given < target) {
+                    int best = -1;
+                    for (int q = 0; q < ra.n_chunks; q++)
+                        if (ra.chunk_bands[q] < ra.chunk_l1[q] - ra.chunk_l0[q] && (best < 0 || rem[q] > rem[best])) best = q;
+                    if (best < 0) break;
+                    ra.chunk_bands[best]++;
+                    rem[best] -= 1.0;
+                    given++;
+                }
+                return given;
+            };
+            const int64_t t_min = std::max<int64_t>(1, (total + band_cap - 1) / band_cap);
+            int64_t best_t = t_min;
+            double best_eff = 0.0;
+            for (int64_t tg = t_min; tg < t_min + 4 * n_blocks && tg <= std::max<int64_t>(t_min, total / (env_band > 0 ? 1 : 16)); tg++) {
+                const int64_t units = allocate(tg) * n_seg;
+                const double eff = (double)units / (double)((units + n_blocks - 1) / n_blocks * n_blocks);
+                if (eff > best_eff + 1e-9) { best_eff = eff; best_t = tg; }
+                if (env_band > 0 || (best_eff >= 0.97 && tg >= best_t + 8)) break;   // good enough; look a little further for a full wave
             }
-            while (given < target) {
-                int best = -1;
-                for (int q = 0; q < ra.n_chunks; q++)
-                    if (ra.chunk_bands[q] < ra.chunk_l1[q] - ra.chunk_l0[q] && (best < 0 || rem[q] > rem[best])) best = q;
-                if (best < 0) break;
-                ra.chunk_bands[best]++;
-                rem[best] -= 1.0;
-                given++;
-            }
+            allocate(best_t);
             for (int q = 0; q < ra.n_chunks; q++) ra.chunk_unit_base[q + 1] = ra.chunk_unit_base[q] + ra.chunk_bands[q] * n_seg;
         }
         ra.n_units = ra.chunk_unit_base[ra.n_chunks];
