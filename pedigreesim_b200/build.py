@@ -8,7 +8,8 @@ PKG = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(PKG, "csrc")
 LIB = os.path.join(PKG, "libpsim.so")
 SOURCES = ["psim.cu"]
-HEADERS = ["psim_meiosis.cuh", "psim_rng.cuh", os.path.join("..", "..", "include", "psim.h")]
+HEADERS = ["psim_meiosis.cuh", "psim_rng.cuh", "psim_k1.cuh", "psim_k0.cuh", "psim_emit_tiles.cuh", "psim_emit_rows.cuh",
+           "psim_emit_generic.cuh", "psim_text.cuh", "psim_stats.cuh", "psim_misc.cuh", os.path.join("..", "..", "include", "psim.h")]
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",

@@ -1,0 +1,276 @@
+// K2 (row-image path) — band plan and shared-memory row + TMA bulk store emission
+// (part of libpsim: included by psim.cu inside namespace psim)
+#pragma once
+
+// ------------------------------------------------------------------------------------------
+// K2 "row image" path — the roofline kernel for founder + dose tables.
+// A block owns a band of consecutive locus rows of one chromosome and a segment of at most ~46 KB of
+// the founder row. It keeps the CURRENT ROW of that segment in shared memory (1 byte per cell; with
+// founder genotypes also a 4-bit copy used as PRMT selectors), patches the few cells whose homolog
+// starts a new run on the row, and sends the row to global memory as ONE contiguous TMA bulk store
+// (cp.async.bulk shared -> global): every table row leaves the SM as 40 KB + 10 KB of consecutive
+// bytes, which is the write pattern HBM likes (tools/write_rowimage.cu, profiles/README.md), and it
+// stays that way however the blocks drift against each other. The dose row is recomputed per locus
+// from the 4-bit image (A <= 8, ploidy 2 or 4) or patched like the founder row (no genotypes).
+// The plan (k_band_plan) holds, per (band, segment) unit, the founder byte of every cell on the
+// band's first row and the unordered list of run starts inside the band: 1 byte per cell and BAND,
+// bands being ~80 rows, so plan reads are ~1 % of the bytes written.
+struct RowsArgs {
+    int C, R, P;
+    int64_t N;
+    const uint64_t* run_desc;
+    const uint32_t* run_lb;
+    const uint16_t* run_founder;
+    int64_t ind_first, ind_count, n_cols_ind;
+    int64_t locus_first;          // global locus of output row 0
+    int n_chunks;                 // chromosome pieces of this launch (<= 64)
+    int chunk_chrom[64];
+    int64_t chunk_l0[64], chunk_l1[64], chunk_coff[64];
+    int chunk_bands[64];          // bands the piece is cut into (equal row counts, +-1)
+    int chunk_unit_base[65];
+    int n_seg, seg_cells;         // segments per row; cells per segment (a multiple of 16 * P)
+    int n_units, cap;             // units = sum(bands) * n_seg; run starts a unit's list can hold
+    uint8_t* plan;                // per unit: [count u32, 12 bytes pad][seg_cells state bytes][cap run starts]
+    int64_t plan_stride;
+    int* unit_counter;            // ticket
+    int* overflow;                // [0] = number of units whose list overflowed, then their ids
+    uint8_t* founder; int64_t founder_pitch;
+    uint8_t* dose;    int64_t dose_pitch;
+    int dose_which;               // without genotypes: founder allele to count
+    const uint4* mtab;            // with genotypes: per-locus byte tables of the counted allele (k_match_codes)
+};
+
+__device__ __forceinline__ void band_rows(const RowsArgs& a, int k, int j, int64_t& g0, int64_t& g1) {
+    const int64_t len = a.chunk_l1[k] - a.chunk_l0[k];
+    g0 = a.chunk_l0[k] + len * j / a.chunk_bands[k];
+    g1 = a.chunk_l0[k] + len * (j + 1) / a.chunk_bands[k];
+}
+
+// One thread per (chromosome piece, emitted cell column): walks the homolog's runs once down the
+// piece and leaves the state byte of every band plus the run starts inside it.
+__global__ void __launch_bounds__(256) k_band_plan(const RowsArgs a) {
+    const int k = blockIdx.y;
+    const int64_t col = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    const int P = a.P;
+    if (col >= a.n_cols_ind * P) return;
+    const int c = a.chunk_chrom[k];
+    const int64_t q = col / P;
+    const int h = (int)(col % P);
+    const int64_t r = q / a.ind_count, i = a.ind_first + q % a.ind_count;
+    const int64_t hid = (((int64_t)c * a.R + r) * a.N + i) * P + h;
+    const int s = (int)(col / a.seg_cells);
+    const uint32_t cs = (uint32_t)(col % a.seg_cells);
+    const uint64_t d = __ldg(a.run_desc + hid);
+    const uint32_t b = (uint32_t)desc_begin(d), n = desc_count(d);
+    const int64_t c_off = a.chunk_coff[k];
+    const uint32_t l_begin = (uint32_t)(a.chunk_l0[k] - c_off);
+    uint32_t lo = 0, hi = n;   // last run with lb <= l_begin
+    while (hi - lo > 1) { const uint32_t mid = (lo + hi) >> 1; if (__ldg(a.run_lb + b + mid) <= l_begin) lo = mid; else hi = mid; }
+    uint32_t f = n ? __ldg(a.run_founder + b + lo) : 0;
+    uint32_t kx = lo + 1;
+    uint32_t nxt = kx < n ? __ldg(a.run_lb + b + kx) : NO_EVENT;
+    for (int j = 0; j < a.chunk_bands[k]; j++) {
+        int64_t g0, g1;
+        band_rows(a, k, j, g0, g1);
+        const uint32_t tl0 = (uint32_t)(g0 - c_off), tl1 = (uint32_t)(g1 - c_off);
+        uint8_t* pu = a.plan + (int64_t)(a.chunk_unit_base[k] + j * a.n_seg + s) * a.plan_stride;
+        while (nxt <= tl0) {   // a run starting exactly on the band's first row is its start state
+            f = __ldg(a.run_founder + b + kx);
+            kx++;
+            nxt = kx < n ? __ldg(a.run_lb + b + kx) : NO_EVENT;
+        }
+        pu[16 + cs] = (uint8_t)f;
+        while (nxt < tl1) {
+            f = __ldg(a.run_founder + b + kx);
+            const uint32_t idx = atomicAdd(reinterpret_cast<uint32_t*>(pu), 1u);
+            if (idx < (uint32_t)a.cap)
+                reinterpret_cast<uint32_t*>(pu + 16 + a.seg_cells)[idx] = ((nxt - tl0) << 24) | (cs << 8) | f;
+            kx++;
+            nxt = kx < n ? __ldg(a.run_lb + b + kx) : NO_EVENT;
+        }
+    }
+}
+
+constexpr int ROWS_THREADS = 512;
+constexpr int ROWS_MAX_BAND = 255;     // the row of a run start inside its band is 8 bits
+constexpr int ROWS_SMEM = 220 * 1024;  // one block per SM
+#ifndef PSIM_ROWS_NBUF
+#define PSIM_ROWS_NBUF 2
+#endif
+constexpr int ROWS_NBUF = PSIM_ROWS_NBUF;   // row buffers: NBUF-1 rows can be queued at the bulk engine while the next is made
+
+__device__ __forceinline__ void bulk_store(void* gdst, const void* ssrc, uint32_t bytes) {
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst),
+                 "r"((uint32_t)__cvta_generic_to_shared(ssrc)), "r"(bytes) : "memory");
+}
+
+// DK: how the dose row is made. 0 = no dose table, 1 = no genotypes (count of one founder allele:
+// patched like the founder row), 2 = genotypes, A <= 8, ploidy 4, 3 = genotypes, A <= 8, ploidy 2.
+// Founder and dose rows are double-buffered: while the bulk engine streams row r-1 out of one
+// buffer, row r is made in the other (copy + patch, or recomputed), so the engine always has a
+// row queued and the block never waits for the row it has just issued.
+template <int DK>
+__global__ void __launch_bounds__(ROWS_THREADS, 1) k_emit_rows(const RowsArgs a) {
+    extern __shared__ __align__(128) uint8_t smem[];
+    const int tid = threadIdx.x;
+    const int P = a.P;
+    const int seg_cells = a.seg_cells, seg_ind = seg_cells / P;
+    constexpr int NB = ROWS_NBUF;
+    uint8_t* const img0 = smem;                                              // founder byte of every cell on the current row (x NB)
+    uint32_t* const nib = reinterpret_cast<uint32_t*>(img0 + (size_t)NB * seg_cells);   // DK >= 2: the same, 4 bits per cell
+    uint8_t* const dose0 = reinterpret_cast<uint8_t*>(nib) + (DK >= 2 ? seg_cells / 2 : 0);
+    uint32_t* const evs = reinterpret_cast<uint32_t*>(dose0 + (DK >= 1 ? (size_t)NB * seg_ind : 0));   // the unit's run starts sorted by row
+    uint32_t* const start = evs + a.cap;                                     // [band rows + 1] first run start of each row
+    uint32_t* const cursor = start + ROWS_MAX_BAND + 2;
+    __shared__ int s_unit;
+    const int64_t n_cols = a.n_cols_ind * P;
+    const bool count_ok = a.dose_which >= 0 && a.dose_which < 256;           // DK 1: a founder allele that exists
+
+    for (;;) {
+        __syncthreads();
+        if (tid == 0) s_unit = atomicAdd(a.unit_counter, 1);
+        __syncthreads();
+        const int u = s_unit;
+        if (u >= a.n_units) break;
+        int k = 0;
+        while (u >= a.chunk_unit_base[k + 1]) k++;
+        const int j = (u - a.chunk_unit_base[k]) / a.n_seg, s = (u - a.chunk_unit_base[k]) % a.n_seg;
+        int64_t g0, g1;
+        band_rows(a, k, j, g0, g1);
+        const int n_rows = (int)(g1 - g0);
+        const int64_t out_row0 = g0 - a.locus_first;
+        const int64_t c0 = (int64_t)s * seg_cells;                            // first cell column of the segment
+        const int n_cell = (int)min((int64_t)seg_cells, n_cols - c0);         // a multiple of P
+        const int n_ind = n_cell / P;
+        const uint8_t* pu = a.plan + (int64_t)u * a.plan_stride;
+        const uint32_t n_ev = *reinterpret_cast<const uint32_t*>(pu);
+        if (n_ev > (uint32_t)a.cap) {   // sparse map: searched per cell afterwards (k_emit_generic)
+            if (tid == 0) a.overflow[1 + atomicAdd(a.overflow, 1)] = u;
+            continue;
+        }
+        // the bulk engine must be done reading the previous unit's rows out of shared memory
+        if (tid == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+        __syncthreads();
+
+        // ---- start state of the band, run starts bucketed by row
+        for (int i = tid * 16; i < seg_cells; i += ROWS_THREADS * 16)
+            *reinterpret_cast<uint4*>(img0 + i) = __ldg(reinterpret_cast<const uint4*>(pu + 16 + i));
+        for (int i = tid; i <= n_rows; i += ROWS_THREADS) start[i] = 0;
+        __syncthreads();
+        const uint32_t* ev_g = reinterpret_cast<const uint32_t*>(pu + 16 + seg_cells);
+        for (uint32_t e = tid; e < n_ev; e += ROWS_THREADS) atomicAdd(&start[__ldg(ev_g + e) >> 24], 1u);
+        __syncthreads();
+        if (tid < 32) {   // exclusive scan of the row histogram (<= 256 bins) by one warp
+            uint32_t carry = 0;
+            for (int base = 0; base <= n_rows; base += 32) {
+                const int i = base + tid;
+                const uint32_t v = i <= n_rows ? start[i] : 0;
+                uint32_t x = v;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) { const uint32_t y = __shfl_up_sync(0xFFFFFFFFu, x, o); if (tid >= o) x += y; }
+                if (i <= n_rows) { start[i] = carry + x - v; cursor[i] = carry + x - v; }
+                carry += __shfl_sync(0xFFFFFFFFu, x, 31);
+            }
+        }
+        __syncthreads();
+        for (uint32_t e = tid; e < n_ev; e += ROWS_THREADS) {
+            const uint32_t w = __ldg(ev_g + e);
+            evs[atomicAdd(&cursor[w >> 24], 1u)] = w;
+        }
+        if (DK >= 2) {   // 4-bit image: low 3 bits of every cell, the PRMT selectors of the dose lookup
+            for (int i = tid; i < seg_cells / 16; i += ROWS_THREADS) {
+                const uint4 v = reinterpret_cast<const uint4*>(img0)[i];
+                auto pack = [](uint32_t x) { return (x & 0x7) | ((x >> 4) & 0x70) | ((x >> 8) & 0x700) | ((x >> 12) & 0x7000); };
+                reinterpret_cast<uint2*>(nib)[i] = make_uint2(pack(v.x) | (pack(v.y) << 16), pack(v.z) | (pack(v.w) << 16));
+            }
+        }
+        if (DK == 1) {   // dose of one founder allele on the band's first row
+            for (int i = tid; i < seg_ind; i += ROWS_THREADS) {
+                int dsum = 0;
+                for (int h = 0; h < P; h++) dsum += img0[i * P + h] == (uint8_t)a.dose_which;
+                dose0[i] = (uint8_t)(count_ok ? dsum : 0);
+            }
+        }
+        uint4 Tn = make_uint4(0, 0, 0, 0);
+        if (DK >= 2) Tn = __ldg(a.mtab + g0);
+        __syncthreads();
+        // the other buffers start from the same state (they become rows 1 .. NB-1)
+        for (int b = 1; b < NB; b++) {
+            for (int i = tid; i < seg_cells / 16; i += ROWS_THREADS)
+                reinterpret_cast<uint4*>(img0 + (size_t)b * seg_cells)[i] = reinterpret_cast<const uint4*>(img0)[i];
+            if (DK == 1)
+                for (int i = tid; i < seg_ind / 16; i += ROWS_THREADS)
+                    reinterpret_cast<uint4*>(dose0 + (size_t)b * seg_ind)[i] = reinterpret_cast<const uint4*>(dose0)[i];
+        }
+
+        // ---- the rows. Buffer r % NB holds row r-NB when row r begins: it takes the run starts of rows r-NB+1 .. r.
+        auto patch = [&](uint8_t* img, uint8_t* drow, uint32_t e0, uint32_t e1) {
+            for (uint32_t e = e0 + tid; e < e1; e += ROWS_THREADS) {
+                const uint32_t w = evs[e], cs = (w >> 8) & 0xFFFF, f = w & 0xFF;
+                if (DK == 1) {
+                    const int delta = (int)(f == (uint32_t)a.dose_which) - (int)(count_ok && img[cs] == (uint8_t)a.dose_which);
+                    const uint32_t ind = cs / P;
+                    if (delta) atomicAdd(reinterpret_cast<uint32_t*>(drow) + (ind >> 2), (uint32_t)delta << (8 * (ind & 3)));
+                }
+                img[cs] = (uint8_t)f;
+            }
+        };
+        for (int r = 0; r < n_rows; r++) {
+            const uint32_t e0 = start[r], e1 = start[r + 1];   // this row's run starts (row 0 has none: they are the state)
+            uint8_t* const img = img0 + (size_t)(r % NB) * seg_cells;
+            uint8_t* const drow = dose0 + (size_t)(r % NB) * seg_ind;
+            // buffers of row r were last read by the bulk stores of row r-NB
+            if (r >= NB && tid == 0) asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(NB - 1) : "memory");
+            if (DK >= 2) {
+                for (uint32_t e = e0 + tid; e < e1; e += ROWS_THREADS) {
+                    const uint32_t w = evs[e], cs = (w >> 8) & 0xFFFF, sh = (cs & 7) * 4;
+                    atomicAnd(&nib[cs >> 3], ~(0xFu << sh));
+                    atomicOr(&nib[cs >> 3], (w & 7) << sh);
+                }
+            }
+            __syncthreads();
+            // catch up with the rows this buffer missed, oldest first (a cell may change on two of them)
+            for (int m = NB - 1; m >= 1; m--) {
+                if (r - m >= 1) patch(img, drow, start[r - m], start[r - m + 1]);
+                if (m > 1) __syncthreads();
+            }
+            if (DK >= 2) {
+                const uint4 T = Tn;
+                if (r + 1 < n_rows) Tn = __ldg(a.mtab + g0 + r + 1);
+                if (DK == 2) {   // 8 individuals per step: 4 words of the 4-bit image in, 8 dose bytes out
+                    for (int i = tid; i < seg_ind / 8; i += ROWS_THREADS) {
+                        const uint4 v = reinterpret_cast<const uint4*>(nib)[i];
+                        auto two = [&](uint32_t w) { return __dp4a(prmt(T.x, T.y, w) + prmt(T.z, T.w, w >> 16), 0x01010101u, 0u); };
+                        const uint32_t lo = two(v.x) | (two(v.y) << 8), hi = two(v.z) | (two(v.w) << 8);   // dose nibbles
+                        reinterpret_cast<uint2*>(drow)[i] = make_uint2(prmt(0x03020100u, 0x07060504u, lo), prmt(0x03020100u, 0x07060504u, hi));
+                    }
+                } else {         // ploidy 2: 16 individuals per step
+                    for (int i = tid; i < seg_ind / 16; i += ROWS_THREADS) {
+                        const uint4 v = reinterpret_cast<const uint4*>(nib)[i];
+                        auto four = [&](uint32_t w) {
+                            const uint32_t xl = prmt(T.x, T.y, w), xh = prmt(T.x, T.y, w >> 16);
+                            return prmt(xl + (xl >> 8), xh + (xh >> 8), 0x6420u);
+                        };
+                        reinterpret_cast<uint4*>(drow)[i] = make_uint4(four(v.x), four(v.y), four(v.z), four(v.w));
+                    }
+                }
+            }
+            __syncthreads();
+            patch(img, drow, e0, e1);
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            __syncthreads();
+            uint8_t* const gf = a.founder ? a.founder + (out_row0 + r) * a.founder_pitch + c0 : nullptr;
+            uint8_t* const gd = a.dose ? a.dose + (out_row0 + r) * a.dose_pitch + c0 / P : nullptr;
+            if (tid == 0) {
+                if (gf && (n_cell & ~15)) bulk_store(gf, img, (uint32_t)(n_cell & ~15));
+                if (DK >= 1 && gd && (n_ind & ~15)) bulk_store(gd, drow, (uint32_t)(n_ind & ~15));
+                asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+            }
+            // ragged ends (a bulk store moves multiples of 16 bytes)
+            if (gf && tid < (n_cell & 15)) gf[(n_cell & ~15) + tid] = img[(n_cell & ~15) + tid];
+            if (DK >= 1 && gd && tid >= 32 && tid - 32 < (n_ind & 15)) gd[(n_ind & ~15) + tid - 32] = drow[(n_ind & ~15) + tid - 32];
+        }
+    }
+    if (tid == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+}
+

@@ -1,0 +1,53 @@
+// K0 — breakpoints to locus-index runs
+// (part of libpsim: included by psim.cu inside namespace psim)
+#pragma once
+
+// ------------------------------------------------------------------------------------------
+// K0 — breakpoints (fp64 Morgan) -> runs in locus-index space, so that emission is integer-only.
+// Locus l belongs to the last segment s with pos[s] <= locus position (HaploStruct.findSegment
+// :107-112, segment 0 catches everything below); with lb[s] = #loci strictly left of pos[s] that is
+// "last s with lb[s] <= l" (ties: a locus exactly on a breakpoint belongs to the segment starting
+// there). A suffix minimum makes lb monotone without changing that answer, empty runs are
+// dropped and neighbours with the same founder merged.
+__global__ void __launch_bounds__(128) k_index_runs(int64_t n_hom, int64_t hom_per_chrom, const uint64_t* __restrict__ desc,
+                                                    const double* __restrict__ seg_pos, const int32_t* __restrict__ seg_founder,
+                                                    const int64_t* __restrict__ locus_off, const double* __restrict__ locus_pos,
+                                                    uint64_t* __restrict__ run_desc, uint32_t* __restrict__ run_lb,
+                                                    uint16_t* __restrict__ run_founder) {
+    const int64_t hid = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (hid >= n_hom) return;
+    const uint64_t d = desc[hid];
+    const int64_t b = (int64_t)desc_begin(d);
+    const int n = (int)desc_count(d);
+    if (n == 0) { run_desc[hid] = 0; return; }
+    const int c = (int)(hid / hom_per_chrom);
+    const double* lp = locus_pos + locus_off[c];
+    const uint32_t Lc = (uint32_t)(locus_off[c + 1] - locus_off[c]);
+    // pass 1: lb[s]
+    for (int s = 0; s < n; s++) {
+        uint32_t lo = 0;
+        if (s > 0) {
+            const double p = seg_pos[b + s];
+            uint32_t hi = Lc;
+            while (lo < hi) { const uint32_t mid = (lo + hi) >> 1; if (lp[mid] < p) lo = mid + 1; else hi = mid; }
+        }
+        run_lb[b + s] = lo;
+    }
+    // pass 2: suffix minimum
+    uint32_t mn = Lc;
+    for (int s = n - 1; s >= 0; s--) { const uint32_t v = run_lb[b + s]; mn = v < mn ? v : mn; run_lb[b + s] = mn; }
+    // pass 3: compact in place
+    int w = 0;
+    for (int s = 0; s < n; s++) {
+        const uint32_t start = run_lb[b + s];
+        const uint32_t end = s + 1 < n ? run_lb[b + s + 1] : Lc;
+        if (start >= end) continue;
+        const uint16_t f = (uint16_t)seg_founder[b + s];
+        if (w > 0 && run_founder[b + w - 1] == f) continue;
+        run_lb[b + w] = start;
+        run_founder[b + w] = f;
+        w++;
+    }
+    run_desc[hid] = make_desc((uint64_t)b, (uint64_t)w);
+}
+
