@@ -697,11 +697,20 @@ static int simulate_impl(psim_ctx_impl* c, int32_t max_founder_allele, const int
             pa.task_quad = pa.task_bi + cap_bi;
             CUDA_TRY(cudaMemsetAsync(pa.task_count, 0, 16, c->stream));
             k_meiosis_config<<<grid_for(n_half, 128), 128, 0, c->stream>>>(pa);
-            k_meiosis_mv<false><<<grid_for(cap_bi, 128), 128, 0, c->stream>>>(pa);
-            c->stats.kernel_launches += 2;
-            if (cap_quad > 0) {
-                k_meiosis_mv<true><<<grid_for(cap_quad, 128), 128, 0, c->stream>>>(pa);
+            auto launch_mv = [&](auto kos, auto anr) {
+                constexpr bool KOS = decltype(kos)::value, ANR = decltype(anr)::value;
+                k_meiosis_mv<false, KOS, ANR><<<grid_for(cap_bi, 128), 128, 0, c->stream>>>(pa);
                 c->stats.kernel_launches++;
+                if (cap_quad > 0) {
+                    k_meiosis_mv<true, KOS, ANR><<<grid_for(cap_quad, 128), 128, 0, c->stream>>>(pa);
+                    c->stats.kernel_launches++;
+                }
+            };
+            c->stats.kernel_launches++;
+            if (c->model.chiasma_interference) {
+                if (c->model.allow_no_recomb) launch_mv(std::true_type{}, std::true_type{}); else launch_mv(std::true_type{}, std::false_type{});
+            } else {
+                if (c->model.allow_no_recomb) launch_mv(std::false_type{}, std::true_type{}); else launch_mv(std::false_type{}, std::false_type{});
             }
             CUDA_TRY(cudaGetLastError());
             CUDA_TRY(cudaMemsetAsync(plan_cnt + nu, 0, sizeof(int64_t), c->stream));

@@ -117,7 +117,10 @@ __global__ void __launch_bounds__(128) k_meiosis_config(PlanArgs a) {
     for (int v = 0; v < n_bi; v++) a.task_bi[base_b + v] = t * 8 + n_quad + v;
 }
 
-template <bool QUAD>
+// KOS / ANR: MAPFUNCTION=KOSAMBI and ALLOWNORECOMBINATION as compile-time constants, so that the code
+// of the other model (gamma sampler, pow, retry loop) is not in the kernel at all: the kernels are
+// instruction-cache bound (ncu: 3.2 'no instruction' stall cycles per issue with everything inlined).
+template <bool QUAD, bool KOS, bool ANR>
 __global__ void __launch_bounds__(128) k_meiosis_mv(PlanArgs a) {
     const int64_t ti = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (ti >= (int64_t)a.task_count[QUAD ? 1 : 0]) return;
@@ -129,7 +132,9 @@ __global__ void __launch_bounds__(128) k_meiosis_mv(PlanArgs a) {
     const int32_t child = a.lev_ind[j];
     const int32_t parent = par == 0 ? a.par0[child] : a.par1[child];
     const ChromParams ch = a.chrom[c];
-    const ModelParams& m = a.model;
+    ModelParams m = a.model;
+    m.chiasma_interference = KOS;
+    m.allow_no_recomb = ANR;
     const int64_t phid0 = (((int64_t)c * a.R + r) * a.N + parent) * P;
     const int64_t q = (((int64_t)r * a.N + child) * a.C + c) * 2 + par;
     const int quad = a.cfg_quad[q];
