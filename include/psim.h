@@ -205,6 +205,13 @@ typedef struct psim_gamete_stats {
 } psim_gamete_stats;
 int psim_gamete_stats_run(psim_ctx* ctx, int64_t ind_first, int64_t ind_count, int32_t chrom, psim_gamete_stats* out);
 
+/* _allAlleledose.dat as text (Main.writeAllAlleledoseFile, Main.java:1037-1088): per locus one line
+ * per allele,  <locus name> '\t' <allele> { '\t' <dose> } '\n',  the allele being the founder allele
+ * number (no allele codes set) or the locus' k-th sorted unique allele name. Host buffer; *bytes
+ * receives the length (the bytes needed when the call fails with PSIM_ECAPACITY). */
+int psim_emit_all_dose_text(psim_ctx* ctx, int64_t ind_first, int64_t ind_count, int64_t locus_first, int64_t locus_count,
+                            char* text, int64_t capacity, int64_t* bytes);
+
 /* Drop every haplostruct and meiotic configuration (pedigree, chromosomes, map and allele codes
  * stay resident) and give the context a new RNG identity: the next psim_simulate is an
  * independent draw. Used by Monte Carlo drivers that re-simulate the same pedigree. */

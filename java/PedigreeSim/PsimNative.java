@@ -67,6 +67,8 @@ final class PsimNative implements AutoCloseable {
     // TEST-mode counters on the device: int psim_gamete_stats_run(ctx, ind_first, ind_count, chrom, psim_gamete_stats*)
     private static final MethodHandle GAMETE_STATS = fn("psim_gamete_stats_run",
             FunctionDescriptor.of(JAVA_INT, ADDRESS, JAVA_LONG, JAVA_LONG, JAVA_INT, ADDRESS));
+    private static final MethodHandle EMIT_ALL_DOSE_TEXT = fn("psim_emit_all_dose_text",
+            FunctionDescriptor.of(JAVA_INT, ADDRESS, JAVA_LONG, JAVA_LONG, JAVA_LONG, JAVA_LONG, ADDRESS, JAVA_LONG, ADDRESS));
     // page-locked target tables: int psim_alloc_host(psim_ctx*, size_t, void**), int psim_free_host(psim_ctx*, void*)
     private static final MethodHandle ALLOC_HOST = fn("psim_alloc_host", FunctionDescriptor.of(JAVA_INT, ADDRESS, JAVA_LONG, ADDRESS));
     private static final MethodHandle FREE_HOST = fn("psim_free_host", FunctionDescriptor.of(JAVA_INT, ADDRESS, ADDRESS));

@@ -71,7 +71,7 @@ EXPORTS = [
     "psim_set_map", "psim_set_allele_codes", "psim_emit", "psim_all_dose_rows", "psim_emit_all_dose", "psim_get_stats",
     "psim_export_haplostructs_device", "psim_import_haplostructs_device", "psim_reset", "psim_set_stream", "psim_simulate_subset",
     "psim_alloc_host", "psim_free_host", "psim_set_locus_names", "psim_set_allele_names", "psim_emit_text",
-    "psim_gamete_stats_run",
+    "psim_gamete_stats_run", "psim_emit_all_dose_text",
 ]
 
 _lib = None
@@ -112,6 +112,7 @@ def load():
     L.psim_set_allele_names.argtypes = [vp, vp, vp, vp]
     L.psim_emit_text.argtypes = [vp, i64, i64, i64, i64, C.POINTER(TextTargets)]
     L.psim_gamete_stats_run.argtypes = [vp, i64, i64, i32, C.POINTER(GameteStats)]
+    L.psim_emit_all_dose_text.argtypes = [vp, i64, i64, i64, i64, vp, i64, C.POINTER(i64)]
     L.psim_alloc_host.argtypes = [vp, C.c_size_t, C.POINTER(vp)]
     L.psim_free_host.argtypes = [vp, vp]
     L.psim_get_stats.argtypes = [vp, C.POINTER(Stats)]
@@ -314,6 +315,16 @@ class PsimContext:
                 setattr(t, name + "_capacity", cap)
         self._chk(self.L.psim_emit_text(self.h, ind_first, ind_count, loc_first, loc_count, C.byref(t)))
         return {k: bytes(v[:getattr(t, k + "_bytes")]) for k, v in bufs.items()}
+
+    def emit_all_dose_text(self, ind_first=0, ind_count=None, loc_first=0, loc_count=None, capacity=None):
+        ind_count = self.N - ind_first if ind_count is None else ind_count
+        loc_count = self.Ltot - loc_first if loc_count is None else loc_count
+        rows = int(self.all_dose_rows(loc_first, loc_count)[-1])
+        cap = capacity if capacity is not None else rows * (self.R * ind_count * 3 + 4096)
+        buf = np.zeros(cap, dtype=np.uint8)
+        n = C.c_int64()
+        self._chk(self.L.psim_emit_all_dose_text(self.h, ind_first, ind_count, loc_first, loc_count, _p(buf), cap, C.byref(n)))
+        return bytes(buf[:n.value])
 
     def gamete_stats(self, chrom, n_loci, n_alleles, ind_first=0, ind_count=None, recomb=True):
         """TEST-mode counters of one chromosome over the gametes of the given individuals (dict of arrays)."""

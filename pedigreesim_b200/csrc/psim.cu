@@ -1445,6 +1445,91 @@ int psim_emit_all_dose(psim_ctx* ctx, int64_t ind_first, int64_t ind_count, int6
     return PSIM_OK;
 }
 
+int psim_emit_all_dose_text(psim_ctx* ctx, int64_t ind_first, int64_t ind_count, int64_t locus_first, int64_t locus_count,
+                            char* text, int64_t capacity, int64_t* bytes) {
+    psim_ctx_impl* c = CTX;
+    if (!c || !text || !bytes) return PSIM_EINVAL;
+    cudaSetDevice(c->cfg.device);
+    *bytes = 0;
+    if (int rc = emit_prepare(c, ind_first, ind_count, locus_first, locus_count)) return rc;
+    if (!c->label_off_d) return fail(c, PSIM_ESTATE, "psim_set_locus_names must be called first");
+    if (c->code_d && !c->code_off_d) return fail(c, PSIM_ESTATE, "allele codes are set but no allele names");
+    const int64_t n_cols_ind = (int64_t)c->R * ind_count;
+    std::vector<int64_t> row_off(locus_count + 1);
+    if (int rc = psim_all_dose_rows(ctx, locus_first, locus_count, row_off.data())) return rc;
+    int64_t* row_off_d = nullptr;
+    CUDA_TRY(dev_alloc(&row_off_d, (size_t)locus_count + 1));
+    CUDA_TRY(cudaMemcpyAsync(row_off_d, row_off.data(), (locus_count + 1) * sizeof(int64_t), cudaMemcpyHostToDevice, c->stream));
+    AllDoseArgs aa{};
+    aa.C = c->C; aa.R = c->R; aa.P = c->P; aa.N = c->N;
+    aa.run_desc = c->run_desc_d; aa.run_lb = c->run_lb_d; aa.run_founder = c->run_founder_d; aa.locus_off = c->locus_off_d;
+    aa.ind_first = ind_first; aa.ind_count = ind_count; aa.n_cols_ind = n_cols_ind;
+    aa.code = c->code_d; aa.A = c->A;
+    const int64_t sp = (n_cols_ind + 255) / 256 * 256;
+    bool too_small = false;
+    int rc_out = PSIM_OK;
+    int64_t k0 = 0;
+    while (k0 < locus_count && rc_out == PSIM_OK) {
+        int64_t k1 = k0 + 1;
+        while (k1 < locus_count && (row_off[k1 + 1] - row_off[k0]) * sp <= (256LL << 20)) k1++;
+        const int64_t nrows = row_off[k1] - row_off[k0];
+        if ((rc_out = ensure_staging(c, (size_t)(nrows * sp)))) break;
+        aa.l_begin = locus_first + k0; aa.l_count = k1 - k0; aa.row_off = row_off_d + k0; aa.row_first = row_off[k0];
+        aa.out = (uint8_t*)c->staging; aa.pitch = sp;
+        k_emit_all_dose<<<grid_for(aa.l_count * n_cols_ind, 256), 256, 0, c->stream>>>(aa);
+        c->stats.kernel_launches++;
+        // row -> (locus, allele) for the labels
+        std::vector<int32_t> rl((size_t)nrows * 2);
+        for (int64_t k = k0; k < k1; k++)
+            for (int64_t r = row_off[k]; r < row_off[k + 1]; r++) {
+                rl[(size_t)(r - row_off[k0])] = (int32_t)(k - k0);
+                rl[(size_t)(nrows + r - row_off[k0])] = (int32_t)(r - row_off[k]);
+            }
+        if ((rc_out = ensure_buf(c, c->b_rowlen, ((size_t)nrows + 1) * sizeof(int64_t)))) break;
+        if ((rc_out = ensure_buf(c, c->b_rowoff, ((size_t)nrows + 1) * sizeof(int64_t) + (size_t)nrows * 8))) break;
+        int32_t* rl_d = (int32_t*)((int64_t*)c->b_rowoff.p + nrows + 1);
+        CUDA_TRY(cudaMemcpyAsync(rl_d, rl.data(), (size_t)nrows * 8, cudaMemcpyHostToDevice, c->stream));
+        TextArgs ta{};
+        ta.cells = (const uint8_t*)c->staging; ta.pitch = sp; ta.cell_bytes = 1;
+        ta.n_cells = n_cols_ind; ta.row0_locus = locus_first + k0; ta.n_rows = (int)nrows;
+        ta.label_off = c->label_off_d; ta.labels = c->labels_d;
+        ta.kind = 0; ta.code_off = c->code_off_d; ta.name_off = c->aname_off_d; ta.names = c->anames_d;
+        ta.row_locus = rl_d; ta.row_sub = rl_d + nrows; ta.sub_kind = c->code_d ? 2 : 1;
+        ta.max_tok = 3;
+        ta.chunk = 8192;
+        const size_t smem = (size_t)ta.chunk * (1 + ta.max_tok) + 16;
+        ta.row_len = (int64_t*)c->b_rowlen.p;
+        const int blocks = (int)std::min<int64_t>(nrows, (int64_t)c->sm_count * 8);
+        cudaFuncSetAttribute(k_text_rows<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaFuncSetAttribute(k_text_rows<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        CUDA_TRY(cudaMemsetAsync(ta.row_len + nrows, 0, sizeof(int64_t), c->stream));
+        k_text_rows<false><<<blocks, TEXT_THREADS, smem, c->stream>>>(ta);
+        c->stats.kernel_launches++;
+        CUDA_TRY(cudaGetLastError());
+        if ((rc_out = exclusive_scan_i64(c, (int64_t*)c->b_rowlen.p, (int64_t*)c->b_rowoff.p, nrows + 1))) break;
+        int64_t total = 0;
+        CUDA_TRY(cudaMemcpyAsync(&total, (int64_t*)c->b_rowoff.p + nrows, sizeof(int64_t), cudaMemcpyDeviceToHost, c->stream));
+        CUDA_TRY(cudaStreamSynchronize(c->stream));   // also: rl (host vector) has been read
+        if (*bytes + total > capacity) too_small = true;
+        if (!too_small) {
+            if ((rc_out = ensure_buf(c, c->b_text, (size_t)total))) break;
+            ta.row_off = (int64_t*)c->b_rowoff.p;
+            ta.text = (char*)c->b_text.p;
+            k_text_rows<true><<<blocks, TEXT_THREADS, smem, c->stream>>>(ta);
+            c->stats.kernel_launches++;
+            CUDA_TRY(cudaGetLastError());
+            CUDA_TRY(cudaMemcpyAsync(text + *bytes, c->b_text.p, (size_t)total, cudaMemcpyDeviceToHost, c->stream));
+            CUDA_TRY(cudaStreamSynchronize(c->stream));
+        }
+        *bytes += total;
+        k0 = k1;
+    }
+    cudaFree(row_off_d);
+    if (rc_out != PSIM_OK) return rc_out;
+    if (too_small) return fail(c, PSIM_ECAPACITY, "the text buffer is too small (the bytes needed are in *bytes)");
+    return PSIM_OK;
+}
+
 int psim_reset(psim_ctx* ctx, int64_t seed, uint32_t replicate_first) {
     psim_ctx_impl* c = CTX;
     if (!c) return PSIM_EINVAL;

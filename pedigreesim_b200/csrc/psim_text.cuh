@@ -25,6 +25,10 @@ struct TextArgs {
     const char* names;
     int max_tok;                   // longest token including its tab
     int chunk;                     // cells per chunk, a multiple of TEXT_THREADS
+    // _allAlleledose rows: several rows per locus, labelled "name TAB allele"
+    const int32_t* row_locus;      // [n_rows] locus of the row relative to row0_locus (null: row r is locus row0_locus + r)
+    const int32_t* row_sub;        // [n_rows] which allele of the locus the row counts
+    int sub_kind;                  // 0 none, 1 the founder allele number, 2 the locus' allele name number row_sub
     int64_t* row_len;              // pass 1 out [n_rows]
     const int64_t* row_off;        // pass 2 in  [n_rows+1]
     char* text;                    // pass 2 out
@@ -40,13 +44,33 @@ __global__ void __launch_bounds__(TEXT_THREADS) k_text_rows(const TextArgs a) {
     char* const s_text = reinterpret_cast<char*>(smem + (size_t)a.chunk * a.cell_bytes);   // chunk * max_tok (pass 2)
     const int cpt = a.chunk / TEXT_THREADS;
     for (int r = blockIdx.x; r < a.n_rows; r += gridDim.x) {
-        const int64_t gl = a.row0_locus + r;
+        const int64_t gl = a.row0_locus + (a.row_locus ? a.row_locus[r] : r);
         const uint8_t* row = a.cells + (int64_t)r * a.pitch;
         const int64_t lab0 = a.label_off[gl];
-        const int lab_n = (int)(a.label_off[gl + 1] - lab0);
+        int lab_n = (int)(a.label_off[gl + 1] - lab0);
         char* out = WRITE ? a.text + a.row_off[r] : nullptr;
         if (WRITE)
             for (int i = tid; i < lab_n; i += TEXT_THREADS) out[i] = a.labels[lab0 + i];
+        if (a.sub_kind) {   // "TAB allele" after the locus name
+            const uint32_t sub = (uint32_t)a.row_sub[r];
+            if (a.sub_kind == 1) {
+                const int nd = sub < 10 ? 1 : sub < 100 ? 2 : sub < 1000 ? 3 : sub < 10000 ? 4 : 5;
+                if (WRITE && tid == 0) {
+                    out[lab_n] = '\t';
+                    uint32_t v = sub;
+                    for (int k = nd - 1; k >= 0; k--) { out[lab_n + 1 + k] = (char)('0' + v % 10); v /= 10; }
+                }
+                lab_n += 1 + nd;
+            } else {
+                const int64_t nb = a.code_off[gl] + sub;
+                const int nl = (int)(a.name_off[nb + 1] - a.name_off[nb]);
+                if (WRITE) {
+                    if (tid == 0) out[lab_n] = '\t';
+                    for (int i = tid; i < nl; i += TEXT_THREADS) out[lab_n + 1 + i] = a.names[a.name_off[nb] + i];
+                }
+                lab_n += 1 + nl;
+            }
+        }
         int64_t base = 0;   // first name of the locus
         if (a.kind == 1) {
             base = a.code_off[gl];

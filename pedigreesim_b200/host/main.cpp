@@ -512,36 +512,30 @@ int run(const Options& opt) {
         }
 
         if (all_dose) {
-            // rows per locus: founder alleles 0..A-1, or the locus' unique allele names in sorted order
+            // rows per locus: founder alleles 0..A-1, or the locus' unique allele names in sorted order;
+            // also formatted on the device (psim_emit_all_dose_text), same writer-thread pipeline
             const int64_t max_rows_per_locus = founder_genotypes ? mp.max_allele_count : A;
-            const int64_t loci_blk =
-                std::max<int64_t>(1, std::min<int64_t>(L, opt.block_bytes / std::max<int64_t>(1, max_rows_per_locus * N)));
-            void* b_all = nullptr;
-            lib.chk(psim_alloc_host(lib.ctx, (size_t)(loci_blk * max_rows_per_locus * N), &b_all));
-            std::vector<int64_t> row_off((size_t)loci_blk + 1);
-            std::vector<int64_t> locus_of_row;
-            for (int64_t l0 = 0; l0 < L; l0 += loci_blk) {
-                const int64_t nl = std::min(loci_blk, L - l0);
-                lib.chk(psim_all_dose_rows(lib.ctx, l0, nl, row_off.data()));
-                lib.chk(psim_emit_all_dose(lib.ctx, 0, N, l0, nl, b_all, N, PSIM_MEM_HOST));
-                const int64_t rows = row_off[(size_t)nl];
-                locus_of_row.resize((size_t)rows);
-                for (int64_t k = 0; k < nl; k++)
-                    for (int64_t r = row_off[(size_t)k]; r < row_off[(size_t)k + 1]; r++) locus_of_row[(size_t)r] = k;
-                append_rows(
-                    *f_all, rows,
-                    [&](int64_t r, std::string& o) {
-                        int64_t k = locus_of_row[(size_t)r], a = r - row_off[(size_t)k];
-                        o += *mp.flat_name[(size_t)(l0 + k)];
-                        o.push_back('\t');
-                        if (founder_genotypes)
-                            o += mp.unique_names[(size_t)(l0 + k)][(size_t)a];
-                        else
-                            o += std::to_string(a);
-                    },
-                    [&](int64_t r, std::string& o) { format_u8_row((const uint8_t*)b_all + r * N, N, o); });
+            const int64_t sub_max = founder_genotypes ? name_max : digits(std::max(0, A - 1));
+            const int64_t line_all = label_max + 1 + sub_max + N * (1 + digits(P)) + 1;
+            const int64_t loci_blk = std::max<int64_t>(1, std::min<int64_t>(L, opt.block_bytes / (max_rows_per_locus * line_all)));
+            void* buf[2] = {nullptr, nullptr};
+            int64_t bytes[2] = {0, 0};
+            for (void*& b2 : buf) lib.chk(psim_alloc_host(lib.ctx, (size_t)(loci_blk * max_rows_per_locus * line_all), &b2));
+            std::thread wr;
+            int cur2 = 0;
+            try {
+                for (int64_t l0 = 0; l0 < L; l0 += loci_blk, cur2 ^= 1) {
+                    const int64_t nl = std::min(loci_blk, L - l0);
+                    lib.chk(psim_emit_all_dose_text(lib.ctx, 0, N, l0, nl, (char*)buf[cur2], loci_blk * max_rows_per_locus * line_all, &bytes[cur2]));
+                    if (wr.joinable()) wr.join();
+                    wr = std::thread([&, cur2] { f_all->write((const char*)buf[cur2], (size_t)bytes[cur2]); });
+                }
+            } catch (...) {
+                if (wr.joinable()) wr.join();
+                throw;
             }
-            psim_free_host(lib.ctx, b_all);
+            if (wr.joinable()) wr.join();
+            for (void* b2 : buf) psim_free_host(lib.ctx, b2);
         }
     } catch (const HostError& ex) {
         say(std::string("Error writing files: ") + ex.what());

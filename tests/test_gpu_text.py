@@ -92,3 +92,21 @@ def test_names_are_required():
     g2 = ps.PsimContext(2)
     with pytest.raises(ps.PsimError):
         g2.emit_text(founder=True)
+
+
+@pytest.mark.parametrize("ploidy,n_ind,loci,n_alleles,codes", [(4, 80, [30, 12], 8, 3), (2, 150, [40], 14, 0), (6, 33, [21], 12, 0)])
+def test_all_dose_text_matches_binary_rows(ploidy, n_ind, loci, n_alleles, codes):
+    g, names, allele_names = make_ctx(ploidy, n_ind, loci, n_alleles, codes, seed=n_ind)
+    ro, rows = g.emit_all_dose()
+    expect = b""
+    for l in range(sum(loci)):
+        for k in range(int(ro[l + 1] - ro[l])):
+            sub = allele_names[l][k] if codes else str(k)
+            expect += names[l].encode() + b"\t" + sub.encode() + b"".join(b"\t" + str(int(v)).encode() for v in rows[ro[l] + k]) + b"\n"
+    assert g.emit_all_dose_text() == expect
+    l0, nl, i0, ni = 4, sum(loci) - 6, 2, n_ind - 5
+    sub_ro, sub_rows = g.emit_all_dose(ind_first=i0, ind_count=ni, loc_first=l0, loc_count=nl)
+    got = g.emit_all_dose_text(ind_first=i0, ind_count=ni, loc_first=l0, loc_count=nl)
+    assert got.count(b"\n") == sub_rows.shape[0]
+    first = got.split(b"\n")[0].split(b"\t")
+    assert first[0] == names[l0].encode() and [int(x) for x in first[2:]] == sub_rows[0].tolist()
