@@ -203,3 +203,33 @@ def test_overflowing_units_are_redone_per_cell(monkeypatch):
         got = g.emit(founder=True, dose=True, dose_which=which)
         assert np.array_equal(got["founder"], o.emit(_oracle.EMIT_FOUNDER))
         assert np.array_equal(got["dose"], o.emit(_oracle.EMIT_DOSE, which=which))
+
+
+def test_more_than_64_chromosomes_and_replicates():
+    """Launch arguments hold 64 chromosome pieces: more chromosomes go out in several launches.
+    Three replicate populations side by side widen the rows (columns are replicate-major)."""
+    import pedigreesim_b200 as ps
+    C, P, n = 70, 4, 300
+    lengths = [0.5 + 0.01 * c for c in range(C)]
+    loci = [3 + c % 5 for c in range(C)]
+    off, pos = _cases.uniform_map(lengths, loci)
+    p0, p1 = _cases.std_pedigree("F1", n)
+    g = ps.PsimContext(P, seed=5, replicate_first=7, replicate_count=3)
+    g.set_chromosomes(lengths, [0.4 * x for x in lengths], [0.2] * C, [0.3] * C)
+    g.set_pedigree(p0, p1)
+    g.simulate()
+    g.set_map(off, pos)
+    got = g.emit(founder=True, dose=True, dose_which=5)
+    N = len(p0)
+    assert got["founder"].shape == (sum(loci), 3 * N * P)
+    for r in range(3):
+        o = _oracle.Oracle(P, rng=_oracle.RNG_PHILOX, seed=5, replicate=7 + r)
+        o.set_chromosomes(lengths, [0.4 * x for x in lengths], [0.2] * C, [0.3] * C)
+        o.set_pedigree(p0, p1)
+        o.simulate()
+        o.set_map(off, pos)
+        assert np.array_equal(got["founder"][:, r * N * P:(r + 1) * N * P], o.emit(_oracle.EMIT_FOUNDER))
+        assert np.array_equal(got["dose"][:, r * N:(r + 1) * N], o.emit(_oracle.EMIT_DOSE, which=5))
+    g.set_locus_names(["L%d" % l for l in range(sum(loci))])
+    text = g.emit_text(founder=True)["founder"].split(b"\n")
+    assert text[10].split(b"\t")[1:] == [str(int(v)).encode() for v in got["founder"][10]]
