@@ -23,6 +23,8 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <ctime>
+#include <numeric>
 #include <string>
 #include <type_traits>
 #include <vector>
@@ -64,7 +66,7 @@ struct psim_ctx_impl {
     std::string err;
     int C = 0, P = 0, R = 1;
     int64_t N = 0;
-    cudaStream_t stream = nullptr, own_stream = nullptr, copy_stream = nullptr;
+    cudaStream_t stream = nullptr, own_stream = nullptr, copy_stream = nullptr, aux_stream = nullptr;   // aux: second compute stream of psim_simulate
     cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev2 = nullptr, ev3 = nullptr;
     std::vector<cudaEvent_t> kev;   // event pool: triples (before plan, before stream, after stream) per launch
     int kev_used = 0;
@@ -112,6 +114,11 @@ struct psim_ctx_impl {
     // scratch
     int* error_flag_d = nullptr;
     int* tile_counter_d = nullptr;
+    // Page-locked and mapped: [0] segment total of a batch, [1] error flag, [2] overflowed emission
+    // units. Written by k_publish (a store over PCIe), not by a D2H memcpy: a small copy queues
+    // behind whatever large transfer occupies the device-to-host copy engine.
+    int64_t* scalars_h = nullptr;
+    int64_t* scalars_dev = nullptr;   // the same memory as the device sees it
     void* cub_tmp = nullptr;
     size_t cub_tmp_bytes = 0;
     void* staging = nullptr;
@@ -123,6 +130,7 @@ struct psim_ctx_impl {
     // export buffers
     int64_t* exp_off_d = nullptr; int32_t* exp_founder_d = nullptr; double* exp_pos_d = nullptr;
     int64_t exp_off_cap = 0, exp_seg_cap = 0;
+    int64_t pop_cap_ind = 0, pop_cap_hom = 0, pop_cap_cfg = 0;   // what the population arrays can hold
     psim_stats stats{};
     int sm_count = 148;
 };
@@ -210,6 +218,7 @@ void free_population(psim_ctx_impl* c) {
     cudaFree(c->run_desc_d); cudaFree(c->cfg_quad_d); cudaFree(c->cfg_seq_d);
     c->par0_d = c->par1_d = nullptr; c->desc_d = nullptr; c->run_desc_d = nullptr;
     c->cfg_quad_d = c->cfg_seq_d = nullptr;
+    c->pop_cap_ind = c->pop_cap_hom = c->pop_cap_cfg = 0;
     c->slab_used = 0;
     c->runs_valid = false;
 }
@@ -237,9 +246,9 @@ void launch_tiles(psim_ctx_impl* c, const EmitArgs& ea, int blocks, int mode) {
 // Row-image emission (k_band_plan + k_emit_rows) of loci [l_begin, l_end). Returns PSIM_OK and sets
 // `done` when the request fits the path; otherwise leaves `done` false for the tiled / generic paths.
 template <int DK>
-static void launch_rows(psim_ctx_impl* c, const RowsArgs& ra, int blocks, size_t smem) {
+static void launch_rows(psim_ctx_impl* c, const RowsArgs& ra, int blocks, int threads, size_t smem) {
     cudaFuncSetAttribute(k_emit_rows<DK>, cudaFuncAttributeMaxDynamicSharedMemorySize, ROWS_SMEM);
-    k_emit_rows<DK><<<blocks, ROWS_THREADS, smem, c->stream>>>(ra);
+    k_emit_rows<DK><<<blocks, threads, smem, c->stream>>>(ra);
 }
 
 static int emit_rows_path(psim_ctx_impl* c, int64_t ind_first, int64_t ind_count, int64_t l_begin, int64_t l_end, int64_t row0_locus,
@@ -251,12 +260,18 @@ static int emit_rows_path(psim_ctx_impl* c, int64_t ind_first, int64_t ind_count
     if (disabled || !(mode == 0 || (mode == 1 && (P == 2 || P == 4)))) return PSIM_OK;
     const int DK = !dose ? 0 : mode == 0 ? 1 : P == 4 ? 2 : 3;
     const int64_t n_cols_ind = (int64_t)c->R * ind_count, n_cols = n_cols_ind * P;
-    const int cap = 8192;
+    // tuning knobs (experiments only): list capacity, threads per block, widest row segment
+    static const int env_cap = getenv("PSIM_ROWS_CAP") ? atoi(getenv("PSIM_ROWS_CAP")) : 0;
+    static const int env_thr = getenv("PSIM_ROWS_THREADS") ? atoi(getenv("PSIM_ROWS_THREADS")) : 0;
+    static const int64_t env_seg = getenv("PSIM_SEG_MAX") ? atoll(getenv("PSIM_SEG_MAX")) : 0;
+    const int cap = env_cap > 0 ? env_cap : 8192;
+    const int threads = env_thr >= 64 && env_thr <= ROWS_THREADS ? env_thr / 32 * 32 : ROWS_THREADS;
     const double per_cell = (double)ROWS_NBUF + (DK >= 2 ? 0.5 : 0.0) + (DK >= 1 ? (double)ROWS_NBUF : 0.0) / P;
     const int64_t budget = ROWS_SMEM - 2 * (ROWS_MAX_BAND + 2) * 4 - cap * 4;
     const int64_t quantum = 16 * P;
     int64_t seg_max = (int64_t)(budget / per_cell) / quantum * quantum;
     seg_max = std::min<int64_t>(seg_max, 65535 / quantum * quantum);
+    if (env_seg > 0) seg_max = std::max<int64_t>(quantum, std::min<int64_t>(seg_max, env_seg / quantum * quantum));
     const int n_seg = (int)((n_cols + seg_max - 1) / seg_max);
     const int64_t seg_cells = ((n_cols + n_seg - 1) / n_seg + quantum - 1) / quantum * quantum;
     // run starts per cell and row, from the resident haplostructs (as in the tiled path)
@@ -348,24 +363,26 @@ static int emit_rows_path(psim_ctx_impl* c, int64_t ind_first, int64_t ind_count
         if (int rc = ensure_buf(c, c->b_dense_list, ((size_t)ra.n_units + 1) * sizeof(int))) return rc;
         ra.plan = (uint8_t*)c->b_plan.p;
         ra.overflow = (int*)c->b_dense_list.p;
-        CUDA_TRY(cudaMemset2DAsync(ra.plan, (size_t)ra.plan_stride, 0, 16, (size_t)ra.n_units, c->stream));   // list counters
-        CUDA_TRY(cudaMemsetAsync(ra.overflow, 0, sizeof(int), c->stream));
-        CUDA_TRY(cudaMemsetAsync(c->tile_counter_d, 0, sizeof(int), c->stream));
+        // list counters, overflow count and ticket: one small kernel (a 2-D memset is a copy-engine job
+        // and queues behind the PCIe copy of the previous chunk)
+        k_rows_reset<<<grid_for(ra.n_units + 2, 256), 256, 0, c->stream>>>(ra.plan, ra.plan_stride, ra.n_units, ra.overflow, c->tile_counter_d);
+        c->stats.kernel_launches++;
         k_band_plan<<<dim3((unsigned)((n_cols + 255) / 256), (unsigned)ra.n_chunks), 256, 0, c->stream>>>(ra);
         cudaEventRecord(next_kev(c), c->stream);
         const int blocks = std::min(ra.n_units, n_blocks);
-        if (DK == 0) launch_rows<0>(c, ra, blocks, smem);
-        else if (DK == 1) launch_rows<1>(c, ra, blocks, smem);
-        else if (DK == 2) launch_rows<2>(c, ra, blocks, smem);
-        else launch_rows<3>(c, ra, blocks, smem);
+        if (DK == 0) launch_rows<0>(c, ra, blocks, threads, smem);
+        else if (DK == 1) launch_rows<1>(c, ra, blocks, threads, smem);
+        else if (DK == 2) launch_rows<2>(c, ra, blocks, threads, smem);
+        else launch_rows<3>(c, ra, blocks, threads, smem);
         cudaEventRecord(next_kev(c), c->stream);
         c->stats.kernel_launches += 2;
         c->stats.emit_kernel_launches++;
         CUDA_TRY(cudaGetLastError());
         // units whose run-start list overflowed (not expected with the band heuristic): searched per cell
-        int n_over = 0;
-        CUDA_TRY(cudaMemcpyAsync(&n_over, ra.overflow, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+        c->scalars_h[2] = 0;
+        k_publish<<<1, 32, 0, c->stream>>>(c->scalars_dev, nullptr, nullptr, ra.overflow);
         CUDA_TRY(cudaStreamSynchronize(c->stream));
+        const int n_over = (int)c->scalars_h[2];
         if (n_over > 0) {
             std::vector<int> units((size_t)n_over);
             CUDA_TRY(cudaMemcpy(units.data(), ra.overflow + 1, (size_t)n_over * sizeof(int), cudaMemcpyDeviceToHost));
@@ -438,6 +455,9 @@ int psim_create(const psim_config* cfg, psim_ctx** out) {
     if (cudaGetDeviceProperties(&prop, cfg->device) == cudaSuccess) c->sm_count = prop.multiProcessorCount;
     bool ok = cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking) == cudaSuccess &&
               cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking) == cudaSuccess &&
+              cudaStreamCreateWithFlags(&c->aux_stream, cudaStreamNonBlocking) == cudaSuccess &&
+              cudaHostAlloc((void**)&c->scalars_h, 8 * sizeof(int64_t), cudaHostAllocMapped) == cudaSuccess &&
+              cudaHostGetDevicePointer((void**)&c->scalars_dev, c->scalars_h, 0) == cudaSuccess &&
               cudaEventCreate(&c->ev0) == cudaSuccess && cudaEventCreate(&c->ev1) == cudaSuccess &&
               cudaEventCreate(&c->ev2) == cudaSuccess && cudaEventCreate(&c->ev3) == cudaSuccess &&
               cudaMalloc((void**)&c->error_flag_d, sizeof(int)) == cudaSuccess &&
@@ -471,6 +491,8 @@ void psim_destroy(psim_ctx* ctx) {
     if (c->ev3) cudaEventDestroy(c->ev3);
     if (c->own_stream) cudaStreamDestroy(c->own_stream);
     if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
+    if (c->aux_stream) cudaStreamDestroy(c->aux_stream);
+    if (c->scalars_h) cudaFreeHost(c->scalars_h);
     delete c;
 }
 
@@ -538,25 +560,35 @@ int psim_set_pedigree(psim_ctx* ctx, int64_t n_ind, const int32_t* parent0, cons
         if (f0) { nf++; continue; }
         if (parent0[i] >= i || parent1[i] >= i) return fail(c, PSIM_EINVAL, "pedigree is not in parents-first order");
     }
-    free_population(c);
+    // A Monte Carlo loop sets a pedigree of the same size again and again: the population arrays are
+    // grow-only (cudaFree / cudaMalloc cost 1-10 ms, far more than the simulation of such a pedigree).
+    const int64_t n_hom = (int64_t)c->C * c->R * n_ind * c->P;
+    const int64_t ncfg = (int64_t)c->R * n_ind * c->C * 2;
+    if (n_ind > c->pop_cap_ind || n_hom > c->pop_cap_hom || ncfg > c->pop_cap_cfg) {
+        CUDA_TRY(cudaStreamSynchronize(c->stream));
+        free_population(c);
+        CUDA_TRY(dev_alloc(&c->par0_d, (size_t)n_ind));
+        CUDA_TRY(dev_alloc(&c->par1_d, (size_t)n_ind));
+        CUDA_TRY(dev_alloc(&c->desc_d, (size_t)n_hom));
+        CUDA_TRY(dev_alloc(&c->run_desc_d, (size_t)n_hom));
+        CUDA_TRY(dev_alloc(&c->cfg_quad_d, (size_t)ncfg));
+        CUDA_TRY(dev_alloc(&c->cfg_seq_d, (size_t)ncfg * c->P));
+        c->pop_cap_ind = n_ind; c->pop_cap_hom = n_hom; c->pop_cap_cfg = ncfg;
+    }
+    c->slab_used = 0;
+    c->runs_valid = false;
     c->N = n_ind;
     c->founder_allele_count = nf * c->P;
     c->par0_h.assign(parent0, parent0 + n_ind);
     c->par1_h.assign(parent1, parent1 + n_ind);
     c->hs_reps.assign(n_ind, 0);
-    c->n_hom = (int64_t)c->C * c->R * c->N * c->P;
-    CUDA_TRY(dev_alloc(&c->par0_d, (size_t)n_ind));
-    CUDA_TRY(dev_alloc(&c->par1_d, (size_t)n_ind));
-    CUDA_TRY(cudaMemcpy(c->par0_d, parent0, n_ind * sizeof(int32_t), cudaMemcpyHostToDevice));
-    CUDA_TRY(cudaMemcpy(c->par1_d, parent1, n_ind * sizeof(int32_t), cudaMemcpyHostToDevice));
-    CUDA_TRY(dev_alloc(&c->desc_d, (size_t)c->n_hom));
-    CUDA_TRY(cudaMemset(c->desc_d, 0, c->n_hom * sizeof(uint64_t)));
-    CUDA_TRY(dev_alloc(&c->run_desc_d, (size_t)c->n_hom));
-    const int64_t ncfg = (int64_t)c->R * c->N * c->C * 2;
-    CUDA_TRY(dev_alloc(&c->cfg_quad_d, (size_t)ncfg));
-    CUDA_TRY(dev_alloc(&c->cfg_seq_d, (size_t)ncfg * c->P));
-    CUDA_TRY(cudaMemset(c->cfg_quad_d, 0xFF, ncfg));
-    CUDA_TRY(cudaMemset(c->cfg_seq_d, 0xFF, ncfg * c->P));
+    c->n_hom = n_hom;
+    // stream-ordered with the kernels that follow (the sources are pageable: staged before the calls return)
+    CUDA_TRY(cudaMemcpyAsync(c->par0_d, parent0, n_ind * sizeof(int32_t), cudaMemcpyHostToDevice, c->stream));
+    CUDA_TRY(cudaMemcpyAsync(c->par1_d, parent1, n_ind * sizeof(int32_t), cudaMemcpyHostToDevice, c->stream));
+    CUDA_TRY(cudaMemsetAsync(c->desc_d, 0, n_hom * sizeof(uint64_t), c->stream));
+    CUDA_TRY(cudaMemsetAsync(c->cfg_quad_d, 0xFF, ncfg, c->stream));
+    CUDA_TRY(cudaMemsetAsync(c->cfg_seq_d, 0xFF, ncfg * c->P, c->stream));
     c->stats.n_segments = 0;
     return PSIM_OK;
 }
@@ -631,7 +663,7 @@ static int simulate_impl(psim_ctx_impl* c, int32_t max_founder_allele, const int
                                                                     c->seg_pos_d, c->seg_founder_d, c->slab_used);
         c->stats.kernel_launches++;
         CUDA_TRY(cudaGetLastError());
-        CUDA_TRY(cudaStreamSynchronize(c->stream));  // f_ind / f_allele are stack-owned host buffers
+        // (f_ind / f_allele are pageable: cudaMemcpyAsync has staged them before it returned)
         c->slab_used += nseg;
         for (int32_t i : f_ind) c->hs_reps[i] = R;
     }
@@ -699,12 +731,18 @@ static int simulate_impl(psim_ctx_impl* c, int32_t max_founder_allele, const int
             k_meiosis_config<<<grid_for(n_half, 128), 128, 0, c->stream>>>(pa);
             auto launch_mv = [&](auto kos, auto anr) {
                 constexpr bool KOS = decltype(kos)::value, ANR = decltype(anr)::value;
-                k_meiosis_mv<false, KOS, ANR><<<grid_for(cap_bi, 128), 128, 0, c->stream>>>(pa);
-                c->stats.kernel_launches++;
+                // the two task lists are independent and neither kernel fills the machine (one
+                // wave of divergent warps): they run side by side, the longer (quadrivalents) first
                 if (cap_quad > 0) {
-                    k_meiosis_mv<true, KOS, ANR><<<grid_for(cap_quad, 128), 128, 0, c->stream>>>(pa);
+                    cudaEventRecord(c->ev2, c->stream);
+                    cudaStreamWaitEvent(c->aux_stream, c->ev2, 0);
+                    k_meiosis_mv<true, KOS, ANR><<<grid_for(cap_quad, 128), 128, 0, c->aux_stream>>>(pa);
+                    cudaEventRecord(c->ev3, c->aux_stream);
                     c->stats.kernel_launches++;
                 }
+                k_meiosis_mv<false, KOS, ANR><<<grid_for(cap_bi, 128), 128, 0, c->stream>>>(pa);
+                c->stats.kernel_launches++;
+                if (cap_quad > 0) cudaStreamWaitEvent(c->stream, c->ev3, 0);
             };
             c->stats.kernel_launches++;
             if (c->model.chiasma_interference) {
@@ -715,31 +753,46 @@ static int simulate_impl(psim_ctx_impl* c, int32_t max_founder_allele, const int
             CUDA_TRY(cudaGetLastError());
             CUDA_TRY(cudaMemsetAsync(plan_cnt + nu, 0, sizeof(int64_t), c->stream));
             if (int rc = exclusive_scan_i64(c, plan_cnt, plan_off, nu + 1)) { rc_out = rc; break; }
-            int64_t total = 0; int flag = 0;
-            CUDA_TRY(cudaMemcpyAsync(&total, plan_off + nu, sizeof(int64_t), cudaMemcpyDeviceToHost, c->stream));
-            CUDA_TRY(cudaMemcpyAsync(&flag, c->error_flag_d, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
-            CUDA_TRY(cudaStreamSynchronize(c->stream));
-            if (flag) {
-                cudaMemset(c->error_flag_d, 0, sizeof(int));
-                rc_out = fail(c, flag, "meiosis plan exceeded a device buffer (too many chiasmata on one chromatid)");
-                break;
-            }
-            if (int rc = ensure_slab(c, c->slab_used + total)) { rc_out = rc; break; }
+            // The batch's segment total is only known on the device at this point. The assembly is
+            // launched at once against the slab as it is (the kernel does nothing if the batch does not
+            // fit) so that the device never idles behind a host round trip; the host reads the total
+            // afterwards and, only if the slab was too small, grows it and launches the assembly again.
+            c->scalars_h[0] = 0; c->scalars_h[1] = 0;
+            k_publish<<<1, 32, 0, c->stream>>>(c->scalars_dev, plan_off + nu, c->error_flag_d, nullptr);
             AssembleArgs aa;
             aa.chrom = c->chrom_d; aa.C = C; aa.R = R; aa.P = P; aa.N = N; aa.n_lev = n_lev; aa.lev_ind = lev_d;
             aa.par0 = c->par0_d; aa.par1 = c->par1_d; aa.desc = c->desc_d; aa.seg_pos = c->seg_pos_d;
             aa.seg_founder = c->seg_founder_d; aa.piece_cap = c->piece_cap; aa.plan_np = plan_np; aa.plan_cnt = plan_cnt;
             aa.plan_off = plan_off; aa.plan_pos = plan_pos; aa.plan_hom = plan_hom; aa.slab_base = c->slab_used;
+            aa.slab_cap = c->slab_cap; aa.error_flag = c->error_flag_d;
             k_meiosis_assemble<<<grid_for(nu, 128), 128, 0, c->stream>>>(aa);
             c->stats.kernel_launches++;
             CUDA_TRY(cudaGetLastError());
+            const bool last_batch = lv == max_level && b0 + max_batch >= (int64_t)inds.size();
+            if (last_batch) CUDA_TRY(cudaEventRecord(c->ev1, c->stream));
+            CUDA_TRY(cudaStreamSynchronize(c->stream));
+            const int64_t total = c->scalars_h[0];
+            const int flag = (int)c->scalars_h[1];
+            if (flag) {
+                cudaMemset(c->error_flag_d, 0, sizeof(int));
+                rc_out = fail(c, flag, "meiosis plan exceeded a device buffer (too many chiasmata on one chromatid)");
+                break;
+            }
+            if (c->slab_used + total > c->slab_cap) {
+                if (int rc = ensure_slab(c, c->slab_used + total)) { rc_out = rc; break; }
+                aa.seg_pos = c->seg_pos_d; aa.seg_founder = c->seg_founder_d; aa.slab_cap = c->slab_cap;
+                k_meiosis_assemble<<<grid_for(nu, 128), 128, 0, c->stream>>>(aa);
+                c->stats.kernel_launches++;
+                CUDA_TRY(cudaGetLastError());
+                if (last_batch) CUDA_TRY(cudaEventRecord(c->ev1, c->stream));
+            }
             c->slab_used += total;
             c->stats.n_meioses += (int64_t)n_lev * R * 2;
             c->stats.n_units += (int64_t)n_lev * R * 2 * C;
         }
         for (int32_t i : inds) c->hs_reps[i] = R;
     }
-    CUDA_TRY(cudaEventRecord(c->ev1, c->stream));
+    if (max_level == 0 || rc_out != PSIM_OK) CUDA_TRY(cudaEventRecord(c->ev1, c->stream));   // else recorded behind the last assembly
     CUDA_TRY(cudaStreamSynchronize(c->stream));
     float ms = 0.f;
     cudaEventElapsedTime(&ms, c->ev0, c->ev1);
@@ -843,6 +896,7 @@ int psim_get_meiotic_configs(psim_ctx* ctx, uint32_t replicate, int64_t first, i
     const int64_t nq = count * c->C * 2;
     std::vector<int8_t> q(nq), s(nq * c->P);
     const int64_t base = ((int64_t)r * c->N + first) * c->C * 2;
+    CUDA_TRY(cudaStreamSynchronize(c->stream));   // psim_set_pedigree / psim_reset clear the tables on the stream
     CUDA_TRY(cudaMemcpy(q.data(), c->cfg_quad_d + base, nq, cudaMemcpyDeviceToHost));
     CUDA_TRY(cudaMemcpy(s.data(), c->cfg_seq_d + base * c->P, nq * c->P, cudaMemcpyDeviceToHost));
     for (int64_t k = 0; k < nq; k++) quad[k] = q[k];
@@ -1104,15 +1158,24 @@ int psim_emit(psim_ctx* ctx, int64_t ind_first, int64_t ind_count, int64_t locus
             x.spitch = x.direct ? x.hpitch : up(x.width, 128);
             row_bytes += x.spitch + (x.direct || x.strided ? 0 : x.hpitch);
         }
-        const int64_t slot_budget = 96LL << 20;
-        const int64_t rows = std::max<int64_t>(1, std::min<int64_t>(locus_count, slot_budget / row_bytes));
-        const int64_t slot_bytes = up(rows * row_bytes, 256);
+        const int64_t slot_budget = 384LL << 20;   // few large chunks: every chunk boundary is a small bubble on the PCIe link
+        int64_t rows = std::max<int64_t>(1, std::min<int64_t>(locus_count, slot_budget / row_bytes));
+        // chunk boundaries on 256-byte boundaries of every host table where the pitches allow it: a
+        // PCIe copy into an unaligned host address runs ~10 % slower
+        int64_t row_quantum = 1;
+        for (const Tab& x : tab)
+            if (x.host) row_quantum = std::lcm(row_quantum, (int64_t)256 / std::gcd((int64_t)256, x.hpitch));
+        if (rows >= 2 * row_quantum) rows = rows / row_quantum * row_quantum; else row_quantum = 1;
+        const int64_t slot_bytes = up(rows * row_bytes, 256) + 6 * 256;   // every sub-buffer starts 256-byte aligned
         if (int rc = ensure_staging(c, (size_t)(2 * slot_bytes))) return rc;
         cudaEvent_t ready[2] = {c->ev2, c->ev3};
         cudaEvent_t freed[2] = {next_kev(c), next_kev(c)};
+        static const bool trace = getenv("PSIM_TRACE") != nullptr;
+        std::vector<cudaEvent_t> tev;
         int k = 0;
-        for (int64_t l0 = locus_first; l0 < locus_first + locus_count; l0 += rows, k++) {
-            const int64_t l1 = std::min(l0 + rows, locus_first + locus_count);
+        // the first chunk is short so that the PCIe link starts early
+        for (int64_t l0 = locus_first, l1; l0 < locus_first + locus_count; l0 = l1, k++) {
+            l1 = std::min(l0 + (k == 0 ? std::max<int64_t>(1, rows / 16 / row_quantum) * row_quantum : rows), locus_first + locus_count);
             const int64_t nr = l1 - l0, r0 = l0 - locus_first;
             const int sl = k & 1;
             uint8_t* base = (uint8_t*)c->staging + sl * slot_bytes;
@@ -1122,18 +1185,22 @@ int psim_emit(psim_ctx* ctx, int64_t ind_first, int64_t ind_count, int64_t locus
                 for (int q = 0; q < 3; q++) {
                     sp[q] = dn[q] = nullptr;
                     if (!tab[q].host) continue;
-                    sp[q] = p; p += rows * tab[q].spitch;
-                    if (!tab[q].direct && !tab[q].strided) { dn[q] = p; p += rows * tab[q].hpitch; }
+                    sp[q] = p; p += up(rows * tab[q].spitch, 256);
+                    if (!tab[q].direct && !tab[q].strided) { dn[q] = p; p += up(rows * tab[q].hpitch, 256); }
                 }
             }
             if (k >= 2) CUDA_TRY(cudaStreamWaitEvent(c->stream, freed[sl], 0));   // slot copied out
+            if (trace) { timespec ts; clock_gettime(CLOCK_MONOTONIC, &ts); fprintf(stderr, "psim_emit chunk %d begins at host %.3f ms\n", k, ts.tv_sec * 1e3 + ts.tv_nsec * 1e-6); }
             if (int rc = emit_device(c, ind_first, ind_count, l0, l1, l0, sp[0], tab[0].spitch, fb, sp[1], tab[1].spitch,
                                      sp[2], tab[2].spitch, dose_mode, dose_which)) return rc;
             for (int q = 0; q < 3; q++)
-                if (dn[q])
-                    CUDA_TRY(cudaMemcpy2DAsync(dn[q], tab[q].hpitch, sp[q], tab[q].spitch, tab[q].width, nr, cudaMemcpyDeviceToDevice, c->stream));
+                if (dn[q]) {   // (a 2-D device copy with an unaligned pitch runs at a fraction of this kernel's pace)
+                    k_repack_dense<<<c->sm_count * 8, 256, 0, c->stream>>>(sp[q], tab[q].spitch, dn[q], tab[q].width, nr);
+                    c->stats.kernel_launches++;
+                }
             CUDA_TRY(cudaEventRecord(ready[sl], c->stream));
             CUDA_TRY(cudaStreamWaitEvent(c->copy_stream, ready[sl], 0));
+            if (trace) { cudaEvent_t e; cudaEventCreate(&e); cudaEventRecord(e, c->copy_stream); tev.push_back(e); }
             for (int q = 0; q < 3; q++) {
                 if (!tab[q].host) continue;
                 uint8_t* dst = (uint8_t*)tab[q].host + r0 * tab[q].hpitch;
@@ -1143,10 +1210,21 @@ int psim_emit(psim_ctx* ctx, int64_t ind_first, int64_t ind_count, int64_t locus
                     CUDA_TRY(cudaMemcpyAsync(dst, tab[q].direct ? sp[q] : dn[q], (size_t)(nr * tab[q].width), cudaMemcpyDeviceToHost, c->copy_stream));
             }
             CUDA_TRY(cudaEventRecord(freed[sl], c->copy_stream));
+            if (trace) { cudaEvent_t e; cudaEventCreate(&e); cudaEventRecord(e, c->copy_stream); tev.push_back(e); }
+            if (trace) { timespec ts; clock_gettime(CLOCK_MONOTONIC, &ts); fprintf(stderr, "psim_emit chunk %d enqueued at host %.3f ms\n", k, ts.tv_sec * 1e3 + ts.tv_nsec * 1e-6); }
         }
         CUDA_TRY(cudaStreamSynchronize(c->copy_stream));
         CUDA_TRY(cudaEventRecord(c->ev1, c->stream));
         CUDA_TRY(cudaStreamSynchronize(c->stream));
+        if (trace) {   // PSIM_TRACE: when every chunk's copies started and ended, ms after the call began
+            for (size_t i = 0; i + 1 < tev.size(); i += 2) {
+                float a = 0.f, b = 0.f;
+                cudaEventElapsedTime(&a, c->ev0, tev[i]);
+                cudaEventElapsedTime(&b, c->ev0, tev[i + 1]);
+                fprintf(stderr, "psim_emit chunk %zu: copies start %.3f ms end %.3f ms\n", i / 2, a, b);
+            }
+            for (cudaEvent_t e : tev) cudaEventDestroy(e);
+        }
     }
     float ms_total = 0.f, ms_kernel = 0.f;
     cudaEventElapsedTime(&ms_total, c->ev0, c->ev1);
@@ -1284,9 +1362,9 @@ int psim_emit_text(psim_ctx* ctx, int64_t ind_first, int64_t ind_count, int64_t 
             c->stats.kernel_launches++;
             CUDA_TRY(cudaGetLastError());
             if (int rc = exclusive_scan_i64(c, (int64_t*)c->b_rowlen.p, (int64_t*)c->b_rowoff.p, nr + 1)) return rc;
-            int64_t total = 0;
-            CUDA_TRY(cudaMemcpyAsync(&total, (int64_t*)c->b_rowoff.p + nr, sizeof(int64_t), cudaMemcpyDeviceToHost, c->stream));
+            k_publish<<<1, 32, 0, c->stream>>>(c->scalars_dev, (int64_t*)c->b_rowoff.p + nr, nullptr, nullptr);
             CUDA_TRY(cudaStreamSynchronize(c->stream));
+            const int64_t total = c->scalars_h[0];
             if (*tab[q].bytes + total > tab[q].cap) too_small = true;
             if (!too_small) {
                 CUDA_TRY(cudaStreamSynchronize(c->copy_stream));   // b_text may grow: nothing may be in flight from it

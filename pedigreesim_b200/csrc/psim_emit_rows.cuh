@@ -91,6 +91,14 @@ __global__ void __launch_bounds__(256) k_band_plan(const RowsArgs a) {
     }
 }
 
+// Before every launch: run-start counters of the units, overflow count, unit ticket.
+__global__ void k_rows_reset(uint8_t* plan, int64_t plan_stride, int n_units, int* overflow, int* ticket) {
+    const int u = blockIdx.x * blockDim.x + threadIdx.x;
+    if (u < n_units) *reinterpret_cast<uint4*>(plan + (int64_t)u * plan_stride) = make_uint4(0, 0, 0, 0);
+    else if (u == n_units) *overflow = 0;
+    else if (u == n_units + 1) *ticket = 0;
+}
+
 constexpr int ROWS_THREADS = 512;
 constexpr int ROWS_MAX_BAND = 255;     // the row of a run start inside its band is 8 bits
 constexpr int ROWS_SMEM = 220 * 1024;  // one block per SM
@@ -113,6 +121,7 @@ template <int DK>
 __global__ void __launch_bounds__(ROWS_THREADS, 1) k_emit_rows(const RowsArgs a) {
     extern __shared__ __align__(128) uint8_t smem[];
     const int tid = threadIdx.x;
+    const int NT = blockDim.x;   // ROWS_THREADS, or fewer when several narrow-segment blocks share an SM
     const int P = a.P;
     const int seg_cells = a.seg_cells, seg_ind = seg_cells / P;
     constexpr int NB = ROWS_NBUF;
@@ -153,12 +162,12 @@ __global__ void __launch_bounds__(ROWS_THREADS, 1) k_emit_rows(const RowsArgs a)
         __syncthreads();
 
         // ---- start state of the band, run starts bucketed by row
-        for (int i = tid * 16; i < seg_cells; i += ROWS_THREADS * 16)
+        for (int i = tid * 16; i < seg_cells; i += NT * 16)
             *reinterpret_cast<uint4*>(img0 + i) = __ldg(reinterpret_cast<const uint4*>(pu + 16 + i));
-        for (int i = tid; i <= n_rows; i += ROWS_THREADS) start[i] = 0;
+        for (int i = tid; i <= n_rows; i += NT) start[i] = 0;
         __syncthreads();
         const uint32_t* ev_g = reinterpret_cast<const uint32_t*>(pu + 16 + seg_cells);
-        for (uint32_t e = tid; e < n_ev; e += ROWS_THREADS) atomicAdd(&start[__ldg(ev_g + e) >> 24], 1u);
+        for (uint32_t e = tid; e < n_ev; e += NT) atomicAdd(&start[__ldg(ev_g + e) >> 24], 1u);
         __syncthreads();
         if (tid < 32) {   // exclusive scan of the row histogram (<= 256 bins) by one warp
             uint32_t carry = 0;
@@ -173,19 +182,19 @@ __global__ void __launch_bounds__(ROWS_THREADS, 1) k_emit_rows(const RowsArgs a)
             }
         }
         __syncthreads();
-        for (uint32_t e = tid; e < n_ev; e += ROWS_THREADS) {
+        for (uint32_t e = tid; e < n_ev; e += NT) {
             const uint32_t w = __ldg(ev_g + e);
             evs[atomicAdd(&cursor[w >> 24], 1u)] = w;
         }
         if (DK >= 2) {   // 4-bit image: low 3 bits of every cell, the PRMT selectors of the dose lookup
-            for (int i = tid; i < seg_cells / 16; i += ROWS_THREADS) {
+            for (int i = tid; i < seg_cells / 16; i += NT) {
                 const uint4 v = reinterpret_cast<const uint4*>(img0)[i];
                 auto pack = [](uint32_t x) { return (x & 0x7) | ((x >> 4) & 0x70) | ((x >> 8) & 0x700) | ((x >> 12) & 0x7000); };
                 reinterpret_cast<uint2*>(nib)[i] = make_uint2(pack(v.x) | (pack(v.y) << 16), pack(v.z) | (pack(v.w) << 16));
             }
         }
         if (DK == 1) {   // dose of one founder allele on the band's first row
-            for (int i = tid; i < seg_ind; i += ROWS_THREADS) {
+            for (int i = tid; i < seg_ind; i += NT) {
                 int dsum = 0;
                 for (int h = 0; h < P; h++) dsum += img0[i * P + h] == (uint8_t)a.dose_which;
                 dose0[i] = (uint8_t)(count_ok ? dsum : 0);
@@ -196,16 +205,16 @@ __global__ void __launch_bounds__(ROWS_THREADS, 1) k_emit_rows(const RowsArgs a)
         __syncthreads();
         // the other buffers start from the same state (they become rows 1 .. NB-1)
         for (int b = 1; b < NB; b++) {
-            for (int i = tid; i < seg_cells / 16; i += ROWS_THREADS)
+            for (int i = tid; i < seg_cells / 16; i += NT)
                 reinterpret_cast<uint4*>(img0 + (size_t)b * seg_cells)[i] = reinterpret_cast<const uint4*>(img0)[i];
             if (DK == 1)
-                for (int i = tid; i < seg_ind / 16; i += ROWS_THREADS)
+                for (int i = tid; i < seg_ind / 16; i += NT)
                     reinterpret_cast<uint4*>(dose0 + (size_t)b * seg_ind)[i] = reinterpret_cast<const uint4*>(dose0)[i];
         }
 
         // ---- the rows. Buffer r % NB holds row r-NB when row r begins: it takes the run starts of rows r-NB+1 .. r.
         auto patch = [&](uint8_t* img, uint8_t* drow, uint32_t e0, uint32_t e1) {
-            for (uint32_t e = e0 + tid; e < e1; e += ROWS_THREADS) {
+            for (uint32_t e = e0 + tid; e < e1; e += NT) {
                 const uint32_t w = evs[e], cs = (w >> 8) & 0xFFFF, f = w & 0xFF;
                 if (DK == 1) {
                     const int delta = (int)(f == (uint32_t)a.dose_which) - (int)(count_ok && img[cs] == (uint8_t)a.dose_which);
@@ -222,7 +231,7 @@ __global__ void __launch_bounds__(ROWS_THREADS, 1) k_emit_rows(const RowsArgs a)
             // buffers of row r were last read by the bulk stores of row r-NB
             if (r >= NB && tid == 0) asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(NB - 1) : "memory");
             if (DK >= 2) {
-                for (uint32_t e = e0 + tid; e < e1; e += ROWS_THREADS) {
+                for (uint32_t e = e0 + tid; e < e1; e += NT) {
                     const uint32_t w = evs[e], cs = (w >> 8) & 0xFFFF, sh = (cs & 7) * 4;
                     atomicAnd(&nib[cs >> 3], ~(0xFu << sh));
                     atomicOr(&nib[cs >> 3], (w & 7) << sh);
@@ -238,14 +247,14 @@ __global__ void __launch_bounds__(ROWS_THREADS, 1) k_emit_rows(const RowsArgs a)
                 const uint4 T = Tn;
                 if (r + 1 < n_rows) Tn = __ldg(a.mtab + g0 + r + 1);
                 if (DK == 2) {   // 8 individuals per step: 4 words of the 4-bit image in, 8 dose bytes out
-                    for (int i = tid; i < seg_ind / 8; i += ROWS_THREADS) {
+                    for (int i = tid; i < seg_ind / 8; i += NT) {
                         const uint4 v = reinterpret_cast<const uint4*>(nib)[i];
                         auto two = [&](uint32_t w) { return __dp4a(prmt(T.x, T.y, w) + prmt(T.z, T.w, w >> 16), 0x01010101u, 0u); };
                         const uint32_t lo = two(v.x) | (two(v.y) << 8), hi = two(v.z) | (two(v.w) << 8);   // dose nibbles
                         reinterpret_cast<uint2*>(drow)[i] = make_uint2(prmt(0x03020100u, 0x07060504u, lo), prmt(0x03020100u, 0x07060504u, hi));
                     }
                 } else {         // ploidy 2: 16 individuals per step
-                    for (int i = tid; i < seg_ind / 16; i += ROWS_THREADS) {
+                    for (int i = tid; i < seg_ind / 16; i += NT) {
                         const uint4 v = reinterpret_cast<const uint4*>(nib)[i];
                         auto four = [&](uint32_t w) {
                             const uint32_t xl = prmt(T.x, T.y, w), xh = prmt(T.x, T.y, w >> 16);

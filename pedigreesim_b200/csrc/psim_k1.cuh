@@ -241,12 +241,15 @@ struct AssembleArgs {
     const double* plan_pos;
     const uint8_t* plan_hom;
     int64_t slab_base;
+    int64_t slab_cap;          // segments the slab holds: a batch that does not fit is not written at all
+    const int* error_flag;     // set by the plan kernels: the plan is incomplete, nothing is assembled
 };
 
 __global__ void __launch_bounds__(128) k_meiosis_assemble(AssembleArgs a) {
     const int64_t u = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     const int64_t total = (int64_t)a.C * a.R * a.n_lev * a.P;
     if (u >= total) return;
+    if (*a.error_flag || a.slab_base + a.plan_off[total] > a.slab_cap) return;   // the host reports the error / grows the slab and launches again
     const int P = a.P, p2 = P / 2;
     const int h = (int)(u % P);
     const int j = (int)((u / P) % a.n_lev);

@@ -69,3 +69,54 @@ __global__ void k_match_codes(int64_t L, int A, int which, const uint8_t* __rest
     }
 }
 
+
+// Rows with a 16-byte-aligned pitch -> the same rows back to back (pitch == width, any width): the
+// layout of a dense host table whose row length is not a multiple of 16. One 16-byte word of the
+// destination per thread and step: two aligned loads and a funnel shift when the source bytes are
+// not aligned, byte by byte for the one word per row that straddles two source rows.
+__global__ void __launch_bounds__(256) k_repack_dense(const uint8_t* __restrict__ src, int64_t spitch, uint8_t* __restrict__ dst,
+                                                      int64_t width, int64_t rows) {
+    const int64_t total = rows * width;
+    const int64_t step = (int64_t)gridDim.x * blockDim.x * 16;
+    for (int64_t o = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) * 16; o < total; o += step) {
+        const int64_t row = o / width, col = o - row * width;
+        if (col + 16 <= width) {
+            const uint8_t* p = src + row * spitch + col;
+            const int mis = (int)(col & 15);
+            const uint4* q = reinterpret_cast<const uint4*>(p - mis);
+            const uint4 lo = __ldg(q);
+            uint4 out = lo;
+            if (mis) {
+                const uint4 hi = __ldg(q + 1);   // still inside the padded source row
+                const uint32_t w[8] = {lo.x, lo.y, lo.z, lo.w, hi.x, hi.y, hi.z, hi.w};
+                const int wo = mis >> 2, sh = (mis & 3) * 8;
+                uint32_t r[4];
+#pragma unroll
+                for (int k = 0; k < 4; k++) {
+                    uint32_t a = 0, b = 0;
+#pragma unroll
+                    for (int j = 0; j < 4; j++) if (wo == j) { a = w[j + k]; b = w[j + k + 1 < 8 ? j + k + 1 : 7]; }
+                    r[k] = __funnelshift_r(a, b, sh);
+                }
+                out = make_uint4(r[0], r[1], r[2], r[3]);
+            }
+            *reinterpret_cast<uint4*>(dst + o) = out;
+        } else {
+            for (int b = 0; b < 16 && o + b < total; b++) {
+                const int64_t oo = o + b, rr = oo / width;
+                dst[oo] = src[rr * spitch + (oo - rr * width)];
+            }
+        }
+    }
+}
+
+// Small device values the host needs after the next stream synchronisation, stored straight into
+// mapped page-locked memory (see psim_ctx_impl::scalars_h).
+__global__ void k_publish(volatile int64_t* host, const int64_t* v0, const int* v1, const int* v2) {
+    if (threadIdx.x == 0) {
+        if (v0) host[0] = *v0;
+        if (v1) host[1] = *v1;
+        if (v2) host[2] = *v2;
+        __threadfence_system();
+    }
+}
