@@ -67,7 +67,7 @@ struct psim_ctx_impl {
     int C = 0, P = 0, R = 1;
     int64_t N = 0;
     cudaStream_t stream = nullptr, own_stream = nullptr, copy_stream = nullptr, aux_stream = nullptr;   // aux: second compute stream of psim_simulate
-    cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev2 = nullptr, ev3 = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev2 = nullptr, ev3 = nullptr, ev4 = nullptr;
     std::vector<cudaEvent_t> kev;   // event pool: triples (before plan, before stream, after stream) per launch
     int kev_used = 0;
     ModelParams model{};
@@ -126,7 +126,7 @@ struct psim_ctx_impl {
     // grow-only scratch of psim_simulate (no allocation in the steady state of a Monte Carlo loop)
     struct Buf { void* p = nullptr; size_t cap = 0; };
     Buf b_lev, b_np, b_cnt, b_off, b_ppos, b_phom, b_find, b_fal;
-    Buf b_plan, b_dense_list, b_task, b_text, b_rowlen, b_rowoff;
+    Buf b_plan, b_dense_list, b_task, b_text, b_text2, b_rowlen, b_rowoff;
     // export buffers
     int64_t* exp_off_d = nullptr; int32_t* exp_founder_d = nullptr; double* exp_pos_d = nullptr;
     int64_t exp_off_cap = 0, exp_seg_cap = 0;
@@ -459,7 +459,7 @@ int psim_create(const psim_config* cfg, psim_ctx** out) {
               cudaHostAlloc((void**)&c->scalars_h, 8 * sizeof(int64_t), cudaHostAllocMapped) == cudaSuccess &&
               cudaHostGetDevicePointer((void**)&c->scalars_dev, c->scalars_h, 0) == cudaSuccess &&
               cudaEventCreate(&c->ev0) == cudaSuccess && cudaEventCreate(&c->ev1) == cudaSuccess &&
-              cudaEventCreate(&c->ev2) == cudaSuccess && cudaEventCreate(&c->ev3) == cudaSuccess &&
+              cudaEventCreate(&c->ev2) == cudaSuccess && cudaEventCreate(&c->ev3) == cudaSuccess && cudaEventCreate(&c->ev4) == cudaSuccess &&
               cudaMalloc((void**)&c->error_flag_d, sizeof(int)) == cudaSuccess &&
               cudaMalloc((void**)&c->tile_counter_d, sizeof(int)) == cudaSuccess;
     if (!ok) { g_create_error = std::string("CUDA setup failed: ") + cudaGetErrorString(cudaGetLastError()); delete c; return PSIM_ECUDA; }
@@ -483,12 +483,13 @@ void psim_destroy(psim_ctx* ctx) {
     cudaFree(c->exp_off_d); cudaFree(c->exp_founder_d); cudaFree(c->exp_pos_d);
     for (cudaEvent_t e : c->kev) cudaEventDestroy(e);
     for (psim_ctx_impl::Buf* b : {&c->b_lev, &c->b_np, &c->b_cnt, &c->b_off, &c->b_ppos, &c->b_phom, &c->b_find, &c->b_fal,
-                                 &c->b_plan, &c->b_dense_list, &c->b_task, &c->b_text, &c->b_rowlen, &c->b_rowoff}) cudaFree(b->p);
+                                 &c->b_plan, &c->b_dense_list, &c->b_task, &c->b_text, &c->b_text2, &c->b_rowlen, &c->b_rowoff}) cudaFree(b->p);
     cudaFree(c->label_off_d); cudaFree(c->labels_d); cudaFree(c->code_off_d); cudaFree(c->aname_off_d); cudaFree(c->anames_d);
     if (c->ev0) cudaEventDestroy(c->ev0);
     if (c->ev1) cudaEventDestroy(c->ev1);
     if (c->ev2) cudaEventDestroy(c->ev2);
     if (c->ev3) cudaEventDestroy(c->ev3);
+    if (c->ev4) cudaEventDestroy(c->ev4);
     if (c->own_stream) cudaStreamDestroy(c->own_stream);
     if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
     if (c->aux_stream) cudaStreamDestroy(c->aux_stream);
@@ -1330,6 +1331,12 @@ int psim_emit_text(psim_ctx* ctx, int64_t ind_first, int64_t ind_count, int64_t 
     if (int rc = ensure_buf(c, c->b_rowlen, ((size_t)rows + 1) * sizeof(int64_t))) return rc;
     if (int rc = ensure_buf(c, c->b_rowoff, ((size_t)rows + 1) * sizeof(int64_t))) return rc;
     bool too_small = false;
+    // Two text buffers: while the lines of one table block cross the PCIe link, the next block is
+    // formatted into the other buffer.
+    psim_ctx_impl::Buf* text_buf[2] = {&c->b_text, &c->b_text2};
+    cudaEvent_t text_out[2] = {c->ev3, c->ev4};
+    bool in_flight[2] = {false, false};
+    int tb = 0;
     for (int64_t l0 = locus_first; l0 < locus_first + locus_count; l0 += rows) {
         const int64_t l1 = std::min(l0 + rows, locus_first + locus_count), nr = l1 - l0;
         uint8_t* sp[3];
@@ -1337,7 +1344,7 @@ int psim_emit_text(psim_ctx* ctx, int64_t ind_first, int64_t ind_count, int64_t 
             uint8_t* p = (uint8_t*)c->staging;
             for (int q = 0; q < 3; q++) { sp[q] = nullptr; if (tab[q].host) { sp[q] = p; p += rows * tab[q].pitch; } }
         }
-        CUDA_TRY(cudaStreamSynchronize(c->copy_stream));   // the text of the previous block has left b_text
+        // (the cells in `staging` are read by the text kernels on the same stream as the emission that rewrites them)
         if (int rc = emit_device(c, ind_first, ind_count, l0, l1, l0, sp[0], tab[0].pitch, fb, sp[1], tab[1].pitch, sp[2], tab[2].pitch,
                                  dose_mode, dose_which)) return rc;
         for (int q = 0; q < 3; q++) {
@@ -1367,19 +1374,21 @@ int psim_emit_text(psim_ctx* ctx, int64_t ind_first, int64_t ind_count, int64_t 
             const int64_t total = c->scalars_h[0];
             if (*tab[q].bytes + total > tab[q].cap) too_small = true;
             if (!too_small) {
-                CUDA_TRY(cudaStreamSynchronize(c->copy_stream));   // b_text may grow: nothing may be in flight from it
-                if (int rc = ensure_buf(c, c->b_text, (size_t)total)) return rc;
+                if (in_flight[tb]) CUDA_TRY(cudaEventSynchronize(text_out[tb]));   // this buffer's previous text has left (it may also grow)
+                // the text starts at the same offset modulo 256 on both sides of the PCIe copy
+                const int64_t head = *tab[q].bytes & 255;
+                if (int rc = ensure_buf(c, *text_buf[tb], (size_t)(total + 256))) return rc;
                 ta.row_off = (int64_t*)c->b_rowoff.p;
-                ta.text = (char*)c->b_text.p;
+                ta.text = (char*)text_buf[tb]->p + head;
                 k_text_rows<true><<<blocks, TEXT_THREADS, smem, c->stream>>>(ta);
                 c->stats.kernel_launches++;
                 CUDA_TRY(cudaGetLastError());
                 CUDA_TRY(cudaEventRecord(c->ev2, c->stream));
                 CUDA_TRY(cudaStreamWaitEvent(c->copy_stream, c->ev2, 0));
-                CUDA_TRY(cudaMemcpyAsync(tab[q].host + *tab[q].bytes, c->b_text.p, (size_t)total, cudaMemcpyDeviceToHost, c->copy_stream));
-                // the next table reuses b_text: its write kernel must wait for this copy
-                CUDA_TRY(cudaEventRecord(c->ev3, c->copy_stream));
-                CUDA_TRY(cudaStreamWaitEvent(c->stream, c->ev3, 0));
+                CUDA_TRY(cudaMemcpyAsync(tab[q].host + *tab[q].bytes, ta.text, (size_t)total, cudaMemcpyDeviceToHost, c->copy_stream));
+                CUDA_TRY(cudaEventRecord(text_out[tb], c->copy_stream));
+                in_flight[tb] = true;
+                tb ^= 1;
             }
             *tab[q].bytes += total;
         }
