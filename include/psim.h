@@ -60,7 +60,10 @@ typedef struct psim_config {
     uint32_t replicate_first;      /* first replicate id; replicate r uses Philox key (seed, r) */
     uint32_t replicate_count;      /* >= 1: independent replicate pedigrees simulated side by side */
     int32_t device;                /* CUDA device ordinal */
-    int32_t reserved;
+    int32_t unreduced_gametes;     /* 2NGAMETES (Main.java:179-185; Individual.java:341-383): 0 = haploid gametes,
+                                      1 = FDR, 2 = SDR. Non-zero: every non-founder is formed from ONE unreduced (2n)
+                                      gamete of its parent 0 alone (all P homologs; parent 1 is not used, its meiotic
+                                      configuration stays missing) - the reference analyses such gametes in TEST mode only */
 } psim_config;
 
 int psim_abi_version(void);
@@ -192,11 +195,13 @@ int psim_emit_text(psim_ctx* ctx, int64_t ind_first, int64_t ind_count, int64_t 
  * replicate: homologs [0, P/2) of an individual are the gamete of parent 0's meiosis, [P/2, P) that
  * of parent 1's (Gamete.fertilization, Gamete.java:95-116). One chromosome per call, Lc = its loci,
  * A = founder alleles of the pedigree. Host pointers; NULL skips an output. With an S1 population
- * of one founder this is the reference's TEST setting (one parent, POPSIZE meioses). */
+ * of one founder this is the reference's TEST setting (one parent, POPSIZE meioses). With
+ * unreduced_gametes != 0 an individual IS one 2n gamete: G = P homologs per gamete and one gamete
+ * per individual (Main.java:1546-1548); otherwise G = P/2 and two gametes per individual. */
 typedef struct psim_gamete_stats {
-    int64_t n_gametes;            /* out: 2 * ind_count * replicate_count */
+    int64_t n_gametes;            /* out: (P/G) * ind_count * replicate_count */
     uint32_t* allele_count;       /* [A][Lc]        gamete homologs with founder allele f at the locus (founderAlleleCountSel) */
-    uint32_t* dose_count;         /* [A][Lc][P/2+1] gametes by their dose of founder allele f (founderAlleleDoseSel) */
+    uint32_t* dose_count;         /* [A][Lc][G+1]   gametes by their dose of founder allele f (founderAlleleDoseSel) */
     uint32_t* homozygous_count;   /* [Lc]           gametes holding a founder allele twice or more (founderHomSel) */
     uint32_t* recomb_count;       /* [Lc][Lc]       entry [loc][loc2], loc2 < loc: gamete homologs whose founder alleles
                                                     at the two loci differ (recombCountSel); other entries are 0 */

@@ -31,7 +31,7 @@ final class PsimNative implements AutoCloseable {
             JAVA_INT.withName("natural_pairing"), JAVA_INT.withName("allow_no_recomb"),
             JAVA_DOUBLE.withName("parallel_multivalents"), JAVA_DOUBLE.withName("paired_centromeres"),
             JAVA_LONG.withName("seed"), JAVA_INT.withName("replicate_first"), JAVA_INT.withName("replicate_count"),
-            JAVA_INT.withName("device"), JAVA_INT.withName("reserved"));
+            JAVA_INT.withName("device"), JAVA_INT.withName("unreduced_gametes"));
     // struct psim_emit_targets
     static final StructLayout TARGETS = MemoryLayout.structLayout(
             ADDRESS.withName("founder"), JAVA_LONG.withName("founder_pitch"), JAVA_INT.withName("founder_bytes"),

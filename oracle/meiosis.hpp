@@ -84,6 +84,7 @@ struct Model {
     double paired_centromeres = 0.0;
     bool natural_pairing = true;
     bool allow_no_recomb = true;
+    int unreduced_gametes = 0;          // 2NGAMETES: 0 = haploid gametes, 1 = FDR, 2 = SDR (Main.java:179-185)
     std::vector<Chrom> chrom;
     Rng* rng = nullptr;
 };
@@ -847,6 +848,41 @@ struct MeiosisEngine {
         z.has_parconfig = true;
     }
 
+    // Individual.java:341-383 — the FIRST unreduced (2n) gamete of a meiosis: P homologs per
+    // chromosome taken from the 4 x P/2 homologs do_meiosis leaves.
+    //   FDR (:350-372): gamete 0 ("top") + one of the two "bottom" gametes, 2 unless nextFloat() < 0.5
+    //                   (one draw per meiosis, after all chromosomes);
+    //   SDR (:373-382): gametes 0 and 1 (the second division undone).
+    // The reference only analyses such gametes (TEST mode, Main.testMeiosis); here an "individual"
+    // is formed from the one 2n gamete of its parent 0 alone, so that the emission and statistics
+    // paths see it. parconfig[1] stays missing. In Philox mode the FDR draw has its own stream
+    // (chromosome 0, stage 1022).
+    void unreduced_conception(std::vector<Individual>& pop, int child) {
+        const int P = m.ploidy, C = (int)m.chrom.size(), p2 = P / 2;
+        Individual& z = pop[child];
+        std::vector<std::vector<HS>> g;
+        std::vector<ChromConfig> c0;
+        do_meiosis(pop[z.parent[0]], (uint32_t)child, 0, g, c0);
+        int second = 1;
+        if (m.unreduced_gametes == 1) {
+            rng.seek((uint32_t)child, 0, 0, 1022);
+            second = rng.next_float() < 0.5f ? 3 : 2;
+        }
+        z.hs.assign(C, std::vector<HS>(P));
+        for (int c = 0; c < C; c++)
+            for (int h = 0; h < p2; h++) {
+                z.hs[c][h] = g[c][h];
+                z.hs[c][p2 + h] = g[c][second * p2 + h];
+            }
+        z.has_hs = true;
+        ChromConfig none;
+        none.quad = -1;
+        none.chromseq.assign(P, -1);
+        z.parconfig[0] = c0;
+        z.parconfig[1].assign(C, none);
+        z.has_parconfig = true;
+    }
+
     // Main.java:1504-1520 + Individual.java:155-171
     void simulate_individuals(std::vector<Individual>& pop, int maxfounderallele) {
         const int P = m.ploidy, C = (int)m.chrom.size();
@@ -862,6 +898,8 @@ struct MeiosisEngine {
                 }
                 ind.has_hs = true;
                 maxfounderallele += P;
+            } else if (m.unreduced_gametes != 0) {
+                unreduced_conception(pop, (int)i);
             } else {
                 conception(pop, (int)i);
             }

@@ -49,6 +49,13 @@ void* orc_create(int ploidy, int chiasma_interference, int natural_pairing, int 
     m.rng = h->pop.rng_holder.get();
     return h;
 }
+// 2NGAMETES (Main.java:179-185): 0 = haploid gametes, 1 = FDR, 2 = SDR
+int orc_set_unreduced_gametes(void* p, int kind) {
+    Handle* h = (Handle*)p;
+    if (kind < 0 || kind > 2) return fail(h, "unreduced gametes: 0, 1 (FDR) or 2 (SDR)");
+    h->pop.model.unreduced_gametes = kind;
+    return 0;
+}
 void orc_destroy(void* p) { delete (Handle*)p; }
 const char* orc_last_error(void* p) { return ((Handle*)p)->err.c_str(); }
 

@@ -25,6 +25,7 @@ struct Rng {
     virtual int next_int(int bound) = 0;   // uniform in [0, bound)
     virtual double next_double() = 0;      // uniform in [0, 1), 53 bits
     virtual bool next_bool() = 0;
+    virtual float next_float() = 0;        // uniform in [0, 1), 24 bits (java.util.Random.nextFloat)
     // Select the stream for one unit of work. A no-op for the sequential Java LCG.
     virtual void seek(uint32_t individual, uint32_t chrom, uint32_t parent, uint32_t stage) {
         (void)individual; (void)chrom; (void)parent; (void)stage;
@@ -65,7 +66,7 @@ struct JavaRandom : Rng {
         return (double)((hi << 27) + lo) * 0x1.0p-53;
     }
     bool next_bool() override { return next(1) != 0; }
-    float next_float() { return next(24) / (float)(1 << 24); }
+    float next_float() override { return next(24) / (float)(1 << 24); }
 };
 
 // Philox4x32-10.
@@ -96,7 +97,7 @@ struct Philox4x32 {
 //   the stream yields the four words of block 0, then block 1, ...
 //   next_double = ((a >> 5) * 2^26 + (b >> 6)) * 2^-53  with a, b the next two words
 //   next_int(n) = Lemire multiply-shift with rejection (unbiased), one word per attempt
-//   next_bool   = top bit of the next word
+//   next_bool   = top bit of the next word;  next_float = top 24 bits of the next word * 2^-24
 struct PhiloxStream : Rng {
     uint32_t key[2];
     uint32_t ctr[4];
@@ -130,6 +131,7 @@ struct PhiloxStream : Rng {
         return (double)(((uint64_t)(a >> 5) << 26) | (uint64_t)(b >> 6)) * 0x1.0p-53;
     }
     bool next_bool() override { return (next_u32() >> 31) != 0; }
+    float next_float() override { return (float)(next_u32() >> 8) / (float)(1 << 24); }   // top 24 bits of one word
 };
 
 }  // namespace orc

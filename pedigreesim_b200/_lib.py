@@ -27,7 +27,7 @@ class Config(C.Structure):
         ("ploidy", C.c_int32), ("chiasma_interference", C.c_int32), ("natural_pairing", C.c_int32),
         ("allow_no_recomb", C.c_int32), ("parallel_multivalents", C.c_double), ("paired_centromeres", C.c_double),
         ("seed", C.c_int64), ("replicate_first", C.c_uint32), ("replicate_count", C.c_uint32),
-        ("device", C.c_int32), ("reserved", C.c_int32),
+        ("device", C.c_int32), ("unreduced_gametes", C.c_int32),
     ]
 
 
@@ -130,13 +130,14 @@ class PsimContext:
     """One libpsim context = the device-resident population(s) of one host thread."""
 
     def __init__(self, ploidy, kosambi=False, natural_pairing=True, allow_no_recomb=True, parallel_multivalents=0.0,
-                 paired_centromeres=0.0, seed=12345, replicate_first=0, replicate_count=1, device=0):
+                 paired_centromeres=0.0, seed=12345, replicate_first=0, replicate_count=1, device=0, unreduced_gametes=0):
         self.L = load()
         self.P = ploidy
+        self.unreduced = unreduced_gametes   # 2NGAMETES: 0, 1 = FDR, 2 = SDR
         self.R = replicate_count
         self.replicate_first = replicate_first
         cfg = Config(ploidy, int(kosambi), int(natural_pairing), int(allow_no_recomb), parallel_multivalents,
-                     paired_centromeres, seed, replicate_first, replicate_count, device, 0)
+                     paired_centromeres, seed, replicate_first, replicate_count, device, unreduced_gametes)
         h = C.c_void_p()
         rc = self.L.psim_create(C.byref(cfg), C.byref(h))
         if rc != 0:
@@ -329,7 +330,7 @@ class PsimContext:
     def gamete_stats(self, chrom, n_loci, n_alleles, ind_first=0, ind_count=None, recomb=True):
         """TEST-mode counters of one chromosome over the gametes of the given individuals (dict of arrays)."""
         ind_count = self.N - ind_first if ind_count is None else ind_count
-        nd = self.P // 2 + 1
+        nd = (self.P if self.unreduced else self.P // 2) + 1   # homologs per gamete + 1
         out = {"allele_count": np.zeros((n_alleles, n_loci), np.uint32), "dose_count": np.zeros((n_alleles, n_loci, nd), np.uint32),
                "homozygous_count": np.zeros(n_loci, np.uint32), "segments_hist": np.zeros(64, np.uint32),
                "quadrivalent_hist": np.zeros(self.P // 4 + 1, np.uint32)}

@@ -431,6 +431,7 @@ int psim_create(const psim_config* cfg, psim_ctx** out) {
     if (cfg->ploidy <= 0 || cfg->ploidy % 2 != 0) { g_create_error = "Error in PopulationData: ploidy must be even"; return PSIM_EINVAL; }
     if (cfg->ploidy > MAXP) { g_create_error = "ploidy above 16 is not supported by the device path"; return PSIM_EINVAL; }
     if (cfg->replicate_count < 1) { g_create_error = "replicate_count must be >= 1"; return PSIM_EINVAL; }
+    if (cfg->unreduced_gametes < 0 || cfg->unreduced_gametes > 2) { g_create_error = "unreduced_gametes must be 0, 1 (FDR) or 2 (SDR)"; return PSIM_EINVAL; }
     int ndev = 0;
     cudaError_t e = cudaGetDeviceCount(&ndev);
     if (e != cudaSuccess || ndev == 0) {
@@ -451,6 +452,7 @@ int psim_create(const psim_config* cfg, psim_ctx** out) {
     c->model.parallel_multivalents = cfg->parallel_multivalents;
     c->model.paired_centromeres = cfg->paired_centromeres;
     c->model.seed = (uint32_t)cfg->seed;
+    c->model.unreduced = cfg->unreduced_gametes;
     cudaDeviceProp prop;
     if (cudaGetDeviceProperties(&prop, cfg->device) == cudaSuccess) c->sm_count = prop.multiProcessorCount;
     bool ok = cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking) == cudaSuccess &&
@@ -765,7 +767,7 @@ static int simulate_impl(psim_ctx_impl* c, int32_t max_founder_allele, const int
             aa.par0 = c->par0_d; aa.par1 = c->par1_d; aa.desc = c->desc_d; aa.seg_pos = c->seg_pos_d;
             aa.seg_founder = c->seg_founder_d; aa.piece_cap = c->piece_cap; aa.plan_np = plan_np; aa.plan_cnt = plan_cnt;
             aa.plan_off = plan_off; aa.plan_pos = plan_pos; aa.plan_hom = plan_hom; aa.slab_base = c->slab_used;
-            aa.slab_cap = c->slab_cap; aa.error_flag = c->error_flag_d;
+            aa.slab_cap = c->slab_cap; aa.error_flag = c->error_flag_d; aa.unreduced = c->model.unreduced;
             k_meiosis_assemble<<<grid_for(nu, 128), 128, 0, c->stream>>>(aa);
             c->stats.kernel_launches++;
             CUDA_TRY(cudaGetLastError());
@@ -788,8 +790,8 @@ static int simulate_impl(psim_ctx_impl* c, int32_t max_founder_allele, const int
                 if (last_batch) CUDA_TRY(cudaEventRecord(c->ev1, c->stream));
             }
             c->slab_used += total;
-            c->stats.n_meioses += (int64_t)n_lev * R * 2;
-            c->stats.n_units += (int64_t)n_lev * R * 2 * C;
+            c->stats.n_meioses += (int64_t)n_lev * R * (c->model.unreduced ? 1 : 2);
+            c->stats.n_units += (int64_t)n_lev * R * (c->model.unreduced ? 1 : 2) * C;
         }
         for (int32_t i : inds) c->hs_reps[i] = R;
     }
@@ -1411,7 +1413,8 @@ int psim_gamete_stats_run(psim_ctx* ctx, int64_t ind_first, int64_t ind_count, i
     if (int rc = emit_prepare(c, ind_first, ind_count, c->locus_off_h[chrom], std::max<int64_t>(1, c->locus_off_h[chrom + 1] - c->locus_off_h[chrom]))) return rc;
     const int64_t Lc = c->locus_off_h[chrom + 1] - c->locus_off_h[chrom];
     if (Lc <= 0) return fail(c, PSIM_EINVAL, "the chromosome has no loci");
-    const int A = c->founder_allele_count, P = c->P, nd = P / 2 + 1;
+    const int A = c->founder_allele_count, P = c->P;
+    const int gp = c->model.unreduced ? P : P / 2, nd = gp + 1;   // homologs per gamete (Main.java:1546-1548)
     if (A <= 0 || A > 4096) return fail(c, PSIM_EINVAL, "gamete statistics need 1..4096 founder alleles");
     const size_t n_ac = (size_t)A * Lc, n_dc = n_ac * nd, n_diff = (size_t)(Lc + 1) * (Lc + 1);
     const size_t n_words = n_ac + n_dc + (size_t)Lc + (out->recomb_count ? n_diff : 0) + 64 + (size_t)(P / 4 + 1);
@@ -1419,7 +1422,7 @@ int psim_gamete_stats_run(psim_ctx* ctx, int64_t ind_first, int64_t ind_count, i
     uint32_t* w = (uint32_t*)c->b_text.p;
     CUDA_TRY(cudaMemsetAsync(w, 0, n_words * 4, c->stream));
     StatsArgs sa{};
-    sa.C = c->C; sa.R = c->R; sa.P = P; sa.A = A; sa.N = c->N;
+    sa.C = c->C; sa.R = c->R; sa.P = P; sa.A = A; sa.N = c->N; sa.gp = gp;
     sa.run_desc = c->run_desc_d; sa.run_lb = c->run_lb_d; sa.run_founder = c->run_founder_d;
     sa.desc = c->desc_d; sa.cfg_quad = c->cfg_quad_d;
     sa.ind_first = ind_first; sa.ind_count = ind_count; sa.chrom = chrom; sa.Lc = (uint32_t)Lc;
@@ -1445,7 +1448,7 @@ int psim_gamete_stats_run(psim_ctx* ctx, int64_t ind_first, int64_t ind_count, i
         c->stats.kernel_launches++;
     }
     CUDA_TRY(cudaGetLastError());
-    out->n_gametes = 2 * ind_count * c->R;
+    out->n_gametes = (P / gp) * ind_count * c->R;
     if (out->allele_count) CUDA_TRY(cudaMemcpyAsync(out->allele_count, sa.allele_count, n_ac * 4, cudaMemcpyDeviceToHost, c->stream));
     if (out->dose_count) CUDA_TRY(cudaMemcpyAsync(out->dose_count, sa.dose_count, n_dc * 4, cudaMemcpyDeviceToHost, c->stream));
     if (out->homozygous_count) CUDA_TRY(cudaMemcpyAsync(out->homozygous_count, sa.homozygous_count, (size_t)Lc * 4, cudaMemcpyDeviceToHost, c->stream));

@@ -72,7 +72,7 @@ __global__ void __launch_bounds__(128) k_meiosis_config(PlanArgs a) {
     const int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     const int64_t total = (int64_t)a.C * a.R * a.n_lev * 2;
     int n_quad = 0, n_bi = 0;
-    if (t < total) {
+    if (t < total && !(a.model.unreduced && (t & 1))) {   // 2NGAMETES: the individual is parent 0's 2n gamete alone
         int par, j, r, c;
         plan_decode(a, t, par, j, r, c);
         const int P = a.P;
@@ -145,12 +145,26 @@ __global__ void __launch_bounds__(128) k_meiosis_mv(PlanArgs a) {
     // will occupy after the gamete's homolog shuffle. The shuffle draws come from their own stream:
     // slot h of the transmitted gamete receives pre-shuffle slot shuf[h] (Individual.java:325-335).
     const int64_t u0 = (((int64_t)c * a.R + r) * a.n_lev + j) * P + (int64_t)par * p2;
-    int8_t shuf[MAXP / 2];
-    for (int s = 0; s < p2; s++) shuf[s] = (int8_t)s;
+    // Transmitted gametes: gamete 0 (Individual.java:258-259), plus with 2NGAMETES the second half
+    // of the unreduced gamete (:350-382): gamete 1 (SDR) or bottom gamete 3 / 2 (FDR, one draw per
+    // meiosis); their chromatids fill the child's homologs P/2 .. P-1.
+    const int unred = m.unreduced;
+    int g_second = 0;
+    if (unred == 2) g_second = 1;
+    else if (unred == 1) {
+        rng.seek((uint32_t)child, 0u, (uint32_t)par, STAGE_UNREDUCED);
+        g_second = rng.next_float() < 0.5f ? 3 : 2;
+    }
+    const int n_gam = unred ? 2 : 1;
+    int8_t dest_of_slot[2][MAXP / 2];  // [transmitted gamete][pre-shuffle slot] -> final homolog position in that gamete
     rng.seek((uint32_t)child, (uint32_t)c, (uint32_t)par, STAGE_SHUFFLE);
-    shuffle_small(rng, shuf, p2);
-    int8_t dest_of_slot[MAXP / 2];  // pre-shuffle slot -> final homolog position
-    for (int h = 0; h < p2; h++) dest_of_slot[shuf[h]] = (int8_t)h;
+    for (int g = 0; g <= g_second; g++) {   // the four gametes are shuffled in order on one stream
+        int8_t shuf[MAXP / 2];
+        for (int s = 0; s < p2; s++) shuf[s] = (int8_t)s;
+        shuffle_small(rng, shuf, p2);
+        if (g == 0) for (int h = 0; h < p2; h++) dest_of_slot[0][shuf[h]] = (int8_t)h;
+        if (g == g_second) for (int h = 0; h < p2; h++) dest_of_slot[1][shuf[h]] = (int8_t)h;
+    }
 
     const int firstbi = quad * 4;
     constexpr int k = QUAD ? 4 : 2;
@@ -165,17 +179,19 @@ __global__ void __launch_bounds__(128) k_meiosis_mv(PlanArgs a) {
     int8_t centro[8];
     if (QUAD) quadrivalent_centromere_order(rng, m, ch, exchange_lim1, centro);
     else multivalent_centromere_order(rng, 2, centro);
-    int start_slots[2];
-    select_gamete0(x, rng, k, ch, centro, start_slots);
+    int8_t pattern_slot[8];
+    select_gametes(x, rng, k, ch, centro, pattern_slot);
     constexpr int n_out = QUAD ? 2 : 1;
-    for (int o = 0; o < n_out; o++) {
+    for (int go = 0; go < n_gam * n_out; go++) {
+        const int gi = go / n_out, o = go % n_out;
+        const int g = gi == 0 ? 0 : g_second;
         // Individual.java:297-321: quadrivalent v fills gamete slots 2v, 2v+1; bivalent v' fills firstbi/2 + v'
         const int pre_slot = QUAD ? 2 * v + o : firstbi / 2 + (v - quad);
-        const int64_t u = u0 + dest_of_slot[pre_slot];
+        const int64_t u = u0 + gi * p2 + dest_of_slot[gi][pre_slot];
         double* ppos = a.plan_pos + u * a.piece_cap;
         uint8_t* phom = a.plan_hom + u * a.piece_cap;
         // Multivalent.slotsToPatterns (:332-357) for the selected chromatid
-        int cur = start_slots[o];
+        int cur = pattern_slot[QUAD ? 2 * g + o : g];
         int np = 0;
         ppos[0] = ch.head;
         phom[0] = (uint8_t)chromseq[base + (cur >> 1)];
@@ -243,6 +259,7 @@ struct AssembleArgs {
     int64_t slab_base;
     int64_t slab_cap;          // segments the slab holds: a batch that does not fit is not written at all
     const int* error_flag;     // set by the plan kernels: the plan is incomplete, nothing is assembled
+    int unreduced;             // ModelParams::unreduced
 };
 
 __global__ void __launch_bounds__(128) k_meiosis_assemble(AssembleArgs a) {
@@ -256,7 +273,7 @@ __global__ void __launch_bounds__(128) k_meiosis_assemble(AssembleArgs a) {
     const int r = (int)((u / ((int64_t)P * a.n_lev)) % a.R);
     const int c = (int)(u / ((int64_t)P * a.n_lev * a.R));
     const int32_t child = a.lev_ind[j];
-    const int32_t parent = h < p2 ? a.par0[child] : a.par1[child];
+    const int32_t parent = (h < p2 || a.unreduced) ? a.par0[child] : a.par1[child];   // 2NGAMETES: all P homologs from parent 0
     const int64_t phid0 = (((int64_t)c * a.R + r) * a.N + parent) * P;
     const double tail = a.chrom[c].tail;
     const int np = a.plan_np[u];

@@ -29,6 +29,7 @@ struct ModelParams {
     double parallel_multivalents;
     double paired_centromeres;
     uint32_t seed;
+    int unreduced;   // 2NGAMETES: 0 = haploid gametes, 1 = FDR, 2 = SDR (Individual.java:341-383)
 };
 struct ChromParams {
     double head, tail, centro;
@@ -531,12 +532,13 @@ __device__ inline void quadrivalent_centromere_order(PhiloxStream& rng, const Mo
     for (int g = 0; g < 4; g++) { shuffle_small(rng, gam[g], 2); centro[2 * g] = gam[g][0]; centro[2 * g + 1] = gam[g][1]; }
 }
 
-// Multivalent.patternsToGametes :486-518 on indices: which starting slots end up as the
-// chromatids of gamete 0 (one for a bivalent, two for a quadrivalent).
-__device__ inline void select_gamete0(const Chiasmata& x, PhiloxStream& rng, int k, const ChromParams& ch,
-                                      const int8_t* centro, int* out_slots) {
+// Multivalent.patternsToGametes :486-518 on indices: idx[s] = the starting slot of the chromatid
+// that ends up as output pattern s. Gamete g receives pattern g of a bivalent, patterns 2g and
+// 2g+1 of a quadrivalent.
+__device__ inline void select_gametes(const Chiasmata& x, PhiloxStream& rng, int k, const ChromParams& ch,
+                                      const int8_t* centro, int8_t* idx) {
     const int n = 2 * k;
-    int8_t idx[8], fac[8];
+    int8_t fac[8];
     for (int p = 0; p < n; p++) { idx[p] = (int8_t)p; fac[p] = (int8_t)pattern_chrom_at(x, p, ch.centro); }
     for (int s = 0; s < n - 1; s++) {
         if (fac[idx[s]] != centro[s]) {
@@ -553,10 +555,6 @@ __device__ inline void select_gamete0(const Chiasmata& x, PhiloxStream& rng, int
                 const int8_t tmp = idx[first]; idx[first] = idx[second]; idx[second] = tmp;
             }
         }
-        out_slots[0] = idx[0];
-        out_slots[1] = idx[1];
-    } else {
-        out_slots[0] = idx[0];
     }
 }
 

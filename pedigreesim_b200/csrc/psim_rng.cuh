@@ -2,7 +2,7 @@
 //   key = { (u32) seed, replicate }
 //   ctr = { block#, individual, chrom | parent << 20 | stage << 21, 0x5053494d }
 // One stream per (replicate, individual, chromosome, parent, stage): stage 0 = pairing
-// configuration, 1 + v = multivalent v, 1023 = gamete homolog shuffle. The draw order inside a
+// configuration, 1 + v = multivalent v, 1023 = gamete homolog shuffle, 1022 = FDR draw. The draw order inside a
 // stream is the reference's (SURVEY.md §8a "RNG call sites"); the primitives replace
 // java.util.Random's (Tools.java:22-27): next_int is Lemire's unbiased multiply-shift,
 // next_double takes 53 bits from two words, next_bool the top bit of one word.
@@ -13,6 +13,7 @@ namespace psim {
 
 constexpr uint32_t STAGE_CONFIG = 0;
 constexpr uint32_t STAGE_SHUFFLE = 1023;
+constexpr uint32_t STAGE_UNREDUCED = 1022;   // the FDR draw of a meiosis (chromosome 0)
 
 struct PhiloxStream {
     uint32_t k0, k1;
@@ -61,6 +62,7 @@ struct PhiloxStream {
         return (double)(((uint64_t)(a >> 5) << 26) | (uint64_t)(b >> 6)) * 0x1.0p-53;
     }
     __device__ __forceinline__ bool next_bool() { return (next_u32() >> 31) != 0; }
+    __device__ __forceinline__ float next_float() { return (float)(next_u32() >> 8) * 0x1.0p-24f; }   // java.util.Random.nextFloat: 24 bits
 };
 
 }  // namespace psim

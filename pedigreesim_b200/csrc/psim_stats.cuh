@@ -8,6 +8,7 @@
 // of parent 0's meiosis, [P/2, P) that of parent 1's. All of it works on the locus-index runs of K0.
 struct StatsArgs {
     int C, R, P, A;
+    int gp;                           // homologs per gamete: P/2, or P with unreduced gametes
     int64_t N;
     const uint64_t* run_desc; const uint32_t* run_lb; const uint16_t* run_founder;
     const uint64_t* desc;             // unmerged segment lists (segment counts as the reference holds them)
@@ -15,7 +16,7 @@ struct StatsArgs {
     int64_t ind_first, ind_count;
     int chrom; uint32_t Lc;
     uint32_t* allele_count;           // [A][Lc]
-    uint32_t* dose_count;             // [A][Lc][P/2+1]
+    uint32_t* dose_count;             // [A][Lc][gp+1]
     uint32_t* homozygous_count;       // [Lc]
     int32_t* diff;                    // [(Lc+1)][(Lc+1)] 2-D difference array of the recombination counts
     uint32_t* segments_hist;          // [64]
@@ -32,20 +33,20 @@ __device__ __forceinline__ uint32_t founder_at_row(const StatsArgs& a, int64_t h
 
 // one block per locus: founder-allele counts, dose histogram and homozygosity over all gametes
 __global__ void __launch_bounds__(256) k_stats_locus(const StatsArgs a) {
-    extern __shared__ uint32_t s_hist[];     // [A] counts, then [A][P/2+1] doses, then 1 homozygous
+    extern __shared__ uint32_t s_hist[];     // [A] counts, then [A][gp+1] doses, then 1 homozygous
     const uint32_t l = blockIdx.x;
-    const int p2 = a.P / 2, nd = p2 + 1;
+    const int p2 = a.gp, nd = p2 + 1, per_ind = a.P / a.gp;
     const int n_bins = a.A + a.A * nd + 1;
     for (int i = threadIdx.x; i < n_bins; i += blockDim.x) s_hist[i] = 0;
     __syncthreads();
-    const int64_t n_gam = 2 * a.ind_count * a.R;
+    const int64_t n_gam = (int64_t)per_ind * a.ind_count * a.R;
     uint32_t zero_gametes = 0;   // gametes seen by this thread: dose 0 bins are filled in bulk at the end
     for (int64_t g = threadIdx.x; g < n_gam; g += blockDim.x) {
-        const int half = (int)(g & 1);
-        const int64_t q = g >> 1;
+        const int half = (int)(g % per_ind);
+        const int64_t q = g / per_ind;
         const int64_t r = q / a.ind_count, i = a.ind_first + q % a.ind_count;
         const int64_t hid0 = (((int64_t)a.chrom * a.R + r) * a.N + i) * a.P + (int64_t)half * p2;
-        uint32_t f[MAXP / 2];
+        uint32_t f[MAXP];
         for (int h = 0; h < p2; h++) f[h] = founder_at_row(a, hid0 + h, l);
         bool homoz = false;
         for (int h = 0; h < p2; h++) {

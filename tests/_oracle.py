@@ -40,6 +40,7 @@ def lib():
         L.orc_create.restype = vp
         L.orc_create.argtypes = [i32, i32, i32, i32, dbl, dbl, i32, i64, u32]
         L.orc_destroy.argtypes = [vp]
+        L.orc_set_unreduced_gametes.argtypes = [vp, i32]
         L.orc_last_error.restype = C.c_char_p
         L.orc_last_error.argtypes = [vp]
         L.orc_set_chromosomes.argtypes = [vp, i32, vp, vp, vp, vp]
@@ -80,11 +81,14 @@ class Oracle:
     """CPU restatement of the reference's meiosis + emission path."""
 
     def __init__(self, ploidy, kosambi=False, natural_pairing=True, allow_no_recomb=True,
-                 parallel_multivalents=0.0, paired_centromeres=0.0, rng=RNG_PHILOX, seed=12345, replicate=0):
+                 parallel_multivalents=0.0, paired_centromeres=0.0, rng=RNG_PHILOX, seed=12345, replicate=0,
+                 unreduced_gametes=0):
         self.L = lib()
         self.P = ploidy
         self.h = self.L.orc_create(ploidy, int(kosambi), int(natural_pairing), int(allow_no_recomb),
                                    parallel_multivalents, paired_centromeres, rng, seed, replicate)
+        if unreduced_gametes:
+            self._chk(self.L.orc_set_unreduced_gametes(self.h, unreduced_gametes))
         self.C = 0
         self.N = 0
 

@@ -182,3 +182,33 @@ def test_sharded_generations_on_one_gpu_match_oracle():
         sg, fg, pg = sh.ctx.get_haplostructs()
         assert np.array_equal(so, sg) and np.array_equal(fo, fg)
         assert np.allclose(po, pg, rtol=POS_RTOL, atol=1e-15)
+
+
+@pytest.mark.parametrize("kind", [1, 2])   # 2NGAMETES = FDR, SDR (Individual.java:341-383)
+@pytest.mark.parametrize("ploidy,natural", [(2, True), (4, False), (4, True), (6, True)])
+def test_unreduced_gametes_fdr_and_sdr(ploidy, natural, kind):
+    p0, p1 = _cases.std_pedigree("F2", 150)   # the 2n "individuals" of one generation are the parents of the next
+    o, g = run_pair(ploidy, p0, p1, [1.0, 1.4, 0.7], [0.4, 0.7, 0.0], pref=[0.0, 0.4, 1.0], fq=[0.5, 1.0, 0.0],
+                    natural_pairing=natural, unreduced_gametes=kind, seed=500 + kind)
+    assert_same_population(o, g)
+    quad, seq = g.get_meiotic_configs()
+    assert (quad[3:, :, 1] == -1).all() and (seq[3:, :, 1] == -1).all()   # parent 1 took no part
+    if ploidy == 4 and not natural:
+        assert quad[3:, :2, 0].max() >= 1
+
+
+def test_unreduced_gametes_kosambi_replicates():
+    p0, p1 = _cases.std_pedigree("S1", 100)
+    import pedigreesim_b200
+    g = pedigreesim_b200.PsimContext(4, kosambi=True, natural_pairing=False, seed=9, replicate_first=2, replicate_count=2,
+                                     unreduced_gametes=1, paired_centromeres=0.5)
+    g.set_chromosomes([1.2], [0.5], [0.3], [0.6])
+    g.set_pedigree(p0, p1)
+    g.simulate()
+    for r in (2, 3):
+        o = _cases.make_engine("oracle-philox", 4, kosambi=True, natural_pairing=False, seed=9, replicate_first=r,
+                               unreduced_gametes=1, paired_centromeres=0.5)
+        o.set_chromosomes([1.2], [0.5], [0.3], [0.6])
+        o.set_pedigree(p0, p1)
+        o.simulate()
+        assert_same_population(o, g, replicate=r)

@@ -185,11 +185,11 @@ def test_full_size_configs1_emission_properties():
 
 
 # ------------------------------------------------------------------ device reductions
-def _numpy_gamete_stats(F, P, A):
+def _numpy_gamete_stats(F, P, A, unreduced=False):
     """Main.testMeiosis counters (Main.java:1660-1721) from the founder table F [L][n_ind][P]."""
     L, n, _ = F.shape
-    p2 = P // 2
-    G = F.reshape(L, n * 2, p2)                      # gametes: the two halves of every individual
+    p2 = P if unreduced else P // 2                  # homologs per gamete (Main.java:1546-1548)
+    G = F.reshape(L, n * (P // p2), p2)              # gametes: the two halves of every individual, or all of it
     allele = np.stack([(G == f).sum(axis=(1, 2)) for f in range(A)])                       # [A][L]
     dose = np.stack([np.stack([((G == f).sum(axis=2) == d).sum(axis=1) for d in range(p2 + 1)], axis=1) for f in range(A)])
     srt = np.sort(G, axis=2)
@@ -268,3 +268,36 @@ def test_test_mode_setting_double_reduction_and_recombination_on_device():
     # returning to the same founder needs an even number of exchanges with the SAME partner
     se = np.sqrt(0.25 / (st["n_gametes"] * 2))
     assert abs(r - expect) < stats.norm.isf(P_FLOOR / 2) * se
+
+
+@pytest.mark.parametrize("kind", [1, 2])
+def test_unreduced_gametes_on_device_fdr_and_sdr(kind):
+    """2NGAMETES (Individual.java:341-383): device counters over 2n gametes (one per individual, G = P
+    homologs) against the same counts taken from the emitted table, and the tetrad-analysis closed
+    forms of tests/test_oracle_pins.py on a diploid bivalent."""
+    n = 20000
+    p0, p1 = _cases.std_pedigree("S1", n)
+    ce = 0.2
+    g = _gpu(2, p0, p1, [1.0], [ce], unreduced_gametes=kind)
+    pos = np.array([ce, 0.3, 0.5, 1.0])
+    g.set_map([0, 4], pos)
+    st = g.gamete_stats(0, 4, 2, ind_first=1)
+    assert st["n_gametes"] == n and st["dose_count"].shape == (2, 4, 3)
+    F = g.emit(founder=True, ind_first=1)["founder"].reshape(4, n, 2)
+    allele, dose, homoz, rec = _numpy_gamete_stats(F, 2, 2, unreduced=True)
+    assert np.array_equal(st["allele_count"], allele) and np.array_equal(st["dose_count"], dose)
+    assert np.array_equal(st["homozygous_count"], homoz) and np.array_equal(st["recomb_count"], rec)
+    het = 1.0 - st["homozygous_count"] / n
+    assert het[0] == (1.0 if kind == 1 else 0.0)
+    for k in range(1, 4):
+        y = 2.0 / 3.0 * (1 - np.exp(-3 * (pos[k] - ce)))
+        expect = 1 - y / 2 if kind == 1 else y
+        assert abs(het[k] - expect) < stats.norm.isf(P_FLOOR / 2) * np.sqrt(expect * (1 - expect) / n), (kind, k, het[k], expect)
+    # tetraploid, all quadrivalents: same counters, table cross-check only
+    g = _gpu(4, p0[:3001], p1[:3001], [1.0], [0.4], [0.2], [1.0], natural_pairing=False, unreduced_gametes=kind)
+    g.set_map([0, 4], pos)
+    st = g.gamete_stats(0, 4, 4, ind_first=1)
+    F = g.emit(founder=True, ind_first=1)["founder"].reshape(4, 3000, 4)
+    allele, dose, homoz, rec = _numpy_gamete_stats(F, 4, 4, unreduced=True)
+    assert st["n_gametes"] == 3000 and np.array_equal(st["dose_count"], dose) and np.array_equal(st["homozygous_count"], homoz)
+    assert np.array_equal(st["recomb_count"], rec) and st["quadrivalent_hist"].tolist() == [0, 3000]

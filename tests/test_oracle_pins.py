@@ -181,3 +181,46 @@ def test_founder_columns_are_their_own_alleles():
     # offspring: first two homologs from P1 (alleles 0-3), last two from P2 (4-7): Gamete.java:95-116
     kids = F[:, 8:].reshape(4, 10, 4)
     assert kids[:, :, :2].max() <= 3 and kids[:, :, 2:].min() >= 4
+
+
+@pytest.mark.parametrize("rng", [RNG_JAVA, RNG_PHILOX])
+@pytest.mark.parametrize("kind", [1, 2])
+def test_unreduced_gametes_heterozygosity_follows_tetrad_analysis(rng, kind):
+    """2NGAMETES (Individual.java:341-383) on a diploid bivalent, Haldane. An SDR gamete holds the two
+    sister chromatids of one centromere, an FDR gamete one chromatid of each centromere. With y(d) the
+    frequency of second-division segregation at d Morgan from the centromere (Mather: per chiasma a
+    first-division pattern always becomes second-division, a second-division one stays so with
+    probability 1/2; chiasmata Poisson with mean 2d), y = 2/3 (1 - exp(-3d)), the gamete is
+    heterozygous with probability y (SDR) or 1 - y/2 (FDR)."""
+    n = 8000
+    ce = 0.2
+    o = _selfed_founder(2, n, [1.0], [ce], None, None, rng, seed=77 + kind, unreduced_gametes=kind)
+    pos = np.array([ce, 0.3, 0.5, 1.0])
+    o.set_map([0, len(pos)], pos)
+    F = o.emit(_oracle.EMIT_FOUNDER, ind_first=1).reshape(len(pos), n, 2)
+    het = (F[:, :, 0] != F[:, :, 1]).mean(axis=1)
+    assert het[0] == (1.0 if kind == 1 else 0.0)        # at the centromere: FDR always, SDR never
+    for k in range(1, len(pos)):
+        y = 2.0 / 3.0 * (1 - np.exp(-3 * (pos[k] - ce)))
+        expect = 1 - y / 2 if kind == 1 else y
+        assert abs(het[k] - expect) < 5 * np.sqrt(expect * (1 - expect) / n), (kind, pos[k], het[k], expect)
+    if kind == 2:   # SDR: either centromere with probability 1/2
+        c0 = (F[0, :, 0] == 0).mean()
+        assert abs(c0 - 0.5) < 5 * np.sqrt(0.25 / n)
+    quad, seq = o.get_meiotic_configs(first=1)
+    assert (quad[:, :, 1] == -1).all() and (seq[:, :, 1] == -1).all()
+
+
+def test_unreduced_tetraploid_gametes_carry_every_centromere_once_under_fdr():
+    """FDR 'each gamete must get one copy of the centromere of each parental homologue'
+    (Individual.java:357-358) - true for bivalent pairing; SDR gametes carry half of them twice."""
+    n = 3000
+    ce = 0.45
+    for kind in (1, 2):
+        o = _selfed_founder(4, n, [1.0], [ce], [0.5], [0.0], RNG_PHILOX, seed=21, natural_pairing=False, unreduced_gametes=kind)
+        o.set_map([0, 1], [ce])
+        F = np.sort(o.emit(_oracle.EMIT_FOUNDER, ind_first=1).reshape(n, 4), axis=1)
+        if kind == 1:
+            assert (F == np.arange(4)).all()
+        else:
+            assert (F[:, 0] == F[:, 1]).all() and (F[:, 2] == F[:, 3]).all() and (F[:, 1] != F[:, 2]).all()
