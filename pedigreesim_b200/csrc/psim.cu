@@ -131,6 +131,14 @@ struct psim_ctx_impl {
     int64_t* exp_off_d = nullptr; int32_t* exp_founder_d = nullptr; double* exp_pos_d = nullptr;
     int64_t exp_off_cap = 0, exp_seg_cap = 0;
     int64_t pop_cap_ind = 0, pop_cap_hom = 0, pop_cap_cfg = 0;   // what the population arrays can hold
+    // founder list and generation lists of a simulation that starts from the empty population
+    struct SimPlan {
+        bool valid = false, on_device = false;
+        int32_t maxf_in = 0, max_level = 0;
+        std::vector<int32_t> f_ind, f_allele, order;
+        std::vector<int64_t> level_off;
+    } plan;
+    bool fresh = false;   // no individual has a haplostruct (after psim_set_pedigree / psim_reset)
     psim_stats stats{};
     int sm_count = 148;
 };
@@ -580,6 +588,8 @@ int psim_set_pedigree(psim_ctx* ctx, int64_t n_ind, const int32_t* parent0, cons
     }
     c->slab_used = 0;
     c->runs_valid = false;
+    c->fresh = true;
+    c->plan.valid = false;
     c->N = n_ind;
     c->founder_allele_count = nf * c->P;
     c->par0_h.assign(parent0, parent0 + n_ind);
@@ -630,6 +640,7 @@ int psim_set_haplostructs(psim_ctx* ctx, uint32_t replicate, int64_t first, int6
     c->stats.n_segments = c->slab_used;
     for (int64_t i = first; i < first + count; i++) c->hs_reps[i] = std::min(c->hs_reps[i] + 1, c->R);
     c->runs_valid = false;
+    c->fresh = false;
     return PSIM_OK;
 }
 
@@ -641,81 +652,110 @@ static int simulate_impl(psim_ctx_impl* c, int32_t max_founder_allele, const int
     cudaSetDevice(c->cfg.device);
     const int C = c->C, P = c->P, R = c->R;
     const int64_t N = c->N;
-    for (int64_t i = 0; i < N; i++)
-        if (c->hs_reps[i] != 0 && c->hs_reps[i] != R)
-            return fail(c, PSIM_EINVAL, "preset haplostructs must cover the same individuals in every replicate");
+    // A Monte Carlo loop (psim_reset, psim_simulate, ...) simulates the same pedigree from the same
+    // empty state again and again: the founder list and the generation lists are then kept, on the
+    // host and on the device, instead of being rebuilt and uploaded every time.
+    psim_ctx_impl::SimPlan& sp = c->plan;
+    const bool fresh = c->fresh && !subset;
+    const bool reuse = fresh && sp.valid && sp.maxf_in == max_founder_allele;
+    if (!fresh)
+        for (int64_t i = 0; i < N; i++)
+            if (c->hs_reps[i] != 0 && c->hs_reps[i] != R)
+                return fail(c, PSIM_EINVAL, "preset haplostructs must cover the same individuals in every replicate");
     CUDA_TRY(cudaEventRecord(c->ev0, c->stream));
-    // --- founders (Main.java:1510-1513)
-    std::vector<int32_t> f_ind, f_allele;
-    int32_t maxf = max_founder_allele;
-    for (int64_t i = 0; i < N; i++) {
-        if (c->hs_reps[i]) continue;
-        if (c->par0_h[i] < 0) { f_ind.push_back((int32_t)i); f_allele.push_back(maxf + 1); maxf += P; }
+    psim_ctx_impl::SimPlan local;
+    psim_ctx_impl::SimPlan& pl = reuse ? sp : local;
+    if (!reuse) {
+        // --- founders (Main.java:1510-1513)
+        int32_t maxf = max_founder_allele;
+        for (int64_t i = 0; i < N; i++) {
+            if (c->hs_reps[i]) continue;
+            if (c->par0_h[i] < 0) { pl.f_ind.push_back((int32_t)i); pl.f_allele.push_back(maxf + 1); maxf += P; }
+        }
+        if (maxf > 65535) return fail(c, PSIM_ECAPACITY, "more than 65536 founder alleles");
+        // --- generations: level = 1 + max(level of parents) over individuals still to simulate
+        std::vector<int32_t> level(N, 0);
+        int32_t max_level = 0;
+        std::vector<uint8_t> wanted;
+        if (subset) {
+            wanted.assign(N, 0);
+            for (int64_t k = 0; k < n_subset; k++) {
+                if (subset[k] < 0 || subset[k] >= N) return fail(c, PSIM_EINVAL, "individual index out of bounds");
+                wanted[subset[k]] = 1;
+            }
+        }
+        for (int64_t i = 0; i < N; i++) {
+            if (c->hs_reps[i] || c->par0_h[i] < 0) continue;   // has a haplostruct, or is a founder about to get one
+            if (subset && !wanted[i]) { level[i] = -1; continue; }   // left for another rank / a later call
+            const int32_t l0 = level[c->par0_h[i]], l1 = level[c->par1_h[i]];
+            if (l0 < 0 || l1 < 0) return fail(c, PSIM_ESTATE, "a parent of individual " + std::to_string(i) + " has no haplostruct yet");
+            level[i] = 1 + std::max(l0, l1);
+            max_level = std::max(max_level, level[i]);
+        }
+        std::vector<int64_t> cnt(max_level + 2, 0);
+        for (int64_t i = 0; i < N; i++) if (level[i] > 0) cnt[level[i] + 1]++;
+        for (int lv = 1; lv <= max_level + 1; lv++) cnt[lv] += cnt[lv - 1];
+        pl.level_off = cnt;                                   // individuals of level lv: order[level_off[lv] .. level_off[lv+1])
+        pl.order.assign((size_t)cnt[max_level + 1], 0);
+        std::vector<int64_t> fill(cnt.begin(), cnt.end());
+        for (int64_t i = 0; i < N; i++) if (level[i] > 0) pl.order[(size_t)fill[level[i]]++] = (int32_t)i;
+        pl.max_level = max_level;
+        pl.maxf_in = max_founder_allele;
+        pl.on_device = false;
     }
-    if (maxf > 65535) return fail(c, PSIM_ECAPACITY, "more than 65536 founder alleles");
-    if (!f_ind.empty()) {
-        const int n_new = (int)f_ind.size();
+    const int32_t max_level = pl.max_level;
+    const bool upload = !(reuse && sp.on_device);
+    if (upload && !fresh) sp.on_device = false;   // the device copies of the lists are about to be overwritten
+    if (!pl.f_ind.empty()) {
+        const int n_new = (int)pl.f_ind.size();
         const int64_t nseg = (int64_t)n_new * R * C * P;
         if (int rc = ensure_slab(c, c->slab_used + nseg)) return rc;
         if (int rc = ensure_buf(c, c->b_find, n_new * sizeof(int32_t))) return rc;
         if (int rc = ensure_buf(c, c->b_fal, n_new * sizeof(int32_t))) return rc;
         int32_t *ind_d = (int32_t*)c->b_find.p, *al_d = (int32_t*)c->b_fal.p;
-        CUDA_TRY(cudaMemcpyAsync(ind_d, f_ind.data(), n_new * sizeof(int32_t), cudaMemcpyHostToDevice, c->stream));
-        CUDA_TRY(cudaMemcpyAsync(al_d, f_allele.data(), n_new * sizeof(int32_t), cudaMemcpyHostToDevice, c->stream));
+        if (upload) {   // (pageable sources: cudaMemcpyAsync has staged them before it returns)
+            CUDA_TRY(cudaMemcpyAsync(ind_d, pl.f_ind.data(), n_new * sizeof(int32_t), cudaMemcpyHostToDevice, c->stream));
+            CUDA_TRY(cudaMemcpyAsync(al_d, pl.f_allele.data(), n_new * sizeof(int32_t), cudaMemcpyHostToDevice, c->stream));
+        }
         k_init_founders<<<grid_for(nseg, 256), 256, 0, c->stream>>>(n_new * R, n_new, ind_d, al_d, C, R, N, P, c->chrom_d, c->desc_d,
                                                                     c->seg_pos_d, c->seg_founder_d, c->slab_used);
         c->stats.kernel_launches++;
         CUDA_TRY(cudaGetLastError());
-        // (f_ind / f_allele are pageable: cudaMemcpyAsync has staged them before it returned)
         c->slab_used += nseg;
-        for (int32_t i : f_ind) c->hs_reps[i] = R;
+        for (int32_t i : pl.f_ind) c->hs_reps[i] = R;
     }
-    // --- generations: level = 1 + max(level of parents) over individuals still to simulate
-    std::vector<int32_t> level(N, 0);
-    int32_t max_level = 0;
-    std::vector<uint8_t> wanted;
-    if (subset) {
-        wanted.assign(N, 0);
-        for (int64_t k = 0; k < n_subset; k++) {
-            if (subset[k] < 0 || subset[k] >= N) return fail(c, PSIM_EINVAL, "individual index out of bounds");
-            wanted[subset[k]] = 1;
-        }
-    }
-    for (int64_t i = 0; i < N; i++) {
-        if (c->hs_reps[i]) continue;
-        if (subset && !wanted[i]) { level[i] = -1; continue; }   // left for another rank / a later call
-        const int32_t l0 = level[c->par0_h[i]], l1 = level[c->par1_h[i]];
-        if (l0 < 0 || l1 < 0) return fail(c, PSIM_ESTATE, "a parent of individual " + std::to_string(i) + " has no haplostruct yet");
-        level[i] = 1 + std::max(l0, l1);
-        max_level = std::max(max_level, level[i]);
-    }
-    std::vector<std::vector<int32_t>> by_level(max_level + 1);
-    for (int64_t i = 0; i < N; i++) if (level[i] > 0) by_level[level[i]].push_back((int32_t)i);
     // batch size: bound the plan scratch to about 1.5 GiB
     const int64_t per_ind = (int64_t)C * R * P * (c->piece_cap * 9 + 4 + 16);
     const int64_t max_batch = std::max<int64_t>(1, (int64_t)(1536LL << 20) / per_ind);
     int64_t scratch_ind = 0;
-    for (auto& v : by_level) scratch_ind = std::max<int64_t>(scratch_ind, std::min<int64_t>((int64_t)v.size(), max_batch));
-    int32_t* lev_d = nullptr; int32_t* plan_np = nullptr; int64_t* plan_cnt = nullptr; int64_t* plan_off = nullptr;
+    for (int lv = 1; lv <= max_level; lv++)
+        scratch_ind = std::max<int64_t>(scratch_ind, std::min<int64_t>(pl.level_off[lv + 1] - pl.level_off[lv], max_batch));
+    int32_t* lev_all_d = nullptr; int32_t* plan_np = nullptr; int64_t* plan_cnt = nullptr; int64_t* plan_off = nullptr;
     double* plan_pos = nullptr; uint8_t* plan_hom = nullptr;
     if (scratch_ind > 0) {
         const size_t nu = (size_t)scratch_ind * C * R * P;
-        if (int rc = ensure_buf(c, c->b_lev, scratch_ind * sizeof(int32_t))) return rc;
+        if (int rc = ensure_buf(c, c->b_lev, pl.order.size() * sizeof(int32_t))) return rc;
         if (int rc = ensure_buf(c, c->b_np, nu * sizeof(int32_t))) return rc;
         if (int rc = ensure_buf(c, c->b_cnt, (nu + 1) * sizeof(int64_t))) return rc;
         if (int rc = ensure_buf(c, c->b_off, (nu + 1) * sizeof(int64_t))) return rc;
         if (int rc = ensure_buf(c, c->b_ppos, nu * c->piece_cap * sizeof(double))) return rc;
         if (int rc = ensure_buf(c, c->b_phom, nu * c->piece_cap)) return rc;
-        lev_d = (int32_t*)c->b_lev.p; plan_np = (int32_t*)c->b_np.p; plan_cnt = (int64_t*)c->b_cnt.p;
+        lev_all_d = (int32_t*)c->b_lev.p; plan_np = (int32_t*)c->b_np.p; plan_cnt = (int64_t*)c->b_cnt.p;
         plan_off = (int64_t*)c->b_off.p; plan_pos = (double*)c->b_ppos.p; plan_hom = (uint8_t*)c->b_phom.p;
+        if (upload)   // every generation list in one copy
+            CUDA_TRY(cudaMemcpyAsync(lev_all_d, pl.order.data(), pl.order.size() * sizeof(int32_t), cudaMemcpyHostToDevice, c->stream));
     }
+    if (fresh && !reuse) { sp = std::move(local); sp.valid = true; }
+    psim_ctx_impl::SimPlan& plan = fresh ? sp : local;
+    if (fresh) sp.on_device = true;
+    c->fresh = false;
     int rc_out = PSIM_OK;
     for (int lv = 1; lv <= max_level && rc_out == PSIM_OK; lv++) {
-        const std::vector<int32_t>& inds = by_level[lv];
-        for (int64_t b0 = 0; b0 < (int64_t)inds.size() && rc_out == PSIM_OK; b0 += max_batch) {
-            const int n_lev = (int)std::min<int64_t>(max_batch, (int64_t)inds.size() - b0);
+        const int64_t lev_begin = plan.level_off[lv], lev_size = plan.level_off[lv + 1] - lev_begin;
+        for (int64_t b0 = 0; b0 < lev_size && rc_out == PSIM_OK; b0 += max_batch) {
+            const int n_lev = (int)std::min<int64_t>(max_batch, lev_size - b0);
             const int64_t nu = (int64_t)n_lev * C * R * P;
-            CUDA_TRY(cudaMemcpyAsync(lev_d, inds.data() + b0, n_lev * sizeof(int32_t), cudaMemcpyHostToDevice, c->stream));
+            int32_t* const lev_d = lev_all_d + lev_begin + b0;
             PlanArgs pa;
             pa.model = c->model; pa.chrom = c->chrom_d; pa.C = C; pa.R = R; pa.P = P; pa.N = N;
             pa.replicate_first = c->cfg.replicate_first;
@@ -771,7 +811,7 @@ static int simulate_impl(psim_ctx_impl* c, int32_t max_founder_allele, const int
             k_meiosis_assemble<<<grid_for(nu, 128), 128, 0, c->stream>>>(aa);
             c->stats.kernel_launches++;
             CUDA_TRY(cudaGetLastError());
-            const bool last_batch = lv == max_level && b0 + max_batch >= (int64_t)inds.size();
+            const bool last_batch = lv == max_level && b0 + max_batch >= lev_size;
             if (last_batch) CUDA_TRY(cudaEventRecord(c->ev1, c->stream));
             CUDA_TRY(cudaStreamSynchronize(c->stream));
             const int64_t total = c->scalars_h[0];
@@ -793,7 +833,7 @@ static int simulate_impl(psim_ctx_impl* c, int32_t max_founder_allele, const int
             c->stats.n_meioses += (int64_t)n_lev * R * (c->model.unreduced ? 1 : 2);
             c->stats.n_units += (int64_t)n_lev * R * (c->model.unreduced ? 1 : 2) * C;
         }
-        for (int32_t i : inds) c->hs_reps[i] = R;
+        for (int64_t k = 0; k < lev_size; k++) c->hs_reps[plan.order[(size_t)(lev_begin + k)]] = R;
     }
     if (max_level == 0 || rc_out != PSIM_OK) CUDA_TRY(cudaEventRecord(c->ev1, c->stream));   // else recorded behind the last assembly
     CUDA_TRY(cudaStreamSynchronize(c->stream));
@@ -1636,6 +1676,7 @@ int psim_reset(psim_ctx* ctx, int64_t seed, uint32_t replicate_first) {
     c->slab_used = 0;
     c->stats.n_segments = 0;
     c->runs_valid = false;
+    c->fresh = true;
     return PSIM_OK;
 }
 
@@ -1711,6 +1752,7 @@ int psim_import_haplostructs_device(psim_ctx* ctx, int64_t first, int64_t count,
     c->stats.n_segments = c->slab_used;
     for (int64_t i = first; i < first + count; i++) c->hs_reps[i] = c->R;
     c->runs_valid = false;
+    c->fresh = false;
     return PSIM_OK;
 }
 

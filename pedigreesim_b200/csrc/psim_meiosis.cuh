@@ -62,6 +62,7 @@ __device__ inline double ran_gamma_cheng(PhiloxStream& rng, double k, double the
     const double cheng = 1 + log(4.5);
     double x;
     for (;;) {
+        rng.prefetch();
         const double u = rng.next_double();
         const double v = rng.next_double();
         const double y = (1 / lam) * log(v / (1 - v));
@@ -396,6 +397,7 @@ __device__ inline void parallel_crossing_over(Chiasmata& x, PhiloxStream& rng, c
         x.clear();
         double p = ch.head + dist_to_first_recomb(rng, m, recomb_dist);
         while (p < ch.tail) {
+            rng.prefetch();
             const int i0 = rng.next_int(slotcount);
             int i1;
             do { i1 = rng.next_int(slotcount); } while (i1 / 2 == i0 / 2);
@@ -426,6 +428,7 @@ __device__ inline double quadrivalent_crossing_over(Chiasmata& x, PhiloxStream& 
         exchange_lim[0] = ch.head;
         exchange_lim[1] = ch.tail;
         do {
+            rng.prefetch();
             const int a = rng.next_int(4);
             if (arm_finished[a]) continue;
             // generateRecombination, Quadrivalent.java:108-139

@@ -212,3 +212,57 @@ def test_unreduced_gametes_kosambi_replicates():
         o.set_pedigree(p0, p1)
         o.simulate()
         assert_same_population(o, g, replicate=r)
+
+
+def test_monte_carlo_loop_reuses_the_generation_lists():
+    """psim_reset + psim_simulate again and again (the benchmark's loop): the cached founder and
+    generation lists must give what a new context gives, also after calls that overwrite the device
+    copies (a subset simulation, preset haplostructs) and after a pedigree of another shape."""
+    import pedigreesim_b200
+    p0, p1 = _cases.ril_pedigree(40, 4)
+    lengths, centro = [1.0, 0.7], [0.5, 0.2]
+
+    def oracle_run(pa, pb, seed, rep, preset=None):
+        o = _cases.make_engine("oracle-philox", 2, seed=seed, replicate_first=rep)
+        o.set_chromosomes(lengths, centro)
+        o.set_pedigree(pa, pb)
+        if preset is not None:
+            o.set_haplostructs(0, *preset)
+        o.simulate(maxfounderallele=3 if preset is not None else -1)
+        return o
+
+    g = pedigreesim_b200.PsimContext(2, seed=11)
+    g.set_chromosomes(lengths, centro)
+    g.set_pedigree(p0, p1)
+    g.simulate()
+    assert_same_population(oracle_run(p0, p1, 11, 0), g)
+    for seed, rep in ((11, 0), (12, 3), (11, 7)):          # cached lists, other streams
+        g.reset(seed, rep)
+        g.simulate()
+        assert_same_population(oracle_run(p0, p1, seed, rep), g, replicate=rep)
+    # a sharded-style call sequence overwrites the device copies of the lists
+    g.reset(5, 1)
+    lev1 = [2]
+    g.simulate_subset(lev1)
+    g.simulate()
+    assert_same_population(oracle_run(p0, p1, 5, 1), g, replicate=1)
+    g.reset(6, 2)
+    g.simulate()
+    assert_same_population(oracle_run(p0, p1, 6, 2), g, replicate=2)
+    # preset founders (replay / extend), then the empty state again
+    so, fo, po = g.get_haplostructs(0, 2, replicate=2)
+    g.reset(8, 0)
+    g.set_haplostructs(0, so, fo, po)
+    g.simulate(maxfounderallele=3)
+    assert_same_population(oracle_run(p0, p1, 8, 0, preset=(so, fo, po)), g, replicate=0)
+    g.reset(9, 0)
+    g.simulate()
+    assert_same_population(oracle_run(p0, p1, 9, 0), g, replicate=0)
+    # another pedigree on the same context
+    q0, q1 = _cases.std_pedigree("F2", 90)
+    g.set_pedigree(q0, q1)
+    g.simulate()
+    assert_same_population(oracle_run(q0, q1, 9, 0), g, replicate=0)
+    g.reset(10, 4)
+    g.simulate()
+    assert_same_population(oracle_run(q0, q1, 10, 4), g, replicate=4)
