@@ -151,8 +151,9 @@ def _reference_worker(job):
 
 def run_reference(args):
     """The reference's CPU path on this job. One population is one single-threaded run (the jar shares
-    one java.util.Random and cannot be threaded); a job of N replicate populations (N > 1 ranks) runs
-    them side by side, one process per population, on the host cores that are there."""
+    one java.util.Random and cannot be threaded), but the job is a sequence of independent replicate
+    populations (one per step and rank), so the host runs one population per core side by side on
+    every core it has - the way PedigreeSim is run for a Monte Carlo sweep (one JVM per core)."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
@@ -165,7 +166,8 @@ def run_reference(args):
         n_cpu = len(os.sched_getaffinity(0))
     except AttributeError:
         n_cpu = os.cpu_count() or 1
-    procs = max(1, min(args.gpus, n_cpu))
+    procs = max(1, n_cpu)
+    offspring = int(max(100, min(offspring, 16e9 / (procs * w["L"] * (w["P"] + 1)))))   # tables of all populations within 16 GB
     if procs == 1:
         v, t, ws = cpu_port_run(w, offspring, args.steps, args.warmup)
         meioses_per_s = ws["M"] / t

@@ -363,6 +363,8 @@ static int emit_rows_path(psim_ctx_impl* c, int64_t ind_first, int64_t ind_count
                 if (eff > best_eff + 1e-9) { best_eff = eff; best_t = tg; }
                 if (env_band > 0 || (best_eff >= 0.97 && tg >= best_t + 8)) break;   // good enough; look a little further for a full wave
             }
+            static const int env_units = getenv("PSIM_ROWS_UNITS") ? atoi(getenv("PSIM_ROWS_UNITS")) : 0;   // tuning knob: bands per launch
+            if (env_units > 0) best_t = std::max<int64_t>(t_min, env_units);
             allocate(best_t);
             for (int q = 0; q < ra.n_chunks; q++) ra.chunk_unit_base[q + 1] = ra.chunk_unit_base[q] + ra.chunk_bands[q] * n_seg;
         }
