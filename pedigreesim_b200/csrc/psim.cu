@@ -139,6 +139,9 @@ struct psim_ctx_impl {
         std::vector<int64_t> level_off;
     } plan;
     bool fresh = false;   // no individual has a haplostruct (after psim_set_pedigree / psim_reset)
+    bool check_reps = false;            // psim_set_haplostructs was called: replicate coverage to be verified
+    std::vector<int32_t> founder_idx;   // founders of the pedigree, ascending
+    std::vector<int32_t> level_scratch; // N zeros between calls (simulate_impl)
     psim_stats stats{};
     int sm_count = 148;
 };
@@ -592,6 +595,10 @@ int psim_set_pedigree(psim_ctx* ctx, int64_t n_ind, const int32_t* parent0, cons
     c->runs_valid = false;
     c->fresh = true;
     c->plan.valid = false;
+    c->check_reps = false;
+    c->level_scratch.clear();
+    c->founder_idx.clear();
+    for (int64_t i = 0; i < n_ind; i++) if (parent0[i] < 0) c->founder_idx.push_back((int32_t)i);
     c->N = n_ind;
     c->founder_allele_count = nf * c->P;
     c->par0_h.assign(parent0, parent0 + n_ind);
@@ -643,6 +650,7 @@ int psim_set_haplostructs(psim_ctx* ctx, uint32_t replicate, int64_t first, int6
     for (int64_t i = first; i < first + count; i++) c->hs_reps[i] = std::min(c->hs_reps[i] + 1, c->R);
     c->runs_valid = false;
     c->fresh = false;
+    if (c->R > 1) c->check_reps = true;
     return PSIM_OK;
 }
 
@@ -660,47 +668,67 @@ static int simulate_impl(psim_ctx_impl* c, int32_t max_founder_allele, const int
     psim_ctx_impl::SimPlan& sp = c->plan;
     const bool fresh = c->fresh && !subset;
     const bool reuse = fresh && sp.valid && sp.maxf_in == max_founder_allele;
-    if (!fresh)
+    if (c->check_reps) {   // only after psim_set_haplostructs with several replicates
         for (int64_t i = 0; i < N; i++)
             if (c->hs_reps[i] != 0 && c->hs_reps[i] != R)
                 return fail(c, PSIM_EINVAL, "preset haplostructs must cover the same individuals in every replicate");
+        c->check_reps = false;
+    }
     CUDA_TRY(cudaEventRecord(c->ev0, c->stream));
     psim_ctx_impl::SimPlan local;
     psim_ctx_impl::SimPlan& pl = reuse ? sp : local;
     if (!reuse) {
         // --- founders (Main.java:1510-1513)
         int32_t maxf = max_founder_allele;
-        for (int64_t i = 0; i < N; i++) {
+        for (int32_t i : c->founder_idx) {
             if (c->hs_reps[i]) continue;
-            if (c->par0_h[i] < 0) { pl.f_ind.push_back((int32_t)i); pl.f_allele.push_back(maxf + 1); maxf += P; }
+            pl.f_ind.push_back(i); pl.f_allele.push_back(maxf + 1); maxf += P;
         }
         if (maxf > 65535) return fail(c, PSIM_ECAPACITY, "more than 65536 founder alleles");
-        // --- generations: level = 1 + max(level of parents) over individuals still to simulate
-        std::vector<int32_t> level(N, 0);
+        // --- generations: level = 1 + max(level of parents) over individuals still to simulate.
+        // `level` is a context-owned array of N zeros; only the entries touched here are reset
+        // afterwards, so that a subset call costs O(subset), not O(N) (a sharded pedigree of 10^6+
+        // individuals makes one such call per generation and rank).
+        if ((int64_t)c->level_scratch.size() != N) c->level_scratch.assign((size_t)N, 0);
+        std::vector<int32_t>& level = c->level_scratch;
+        std::vector<int32_t> touched;
         int32_t max_level = 0;
-        std::vector<uint8_t> wanted;
-        if (subset) {
-            wanted.assign(N, 0);
-            for (int64_t k = 0; k < n_subset; k++) {
-                if (subset[k] < 0 || subset[k] >= N) return fail(c, PSIM_EINVAL, "individual index out of bounds");
-                wanted[subset[k]] = 1;
+        auto reset_levels = [&]() { for (int32_t i : touched) level[i] = 0; };
+        auto visit = [&](int32_t i) -> bool {   // false: a parent is neither simulated nor scheduled
+            if (c->hs_reps[i] || c->par0_h[i] < 0) return true;   // has a haplostruct, or is a founder about to get one
+            int32_t lv = 0;
+            for (int32_t par : {c->par0_h[i], c->par1_h[i]}) {
+                if (c->hs_reps[par] || c->par0_h[par] < 0) continue;
+                if (level[par] <= 0) return false;
+                lv = std::max(lv, level[par]);
             }
+            level[i] = lv + 1;
+            touched.push_back(i);
+            max_level = std::max(max_level, lv + 1);
+            return true;
+        };
+        int64_t bad = -1;
+        if (subset) {
+            std::vector<int32_t> sub(subset, subset + n_subset);
+            std::sort(sub.begin(), sub.end());   // parents-first order: a parent has the smaller index
+            sub.erase(std::unique(sub.begin(), sub.end()), sub.end());
+            if (!sub.empty() && (sub.front() < 0 || sub.back() >= N)) return fail(c, PSIM_EINVAL, "individual index out of bounds");
+            for (int32_t i : sub) if (!visit(i)) { bad = i; break; }
+        } else {
+            for (int64_t i = 0; i < N; i++) if (!visit((int32_t)i)) { bad = i; break; }
         }
-        for (int64_t i = 0; i < N; i++) {
-            if (c->hs_reps[i] || c->par0_h[i] < 0) continue;   // has a haplostruct, or is a founder about to get one
-            if (subset && !wanted[i]) { level[i] = -1; continue; }   // left for another rank / a later call
-            const int32_t l0 = level[c->par0_h[i]], l1 = level[c->par1_h[i]];
-            if (l0 < 0 || l1 < 0) return fail(c, PSIM_ESTATE, "a parent of individual " + std::to_string(i) + " has no haplostruct yet");
-            level[i] = 1 + std::max(l0, l1);
-            max_level = std::max(max_level, level[i]);
+        if (bad >= 0) {
+            reset_levels();
+            return fail(c, PSIM_ESTATE, "a parent of individual " + std::to_string(bad) + " has no haplostruct yet");
         }
         std::vector<int64_t> cnt(max_level + 2, 0);
-        for (int64_t i = 0; i < N; i++) if (level[i] > 0) cnt[level[i] + 1]++;
+        for (int32_t i : touched) cnt[level[i] + 1]++;
         for (int lv = 1; lv <= max_level + 1; lv++) cnt[lv] += cnt[lv - 1];
         pl.level_off = cnt;                                   // individuals of level lv: order[level_off[lv] .. level_off[lv+1])
         pl.order.assign((size_t)cnt[max_level + 1], 0);
         std::vector<int64_t> fill(cnt.begin(), cnt.end());
-        for (int64_t i = 0; i < N; i++) if (level[i] > 0) pl.order[(size_t)fill[level[i]]++] = (int32_t)i;
+        for (int32_t i : touched) pl.order[(size_t)fill[level[i]]++] = i;   // (touched is ascending: so is every level)
+        reset_levels();
         pl.max_level = max_level;
         pl.maxf_in = max_founder_allele;
         pl.on_device = false;
@@ -1679,6 +1707,7 @@ int psim_reset(psim_ctx* ctx, int64_t seed, uint32_t replicate_first) {
     c->stats.n_segments = 0;
     c->runs_valid = false;
     c->fresh = true;
+    c->check_reps = false;
     return PSIM_OK;
 }
 

@@ -23,30 +23,54 @@ __global__ void __launch_bounds__(128) k_index_runs(int64_t n_hom, int64_t hom_p
     const int c = (int)(hid / hom_per_chrom);
     const double* lp = locus_pos + locus_off[c];
     const uint32_t Lc = (uint32_t)(locus_off[c + 1] - locus_off[c]);
-    // pass 1: lb[s]
-    for (int s = 0; s < n; s++) {
-        uint32_t lo = 0;
-        if (s > 0) {
-            const double p = seg_pos[b + s];
-            uint32_t hi = Lc;
-            while (lo < hi) { const uint32_t mid = (lo + hi) >> 1; if (lp[mid] < p) lo = mid + 1; else hi = mid; }
-        }
-        run_lb[b + s] = lo;
-    }
-    // pass 2: suffix minimum
-    uint32_t mn = Lc;
-    for (int s = n - 1; s >= 0; s--) { const uint32_t v = run_lb[b + s]; mn = v < mn ? v : mn; run_lb[b + s] = mn; }
-    // pass 3: compact in place
+    auto lower_bound = [&](double p) {   // #loci strictly left of p
+        uint32_t lo = 0, hi = Lc;
+        while (lo < hi) { const uint32_t mid = (lo + hi) >> 1; if (__ldg(lp + mid) < p) lo = mid + 1; else hi = mid; }
+        return lo;
+    };
     int w = 0;
-    for (int s = 0; s < n; s++) {
-        const uint32_t start = run_lb[b + s];
-        const uint32_t end = s + 1 < n ? run_lb[b + s + 1] : Lc;
-        if (start >= end) continue;
-        const uint16_t f = (uint16_t)seg_founder[b + s];
-        if (w > 0 && run_founder[b + w - 1] == f) continue;
-        run_lb[b + w] = start;
-        run_founder[b + w] = f;
-        w++;
+    constexpr int SMALL = 8;
+    if (n <= SMALL) {
+        // the common case (a homolog a few generations from its founders): everything in registers,
+        // one pass over global memory instead of three
+        uint32_t lb[SMALL];
+        uint16_t fo[SMALL];
+#pragma unroll
+        for (int s = 0; s < SMALL; s++) {
+            lb[s] = Lc; fo[s] = 0;
+            if (s < n) { lb[s] = s > 0 ? lower_bound(seg_pos[b + s]) : 0u; fo[s] = (uint16_t)seg_founder[b + s]; }
+        }
+        uint32_t mn = Lc;
+#pragma unroll
+        for (int s = SMALL - 1; s >= 0; s--) { mn = lb[s] < mn ? lb[s] : mn; lb[s] = mn; }   // suffix minimum (entries >= n hold Lc)
+        uint32_t last_f = 0x10000u;
+#pragma unroll
+        for (int s = 0; s < SMALL; s++) {
+            const uint32_t end = s + 1 < SMALL ? lb[s + 1] : Lc;
+            if (s < n && lb[s] < end && fo[s] != last_f) {
+                run_lb[b + w] = lb[s];
+                run_founder[b + w] = fo[s];
+                last_f = fo[s];
+                w++;
+            }
+        }
+    } else {
+        // pass 1: lb[s]
+        for (int s = 0; s < n; s++) run_lb[b + s] = s > 0 ? lower_bound(seg_pos[b + s]) : 0u;
+        // pass 2: suffix minimum
+        uint32_t mn = Lc;
+        for (int s = n - 1; s >= 0; s--) { const uint32_t v = run_lb[b + s]; mn = v < mn ? v : mn; run_lb[b + s] = mn; }
+        // pass 3: compact in place
+        for (int s = 0; s < n; s++) {
+            const uint32_t start = run_lb[b + s];
+            const uint32_t end = s + 1 < n ? run_lb[b + s + 1] : Lc;
+            if (start >= end) continue;
+            const uint16_t f = (uint16_t)seg_founder[b + s];
+            if (w > 0 && run_founder[b + w - 1] == f) continue;
+            run_lb[b + w] = start;
+            run_founder[b + w] = f;
+            w++;
+        }
     }
     run_desc[hid] = make_desc((uint64_t)b, (uint64_t)w);
 }
