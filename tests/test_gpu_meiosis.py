@@ -266,3 +266,33 @@ def test_monte_carlo_loop_reuses_the_generation_lists():
     g.reset(10, 4)
     g.simulate()
     assert_same_population(oracle_run(q0, q1, 10, 4), g, replicate=4)
+
+
+def test_subset_simulation_edge_cases():
+    """psim_simulate_subset: unordered lists with duplicates, several generations in one call, a parent
+    that is neither simulated nor listed (error, and the context stays usable), indices out of range."""
+    import pedigreesim_b200
+    p0, p1 = _cases.ril_pedigree(30, 4)          # 2 founders, F1, then 3 generations of 30 lines
+    lengths, centro = [1.0, 0.5], [0.3, 0.25]
+    o = _cases.make_engine("oracle-philox", 2, seed=3)
+    o.set_chromosomes(lengths, centro)
+    o.set_pedigree(p0, p1)
+    o.simulate()
+    g = pedigreesim_b200.PsimContext(2, seed=3)
+    g.set_chromosomes(lengths, centro)
+    g.set_pedigree(p0, p1)
+    n = len(p0)
+    with pytest.raises(pedigreesim_b200.PsimError, match="has no haplostruct yet"):
+        g.simulate_subset([n - 1])               # its parent (previous generation) is not there
+    with pytest.raises(pedigreesim_b200.PsimError, match="out of bounds"):
+        g.simulate_subset([2, n])
+    # F1 and two generations of the even lines in one call, unordered, with duplicates
+    gen = lambda k: np.arange(3 + 30 * k, 3 + 30 * (k + 1))
+    even = np.concatenate([gen(0)[::2], gen(1)[::2]])
+    lst = np.concatenate([even[::-1], [2, 2], even[:5]]).astype(np.int32)
+    g.simulate_subset(lst)
+    with pytest.raises(pedigreesim_b200.PsimError, match="has no haplostruct yet"):
+        g.simulate_subset(gen(1)[1::2])          # odd lines of generation 2: generation 1 odd lines are missing
+    g.simulate_subset(np.concatenate([gen(1)[1::2], gen(0)[1::2]]))
+    g.simulate()                                 # the rest
+    assert_same_population(o, g)

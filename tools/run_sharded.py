@@ -57,6 +57,12 @@ def main():
     ctx.set_chromosomes(lengths, centro)
     ctx.set_pedigree(p0, p1)
     drv = sharded.ShardedPedigree(sharded.PsimShard(ctx), p0, p1)
+    # first pass: the slab and the exchange buffers grow to their final size (cudaMalloc / cudaFree of
+    # gigabytes); the timed pass re-simulates the same pedigree after psim_reset into that memory
+    drv.simulate()
+    torch.cuda.synchronize()
+    ctx.reset(12345, 0)
+    drv.exchanged_segments = 0
     dist.barrier()
     torch.cuda.synchronize()
     t0 = time.perf_counter()
