@@ -141,9 +141,15 @@ class ShardedPedigree:
         self.rank = dist.get_rank(group)
         self.world = dist.get_world_size(group)
         self.exchanged_segments = 0
+        self._levels = None   # generations of the whole pedigree (has_hs None): computed once, the pedigree is fixed
 
     def simulate(self, maxfounderallele=-1, has_hs=None):
-        levels = levelize(self.p0, self.p1, has_hs)
+        if has_hs is None:
+            if self._levels is None:
+                self._levels = levelize(self.p0, self.p1)
+            levels = self._levels
+        else:
+            levels = levelize(self.p0, self.p1, has_hs)
         # founders are initialised by every rank (deterministic, no exchange needed)
         self.shard.simulate_subset(np.zeros(0, np.int32), maxfounderallele)
         for inds in levels:

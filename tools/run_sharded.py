@@ -72,6 +72,7 @@ def main():
     dt = time.perf_counter() - t0
     n = len(p0)
     ok = True
+    unsharded_dt = None
     if args.check:
         last = n - args.lines
         so, fo, po = ctx.get_haplostructs(first=last, count=args.lines)
@@ -80,6 +81,12 @@ def main():
             ref.set_chromosomes(lengths, centro)
             ref.set_pedigree(p0, p1)
             ref.simulate()
+            ref.reset(12345, 0)          # warm pass like the sharded run, then the timed one
+            torch.cuda.synchronize()
+            t1 = time.perf_counter()
+            ref.simulate()
+            torch.cuda.synchronize()
+            unsharded_dt = time.perf_counter() - t1
             s2, f2, x2 = ref.get_haplostructs(first=last, count=args.lines)
             ok = bool(np.array_equal(so, s2) and np.array_equal(fo, f2) and np.array_equal(po, x2))
             if not ok:
@@ -97,7 +104,8 @@ def main():
     if rank == 0:
         meioses = 2 * (n - 2)
         print(json.dumps({"n_gpus": world, "individuals": n, "meioses": meioses, "seconds": dt, "meioses_per_s": meioses / dt,
-                          "exchanged_segments_per_rank": drv.exchanged_segments, "bit_identical_to_unsharded": ok}))
+                          "exchanged_segments_per_rank": drv.exchanged_segments, "bit_identical_to_unsharded": ok,
+                          "unsharded_seconds_one_gpu": unsharded_dt}))
     ctx.close()
     dist.destroy_process_group()
     if not ok:
