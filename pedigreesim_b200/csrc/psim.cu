@@ -709,11 +709,23 @@ static int simulate_impl(psim_ctx_impl* c, int32_t max_founder_allele, const int
         };
         int64_t bad = -1;
         if (subset) {
-            std::vector<int32_t> sub(subset, subset + n_subset);
-            std::sort(sub.begin(), sub.end());   // parents-first order: a parent has the smaller index
-            sub.erase(std::unique(sub.begin(), sub.end()), sub.end());
-            if (!sub.empty() && (sub.front() < 0 || sub.back() >= N)) return fail(c, PSIM_EINVAL, "individual index out of bounds");
-            for (int32_t i : sub) if (!visit(i)) { bad = i; break; }
+            // parents-first order: a parent has the smaller index, so the list is walked ascending.
+            // Drivers pass strictly ascending lists: only others are copied, sorted and de-duplicated.
+            bool ascending = true;
+            for (int64_t k = 1; k < n_subset && ascending; k++) ascending = subset[k - 1] < subset[k];
+            std::vector<int32_t> sorted_copy;
+            const int32_t* sub = subset;
+            int64_t n_sub = n_subset;
+            if (!ascending) {
+                sorted_copy.assign(subset, subset + n_subset);
+                std::sort(sorted_copy.begin(), sorted_copy.end());
+                sorted_copy.erase(std::unique(sorted_copy.begin(), sorted_copy.end()), sorted_copy.end());
+                sub = sorted_copy.data();
+                n_sub = (int64_t)sorted_copy.size();
+            }
+            if (n_sub > 0 && (sub[0] < 0 || sub[n_sub - 1] >= N)) return fail(c, PSIM_EINVAL, "individual index out of bounds");
+            touched.reserve((size_t)n_sub);
+            for (int64_t k = 0; k < n_sub; k++) if (!visit(sub[k])) { bad = sub[k]; break; }
         } else {
             for (int64_t i = 0; i < N; i++) if (!visit((int32_t)i)) { bad = i; break; }
         }

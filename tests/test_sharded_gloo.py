@@ -80,15 +80,23 @@ def _pedigrees():
     }
 
 
-def _worker(rank, world, port, name, q):
+def _worker(rank, world, port, name, q, partition="block"):
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
     p0, p1 = _pedigrees()[name]
     shard = FakeShard(p0, p1)
-    drv = sharded.ShardedPedigree(shard, p0, p1)
+    drv = sharded.ShardedPedigree(shard, p0, p1, partition=partition)
     drv.simulate()
-    q.put((rank, {i: shard.hs[i] for i in range(len(p0))}, drv.exchanged_segments))
+    if partition == "block":
+        q.put((rank, {i: shard.hs[i] for i in range(len(p0))}, drv.exchanged_segments))
+    else:
+        before = dict(shard.hs)
+        collectives = drv.collectives
+        owned = drv.owned().tolist()
+        last = sharded.levelize(p0, p1)[-1]
+        drv.gather(last)                       # e.g. for a joint emission of the last generation
+        q.put((rank, before, collectives, owned, {int(i): shard.hs[int(i)] for i in last}))
     dist.barrier()
     dist.destroy_process_group()
 
@@ -135,3 +143,54 @@ def test_replicate_ids_partition_without_overlap():
     seen = [r + world * (k + 1) for r in range(world) for k in range(steps)]
     assert len(set(seen)) == world * steps
     assert sorted(seen) == list(range(world, world * (steps + 1)))
+
+
+@pytest.mark.parametrize("name", ["f1", "ril", "random"])
+def test_lineage_partition_exchanges_only_what_another_rank_needs(name):
+    """partition="lineage": a rank keeps its lines; F1-from-founders needs no collective at all, a
+    selfing chain one (its single F1 plant); every rank's individuals equal the single-process run,
+    the owned sets partition the non-founders, and gather() completes a generation everywhere."""
+    p0, p1 = _pedigrees()[name]
+    ref = FakeShard(p0, p1)
+    ref.simulate_subset(np.zeros(0, np.int32))
+    levels = sharded.levelize(p0, p1)
+    for lvl in levels:
+        ref.simulate_subset(lvl)
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, name, q, "lineage")) for r in range(2)]
+    for p in procs:
+        p.start()
+    results = [q.get(timeout=120) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    owned_all = []
+    for rank, hs, collectives, owned, last_gen in results:
+        for i, v in hs.items():
+            assert v == ref.hs[i], "rank %d individual %d diverged" % (rank, i)
+        assert set(owned) <= set(hs)
+        owned_all += owned
+        assert last_gen == {int(i): ref.hs[int(i)] for i in levels[-1]}
+        if name == "f1":
+            assert collectives == 0
+        if name == "ril":
+            assert collectives == 1 and len(hs) < len(p0)     # only the F1 plant was shared
+    assert sorted(owned_all) == [i for i in range(len(p0)) if p0[i] >= 0]
+
+
+def test_lineage_partition_invariants():
+    rng = np.random.default_rng(3)
+    for p0, p1 in (_cases.ril_pedigree(1000, 6), _cases.std_pedigree("F2", 501), _cases.random_pedigree(rng, 12, 800)):
+        levels = sharded.levelize(p0, p1)
+        for world in (2, 3, 8):
+            owner, share = sharded.lineage_partition(levels, p0, p1, world)
+            assert (owner[p0 < 0] == -1).all() and (owner[p0 >= 0] >= 0).all() and owner.max() < world
+            for inds in levels:
+                for par in (p0[inds], p1[inds]):
+                    assert ((owner[par] == -1) | (owner[par] == owner[inds]) | share[par]).all()
+    p0, p1 = _cases.ril_pedigree(1000, 6)
+    owner, share = sharded.lineage_partition(sharded.levelize(p0, p1), p0, p1, 8)
+    load = np.bincount(owner[owner >= 0], minlength=8)
+    assert load.max() - load.min() <= 1 + 1 and share.sum() == 1   # balanced, only the F1 plant is shared

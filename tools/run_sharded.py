@@ -44,6 +44,8 @@ def main():
     ap.add_argument("--generations", type=int, default=8)
     ap.add_argument("--chromosomes", type=int, default=10)
     ap.add_argument("--check", type=int, default=1)
+    ap.add_argument("--partition", default="block", choices=["block", "lineage"],
+                    help="lineage: a rank keeps its lines, only individuals with a child on another rank are shared")
     args = ap.parse_args()
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -56,13 +58,14 @@ def main():
     ctx = ps.PsimContext(2, seed=12345, device=local)
     ctx.set_chromosomes(lengths, centro)
     ctx.set_pedigree(p0, p1)
-    drv = sharded.ShardedPedigree(sharded.PsimShard(ctx), p0, p1)
+    drv = sharded.ShardedPedigree(sharded.PsimShard(ctx), p0, p1, partition=args.partition)
     # first pass: the slab and the exchange buffers grow to their final size (cudaMalloc / cudaFree of
     # gigabytes); the timed pass re-simulates the same pedigree after psim_reset into that memory
     drv.simulate()
     torch.cuda.synchronize()
     ctx.reset(12345, 0)
     drv.exchanged_segments = 0
+    drv.collectives = 0
     dist.barrier()
     torch.cuda.synchronize()
     t0 = time.perf_counter()
@@ -73,8 +76,11 @@ def main():
     n = len(p0)
     ok = True
     unsharded_dt = None
+    exchanged, collectives = drv.exchanged_segments, drv.collectives
     if args.check:
         last = n - args.lines
+        if args.partition == "lineage":   # outside the timed region: bring the last generation together for the check
+            drv.gather(np.arange(last, n))
         so, fo, po = ctx.get_haplostructs(first=last, count=args.lines)
         if rank == 0:
             ref = ps.PsimContext(2, seed=12345, device=local)
@@ -104,7 +110,8 @@ def main():
     if rank == 0:
         meioses = 2 * (n - 2)
         print(json.dumps({"n_gpus": world, "individuals": n, "meioses": meioses, "seconds": dt, "meioses_per_s": meioses / dt,
-                          "exchanged_segments_per_rank": drv.exchanged_segments, "bit_identical_to_unsharded": ok,
+                          "partition": args.partition, "exchanged_segments_per_rank": exchanged, "collectives": collectives,
+                          "bit_identical_to_unsharded": ok,
                           "unsharded_seconds_one_gpu": unsharded_dt}))
     ctx.close()
     dist.destroy_process_group()
