@@ -394,6 +394,7 @@ static int emit_rows_path(psim_ctx_impl* c, int64_t ind_first, int64_t ind_count
         // units whose run-start list overflowed (not expected with the band heuristic): searched per cell
         c->scalars_h[2] = 0;
         k_publish<<<1, 32, 0, c->stream>>>(c->scalars_dev, nullptr, nullptr, ra.overflow);
+        c->stats.kernel_launches++;
         CUDA_TRY(cudaStreamSynchronize(c->stream));
         const int n_over = (int)c->scalars_h[2];
         if (n_over > 0) {
@@ -605,9 +606,10 @@ int psim_set_pedigree(psim_ctx* ctx, int64_t n_ind, const int32_t* parent0, cons
     c->par1_h.assign(parent1, parent1 + n_ind);
     c->hs_reps.assign(n_ind, 0);
     c->n_hom = n_hom;
-    // stream-ordered with the kernels that follow (the sources are pageable: staged before the calls return)
-    CUDA_TRY(cudaMemcpyAsync(c->par0_d, parent0, n_ind * sizeof(int32_t), cudaMemcpyHostToDevice, c->stream));
-    CUDA_TRY(cudaMemcpyAsync(c->par1_d, parent1, n_ind * sizeof(int32_t), cudaMemcpyHostToDevice, c->stream));
+    // stream-ordered with the kernels that follow; the sources are the library's own copies (the
+    // caller's arrays may be page-locked, and then an asynchronous copy would outlive this call)
+    CUDA_TRY(cudaMemcpyAsync(c->par0_d, c->par0_h.data(), n_ind * sizeof(int32_t), cudaMemcpyHostToDevice, c->stream));
+    CUDA_TRY(cudaMemcpyAsync(c->par1_d, c->par1_h.data(), n_ind * sizeof(int32_t), cudaMemcpyHostToDevice, c->stream));
     CUDA_TRY(cudaMemsetAsync(c->desc_d, 0, n_hom * sizeof(uint64_t), c->stream));
     CUDA_TRY(cudaMemsetAsync(c->cfg_quad_d, 0xFF, ncfg, c->stream));
     CUDA_TRY(cudaMemsetAsync(c->cfg_seq_d, 0xFF, ncfg * c->P, c->stream));
@@ -844,6 +846,7 @@ static int simulate_impl(psim_ctx_impl* c, int32_t max_founder_allele, const int
             // afterwards and, only if the slab was too small, grows it and launches the assembly again.
             c->scalars_h[0] = 0; c->scalars_h[1] = 0;
             k_publish<<<1, 32, 0, c->stream>>>(c->scalars_dev, plan_off + nu, c->error_flag_d, nullptr);
+            c->stats.kernel_launches++;
             AssembleArgs aa;
             aa.chrom = c->chrom_d; aa.C = C; aa.R = R; aa.P = P; aa.N = N; aa.n_lev = n_lev; aa.lev_ind = lev_d;
             aa.par0 = c->par0_d; aa.par1 = c->par1_d; aa.desc = c->desc_d; aa.seg_pos = c->seg_pos_d;
@@ -1454,6 +1457,7 @@ int psim_emit_text(psim_ctx* ctx, int64_t ind_first, int64_t ind_count, int64_t 
             CUDA_TRY(cudaGetLastError());
             if (int rc = exclusive_scan_i64(c, (int64_t*)c->b_rowlen.p, (int64_t*)c->b_rowoff.p, nr + 1)) return rc;
             k_publish<<<1, 32, 0, c->stream>>>(c->scalars_dev, (int64_t*)c->b_rowoff.p + nr, nullptr, nullptr);
+            c->stats.kernel_launches++;
             CUDA_TRY(cudaStreamSynchronize(c->stream));
             const int64_t total = c->scalars_h[0];
             if (*tab[q].bytes + total > tab[q].cap) too_small = true;
