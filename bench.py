@@ -329,23 +329,6 @@ def run_ours(args):
     e2e_value = world * cells * e2e_steps / (ms_e2e * 1e-3) / 1e9
     peak, peak_src = measured_peak()
     k2_ms = acc["emit"] / max(1, acc["emit_launches"])
-    # context for the roofline fraction: what a plain memset of the same tables reaches on THIS box
-    # (boxes of one pool differ by several percent in what their HBM takes; not used as the peak)
-    memset_gbs = None
-    try:
-        with torch.cuda.stream(stream):
-            m0, m1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            for _ in range(3):
-                d_founder.zero_(); d_dose.zero_()
-            torch.cuda.synchronize()
-            m0.record(stream)
-            for _ in range(5):
-                d_founder.zero_(); d_dose.zero_()
-            m1.record(stream)
-            torch.cuda.synchronize()
-            memset_gbs = 5 * (d_founder.numel() + d_dose.numel()) / (m0.elapsed_time(m1) * 1e-3) / 1e9
-    except Exception:   # context only: never in the way of the benchmark line
-        memset_gbs = None
     algo_bytes = N * L * (P + 1)
     achieved = algo_bytes / (k2_ms * 1e-3) / 1e9 if k2_ms > 0 else 0.0
     if rank == 0:
@@ -363,7 +346,7 @@ def run_ours(args):
                           "emit_kernel_share_of_step": acc["emit"] / ms if ms > 0 else None},
             "roofline": {"bound": "hbm", "kernel": "k_emit_rows<2> (row-image emission: shared-memory row + TMA bulk store per table row; the band-plan helper kernels are reported under kernel_ms)", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": None, "algorithmic_bytes_per_launch": algo_bytes,
-                         "peak_source": peak_src, "memset_same_tables_this_box": memset_gbs},
+                         "peak_source": peak_src},
             "e2e": {"value": e2e_value, "unit": "G allele-loci/s", "steps": e2e_steps, "ms_per_step": ms_e2e / e2e_steps,
                     "h2d_bytes_per_step": int(w["p0"].nbytes * 2 + w["off"].nbytes + w["pos"].nbytes + w["code"].nbytes),
                     "d2h_bytes_per_step": int(L * N * P + L * N)},
