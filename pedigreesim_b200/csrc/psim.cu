@@ -814,8 +814,12 @@ static int simulate_impl(psim_ctx_impl* c, int32_t max_founder_allele, const int
             pa.task_count = (int*)c->b_task.p;
             pa.task_bi = (int64_t*)((uint8_t*)c->b_task.p + 16);
             pa.task_quad = pa.task_bi + cap_bi;
-            CUDA_TRY(cudaMemsetAsync(pa.task_count, 0, 16, c->stream));
-            k_meiosis_config<<<grid_for(n_half, 128), 128, 0, c->stream>>>(pa);
+            pa.direct_diploid = P == 2;
+            if (!pa.direct_diploid) {
+                CUDA_TRY(cudaMemsetAsync(pa.task_count, 0, 16, c->stream));
+                k_meiosis_config<<<grid_for(n_half, 128), 128, 0, c->stream>>>(pa);
+                c->stats.kernel_launches++;
+            }
             auto launch_mv = [&](auto kos, auto anr) {
                 constexpr bool KOS = decltype(kos)::value, ANR = decltype(anr)::value;
                 // the two task lists are independent and neither kernel fills the machine (one
@@ -831,7 +835,6 @@ static int simulate_impl(psim_ctx_impl* c, int32_t max_founder_allele, const int
                 c->stats.kernel_launches++;
                 if (cap_quad > 0) cudaStreamWaitEvent(c->stream, c->ev3, 0);
             };
-            c->stats.kernel_launches++;
             if (c->model.chiasma_interference) {
                 if (c->model.allow_no_recomb) launch_mv(std::true_type{}, std::true_type{}); else launch_mv(std::true_type{}, std::false_type{});
             } else {

@@ -51,6 +51,8 @@ struct PlanArgs {
     int64_t* task_bi;            // bivalents of the batch: (thread id of the unit) * 8 + multivalent number
     int64_t* task_quad;          // quadrivalents
     int* task_count;             // [0] bivalents, [1] quadrivalents
+    int direct_diploid;          // ploidy 2: no configuration kernel and no task lists - thread t of the bivalent
+                                 // kernel IS unit t and draws the unit's configuration (one shuffle of two) itself
 };
 
 // K1a is split in two so that the warps of the heavy part run one code path:
@@ -123,11 +125,13 @@ __global__ void __launch_bounds__(128) k_meiosis_config(PlanArgs a) {
 template <bool QUAD, bool KOS, bool ANR>
 __global__ void __launch_bounds__(128) k_meiosis_mv(PlanArgs a) {
     const int64_t ti = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-    if (ti >= (int64_t)a.task_count[QUAD ? 1 : 0]) return;
-    const int64_t code = (QUAD ? a.task_quad : a.task_bi)[ti];
+    const bool direct = !QUAD && a.direct_diploid;
+    if (direct ? ti >= (int64_t)a.C * a.R * a.n_lev * 2 : ti >= (int64_t)a.task_count[QUAD ? 1 : 0]) return;
+    const int64_t code = direct ? ti * 8 : (QUAD ? a.task_quad : a.task_bi)[ti];
     const int v = (int)(code & 7);
     int par, j, r, c;
     plan_decode(a, code >> 3, par, j, r, c);
+    if (direct && a.model.unreduced && par == 1) return;   // 2NGAMETES: parent 0's gamete alone
     const int P = a.P, p2 = P / 2;
     const int32_t child = a.lev_ind[j];
     const int32_t parent = par == 0 ? a.par0[child] : a.par1[child];
@@ -137,10 +141,18 @@ __global__ void __launch_bounds__(128) k_meiosis_mv(PlanArgs a) {
     m.allow_no_recomb = ANR;
     const int64_t phid0 = (((int64_t)c * a.R + r) * a.N + parent) * P;
     const int64_t q = (((int64_t)r * a.N + child) * a.C + c) * 2 + par;
-    const int quad = a.cfg_quad[q];
-    const int8_t* chromseq = a.cfg_seq + q * P;
     PhiloxStream rng;
     rng.init(m.seed, a.replicate_first + (uint32_t)r);
+    int8_t own_seq[2] = {0, 1};
+    if (direct) {   // Individual.calcChromConfig for ploidy 2 (Individual.java:603-608): shuffle of (0, 1), no quadrivalent
+        rng.seek((uint32_t)child, (uint32_t)c, (uint32_t)par, STAGE_CONFIG);
+        shuffle_small(rng, own_seq, 2);
+        a.cfg_quad[q] = 0;
+        a.cfg_seq[q * 2] = own_seq[0];
+        a.cfg_seq[q * 2 + 1] = own_seq[1];
+    }
+    const int quad = direct ? 0 : a.cfg_quad[q];
+    const int8_t* chromseq = direct ? own_seq : a.cfg_seq + q * P;
     // Each transmitted chromatid is traced straight into the plan entry of the child homolog it
     // will occupy after the gamete's homolog shuffle. The shuffle draws come from their own stream:
     // slot h of the transmitted gamete receives pre-shuffle slot shuf[h] (Individual.java:325-335).
