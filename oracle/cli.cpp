@@ -5,6 +5,7 @@
 #include <cstring>
 
 #include "popio.hpp"
+#include "device_twin.hpp"
 
 int main(int argc, char** argv) {
     if (argc < 2) { std::printf("PedigreeSim: parameter file PedigreeSim.par not found or not readable.\n"); return 0; }

@@ -87,6 +87,10 @@ struct Model {
     int unreduced_gametes = 0;          // 2NGAMETES: 0 = haploid gametes, 1 = FDR, 2 = SDR (Main.java:179-185)
     std::vector<Chrom> chrom;
     Rng* rng = nullptr;
+    // rng_mode 1 ("twin", device_twin.hpp): the CUDA library's own sampler run on the host
+    bool twin = false;
+    uint64_t twin_seed = 0;
+    uint32_t twin_replicate = 0;
 };
 
 // Genotype.java:38-51
@@ -492,6 +496,13 @@ struct MeiosisStats {
     int64_t bivalents = 0, parallel_quads = 0, cross_quads = 0;
 };
 
+// device_twin.hpp
+struct Individual;
+struct MeiosisStats;
+inline void twin_do_meiosis(const Model& m, const Individual& parent, uint32_t child, uint32_t par,
+                            std::vector<std::vector<HS>>& out_hs, std::vector<ChromConfig>& out_conf, int* second_gamete,
+                            MeiosisStats* stats);
+
 struct MeiosisEngine {
     const Model& m;
     Rng& rng;
@@ -502,6 +513,7 @@ struct MeiosisEngine {
     std::vector<int> paired_with[2];
     int bivalentcount = 0, quadrivalentcount = 0;
     ChromConfig chrconf;
+    int twin_second = 1;
     std::vector<bool> hsdone;
     std::vector<std::vector<int>> genohs;
 
@@ -786,6 +798,7 @@ struct MeiosisEngine {
     void do_meiosis(Individual& ind, uint32_t child_index, uint32_t parent_slot,
                     std::vector<std::vector<HS>>& out_hs, std::vector<ChromConfig>& out_conf) {
         const int P = m.ploidy, C = (int)m.chrom.size(), p2 = P / 2;
+        if (m.twin) { twin_do_meiosis(m, ind, child_index, parent_slot, out_hs, out_conf, &twin_second, stats); return; }
         out_hs.assign(C, std::vector<HS>(2 * P));
         out_conf.assign(C, ChromConfig());
         for (int c = 0; c < C; c++) {
@@ -864,7 +877,8 @@ struct MeiosisEngine {
         std::vector<ChromConfig> c0;
         do_meiosis(pop[z.parent[0]], (uint32_t)child, 0, g, c0);
         int second = 1;
-        if (m.unreduced_gametes == 1) {
+        if (m.twin) second = twin_second;
+        else if (m.unreduced_gametes == 1) {
             rng.seek((uint32_t)child, 0, 0, 1022);
             second = rng.next_float() < 0.5f ? 3 : 2;
         }

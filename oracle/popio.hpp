@@ -781,7 +781,10 @@ inline int run_parameter_file(const std::string& par_path, int rng_mode, std::st
     }
     const std::string output = resolve(par["OUTPUT"]);
     if (rng_mode == 0) pop.rng_holder.reset(new JavaRandom((int64_t)seed));
-    else pop.rng_holder.reset(new PhiloxStream((uint32_t)seed, 0));
+    else {
+        pop.rng_holder.reset(new PhiloxStream((uint32_t)seed, 0));
+        m.twin = true; m.twin_seed = (uint64_t)seed; m.twin_replicate = 0;
+    }
     m.rng = pop.rng_holder.get();
     if (!check_infile("CHROMFILE", par["CHROMFILE"])) return 0;
     try {

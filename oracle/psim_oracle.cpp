@@ -6,6 +6,7 @@
 #include <cstring>
 
 #include "popio.hpp"
+#include "device_twin.hpp"
 
 using namespace orc;
 
@@ -45,7 +46,10 @@ void* orc_create(int ploidy, int chiasma_interference, int natural_pairing, int 
     h->seed = seed;
     h->replicate = replicate;
     if (rng_mode == 0) h->pop.rng_holder.reset(new JavaRandom(seed));
-    else h->pop.rng_holder.reset(new PhiloxStream((uint32_t)seed, replicate));
+    else {
+        h->pop.rng_holder.reset(new PhiloxStream((uint32_t)seed, replicate));
+        m.twin = true; m.twin_seed = (uint64_t)seed; m.twin_replicate = replicate;
+    }
     m.rng = h->pop.rng_holder.get();
     return h;
 }
@@ -270,6 +274,15 @@ void orc_philox_block(const uint32_t* ctr, const uint32_t* key, uint32_t* out) {
 void orc_philox_stream(uint32_t seed, uint32_t replicate, uint32_t individual, uint32_t chrom, uint32_t parent,
                        uint32_t stage, int n, uint32_t* out) {
     PhiloxStream s(seed, replicate);
+    s.seek(individual, chrom, parent, stage);
+    for (int i = 0; i < n; i++) out[i] = s.next_u32();
+}
+// the product's own stream (pedigreesim_b200/csrc/psim_rng.cuh compiled for the host): held word for
+// word against the oracle's restatement of Philox above (tests/test_oracle_pins.py)
+void orc_twin_stream(uint64_t seed, uint32_t replicate, uint32_t individual, uint32_t chrom, uint32_t parent,
+                     uint32_t stage, int n, uint32_t* out) {
+    psim::PhiloxStream s;
+    s.init(seed, replicate);
     s.seek(individual, chrom, parent, stage);
     for (int i = 0; i < n; i++) out[i] = s.next_u32();
 }

@@ -8,7 +8,7 @@
 //   run_desc / run_lb[] u32 / run_founder[] u16           K0 output: per homolog the runs of loci
 //                                                         that carry one founder (locus-index space)
 // Kernels (one header per group, all included below inside namespace psim):
-//   psim_k1.cuh            k_init_founders, k_meiosis_config + k_meiosis_mv (K1a), k_meiosis_assemble (K1b)
+//   psim_k1.cuh            k_init_founders, k_meiosis (K1: one launch per generation batch)
 //   psim_k0.cuh            k_index_runs (K0)
 //   psim_emit_rows.cuh     k_band_plan + k_emit_rows (K2, row image + TMA bulk stores: the roofline kernel)
 //   psim_emit_tiles.cuh    k_emit_plan + k_emit_tiles + k_emit_dense (K2, tiled path)
@@ -29,6 +29,7 @@
 #include <type_traits>
 #include <vector>
 
+#include <cub/block/block_scan.cuh>
 #include <cub/device/device_scan.cuh>
 
 #include "../../include/psim.h"
@@ -74,7 +75,7 @@ struct psim_ctx_impl {
     std::vector<ChromParams> chrom_h;
     ChromParams* chrom_d = nullptr;
     double max_len = 0.0;
-    int piece_cap = 0;
+    int chiasma_cap = 0;           // entries of a thread's column of the chiasma scratch
     std::vector<int32_t> par0_h, par1_h;
     int32_t *par0_d = nullptr, *par1_d = nullptr;
     std::vector<int32_t> hs_reps;  // per individual: number of replicates that have a haplostruct
@@ -112,7 +113,9 @@ struct psim_ctx_impl {
     int match_which = 12345678;
     int founder_allele_count = 0;
     // scratch
-    int* error_flag_d = nullptr;
+    int* status_d = nullptr;                  // [2]: see k_slab_mark
+    unsigned long long* cursor_d = nullptr;   // [0] segments of the slab in use (device copy while a simulation runs), [1] founders' base
+    unsigned long long* mark_d = nullptr;     // slab cursor at the start of every batch (b_mark)
     int* tile_counter_d = nullptr;
     // Page-locked and mapped: [0] segment total of a batch, [1] error flag, [2] overflowed emission
     // units. Written by k_publish (a store over PCIe), not by a D2H memcpy: a small copy queues
@@ -125,8 +128,8 @@ struct psim_ctx_impl {
     size_t staging_bytes = 0;
     // grow-only scratch of psim_simulate (no allocation in the steady state of a Monte Carlo loop)
     struct Buf { void* p = nullptr; size_t cap = 0; };
-    Buf b_lev, b_np, b_cnt, b_off, b_ppos, b_phom, b_find, b_fal;
-    Buf b_plan, b_dense_list, b_task, b_text, b_text2, b_rowlen, b_rowoff;
+    Buf b_lev, b_xpos, b_xab, b_mark, b_find, b_fal;
+    Buf b_plan, b_dense_list, b_text, b_text2, b_rowlen, b_rowoff;
     // export buffers
     int64_t* exp_off_d = nullptr; int32_t* exp_founder_d = nullptr; double* exp_pos_d = nullptr;
     int64_t exp_off_cap = 0, exp_seg_cap = 0;
@@ -137,7 +140,15 @@ struct psim_ctx_impl {
         int32_t maxf_in = 0, max_level = 0;
         std::vector<int32_t> f_ind, f_allele, order;
         std::vector<int64_t> level_off;
-    } plan;
+    } plan, plan_once;   // plan: kept across psim_reset; plan_once: a simulation that starts from a partly filled population
+    // the simulation that has been enqueued (sim_begin) and not yet settled (sim_finish)
+    struct SimRun {
+        struct Batch { int level; int64_t first, count; };   // level 0: the founders; else `count` individuals of plan->order from `first`
+        std::vector<Batch> batches;
+        const SimPlan* plan = nullptr;
+        int units_per_block = 0;
+        bool pending = false;
+    } run;
     bool fresh = false;   // no individual has a haplostruct (after psim_set_pedigree / psim_reset)
     bool check_reps = false;            // psim_set_haplostructs was called: replicate coverage to be verified
     std::vector<int32_t> founder_idx;   // founders of the pedigree, ascending
@@ -465,7 +476,7 @@ int psim_create(const psim_config* cfg, psim_ctx** out) {
     c->model.allow_no_recomb = cfg->allow_no_recomb != 0;
     c->model.parallel_multivalents = cfg->parallel_multivalents;
     c->model.paired_centromeres = cfg->paired_centromeres;
-    c->model.seed = (uint32_t)cfg->seed;
+    c->model.seed = (uint64_t)cfg->seed;
     c->model.unreduced = cfg->unreduced_gametes;
     cudaDeviceProp prop;
     if (cudaGetDeviceProperties(&prop, cfg->device) == cudaSuccess) c->sm_count = prop.multiProcessorCount;
@@ -476,11 +487,13 @@ int psim_create(const psim_config* cfg, psim_ctx** out) {
               cudaHostGetDevicePointer((void**)&c->scalars_dev, c->scalars_h, 0) == cudaSuccess &&
               cudaEventCreate(&c->ev0) == cudaSuccess && cudaEventCreate(&c->ev1) == cudaSuccess &&
               cudaEventCreate(&c->ev2) == cudaSuccess && cudaEventCreate(&c->ev3) == cudaSuccess && cudaEventCreate(&c->ev4) == cudaSuccess &&
-              cudaMalloc((void**)&c->error_flag_d, sizeof(int)) == cudaSuccess &&
+              cudaMalloc((void**)&c->status_d, 2 * sizeof(int)) == cudaSuccess &&
+              cudaMalloc((void**)&c->cursor_d, 2 * sizeof(unsigned long long)) == cudaSuccess &&
               cudaMalloc((void**)&c->tile_counter_d, sizeof(int)) == cudaSuccess;
     if (!ok) { g_create_error = std::string("CUDA setup failed: ") + cudaGetErrorString(cudaGetLastError()); delete c; return PSIM_ECUDA; }
     c->stream = c->own_stream;
-    cudaMemset(c->error_flag_d, 0, sizeof(int));
+    cudaMemset(c->status_d, 0, 2 * sizeof(int));
+    cudaMemset(c->cursor_d, 0, 2 * sizeof(unsigned long long));
     *out = (psim_ctx*)c;
     return PSIM_OK;
 }
@@ -495,11 +508,11 @@ void psim_destroy(psim_ctx* ctx) {
     cudaFree(c->run_lb_d); cudaFree(c->run_founder_d);
     cudaFree(c->locus_off_d); cudaFree(c->locus_pos_d); cudaFree(c->code_d); cudaFree(c->match_d);
     cudaFree(c->code16_d); cudaFree(c->nibmask_d); cudaFree(c->mtab_d);
-    cudaFree(c->error_flag_d); cudaFree(c->tile_counter_d); cudaFree(c->cub_tmp); cudaFree(c->staging);
+    cudaFree(c->status_d); cudaFree(c->cursor_d); cudaFree(c->tile_counter_d); cudaFree(c->cub_tmp); cudaFree(c->staging);
     cudaFree(c->exp_off_d); cudaFree(c->exp_founder_d); cudaFree(c->exp_pos_d);
     for (cudaEvent_t e : c->kev) cudaEventDestroy(e);
-    for (psim_ctx_impl::Buf* b : {&c->b_lev, &c->b_np, &c->b_cnt, &c->b_off, &c->b_ppos, &c->b_phom, &c->b_find, &c->b_fal,
-                                 &c->b_plan, &c->b_dense_list, &c->b_task, &c->b_text, &c->b_text2, &c->b_rowlen, &c->b_rowoff}) cudaFree(b->p);
+    for (psim_ctx_impl::Buf* b : {&c->b_lev, &c->b_xpos, &c->b_xab, &c->b_mark, &c->b_find, &c->b_fal,
+                                 &c->b_plan, &c->b_dense_list, &c->b_text, &c->b_text2, &c->b_rowlen, &c->b_rowoff}) cudaFree(b->p);
     cudaFree(c->label_off_d); cudaFree(c->labels_d); cudaFree(c->code_off_d); cudaFree(c->aname_off_d); cudaFree(c->anames_d);
     if (c->ev0) cudaEventDestroy(c->ev0);
     if (c->ev1) cudaEventDestroy(c->ev1);
@@ -551,12 +564,10 @@ int psim_set_chromosomes(psim_ctx* ctx, int32_t n_chrom, const double* length, c
         }
         c->max_len = std::max(c->max_len, len);
     }
-    // capacity of the per-chromatid piece list and the per-multivalent chiasma list (MAXE):
-    // chiasmata on a 4-strand bundle are Poisson(2 len) (4 len for a parallel quadrivalent).
+    // capacity of a multivalent's chiasma list: chiasmata on a 4-strand bundle are Poisson(2 len)
+    // (4 len for a parallel quadrivalent); a list that overflows all the same is reported as PSIM_ECAPACITY
     const double mean_e = 4.0 * c->max_len;
-    if (mean_e + 12.0 * std::sqrt(mean_e) + 16.0 > MAXE)
-        return fail(c, PSIM_ECAPACITY, "chromosome too long for the device chiasma buffer (limit about 14 Morgan)");
-    c->piece_cap = (int)std::ceil(c->max_len * 2.0 + 12.0 * std::sqrt(c->max_len * 2.0) + 8.0);
+    c->chiasma_cap = (int)std::ceil(mean_e + 12.0 * std::sqrt(mean_e) + 16.0);
     cudaFree(c->chrom_d); c->chrom_d = nullptr;
     CUDA_TRY(dev_alloc(&c->chrom_d, (size_t)n_chrom));
     CUDA_TRY(cudaMemcpy(c->chrom_d, c->chrom_h.data(), n_chrom * sizeof(ChromParams), cudaMemcpyHostToDevice));
@@ -656,10 +667,62 @@ int psim_set_haplostructs(psim_ctx* ctx, uint32_t replicate, int64_t first, int6
     return PSIM_OK;
 }
 
+// ---- psim_simulate: the whole simulation is enqueued (founders, then one k_meiosis launch per
+// generation batch) without the host reading anything back; sim_finish waits once, and only if the
+// slab turned out too small grows it and runs the batches from the first incomplete one again.
+static int sim_enqueue(psim_ctx_impl* c, int from_batch, int64_t cursor_at) {
+    psim_ctx_impl::SimRun& run = c->run;
+    const psim_ctx_impl::SimPlan& pl = *run.plan;
+    const int C = c->C, P = c->P, R = c->R;
+    const int64_t N = c->N;
+    int32_t* const lev_all_d = (int32_t*)c->b_lev.p;
+    for (int b = from_batch; b < (int)run.batches.size(); b++) {
+        const psim_ctx_impl::SimRun::Batch& bt = run.batches[b];
+        const long long restart = b == from_batch ? (long long)cursor_at : -1;
+        if (bt.level == 0) {   // founders (Main.java:1510-1513)
+            const int n_new = (int)pl.f_ind.size();
+            const int64_t nseg = (int64_t)n_new * R * C * P;
+            k_slab_mark<<<1, 1, 0, c->stream>>>(c->cursor_d, c->mark_d, b, nseg, c->slab_cap, c->cursor_d + 1, c->status_d, restart);
+            k_init_founders<<<grid_for(nseg, 256), 256, 0, c->stream>>>(n_new * R, n_new, (const int32_t*)c->b_find.p, (const int32_t*)c->b_fal.p,
+                                                                        C, R, N, P, c->chrom_d, c->desc_d, c->seg_pos_d, c->seg_founder_d,
+                                                                        c->cursor_d + 1, c->slab_cap);
+            c->stats.kernel_launches += 2;
+            continue;
+        }
+        k_slab_mark<<<1, 1, 0, c->stream>>>(c->cursor_d, c->mark_d, b, 0, c->slab_cap, c->cursor_d + 1, c->status_d, restart);
+        MeiosisArgs ma;
+        ma.model = c->model; ma.chrom = c->chrom_d; ma.C = C; ma.R = R; ma.P = P; ma.N = N;
+        ma.replicate_first = c->cfg.replicate_first;
+        ma.n_lev = (int)bt.count; ma.lev_ind = lev_all_d + bt.first; ma.par0 = c->par0_d; ma.par1 = c->par1_d;
+        ma.desc = c->desc_d; ma.seg_pos = c->seg_pos_d; ma.seg_founder = c->seg_founder_d;
+        ma.slab_cap = c->slab_cap; ma.cursor = c->cursor_d; ma.status = c->status_d; ma.batch = b;
+        ma.cfg_quad = c->cfg_quad_d; ma.cfg_seq = c->cfg_seq_d;
+        ma.x_cap = c->chiasma_cap;
+        ma.units_per_block = run.units_per_block;
+        const int64_t n_units = (int64_t)bt.count * C * R * 2;
+        const int64_t blocks = (n_units + run.units_per_block - 1) / run.units_per_block;
+        ma.x_pos = (double*)c->b_xpos.p; ma.x_ab = (uint8_t*)c->b_xab.p;
+        if (c->model.chiasma_interference) {
+            if (c->model.allow_no_recomb) k_meiosis<true, true><<<(unsigned)blocks, MEI_THREADS, 0, c->stream>>>(ma);
+            else k_meiosis<true, false><<<(unsigned)blocks, MEI_THREADS, 0, c->stream>>>(ma);
+        } else {
+            if (c->model.allow_no_recomb) k_meiosis<false, true><<<(unsigned)blocks, MEI_THREADS, 0, c->stream>>>(ma);
+            else k_meiosis<false, false><<<(unsigned)blocks, MEI_THREADS, 0, c->stream>>>(ma);
+        }
+        c->stats.kernel_launches += 2;
+    }
+    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cudaEventRecord(c->ev1, c->stream));
+    k_publish<<<1, 32, 0, c->stream>>>(c->scalars_dev, (const int64_t*)c->cursor_d, c->status_d, c->status_d + 1);
+    c->stats.kernel_launches++;
+    CUDA_TRY(cudaGetLastError());
+    return PSIM_OK;
+}
+
 // subset == nullptr: every individual without a haplostruct; otherwise only the listed non-founders
 // (founders without a haplostruct are always initialised: it is cheap and every rank of a sharded
 // pedigree needs them).
-static int simulate_impl(psim_ctx_impl* c, int32_t max_founder_allele, const int32_t* subset, int64_t n_subset) {
+static int sim_begin(psim_ctx_impl* c, int32_t max_founder_allele, const int32_t* subset, int64_t n_subset) {
     if (c->N == 0) return fail(c, PSIM_ESTATE, "psim_set_pedigree must be called first");
     cudaSetDevice(c->cfg.device);
     const int C = c->C, P = c->P, R = c->R;
@@ -676,16 +739,20 @@ static int simulate_impl(psim_ctx_impl* c, int32_t max_founder_allele, const int
                 return fail(c, PSIM_EINVAL, "preset haplostructs must cover the same individuals in every replicate");
         c->check_reps = false;
     }
-    CUDA_TRY(cudaEventRecord(c->ev0, c->stream));
-    psim_ctx_impl::SimPlan local;
-    psim_ctx_impl::SimPlan& pl = reuse ? sp : local;
+    psim_ctx_impl::SimPlan& pl = reuse ? sp : c->plan_once;
     if (!reuse) {
+        pl = psim_ctx_impl::SimPlan();
         // --- founders (Main.java:1510-1513)
         int32_t maxf = max_founder_allele;
         for (int32_t i : c->founder_idx) {
             if (c->hs_reps[i]) continue;
             pl.f_ind.push_back(i); pl.f_allele.push_back(maxf + 1); maxf += P;
         }
+        // founder alleles are numbered 0 .. founder_allele_count-1 (Main.java:1235 rejects others): the count
+        // decides the width of the founder tables and sizes the statistics histograms
+        if (!pl.f_ind.empty() && maxf >= c->founder_allele_count)
+            return fail(c, PSIM_EINVAL, "invalid founder allele '" + std::to_string(maxf) + "': the pedigree has " +
+                                            std::to_string(c->founder_allele_count) + " founder alleles");
         if (maxf > 65535) return fail(c, PSIM_ECAPACITY, "more than 65536 founder alleles");
         // --- generations: level = 1 + max(level of parents) over individuals still to simulate.
         // `level` is a context-owned array of N zeros; only the entries touched here are reset
@@ -746,151 +813,123 @@ static int simulate_impl(psim_ctx_impl* c, int32_t max_founder_allele, const int
         pl.max_level = max_level;
         pl.maxf_in = max_founder_allele;
         pl.on_device = false;
+        if (fresh) { sp = std::move(pl); sp.valid = true; }
     }
-    const int32_t max_level = pl.max_level;
+    psim_ctx_impl::SimPlan& plan = fresh ? sp : c->plan_once;
     const bool upload = !(reuse && sp.on_device);
     if (upload && !fresh) sp.on_device = false;   // the device copies of the lists are about to be overwritten
-    if (!pl.f_ind.empty()) {
-        const int n_new = (int)pl.f_ind.size();
-        const int64_t nseg = (int64_t)n_new * R * C * P;
-        if (int rc = ensure_slab(c, c->slab_used + nseg)) return rc;
+    // --- batches: the founders, then every generation cut into pieces whose chiasma scratch stays
+    // below about 1 GiB (a thread's column holds chiasma_cap entries of 9 bytes)
+    psim_ctx_impl::SimRun& run = c->run;
+    run.plan = &plan;
+    run.batches.clear();
+    run.units_per_block = P == 2 ? MEI_THREADS : (MEI_THREADS - 32) / (P / 2);
+    const int64_t max_blocks = std::max<int64_t>(1, (int64_t)(1LL << 30) / ((int64_t)MEI_THREADS * c->chiasma_cap * 9));
+    const int64_t max_batch = std::max<int64_t>(1, max_blocks * run.units_per_block / ((int64_t)C * R * 2));
+    if (!plan.f_ind.empty()) run.batches.push_back({0, 0, (int64_t)plan.f_ind.size()});
+    int64_t most_blocks = 0;
+    for (int lv = 1; lv <= plan.max_level; lv++) {
+        const int64_t lev_begin = plan.level_off[lv], lev_size = plan.level_off[lv + 1] - lev_begin;
+        for (int64_t b0 = 0; b0 < lev_size; b0 += max_batch) {
+            const int64_t n = std::min<int64_t>(max_batch, lev_size - b0);
+            run.batches.push_back({lv, lev_begin + b0, n});
+            most_blocks = std::max(most_blocks, (n * C * R * 2 + run.units_per_block - 1) / run.units_per_block);
+        }
+    }
+    if (!plan.f_ind.empty()) {
+        const size_t n_new = plan.f_ind.size();
         if (int rc = ensure_buf(c, c->b_find, n_new * sizeof(int32_t))) return rc;
         if (int rc = ensure_buf(c, c->b_fal, n_new * sizeof(int32_t))) return rc;
-        int32_t *ind_d = (int32_t*)c->b_find.p, *al_d = (int32_t*)c->b_fal.p;
         if (upload) {   // (pageable sources: cudaMemcpyAsync has staged them before it returns)
-            CUDA_TRY(cudaMemcpyAsync(ind_d, pl.f_ind.data(), n_new * sizeof(int32_t), cudaMemcpyHostToDevice, c->stream));
-            CUDA_TRY(cudaMemcpyAsync(al_d, pl.f_allele.data(), n_new * sizeof(int32_t), cudaMemcpyHostToDevice, c->stream));
+            CUDA_TRY(cudaMemcpyAsync(c->b_find.p, plan.f_ind.data(), n_new * sizeof(int32_t), cudaMemcpyHostToDevice, c->stream));
+            CUDA_TRY(cudaMemcpyAsync(c->b_fal.p, plan.f_allele.data(), n_new * sizeof(int32_t), cudaMemcpyHostToDevice, c->stream));
         }
-        k_init_founders<<<grid_for(nseg, 256), 256, 0, c->stream>>>(n_new * R, n_new, ind_d, al_d, C, R, N, P, c->chrom_d, c->desc_d,
-                                                                    c->seg_pos_d, c->seg_founder_d, c->slab_used);
-        c->stats.kernel_launches++;
-        CUDA_TRY(cudaGetLastError());
-        c->slab_used += nseg;
-        for (int32_t i : pl.f_ind) c->hs_reps[i] = R;
     }
-    // batch size: bound the plan scratch to about 1.5 GiB
-    const int64_t per_ind = (int64_t)C * R * P * (c->piece_cap * 9 + 4 + 16);
-    const int64_t max_batch = std::max<int64_t>(1, (int64_t)(1536LL << 20) / per_ind);
-    int64_t scratch_ind = 0;
-    for (int lv = 1; lv <= max_level; lv++)
-        scratch_ind = std::max<int64_t>(scratch_ind, std::min<int64_t>(pl.level_off[lv + 1] - pl.level_off[lv], max_batch));
-    int32_t* lev_all_d = nullptr; int32_t* plan_np = nullptr; int64_t* plan_cnt = nullptr; int64_t* plan_off = nullptr;
-    double* plan_pos = nullptr; uint8_t* plan_hom = nullptr;
-    if (scratch_ind > 0) {
-        const size_t nu = (size_t)scratch_ind * C * R * P;
-        if (int rc = ensure_buf(c, c->b_lev, pl.order.size() * sizeof(int32_t))) return rc;
-        if (int rc = ensure_buf(c, c->b_np, nu * sizeof(int32_t))) return rc;
-        if (int rc = ensure_buf(c, c->b_cnt, (nu + 1) * sizeof(int64_t))) return rc;
-        if (int rc = ensure_buf(c, c->b_off, (nu + 1) * sizeof(int64_t))) return rc;
-        if (int rc = ensure_buf(c, c->b_ppos, nu * c->piece_cap * sizeof(double))) return rc;
-        if (int rc = ensure_buf(c, c->b_phom, nu * c->piece_cap)) return rc;
-        lev_all_d = (int32_t*)c->b_lev.p; plan_np = (int32_t*)c->b_np.p; plan_cnt = (int64_t*)c->b_cnt.p;
-        plan_off = (int64_t*)c->b_off.p; plan_pos = (double*)c->b_ppos.p; plan_hom = (uint8_t*)c->b_phom.p;
+    if (most_blocks > 0) {
+        const size_t n_slots = (size_t)most_blocks * MEI_THREADS;
+        if (int rc = ensure_buf(c, c->b_lev, plan.order.size() * sizeof(int32_t))) return rc;
+        if (int rc = ensure_buf(c, c->b_xpos, n_slots * c->chiasma_cap * sizeof(double))) return rc;
+        if (int rc = ensure_buf(c, c->b_xab, n_slots * c->chiasma_cap)) return rc;
         if (upload)   // every generation list in one copy
-            CUDA_TRY(cudaMemcpyAsync(lev_all_d, pl.order.data(), pl.order.size() * sizeof(int32_t), cudaMemcpyHostToDevice, c->stream));
+            CUDA_TRY(cudaMemcpyAsync(c->b_lev.p, plan.order.data(), plan.order.size() * sizeof(int32_t), cudaMemcpyHostToDevice, c->stream));
     }
-    if (fresh && !reuse) { sp = std::move(local); sp.valid = true; }
-    psim_ctx_impl::SimPlan& plan = fresh ? sp : local;
+    if (int rc = ensure_buf(c, c->b_mark, (run.batches.size() + 1) * sizeof(unsigned long long))) return rc;
+    c->mark_d = (unsigned long long*)c->b_mark.p;
     if (fresh) sp.on_device = true;
     c->fresh = false;
-    int rc_out = PSIM_OK;
-    for (int lv = 1; lv <= max_level && rc_out == PSIM_OK; lv++) {
-        const int64_t lev_begin = plan.level_off[lv], lev_size = plan.level_off[lv + 1] - lev_begin;
-        for (int64_t b0 = 0; b0 < lev_size && rc_out == PSIM_OK; b0 += max_batch) {
-            const int n_lev = (int)std::min<int64_t>(max_batch, lev_size - b0);
-            const int64_t nu = (int64_t)n_lev * C * R * P;
-            int32_t* const lev_d = lev_all_d + lev_begin + b0;
-            PlanArgs pa;
-            pa.model = c->model; pa.chrom = c->chrom_d; pa.C = C; pa.R = R; pa.P = P; pa.N = N;
-            pa.replicate_first = c->cfg.replicate_first;
-            pa.n_lev = n_lev; pa.lev_ind = lev_d; pa.par0 = c->par0_d; pa.par1 = c->par1_d;
-            pa.desc = c->desc_d; pa.seg_pos = c->seg_pos_d; pa.seg_founder = c->seg_founder_d;
-            pa.piece_cap = c->piece_cap; pa.plan_np = plan_np; pa.plan_cnt = plan_cnt;
-            pa.plan_pos = plan_pos; pa.plan_hom = plan_hom;
-            pa.cfg_quad = c->cfg_quad_d; pa.cfg_seq = c->cfg_seq_d; pa.error_flag = c->error_flag_d;
-            const int64_t n_half = (int64_t)n_lev * C * R * 2;
-            const int64_t cap_bi = n_half * (P / 2), cap_quad = n_half * (P / 4);
-            if (int rc = ensure_buf(c, c->b_task, (size_t)(cap_bi + cap_quad) * sizeof(int64_t) + 16)) { rc_out = rc; break; }
-            pa.task_count = (int*)c->b_task.p;
-            pa.task_bi = (int64_t*)((uint8_t*)c->b_task.p + 16);
-            pa.task_quad = pa.task_bi + cap_bi;
-            pa.direct_diploid = P == 2;
-            if (!pa.direct_diploid) {
-                CUDA_TRY(cudaMemsetAsync(pa.task_count, 0, 16, c->stream));
-                k_meiosis_config<<<grid_for(n_half, 128), 128, 0, c->stream>>>(pa);
-                c->stats.kernel_launches++;
-            }
-            auto launch_mv = [&](auto kos, auto anr) {
-                constexpr bool KOS = decltype(kos)::value, ANR = decltype(anr)::value;
-                // the two task lists are independent and neither kernel fills the machine (one
-                // wave of divergent warps): they run side by side, the longer (quadrivalents) first
-                if (cap_quad > 0) {
-                    cudaEventRecord(c->ev2, c->stream);
-                    cudaStreamWaitEvent(c->aux_stream, c->ev2, 0);
-                    k_meiosis_mv<true, KOS, ANR><<<grid_for(cap_quad, 128), 128, 0, c->aux_stream>>>(pa);
-                    cudaEventRecord(c->ev3, c->aux_stream);
-                    c->stats.kernel_launches++;
-                }
-                k_meiosis_mv<false, KOS, ANR><<<grid_for(cap_bi, 128), 128, 0, c->stream>>>(pa);
-                c->stats.kernel_launches++;
-                if (cap_quad > 0) cudaStreamWaitEvent(c->stream, c->ev3, 0);
-            };
-            if (c->model.chiasma_interference) {
-                if (c->model.allow_no_recomb) launch_mv(std::true_type{}, std::true_type{}); else launch_mv(std::true_type{}, std::false_type{});
-            } else {
-                if (c->model.allow_no_recomb) launch_mv(std::false_type{}, std::true_type{}); else launch_mv(std::false_type{}, std::false_type{});
-            }
-            CUDA_TRY(cudaGetLastError());
-            CUDA_TRY(cudaMemsetAsync(plan_cnt + nu, 0, sizeof(int64_t), c->stream));
-            if (int rc = exclusive_scan_i64(c, plan_cnt, plan_off, nu + 1)) { rc_out = rc; break; }
-            // The batch's segment total is only known on the device at this point. The assembly is
-            // launched at once against the slab as it is (the kernel does nothing if the batch does not
-            // fit) so that the device never idles behind a host round trip; the host reads the total
-            // afterwards and, only if the slab was too small, grows it and launches the assembly again.
-            c->scalars_h[0] = 0; c->scalars_h[1] = 0;
-            k_publish<<<1, 32, 0, c->stream>>>(c->scalars_dev, plan_off + nu, c->error_flag_d, nullptr);
-            c->stats.kernel_launches++;
-            AssembleArgs aa;
-            aa.chrom = c->chrom_d; aa.C = C; aa.R = R; aa.P = P; aa.N = N; aa.n_lev = n_lev; aa.lev_ind = lev_d;
-            aa.par0 = c->par0_d; aa.par1 = c->par1_d; aa.desc = c->desc_d; aa.seg_pos = c->seg_pos_d;
-            aa.seg_founder = c->seg_founder_d; aa.piece_cap = c->piece_cap; aa.plan_np = plan_np; aa.plan_cnt = plan_cnt;
-            aa.plan_off = plan_off; aa.plan_pos = plan_pos; aa.plan_hom = plan_hom; aa.slab_base = c->slab_used;
-            aa.slab_cap = c->slab_cap; aa.error_flag = c->error_flag_d; aa.unreduced = c->model.unreduced;
-            k_meiosis_assemble<<<grid_for(nu, 128), 128, 0, c->stream>>>(aa);
-            c->stats.kernel_launches++;
-            CUDA_TRY(cudaGetLastError());
-            const bool last_batch = lv == max_level && b0 + max_batch >= lev_size;
-            if (last_batch) CUDA_TRY(cudaEventRecord(c->ev1, c->stream));
-            CUDA_TRY(cudaStreamSynchronize(c->stream));
-            const int64_t total = c->scalars_h[0];
-            const int flag = (int)c->scalars_h[1];
-            if (flag) {
-                cudaMemset(c->error_flag_d, 0, sizeof(int));
-                rc_out = fail(c, flag, "meiosis plan exceeded a device buffer (too many chiasmata on one chromatid)");
-                break;
-            }
-            if (c->slab_used + total > c->slab_cap) {
-                if (int rc = ensure_slab(c, c->slab_used + total)) { rc_out = rc; break; }
-                aa.seg_pos = c->seg_pos_d; aa.seg_founder = c->seg_founder_d; aa.slab_cap = c->slab_cap;
-                k_meiosis_assemble<<<grid_for(nu, 128), 128, 0, c->stream>>>(aa);
-                c->stats.kernel_launches++;
-                CUDA_TRY(cudaGetLastError());
-                if (last_batch) CUDA_TRY(cudaEventRecord(c->ev1, c->stream));
-            }
-            c->slab_used += total;
-            c->stats.n_meioses += (int64_t)n_lev * R * (c->model.unreduced ? 1 : 2);
-            c->stats.n_units += (int64_t)n_lev * R * (c->model.unreduced ? 1 : 2) * C;
-        }
-        for (int64_t k = 0; k < lev_size; k++) c->hs_reps[plan.order[(size_t)(lev_begin + k)]] = R;
+    // room for the founders and about two segments per homolog, so that the first run of a typical
+    // pedigree does not have to be repeated (a slab that is too small is grown in sim_finish)
+    {
+        int64_t n_sim = 0;
+        for (const auto& bt : run.batches) n_sim += bt.count;
+        if (int rc = ensure_slab(c, c->slab_used + n_sim * R * C * P * 2)) return rc;
     }
-    if (max_level == 0 || rc_out != PSIM_OK) CUDA_TRY(cudaEventRecord(c->ev1, c->stream));   // else recorded behind the last assembly
-    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    for (const auto& bt : run.batches)
+        for (int64_t k = 0; k < bt.count; k++) c->hs_reps[bt.level == 0 ? plan.f_ind[(size_t)k] : plan.order[(size_t)(bt.first + k)]] = R;
+    c->scalars_h[0] = 0; c->scalars_h[1] = 0; c->scalars_h[2] = 0;
+    CUDA_TRY(cudaEventRecord(c->ev0, c->stream));
+    run.pending = true;
+    c->runs_valid = false;
+    return sim_enqueue(c, 0, c->slab_used);
+}
+
+// Waits for an enqueued simulation and settles the slab: PSIM_OK, or the error of the first batch
+// that failed (individuals of that batch and of later ones are left without a haplostruct).
+static int sim_finish(psim_ctx_impl* c) {
+    psim_ctx_impl::SimRun& run = c->run;
+    if (!run.pending) return PSIM_OK;
+    const psim_ctx_impl::SimPlan& pl = *run.plan;
+    const int R = c->R;
+    int rc_out = PSIM_OK;
+    for (;;) {
+        CUDA_TRY(cudaStreamSynchronize(c->stream));
+        const int64_t cursor = c->scalars_h[0];
+        const int status = (int)c->scalars_h[1], failed = (int)c->scalars_h[2];
+        if (status == 0) { c->slab_used = cursor; break; }
+        unsigned long long mark = 0;
+        CUDA_TRY(cudaMemcpy(&mark, c->mark_d + failed, sizeof(mark), cudaMemcpyDeviceToHost));
+        c->slab_used = (int64_t)mark;
+        if (status == STATUS_SLAB_FULL) {
+            // `cursor` counts what the batches so far asked for; the rest is extrapolated
+            int64_t done_ind = 0, all_ind = 0;
+            for (size_t b = 0; b < run.batches.size(); b++) { all_ind += run.batches[b].count; if ((int)b <= failed) done_ind += run.batches[b].count; }
+            const double per_ind = (double)std::max<int64_t>(cursor, c->slab_cap) / (double)std::max<int64_t>(1, done_ind);
+            const int64_t want = (int64_t)(per_ind * (double)all_ind * 1.25) + 1024;
+            if (int rc = ensure_slab(c, std::max<int64_t>(want, c->slab_cap + c->slab_cap / 2))) { rc_out = rc; }
+            else {
+                c->scalars_h[0] = 0; c->scalars_h[1] = 0; c->scalars_h[2] = 0;
+                if (int rc2 = sim_enqueue(c, failed, c->slab_used)) rc_out = rc2; else continue;
+            }
+        } else {
+            rc_out = fail(c, status, "more chiasmata on one multivalent than the device list holds");
+        }
+        // batches from `failed` on did not complete
+        for (size_t b = (size_t)failed; b < run.batches.size(); b++) {
+            const auto& bt = run.batches[b];
+            for (int64_t k = 0; k < bt.count; k++) c->hs_reps[bt.level == 0 ? pl.f_ind[(size_t)k] : pl.order[(size_t)(bt.first + k)]] = 0;
+        }
+        k_slab_mark<<<1, 1, 0, c->stream>>>(c->cursor_d, c->mark_d, 0, 0, c->slab_cap, c->cursor_d + 1, c->status_d, c->slab_used);
+        CUDA_TRY(cudaStreamSynchronize(c->stream));
+        run.batches.resize((size_t)failed);
+        break;
+    }
+    run.pending = false;
+    for (const auto& bt : run.batches) {
+        if (bt.level == 0) continue;
+        c->stats.n_meioses += bt.count * R * (c->model.unreduced ? 1 : 2);
+        c->stats.n_units += bt.count * R * (c->model.unreduced ? 1 : 2) * c->C;
+    }
     float ms = 0.f;
     cudaEventElapsedTime(&ms, c->ev0, c->ev1);
     c->stats.ms_simulate = ms;
     c->stats.n_segments = c->slab_used;
-    c->runs_valid = false;
     return rc_out;
+}
+
+static int simulate_impl(psim_ctx_impl* c, int32_t max_founder_allele, const int32_t* subset, int64_t n_subset) {
+    if (int rc = sim_finish(c)) return rc;
+    if (int rc = sim_begin(c, max_founder_allele, subset, n_subset)) return rc;
+    return sim_finish(c);
 }
 
 int psim_simulate(psim_ctx* ctx, int32_t max_founder_allele) {
@@ -1716,7 +1755,7 @@ int psim_reset(psim_ctx* ctx, int64_t seed, uint32_t replicate_first) {
     cudaSetDevice(c->cfg.device);
     c->cfg.seed = seed;
     c->cfg.replicate_first = replicate_first;
-    c->model.seed = (uint32_t)seed;
+    c->model.seed = (uint64_t)seed;
     CUDA_TRY(cudaMemsetAsync(c->desc_d, 0, c->n_hom * sizeof(uint64_t), c->stream));
     const int64_t ncfg = (int64_t)c->R * c->N * c->C * 2;
     CUDA_TRY(cudaMemsetAsync(c->cfg_quad_d, 0xFF, ncfg, c->stream));

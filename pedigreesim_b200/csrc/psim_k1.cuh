@@ -1,4 +1,5 @@
-// K1 — meiosis kernels: founders, pairing configuration, multivalents, assembly
+// K1 — meiosis: founders, and ONE kernel per generation batch that takes every (child, chromosome,
+// parent) unit from the parent's haplostructs to the child's segments in the slab
 // (part of libpsim: included by psim.cu inside namespace psim)
 #pragma once
 
@@ -8,10 +9,12 @@
 __global__ void k_init_founders(int n_jobs, int n_new, const int32_t* __restrict__ ind, const int32_t* __restrict__ allele0,
                                 int C, int R, int64_t N, int P, const ChromParams* __restrict__ chrom,
                                 uint64_t* __restrict__ desc, double* __restrict__ seg_pos, int32_t* __restrict__ seg_founder,
-                                int64_t slab_base) {
+                                const unsigned long long* __restrict__ taken_at, int64_t slab_cap) {
     const int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     const int64_t total = (int64_t)n_jobs * C * P;
     if (t >= total) return;
+    const int64_t slab_base = (int64_t)*taken_at;   // reserved by k_slab_mark just before this kernel
+    if (slab_base + total > slab_cap) return;       // (which has also set the status)
     const int h = (int)(t % P);
     const int c = (int)((t / P) % C);
     const int job = (int)(t / ((int64_t)P * C));
@@ -23,11 +26,46 @@ __global__ void k_init_founders(int n_jobs, int n_new, const int32_t* __restrict
     desc[hid] = make_desc((uint64_t)s, 1);
 }
 
+// Slab bookkeeping on the device, so that a whole simulation is enqueued without the host reading
+// anything back. status[0]: 0, PSIM_ECAPACITY (a chiasma list overflowed) or STATUS_SLAB_FULL;
+// status[1]: the first batch that did not complete (everything before it is intact).
+constexpr int STATUS_SLAB_FULL = -1;
+// mark[batch] = slab cursor when the batch begins (a batch that is run again starts there); `take`
+// segments are then reserved for a kernel that knows its size in advance (founders): old cursor -> *taken_at.
+// restart >= 0: the first batch of a (re)started simulation - the cursor is set and the status cleared.
+__global__ void k_slab_mark(unsigned long long* cursor, unsigned long long* mark, int batch, long long take, int64_t slab_cap,
+                            unsigned long long* taken_at, int* status, long long restart) {
+    if (threadIdx.x || blockIdx.x) return;
+    if (restart >= 0) { *cursor = (unsigned long long)restart; status[0] = 0; status[1] = 0x7FFFFFFF; }
+    if (status[0] != 0) return;
+    const unsigned long long at = *cursor;
+    mark[batch] = at;
+    if (take > 0) {
+        *taken_at = at;
+        *cursor = at + (unsigned long long)take;
+        if ((int64_t)at + take > slab_cap) { status[0] = STATUS_SLAB_FULL; status[1] = batch; }
+    }
+}
+
 // ------------------------------------------------------------------------------------------
-// K1a — one thread per (child, chromosome, parent): meiosis plan for the transmitted gamete.
-// Output per child homolog u (scan order ((c*R + r)*n_lev + j)*P + h): the pieces
-// (start position, parental homolog) that make up the chromatid, and its segment count.
-struct PlanArgs {
+// The meiosis kernel. A block owns `units_per_block` consecutive units (unit = child, chromosome,
+// parent: one meiosis seen on one chromosome) and works in three steps:
+//   1. one thread per unit draws the pairing configuration (bit masks in registers) and leaves it in
+//      shared memory and in the configuration tables;
+//   2. the multivalents of all the block's units are compacted by kind - quadrivalents first,
+//      bivalents from the next warp boundary - and every thread takes one: chiasmata (into its
+//      column of the chiasma scratch), segregation, the chromatids of the kept gamete(s) traced
+//      once to count the segments they will have;
+//   3. the block reserves its segments in the slab with one atomic, and the same threads trace
+//      again, writing the segments (Multivalent.fillGamete :539-577) and the child's descriptors
+//      (Gamete.fertilization, Gamete.java:95-116: homologs 0..P/2-1 from parent 0's gamete,
+//      P/2..P-1 from parent 1's).
+// Warps therefore run one kind of multivalent, no task list goes through global memory, and a
+// generation is one launch. Every multivalent owns a Philox stream, so results do not depend on the
+// block size or on how the units are batched.
+constexpr int MEI_THREADS = 256;
+
+struct MeiosisArgs {
     ModelParams model;
     const ChromParams* chrom;
     int C, R, P;
@@ -37,283 +75,207 @@ struct PlanArgs {
     const int32_t* lev_ind;      // their indices
     const int32_t* par0;
     const int32_t* par1;
-    const uint64_t* desc;
-    const double* seg_pos;
-    const int32_t* seg_founder;
-    int piece_cap;
-    int32_t* plan_np;            // [n_units_homologs]
-    int64_t* plan_cnt;           // [n_units_homologs] -> segment counts (scanned in place later)
-    double* plan_pos;            // [n_units_homologs][piece_cap]
-    uint8_t* plan_hom;           // [n_units_homologs][piece_cap]
+    uint64_t* desc;
+    double* seg_pos;
+    int32_t* seg_founder;
+    int64_t slab_cap;
+    unsigned long long* cursor;  // segments of the slab in use
+    int* status;
+    int batch;
     int8_t* cfg_quad;            // [R*N][C][2]
     int8_t* cfg_seq;             // [R*N][C][2][P]
-    int* error_flag;
-    int64_t* task_bi;            // bivalents of the batch: (thread id of the unit) * 8 + multivalent number
-    int64_t* task_quad;          // quadrivalents
-    int* task_count;             // [0] bivalents, [1] quadrivalents
-    int direct_diploid;          // ploidy 2: no configuration kernel and no task lists - thread t of the bivalent
-                                 // kernel IS unit t and draws the unit's configuration (one shuffle of two) itself
+    double* x_pos;               // chiasma scratch: entry e of thread slot t at [e * n_slots + t]
+    uint8_t* x_ab;
+    int x_cap;
+    int units_per_block;
 };
 
-// K1a is split in two so that the warps of the heavy part run one code path:
-//   k_meiosis_config  one thread per (child, chromosome, parent): pairing configuration only
-//                     (Individual.calcChromConfig); it also files every multivalent of the unit as a
-//                     task in the bivalent or the quadrivalent list (one atomic per warp and list)
-//   k_meiosis_mv<Q>   one thread per task of one kind: crossing-over, centromere order, choice of
-//                     the transmitted chromatids and their trace into the plan
-// Every multivalent has its own Philox stream (stage 1 + v), so the split changes no draw.
-__device__ __forceinline__ void plan_decode(const PlanArgs& a, int64_t t, int& par, int& j, int& r, int& c) {
+__device__ __forceinline__ void unit_decode(const MeiosisArgs& a, int64_t t, int& par, int& j, int& r, int& c) {
     par = (int)(t & 1);
     const int64_t unit = t >> 1;
     j = (int)(unit % a.n_lev);
     r = (int)((unit / a.n_lev) % a.R);
     c = (int)(unit / ((int64_t)a.n_lev * a.R));
 }
+__device__ __forceinline__ HomologView homolog_view(const MeiosisArgs& a, int64_t hid) {
+    const uint64_t d = a.desc[hid];
+    HomologView hv;
+    hv.pos = a.seg_pos + desc_begin(d);
+    hv.founder = a.seg_founder + desc_begin(d);
+    hv.n = (int)desc_count(d);
+    return hv;
+}
 
-__global__ void __launch_bounds__(128) k_meiosis_config(PlanArgs a) {
-    const int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-    const int64_t total = (int64_t)a.C * a.R * a.n_lev * 2;
-    int n_quad = 0, n_bi = 0;
-    if (t < total && !(a.model.unreduced && (t & 1))) {   // 2NGAMETES: the individual is parent 0's 2n gamete alone
-        int par, j, r, c;
-        plan_decode(a, t, par, j, r, c);
-        const int P = a.P;
-        const int32_t child = a.lev_ind[j];
-        const int32_t parent = par == 0 ? a.par0[child] : a.par1[child];
-        const ChromParams ch = a.chrom[c];
-        HomologView hv[MAXP];
-        const int64_t phid0 = (((int64_t)c * a.R + r) * a.N + parent) * P;
-        for (int h = 0; h < P; h++) {
-            const uint64_t d = a.desc[phid0 + h];
-            hv[h].pos = a.seg_pos + desc_begin(d);
-            hv[h].founder = a.seg_founder + desc_begin(d);
-            hv[h].n = (int)desc_count(d);
+// One chromatid of the kept gamete, followed from the head along the chiasmata it takes part in:
+// the stretch between two of them is copied from the parental homolog the chromatid is on
+// (Multivalent.slotsToPatterns :332-357 + fillGamete :539-577). WRITE = false only counts.
+template <bool WRITE>
+__device__ __forceinline__ int trace_chromatid(const MeiosisArgs& a, const ChiasmaList& x, int strand, Nib16 seq, int base,
+                                               int64_t phid0, double head, double tail, int64_t w) {
+    int first = 0;
+    while (first < x.n && x.a(first) != strand && x.b(first) != strand) first++;
+    if (first == x.n) {   // no exchange: the parental homolog as it is
+        const HomologView hv = homolog_view(a, phid0 + seq.get(base + (strand >> 1)));
+        if (WRITE) for (int s = 0; s < hv.n; s++) { a.seg_pos[w + s] = hv.pos[s]; a.seg_founder[w + s] = hv.founder[s]; }
+        return hv.n;
+    }
+    int n = 0;
+    double from = head;
+    for (int e = first; e <= x.n; e++) {
+        int next = -1;
+        double to = tail;
+        if (e < x.n) {
+            const int sa = x.a(e), sb = x.b(e);
+            if (sa == strand) next = sb; else if (sb == strand) next = sa; else continue;
+            to = x.p(e);
         }
-        PhiloxStream rng;
-        rng.init(a.model.seed, a.replicate_first + (uint32_t)r);
-        PairingState ps;
-        rng.seek((uint32_t)child, (uint32_t)c, (uint32_t)par, STAGE_CONFIG);
-        calc_chrom_config(ps, rng, a.model, ch, hv);
-        const int64_t q = (((int64_t)r * a.N + child) * a.C + c) * 2 + par;
-        a.cfg_quad[q] = (int8_t)ps.quad;
-        for (int h = 0; h < P; h++) a.cfg_seq[q * P + h] = ps.chromseq[h];
-        n_quad = ps.quad;
-        n_bi = (P - 4 * ps.quad) / 2;
+        const HomologView hv = homolog_view(a, phid0 + seq.get(base + (strand >> 1)));
+        int seg = hv.find_segment(from);
+        if (WRITE) { a.seg_pos[w + n] = from; a.seg_founder[w + n] = hv.founder[seg]; }
+        n++;
+        for (seg++; seg < hv.n && hv.pos[seg] < to; seg++) {
+            if (WRITE) { a.seg_pos[w + n] = hv.pos[seg]; a.seg_founder[w + n] = hv.founder[seg]; }
+            n++;
+        }
+        from = to;
+        strand = next;
     }
-    // file the tasks: exclusive prefix inside the warp, one atomic per warp and list
-    const int lane = threadIdx.x & 31;
-    int sq = n_quad, sb = n_bi;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-        const int yq = __shfl_up_sync(0xFFFFFFFFu, sq, o), yb = __shfl_up_sync(0xFFFFFFFFu, sb, o);
-        if (lane >= o) { sq += yq; sb += yb; }
-    }
-    int base_q = 0, base_b = 0;
-    if (lane == 31) {
-        if (sq) base_q = atomicAdd(a.task_count + 1, sq);
-        if (sb) base_b = atomicAdd(a.task_count, sb);
-    }
-    base_q = __shfl_sync(0xFFFFFFFFu, base_q, 31) + sq - n_quad;
-    base_b = __shfl_sync(0xFFFFFFFFu, base_b, 31) + sb - n_bi;
-    for (int v = 0; v < n_quad; v++) a.task_quad[base_q + v] = t * 8 + v;
-    for (int v = 0; v < n_bi; v++) a.task_bi[base_b + v] = t * 8 + n_quad + v;
+    return n;
 }
 
 // KOS / ANR: MAPFUNCTION=KOSAMBI and ALLOWNORECOMBINATION as compile-time constants, so that the code
-// of the other model (gamma sampler, pow, retry loop) is not in the kernel at all: the kernels are
-// instruction-cache bound (ncu: 3.2 'no instruction' stall cycles per issue with everything inlined).
-template <bool QUAD, bool KOS, bool ANR>
-__global__ void __launch_bounds__(128) k_meiosis_mv(PlanArgs a) {
-    const int64_t ti = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-    const bool direct = !QUAD && a.direct_diploid;
-    if (direct ? ti >= (int64_t)a.C * a.R * a.n_lev * 2 : ti >= (int64_t)a.task_count[QUAD ? 1 : 0]) return;
-    const int64_t code = direct ? ti * 8 : (QUAD ? a.task_quad : a.task_bi)[ti];
-    const int v = (int)(code & 7);
-    int par, j, r, c;
-    plan_decode(a, code >> 3, par, j, r, c);
-    if (direct && a.model.unreduced && par == 1) return;   // 2NGAMETES: parent 0's gamete alone
+// of the other model (gamma sampler, pow, retry loop) is not in the kernel at all.
+template <bool KOS, bool ANR>
+__global__ void __launch_bounds__(MEI_THREADS) k_meiosis(const MeiosisArgs a) {
+    typedef cub::BlockScan<int, MEI_THREADS> Scan;
+    __shared__ typename Scan::TempStorage scan_tmp;
+    __shared__ uint64_t s_seq[MEI_THREADS];
+    __shared__ uint8_t s_nquad[MEI_THREADS];
+    __shared__ uint16_t s_task[MEI_THREADS + 32];
+    __shared__ long long s_base;
+    __shared__ int s_stop;
+    const int tid = threadIdx.x;
+    if (tid == 0) s_stop = *(volatile int*)a.status != 0;   // an earlier batch failed: the host runs this one again
+    __syncthreads();
+    if (s_stop) return;
     const int P = a.P, p2 = P / 2;
-    const int32_t child = a.lev_ind[j];
-    const int32_t parent = par == 0 ? a.par0[child] : a.par1[child];
-    const ChromParams ch = a.chrom[c];
-    ModelParams m = a.model;
-    m.chiasma_interference = KOS;
-    m.allow_no_recomb = ANR;
-    const int64_t phid0 = (((int64_t)c * a.R + r) * a.N + parent) * P;
-    const int64_t q = (((int64_t)r * a.N + child) * a.C + c) * 2 + par;
-    PhiloxStream rng;
-    rng.init(m.seed, a.replicate_first + (uint32_t)r);
-    int8_t own_seq[2] = {0, 1};
-    if (direct) {   // Individual.calcChromConfig for ploidy 2 (Individual.java:603-608): shuffle of (0, 1), no quadrivalent
-        rng.seek((uint32_t)child, (uint32_t)c, (uint32_t)par, STAGE_CONFIG);
-        shuffle_small(rng, own_seq, 2);
-        a.cfg_quad[q] = 0;
-        a.cfg_seq[q * 2] = own_seq[0];
-        a.cfg_seq[q * 2 + 1] = own_seq[1];
-    }
-    const int quad = direct ? 0 : a.cfg_quad[q];
-    const int8_t* chromseq = direct ? own_seq : a.cfg_seq + q * P;
-    // Each transmitted chromatid is traced straight into the plan entry of the child homolog it
-    // will occupy after the gamete's homolog shuffle. The shuffle draws come from their own stream:
-    // slot h of the transmitted gamete receives pre-shuffle slot shuf[h] (Individual.java:325-335).
-    const int64_t u0 = (((int64_t)c * a.R + r) * a.n_lev + j) * P + (int64_t)par * p2;
-    // Transmitted gametes: gamete 0 (Individual.java:258-259), plus with 2NGAMETES the second half
-    // of the unreduced gamete (:350-382): gamete 1 (SDR) or bottom gamete 3 / 2 (FDR, one draw per
-    // meiosis); their chromatids fill the child's homologs P/2 .. P-1.
-    const int unred = m.unreduced;
-    int g_second = 0;
-    if (unred == 2) g_second = 1;
-    else if (unred == 1) {
-        rng.seek((uint32_t)child, 0u, (uint32_t)par, STAGE_UNREDUCED);
-        g_second = rng.next_float() < 0.5f ? 3 : 2;
-    }
-    const int n_gam = unred ? 2 : 1;
-    int8_t dest_of_slot[2][MAXP / 2];  // [transmitted gamete][pre-shuffle slot] -> final homolog position in that gamete
-    rng.seek((uint32_t)child, (uint32_t)c, (uint32_t)par, STAGE_SHUFFLE);
-    for (int g = 0; g <= g_second; g++) {   // the four gametes are shuffled in order on one stream
-        int8_t shuf[MAXP / 2];
-        for (int s = 0; s < p2; s++) shuf[s] = (int8_t)s;
-        shuffle_small(rng, shuf, p2);
-        if (g == 0) for (int h = 0; h < p2; h++) dest_of_slot[0][shuf[h]] = (int8_t)h;
-        if (g == g_second) for (int h = 0; h < p2; h++) dest_of_slot[1][shuf[h]] = (int8_t)h;
-    }
+    const int64_t n_units = (int64_t)a.C * a.R * a.n_lev * 2;
+    const int64_t unit0 = (int64_t)blockIdx.x * a.units_per_block;
 
-    const int firstbi = quad * 4;
-    constexpr int k = QUAD ? 4 : 2;
-    const int base = QUAD ? 4 * v : firstbi + 2 * (v - quad);
-    Chiasmata x;
-    x.overflow = false;
-    rng.seek((uint32_t)child, (uint32_t)c, (uint32_t)par, 1u + (uint32_t)v);
-    double exchange_lim1 = 0.0;
-    if (QUAD) exchange_lim1 = quadrivalent_crossing_over(x, rng, m, ch);
-    else parallel_crossing_over(x, rng, m, ch, 2);
-    if (x.overflow) { atomicExch(a.error_flag, PSIM_ECAPACITY); return; }
-    int8_t centro[8];
-    if (QUAD) quadrivalent_centromere_order(rng, m, ch, exchange_lim1, centro);
-    else multivalent_centromere_order(rng, 2, centro);
-    int8_t pattern_slot[8];
-    select_gametes(x, rng, k, ch, centro, pattern_slot);
-    constexpr int n_out = QUAD ? 2 : 1;
-    for (int go = 0; go < n_gam * n_out; go++) {
-        const int gi = go / n_out, o = go % n_out;
-        const int g = gi == 0 ? 0 : g_second;
-        // Individual.java:297-321: quadrivalent v fills gamete slots 2v, 2v+1; bivalent v' fills firstbi/2 + v'
-        const int pre_slot = QUAD ? 2 * v + o : firstbi / 2 + (v - quad);
-        const int64_t u = u0 + gi * p2 + dest_of_slot[gi][pre_slot];
-        double* ppos = a.plan_pos + u * a.piece_cap;
-        uint8_t* phom = a.plan_hom + u * a.piece_cap;
-        // Multivalent.slotsToPatterns (:332-357) for the selected chromatid
-        int cur = pattern_slot[QUAD ? 2 * g + o : g];
-        int np = 0;
-        ppos[0] = ch.head;
-        phom[0] = (uint8_t)chromseq[base + (cur >> 1)];
-        np = 1;
-        bool over = false;
-        for (int e = 0; e < x.n; e++) {
-            int nxt = -1;
-            if (x.a[e] == cur) nxt = x.b[e];
-            else if (x.b[e] == cur) nxt = x.a[e];
-            if (nxt >= 0) {
-                if (np >= a.piece_cap) { over = true; break; }
-                ppos[np] = x.pos[e];
-                phom[np] = (uint8_t)chromseq[base + (nxt >> 1)];
-                np++;
-                cur = nxt;
-            }
+    // ---- 1. pairing configuration of the block's units
+    int nq = 0, nb = 0;
+    if (tid < a.units_per_block && unit0 + tid < n_units) {
+        int par, j, r, c;
+        unit_decode(a, unit0 + tid, par, j, r, c);
+        if (!(a.model.unreduced && par == 1)) {   // 2NGAMETES: the individual is parent 0's 2n gamete alone
+            const int32_t child = a.lev_ind[j];
+            const int32_t parent = par == 0 ? a.par0[child] : a.par1[child];
+            const ChromParams& ch = a.chrom[c];
+            const int64_t phid0 = (((int64_t)c * a.R + r) * a.N + parent) * P;
+            Nib16 g_head, g_tail;   // genome = founder allele % (P/2) at both chromosome ends (Individual.java:437-470)
+            g_head.v = 0; g_tail.v = 0;
+            if (P > 2)
+                for (int h = 0; h < P; h++) {
+                    const HomologView hv = homolog_view(a, phid0 + h);
+                    g_head.set(h, hv.founder[hv.find_segment(ch.head)] % p2);
+                    g_tail.set(h, hv.founder[hv.find_segment(ch.tail)] % p2);
+                }
+            PhiloxStream rng;
+            rng.init(a.model.seed, a.replicate_first + (uint32_t)r);
+            rng.seek((uint32_t)child, (uint32_t)c, (uint32_t)par, STAGE_PAIRING);
+            const PairingResult pr = draw_pairing(rng, a.model, ch, g_head, g_tail);
+            s_seq[tid] = pr.seq.v;
+            s_nquad[tid] = (uint8_t)pr.quad;
+            nq = pr.quad;
+            nb = (P - 4 * pr.quad) / 2;
+            const int64_t q = (((int64_t)r * a.N + child) * a.C + c) * 2 + par;
+            a.cfg_quad[q] = (int8_t)pr.quad;
+            for (int h = 0; h < P; h++) a.cfg_seq[q * P + h] = (int8_t)pr.seq.get(h);
         }
-        if (over) { atomicExch(a.error_flag, PSIM_ECAPACITY); return; }
-        a.plan_np[u] = np;
-        // Multivalent.fillGamete (:539-577): number of segments the chromatid will have
-        auto view = [&](int hom) {
-            const uint64_t d = a.desc[phid0 + hom];
-            HomologView hvw;
-            hvw.pos = a.seg_pos + desc_begin(d);
-            hvw.founder = a.seg_founder + desc_begin(d);
-            hvw.n = (int)desc_count(d);
-            return hvw;
-        };
-        int64_t cnt = 0;
-        if (np == 1) {
-            cnt = view(phom[0]).n;
+    }
+    // ---- 2. one multivalent per thread, quadrivalents and bivalents in different warps
+    int before, all;
+    Scan(scan_tmp).ExclusiveSum(nq | (nb << 16), before, all);
+    const int n_quad = all & 0xFFFF, n_bi = all >> 16, bi0 = (n_quad + 31) & ~31;
+    for (int v = 0; v < nq; v++) s_task[(before & 0xFFFF) + v] = (uint16_t)((tid << 3) | v);
+    for (int v = 0; v < nb; v++) s_task[bi0 + (before >> 16) + v] = (uint16_t)((tid << 3) | (nq + v));
+    __syncthreads();
+    const bool is_quad = tid < n_quad, is_bi = tid >= bi0 && tid < bi0 + n_bi;
+    ChiasmaList x;
+    x.stride = (int64_t)gridDim.x * MEI_THREADS;
+    x.pos = a.x_pos + (int64_t)blockIdx.x * MEI_THREADS + tid;
+    x.ab = a.x_ab + (int64_t)blockIdx.x * MEI_THREADS + tid;
+    x.cap = a.x_cap; x.n = 0; x.overflow = false;
+    int n_out = 0;            // chromatids this thread delivers (<= 4: two per quadrivalent, twice with 2NGAMETES)
+    int strand[4], dest[4], count[4];
+    Nib16 seq; seq.v = 0;
+    int base = 0;
+    int64_t phid0 = 0, chid0 = 0;
+    double head = 0.0, tail = 0.0;
+    if (is_quad || is_bi) {
+        const int code = s_task[tid], i = code >> 3, v = code & 7;
+        int par, j, r, c;
+        unit_decode(a, unit0 + i, par, j, r, c);
+        const int32_t child = a.lev_ind[j];
+        const int32_t parent = par == 0 ? a.par0[child] : a.par1[child];
+        const ChromParams& ch = a.chrom[c];
+        head = ch.head; tail = ch.tail;
+        phid0 = (((int64_t)c * a.R + r) * a.N + parent) * P;
+        chid0 = (((int64_t)c * a.R + r) * a.N + child) * P + (int64_t)par * p2;
+        seq.v = s_seq[i];
+        const int quad = s_nquad[i];
+        PhiloxStream rng;
+        rng.init(a.model.seed, a.replicate_first + (uint32_t)r);
+        rng.seek((uint32_t)child, (uint32_t)c, (uint32_t)par, STAGE_MULTIVALENT + (uint32_t)v);
+        uint32_t at;
+        if (is_quad) at = draw_multivalent<true, KOS, ANR>(x, rng, a.model, ch);
+        else at = draw_multivalent<false, KOS, ANR>(x, rng, a.model, ch);
+        if (x.overflow) {
+            atomicExch(a.status, PSIM_ECAPACITY);
+            atomicMin(a.status + 1, a.batch);
         } else {
-            for (int qq = 0; qq < np; qq++) {
-                const HomologView h = view(phom[qq]);
-                const double patstart = ppos[qq];
-                const double patend = qq < np - 1 ? ppos[qq + 1] : ch.tail;
-                int seg = h.find_segment(patstart) + 1;
-                cnt++;
-                while (seg < h.n && h.pos[seg] < patend) { cnt++; seg++; }
-            }
-        }
-        a.plan_cnt[u] = cnt;
-    }
-}
-
-// K1b — one thread per child homolog: Multivalent.fillGamete (:539-577) + Gamete.fertilization
-// (Gamete.java:95-116: homologs 0..P/2-1 from parent 0's gamete, P/2..P-1 from parent 1's).
-struct AssembleArgs {
-    const ChromParams* chrom;
-    int C, R, P;
-    int64_t N;
-    int n_lev;
-    const int32_t* lev_ind;
-    const int32_t* par0;
-    const int32_t* par1;
-    uint64_t* desc;
-    double* seg_pos;
-    int32_t* seg_founder;
-    int piece_cap;
-    const int32_t* plan_np;
-    const int64_t* plan_cnt;   // per-homolog counts
-    const int64_t* plan_off;   // exclusive scan of plan_cnt
-    const double* plan_pos;
-    const uint8_t* plan_hom;
-    int64_t slab_base;
-    int64_t slab_cap;          // segments the slab holds: a batch that does not fit is not written at all
-    const int* error_flag;     // set by the plan kernels: the plan is incomplete, nothing is assembled
-    int unreduced;             // ModelParams::unreduced
-};
-
-__global__ void __launch_bounds__(128) k_meiosis_assemble(AssembleArgs a) {
-    const int64_t u = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-    const int64_t total = (int64_t)a.C * a.R * a.n_lev * a.P;
-    if (u >= total) return;
-    if (*a.error_flag || a.slab_base + a.plan_off[total] > a.slab_cap) return;   // the host reports the error / grows the slab and launches again
-    const int P = a.P, p2 = P / 2;
-    const int h = (int)(u % P);
-    const int j = (int)((u / P) % a.n_lev);
-    const int r = (int)((u / ((int64_t)P * a.n_lev)) % a.R);
-    const int c = (int)(u / ((int64_t)P * a.n_lev * a.R));
-    const int32_t child = a.lev_ind[j];
-    const int32_t parent = (h < p2 || a.unreduced) ? a.par0[child] : a.par1[child];   // 2NGAMETES: all P homologs from parent 0
-    const int64_t phid0 = (((int64_t)c * a.R + r) * a.N + parent) * P;
-    const double tail = a.chrom[c].tail;
-    const int np = a.plan_np[u];
-    const double* ppos = a.plan_pos + u * a.piece_cap;
-    const uint8_t* phom = a.plan_hom + u * a.piece_cap;
-    int64_t w = a.slab_base + a.plan_off[u];
-    const int64_t w0 = w;
-    if (np == 1) {
-        const uint64_t d = a.desc[phid0 + phom[0]];
-        const int64_t b = (int64_t)desc_begin(d);
-        const int n = (int)desc_count(d);
-        for (int s = 0; s < n; s++) { a.seg_pos[w] = a.seg_pos[b + s]; a.seg_founder[w] = a.seg_founder[b + s]; w++; }
-    } else {
-        for (int q = 0; q < np; q++) {
-            const uint64_t d = a.desc[phid0 + phom[q]];
-            HomologView hv;
-            hv.pos = a.seg_pos + desc_begin(d);
-            hv.founder = a.seg_founder + desc_begin(d);
-            hv.n = (int)desc_count(d);
-            const double patstart = ppos[q];
-            const double patend = q < np - 1 ? ppos[q + 1] : tail;
-            int seg = hv.find_segment(patstart);
-            a.seg_pos[w] = patstart; a.seg_founder[w] = hv.founder[seg]; w++;
-            seg++;
-            while (seg < hv.n && hv.pos[seg] < patend) { a.seg_pos[w] = hv.pos[seg]; a.seg_founder[w] = hv.founder[seg]; w++; seg++; }
+            const Transmission tr = draw_transmission(rng, a.model, (uint32_t)child, (uint32_t)c, (uint32_t)par);
+            // Individual.java:297-321: quadrivalent v fills gamete slots 2v, 2v+1; bivalent v' slot 2 * quad + v'
+            base = is_quad ? 4 * v : 4 * quad + 2 * (v - quad);
+            const int per_gamete = is_quad ? 2 : 1;
+            for (int k = 0; k < tr.n_gametes; k++)
+                for (int o = 0; o < per_gamete; o++) {
+                    const int g = tr.gamete[k];
+                    const int slot = is_quad ? 2 * v + o : 2 * quad + (v - quad);
+                    strand[n_out] = (int)((at >> (4 * (is_quad ? 2 * g + o : g))) & 15u);
+                    dest[n_out] = k * p2 + tr.dest[k].get(slot);
+                    n_out++;
+                }
         }
     }
-    const int64_t hid = (((int64_t)c * a.R + r) * a.N + child) * P + h;
-    a.desc[hid] = make_desc((uint64_t)w0, (uint64_t)(w - w0));
+    int mine = 0;
+#pragma unroll
+    for (int o = 0; o < 4; o++) {
+        count[o] = 0;
+        if (o < n_out) count[o] = trace_chromatid<false>(a, x, strand[o], seq, base, phid0, head, tail, 0);
+        mine += count[o];
+    }
+    // ---- 3. the block's segments: one reservation, then the same traces write
+    __syncthreads();
+    int offset, block_total;
+    Scan(scan_tmp).ExclusiveSum(mine, offset, block_total);
+    if (tid == 0) {
+        const long long at = (long long)atomicAdd(a.cursor, (unsigned long long)block_total);
+        if (at + block_total > a.slab_cap) {
+            atomicCAS(a.status, 0, STATUS_SLAB_FULL);
+            atomicMin(a.status + 1, a.batch);
+            s_base = -1;
+        } else s_base = at;
+    }
+    __syncthreads();
+    if (s_base < 0) return;
+    int64_t w = s_base + offset;
+#pragma unroll
+    for (int o = 0; o < 4; o++) {
+        if (o < n_out) {
+            trace_chromatid<true>(a, x, strand[o], seq, base, phid0, head, tail, w);
+            a.desc[chid0 + dest[o]] = make_desc((uint64_t)w, (uint64_t)count[o]);
+            w += count[o];
+        }
+    }
 }
-

@@ -1,24 +1,32 @@
-// Device-side meiosis of one parent on one chromosome ("half unit"): pairing configuration,
-// chiasma placement, chromatid tracing, centromere segregation, selection of the transmitted
-// gamete. Replaces, for the transmitted gamete only (the reference builds all four and discards
-// three, Individual.java:258-259), the call tree
-//   Individual.doMeiosis / calcChromConfig            Individual.java:281-349, 601-670
-//   Multivalent.doMeiosis and helpers                 Multivalent.java:79-182, 332-527
-//   Quadrivalent.doCrossingOver / getCentromereSortOrder   Quadrivalent.java:108-243, 371-510
-// (paths relative to /root/reference/src/PedigreeSim/). The draw order inside each Philox stream
-// is the reference's, which is what tests/ check bit-for-bit against the CPU oracle.
+// Device-side meiosis of one parent on one chromosome: the pairing configuration, the chiasmata of
+// one multivalent, the choice of the transmitted chromatids and their trace.
+//
+// What is modelled is PedigreeSim's meiosis (paths relative to /root/reference/src/PedigreeSim/):
+//   pairing of the homolog ends, cycles -> bivalents / quadrivalents   Individual.java:483-904
+//   chiasmata of a bivalent / parallel quadrivalent                    Multivalent.java:84-182
+//   chiasmata of a cross-type quadrivalent (four arms)                 Quadrivalent.java:108-243, 371-424
+//   centromere segregation, the transmitted gamete                     Multivalent.java:397-527, Quadrivalent.java:465-510
+// How it is computed is this library's own: everything lives in position space (a random order of
+// the homologs) as bit masks and 4-bit vectors in registers, every random choice is sampled directly
+// from its distribution (a free partner, a non-sister chromatid, an unfinished arm: one bounded draw,
+// no rejection loop, no list surgery), the stationary start of the interference (gamma) renewal
+// process is drawn from its closed form instead of a burn-in, and only the chromatids that reach the
+// transmitted gamete are traced (the reference builds all 4 gametes and keeps one,
+// Individual.java:258-259). Outcome laws are the reference's: tests/test_gpu_stats.py and
+// tests/test_sampler_laws.py hold them (chi-square) against the CPU oracle's restatement of the Java
+// driven by java.util.Random. Everything here is PSIM_HD (host + device) so that the tests can run the
+// very same sampler on the host and hold the kernels against it bit for bit.
 #pragma once
+#include <cmath>
 #include <cstdint>
-#include <math_constants.h>
 
 #include "psim_rng.cuh"
 
 namespace psim {
 
-constexpr int MAXP = 16;        // maximum ploidy
-constexpr int MAXE = 192;       // maximum chiasmata per multivalent held on the device
-constexpr double RECOMBDIST = 0.5;   // Multivalent.java:18
-constexpr double GAMMAFACTOR = 2.63; // Tools.java:317
+constexpr int MAXP = 16;             // ploidy limit of the 4-bit position vectors
+constexpr double RECOMBDIST = 0.5;   // mean chiasma spacing on a 4-strand bundle, Morgan (Multivalent.java:18)
+constexpr double GAMMAFACTOR = 2.63; // shape of the inter-chiasma gamma under interference (Tools.java:317)
 
 // Model flags + per-chromosome constants, passed by value to the kernels.
 struct ModelParams {
@@ -28,7 +36,7 @@ struct ModelParams {
     int allow_no_recomb;
     double parallel_multivalents;
     double paired_centromeres;
-    uint32_t seed;
+    uint64_t seed;
     int unreduced;   // 2NGAMETES: 0 = haploid gametes, 1 = FDR, 2 = SDR (Individual.java:341-383)
 };
 struct ChromParams {
@@ -38,527 +46,482 @@ struct ChromParams {
     double cumul_binomial[MAXP / 4];  // TetraploidChromosome.java:102-108
 };
 
-// Read-only view of the parent's P homologs on this chromosome (segments in the slab).
+// Read-only view of one parental homolog (segments in the slab).
 struct HomologView {
     const double* pos;
     const int32_t* founder;
     int n;
-    // HaploStruct.java:107-112
-    __device__ __forceinline__ int find_segment(double position) const {
+    // HaploStruct.findSegment (HaploStruct.java:107-112): last segment that starts at or before `position`
+    PSIM_HD int find_segment(double position) const {
         int seg = n - 1;
         while (seg > 0 && pos[seg] > position) seg--;
         return seg;
     }
 };
 
-// ---- Tools.java samplers
-__device__ __forceinline__ double ran_exp(PhiloxStream& r, double mean) {  // Tools.java:238-240
-    return -mean * log(1.0 - r.next_double());
+// Sixteen 4-bit entries in one register pair: order of the homologs, partners, genome numbers.
+struct Nib16 {
+    uint64_t v;
+    PSIM_HD int get(int i) const { return (int)((v >> (4 * i)) & 15u); }
+    PSIM_HD void set(int i, int x) { v = (v & ~(15ull << (4 * i))) | ((uint64_t)x << (4 * i)); }
+    PSIM_HD void swap(int i, int j) { const int a = get(i), b = get(j); set(i, b); set(j, a); }
+};
+PSIM_HD Nib16 nib_identity() { Nib16 r; r.v = 0xFEDCBA9876543210ull; return r; }
+PSIM_HD int pick_bit(PhiloxStream& rng, uint32_t mask) {   // a uniformly chosen member of a non-empty set
+    const int n = popc32(mask);
+    return n == 1 ? lowest_bit(mask) : nth_set_bit(mask, rng.next_below(n));
 }
-__device__ inline double ran_gamma_cheng(PhiloxStream& rng, double k, double theta) {  // Tools.java:294-314 (k >= 1)
-    const double b = k - log(4.0);
-    const double lam = sqrt(2 * k - 1);
+PSIM_HD void shuffle_nib(PhiloxStream& rng, Nib16& a, int n) {   // uniform random permutation of entries 0..n-1
+    for (int last = n - 1; last > 0; last--) a.swap(last, rng.next_below(last + 1));
+}
+
+// ---------------------------------------------------------------- distances between chiasmata
+PSIM_HD double draw_exponential(PhiloxStream& r, double mean) { return -mean * log(r.next_open()); }
+// Gamma(k, theta) for k >= 1 by Cheng's GA rejection sampler (the algorithm Tools.ranGamma uses, Tools.java:294-314)
+PSIM_HD_NOINLINE double draw_gamma(PhiloxStream& rng, double k, double theta) {
+    const double lam = sqrt(2.0 * k - 1.0);
+    const double b = k - 1.3862943611198906;     // k - ln 4
     const double c = k + lam;
-    const double cheng = 1 + log(4.5);
-    double x;
     for (;;) {
-        rng.prefetch();
-        const double u = rng.next_double();
-        const double v = rng.next_double();
-        const double y = (1 / lam) * log(v / (1 - v));
-        x = k * exp(y);
+        const double u = rng.next_open(), v = rng.next_unit();
+        if (v <= 0.0) continue;
+        const double y = log(v / (1.0 - v)) / lam;
+        const double x = k * exp(y);
         const double z = u * v * v;
-        const double r = b + (c * y) - x;
-        if ((r >= ((4.5 * z) - cheng)) || (r >= log(z))) break;
+        const double r = b + c * y - x;
+        if (r + 2.504077396776274 >= 4.5 * z || r >= log(z)) return x * theta;   // 1 + ln 4.5
     }
-    return x * theta;
 }
-__device__ __forceinline__ double ran_dist_interference(PhiloxStream& r, double meandist) {  // Tools.java:329-331
-    return ran_gamma_cheng(r, GAMMAFACTOR, meandist / GAMMAFACTOR);
-}
-__device__ inline double dist_to_first_recomb(PhiloxStream& r, const ModelParams& m, double meandist) {  // Multivalent.java:84-97
-    double p = ran_exp(r, meandist);
-    if (m.chiasma_interference) {
-        const double burnin = 10.0 * meandist;
-        while (p < burnin) p += ran_dist_interference(r, meandist);
-        return p - burnin;
-    }
-    return p;
-}
-__device__ __forceinline__ double dist_to_next_recomb(PhiloxStream& r, const ModelParams& m, double meandist) {  // Multivalent.java:99-105
-    return m.chiasma_interference ? ran_dist_interference(r, meandist) : ran_exp(r, meandist);
-}
-// Tools.java:33-51 on a small int8 array
-__device__ __forceinline__ void shuffle_small(PhiloxStream& r, int8_t* a, int n) {
-    int last = n - 1;
-    while (last > 0) {
-        const int ix = r.next_int(last + 1);
-        const int8_t tmp = a[last]; a[last] = a[ix]; a[ix] = tmp;
-        last--;
-    }
+// Distance from a chromosome end (or the previous chiasma) to the next chiasma of a renewal process
+// with mean spacing `mean`: exponential gaps without interference (Haldane), gamma(2.63) gaps with
+// (Kosambi, Multivalent.java:84-105). FIRST: the process is stationary at the chromosome end. The
+// reference gets there by a burn-in of ten mean spacings; the forward recurrence time of a
+// stationary renewal process has the closed form U * G with G the length-biased gap,
+// gamma(2.63 + 1), which is drawn here directly.
+template <bool KOS, bool FIRST>
+PSIM_HD double draw_gap(PhiloxStream& r, double mean) {
+    if (!KOS) return draw_exponential(r, mean);
+    if (FIRST) return r.next_unit() * draw_gamma(r, GAMMAFACTOR + 1.0, mean / GAMMAFACTOR);
+    return draw_gamma(r, GAMMAFACTOR, mean / GAMMAFACTOR);
 }
 
 // ---------------------------------------------------------------- pairing configuration
-struct PairingState {
-    int8_t initorder[MAXP], backorder[MAXP];
-    int8_t paired[2][MAXP];
-    int8_t genomenr[2][MAXP];
-    int8_t ghs[2][MAXP / 2][MAXP];  // Individual.genomehs for this chromosome
-    int8_t ghs_n[2][MAXP / 2];
-    int8_t gen[MAXP / 2][MAXP];     // Individual.genohs (working copy)
-    int8_t gen_n[MAXP / 2];
-    bool hsdone[MAXP];
-    int possible[2];
-    int primary, secondary;
-    int bivalentcount, quadcount;
-    int8_t chromseq[MAXP];
+// Input: the genome number (founder allele % (P/2), Individual.java:456-459) of every homolog at the
+// head and at the tail of the chromosome. Output: Genotype.ChromConfig (Genotype.java:38-51) - the
+// number of quadrivalents and the order of the homologs (quadrivalents first, bivalents filled from
+// the end backwards).
+struct PairingResult {
+    Nib16 seq;
     int quad;
 };
 
-__device__ __forceinline__ int list_index_of(const int8_t* v, int n, int x) {
-    for (int i = 0; i < n; i++) if (v[i] == x) return i;
-    return -1;
-}
-__device__ __forceinline__ void list_remove(int8_t* v, int8_t& n, int idx) {
-    for (int i = idx; i + 1 < n; i++) v[i] = v[i + 1];
-    n--;
-}
-// Individual.java:437-470 for one chromosome
-__device__ inline void calc_genome(PairingState& s, const HomologView* hv, int P, const ChromParams& ch) {
-    for (int side = 0; side < 2; side++) {
-        for (int g = 0; g < P / 2; g++) s.ghs_n[side][g] = 0;
-        for (int h = 0; h < P; h++) {
-            const double at = side == 0 ? ch.head : ch.tail;
-            const int g = hv[h].founder[hv[h].find_segment(at)] % (P / 2);
-            s.genomenr[side][h] = (int8_t)g;
-            s.ghs[side][g][s.ghs_n[side][g]++] = (int8_t)h;
-        }
-        s.possible[side] = 0;
-        for (int g = 0; g < P / 2; g++) s.possible[side] += s.ghs_n[side][g] / 2;
-    }
-}
-// Individual.java:574-593 (removal uses genomenr at `secondary`, whatever `side` is)
-__device__ inline void calc_genohs(PairingState& s, int P, int side) {
-    for (int g = 0; g < P / 2; g++) {
-        s.gen_n[g] = s.ghs_n[side][g];
-        for (int i = 0; i < s.gen_n[g]; i++) s.gen[g][i] = s.ghs[side][g][i];
-    }
-    for (int h = 0; h < P; h++) {
-        if (s.hsdone[h]) {
-            const int gnm = s.genomenr[s.secondary][s.initorder[h]];
-            const int idx = list_index_of(s.gen[gnm], s.gen_n[gnm], s.initorder[h]);
-            list_remove(s.gen[gnm], s.gen_n[gnm], idx);
-        }
-    }
-}
-// Individual.java:483-523
-__device__ inline void get_pairing(PairingState& s, PhiloxStream& rng, int P, int side, double pref) {
-    bool done[MAXP];
-    for (int h = 0; h < P; h++) done[h] = false;
-    calc_genohs(s, P, side);
-    int firsth = 0;
-    while (firsth < P - 1) {
-        while (firsth < P - 1 && done[firsth]) firsth++;
-        if (firsth < P - 1) {
-            done[firsth] = true;
-            int gnm = s.genomenr[side][s.initorder[firsth]];
-            int hidx = list_index_of(s.gen[gnm], s.gen_n[gnm], s.initorder[firsth]);
-            list_remove(s.gen[gnm], s.gen_n[gnm], hidx);
-            int secondh;
-            if (s.gen_n[gnm] != 0 && rng.next_double() < pref) {
-                hidx = rng.next_int(s.gen_n[gnm]);
-                secondh = s.backorder[s.gen[gnm][hidx]];
-            } else {
-                secondh = firsth;
-                while (done[secondh]) secondh = rng.next_int(P - firsth - 1) + firsth + 1;
-                gnm = s.genomenr[side][s.initorder[secondh]];
-                hidx = list_index_of(s.gen[gnm], s.gen_n[gnm], s.initorder[secondh]);
-            }
-            done[secondh] = true;
-            list_remove(s.gen[gnm], s.gen_n[gnm], hidx);
-            s.paired[side][firsth] = (int8_t)secondh;
-            s.paired[side][secondh] = (int8_t)firsth;
-            firsth++;
-        }
-    }
-}
-__device__ __forceinline__ void add_bivalent(PairingState& s, int P, int firsth, int secondh) {  // Individual.java:672-677
-    s.bivalentcount++;
-    s.chromseq[P - 2 * s.bivalentcount] = s.initorder[firsth];
-    s.chromseq[P - 2 * s.bivalentcount + 1] = s.initorder[secondh];
-}
-__device__ __forceinline__ void add_quadrivalent(PairingState& s, int firsth, int secondh, int thirdh, int fourth) {  // Individual.java:679-703
-    const int b = s.quadcount * 4;
-    if (s.primary == 0) {
-        s.chromseq[b] = s.initorder[firsth]; s.chromseq[b + 1] = s.initorder[secondh];
-        s.chromseq[b + 2] = s.initorder[thirdh]; s.chromseq[b + 3] = s.initorder[fourth];
-    } else {
-        s.chromseq[b] = s.initorder[secondh]; s.chromseq[b + 1] = s.initorder[thirdh];
-        s.chromseq[b + 2] = s.initorder[fourth]; s.chromseq[b + 3] = s.initorder[firsth];
-    }
-    s.quadcount++;
-}
-__device__ inline void get_spontaneous_bivalents(PairingState& s, int P, int max_bivalents) {  // Individual.java:705-725
-    int firsth = 0;
-    while (firsth < P - 1 && s.bivalentcount < max_bivalents) {
-        while (firsth < P - 1 && (s.hsdone[firsth] || s.paired[s.primary][firsth] != s.paired[s.secondary][firsth])) firsth++;
-        if (firsth < P - 1) {
-            const int secondh = s.paired[s.primary][firsth];
-            add_bivalent(s, P, firsth, secondh);
-            s.hsdone[firsth] = true;
-            s.hsdone[secondh] = true;
-        }
-        firsth++;
-    }
-}
-__device__ inline void get_spontaneous_quadrivalents(PairingState& s, int P, int max_quadrivalents) {  // Individual.java:727-787
-    bool tmp_bi[MAXP];
-    for (int h = 0; h < P; h++) tmp_bi[h] = false;
-    int firsth = 0;
-    while (firsth < P - 1) {
-        while (firsth < P - 1 && (s.hsdone[firsth] || s.paired[s.primary][firsth] != s.paired[s.secondary][firsth])) firsth++;
-        if (firsth < P - 1) {
-            const int secondh = s.paired[s.primary][firsth];
-            s.hsdone[firsth] = true; s.hsdone[secondh] = true;
-            tmp_bi[firsth] = true; tmp_bi[secondh] = true;
-        }
-        firsth++;
-    }
-    firsth = 0;
-    while (firsth < P - 3 && s.quadcount < max_quadrivalents) {
-        while (firsth < P - 3 && s.hsdone[firsth]) firsth++;
-        if (firsth < P - 3) {
-            const int secondh = s.paired[s.secondary][firsth];
-            const int thirdh = s.paired[s.primary][secondh];
-            const int fourth = s.paired[s.primary][firsth];
-            if (s.paired[s.secondary][thirdh] == fourth) {
-                add_quadrivalent(s, firsth, secondh, thirdh, fourth);
-                s.hsdone[firsth] = true; s.hsdone[secondh] = true;
-                s.hsdone[thirdh] = true; s.hsdone[fourth] = true;
-            }
-        }
-        firsth++;
-    }
-    for (int h = 0; h < P; h++) if (tmp_bi[h]) s.hsdone[h] = false;
-}
-__device__ inline void get_forced_bivalent(PairingState& s, int P) {  // Individual.java:789-799
-    int firsth = 0;
-    while (firsth < P && s.hsdone[firsth]) firsth++;
-    const int secondh = s.paired[s.primary][firsth];
-    add_bivalent(s, P, firsth, secondh);
-    s.hsdone[firsth] = true;
-    s.hsdone[secondh] = true;
-}
-__device__ inline void get_forced_bi_or_quadri(PairingState& s, PhiloxStream& rng, int P, bool bi_allowed, double pref) {  // Individual.java:822-904
-    int firsth = 0, secondh, thirdh, fourth;
-    while (firsth < P - 1 && s.hsdone[firsth]) firsth++;
-    fourth = s.paired[s.primary][firsth];
-    int gnm = s.genomenr[s.secondary][s.initorder[firsth]];
-    int gnm4 = s.genomenr[s.secondary][s.initorder[fourth]];
-    if (s.gen_n[gnm4] > s.gen_n[gnm]) {
-        int t = firsth; firsth = fourth; fourth = t;
-        t = gnm; gnm = gnm4; gnm4 = t;
-    }
-    int hidx = list_index_of(s.gen[gnm], s.gen_n[gnm], s.initorder[firsth]);
-    list_remove(s.gen[gnm], s.gen_n[gnm], hidx);
-    s.hsdone[firsth] = true;
-    // the reference takes fourth's index now and removes it later (after other removals)
-    int hidx4 = list_index_of(s.gen[gnm4], s.gen_n[gnm4], s.initorder[fourth]);
-    if (((bi_allowed && s.gen_n[gnm] > 0) || (!bi_allowed && s.gen_n[gnm] > 1)) && rng.next_double() < pref) {
-        do {
-            hidx = rng.next_int(s.gen_n[gnm]);
-            secondh = s.backorder[s.gen[gnm][hidx]];
-        } while (secondh == fourth && !bi_allowed);
-        s.hsdone[fourth] = true;
-        list_remove(s.gen[gnm4], s.gen_n[gnm4], hidx4);
-        if (secondh == fourth) {
-            add_bivalent(s, P, firsth, secondh);
-        } else {
-            gnm = s.genomenr[s.secondary][s.initorder[secondh]];
-            hidx = list_index_of(s.gen[gnm], s.gen_n[gnm], s.initorder[secondh]);
-            list_remove(s.gen[gnm], s.gen_n[gnm], hidx);
-            s.hsdone[secondh] = true;
-            thirdh = s.paired[s.primary][secondh];
-            gnm = s.genomenr[s.secondary][s.initorder[thirdh]];
-            hidx = list_index_of(s.gen[gnm], s.gen_n[gnm], s.initorder[thirdh]);
-            list_remove(s.gen[gnm], s.gen_n[gnm], hidx);
-            s.hsdone[thirdh] = true;
-            add_quadrivalent(s, firsth, secondh, thirdh, fourth);
-        }
-    } else {
-        secondh = firsth;
-        while (s.hsdone[secondh] || (secondh == fourth && !bi_allowed)) secondh = rng.next_int(P);
-        s.hsdone[fourth] = true;
-        list_remove(s.gen[gnm4], s.gen_n[gnm4], hidx4);
-        if (secondh == fourth) {
-            add_bivalent(s, P, firsth, secondh);
-            s.hsdone[secondh] = true;
-        } else {
-            thirdh = s.paired[s.primary][secondh];
-            s.hsdone[secondh] = true;
-            gnm = s.genomenr[s.secondary][s.initorder[secondh]];
-            hidx = list_index_of(s.gen[gnm], s.gen_n[gnm], s.initorder[secondh]);
-            list_remove(s.gen[gnm], s.gen_n[gnm], hidx);
-            s.hsdone[thirdh] = true;
-            gnm = s.genomenr[s.secondary][s.initorder[thirdh]];
-            hidx = list_index_of(s.gen[gnm], s.gen_n[gnm], s.initorder[thirdh]);
-            list_remove(s.gen[gnm], s.gen_n[gnm], hidx);
-            add_quadrivalent(s, firsth, secondh, thirdh, fourth);
-        }
-    }
-}
-// Individual.java:601-670. Leaves s.chromseq / s.quad.
-__device__ inline void calc_chrom_config(PairingState& s, PhiloxStream& rng, const ModelParams& m,
-                                         const ChromParams& ch, const HomologView* hv) {
-    const int P = m.ploidy;
-    if (P == 2) {
-        s.chromseq[0] = 0; s.chromseq[1] = 1;
-        shuffle_small(rng, s.chromseq, 2);
-        s.quad = 0;
-        return;
-    }
-    for (int h = 0; h < P; h++) s.initorder[h] = (int8_t)h;
-    shuffle_small(rng, s.initorder, P);
-    for (int h = 0; h < P; h++) s.backorder[s.initorder[h]] = (int8_t)h;
-    for (int h = 0; h < P; h++) { s.hsdone[h] = false; s.chromseq[h] = 0; }
-    s.secondary = 0;
-    calc_genome(s, hv, P, ch);
-    for (int side = 0; side < 2; side++) get_pairing(s, rng, P, side, ch.pref_pairing);
-    {   // Individual.java:536-542
-        const int c0 = s.possible[0], c1 = s.possible[1];
-        const double probside0 = c0 == c1 ? 0.5 : (double)c0 / (double)(c0 + c1);
-        s.primary = rng.next_double() < probside0 ? 0 : 1;
-    }
-    s.secondary = 1 - s.primary;
-    s.bivalentcount = 0;
-    s.quadcount = 0;
-    if (m.natural_pairing) {
-        get_spontaneous_bivalents(s, P, P / 2);
-        get_spontaneous_quadrivalents(s, P, (P - 2 * s.bivalentcount) / 4);
-        calc_genohs(s, P, s.secondary);
-        while (2 * s.bivalentcount + 4 * s.quadcount < P) {
-            if (2 * s.bivalentcount + 4 * s.quadcount == P - 2) get_forced_bivalent(s, P);
-            else get_forced_bi_or_quadri(s, rng, P, true, ch.pref_pairing);
-        }
-    } else {
-        // TetraploidChromosome.java:122-128
-        const double p = rng.next_double();
-        int num_quad = 0;
-        while (num_quad < P / 4 && ch.cumul_binomial[num_quad] < p) num_quad++;
-        const int num_bi = (P - 4 * num_quad) / 2;
-        get_spontaneous_bivalents(s, P, num_bi);
-        get_spontaneous_quadrivalents(s, P, num_quad);
-        while (s.bivalentcount < num_bi) get_forced_bivalent(s, P);
-        if (s.quadcount < num_quad) {
-            calc_genohs(s, P, s.secondary);
-            while (s.quadcount < num_quad) get_forced_bi_or_quadri(s, rng, P, false, ch.pref_pairing);
-        }
-    }
-    s.quad = s.quadcount;
-}
+struct PairingWork {
+    int P;
+    Nib16 order;          // order.get(position) = homolog
+    Nib16 genpos[2];      // genome number by position, at the head / tail
+    Nib16 partner[2];     // partner position at the head / tail
+    uint32_t done;        // positions already placed in a bivalent / quadrivalent
+    int primary, n_bi, n_quad;
+    Nib16 seq;
 
-// ---------------------------------------------------------------- chiasmata of one multivalent
-// All chiasmata of a multivalent as one position-sorted list; each involves chromatid slots a, b
-// (slot s belongs to chromosome s/2 of the multivalent). Per slot this is the reference's record
-// list (Multivalent.java:158-177, Quadrivalent.makeRecombination :276-284).
-struct Chiasmata {
-    double pos[MAXE];
-    uint8_t a[MAXE], b[MAXE];
-    int n;
-    bool overflow;
-    __device__ __forceinline__ void clear() { n = 0; }
-    __device__ __forceinline__ void append(double p, int sa, int sb) {
-        if (n >= MAXE) { overflow = true; return; }
-        pos[n] = p; a[n] = (uint8_t)sa; b[n] = (uint8_t)sb; n++;
+    PSIM_HD uint32_t genome_mask(int side, int g) const {   // positions whose end `side` belongs to genome g
+        uint32_t m = 0;
+        for (int p = 0; p < P; p++) m |= (uint32_t)(genpos[side].get(p) == g) << p;
+        return m;
     }
-    // HaploStruct.insertSegment (:129-133): after the last record whose position is <= p
-    __device__ __forceinline__ void insert_sorted(double p, int sa, int sb) {
-        if (n >= MAXE) { overflow = true; return; }
-        int i = n;
-        while (i > 0 && pos[i - 1] > p) { pos[i] = pos[i - 1]; a[i] = a[i - 1]; b[i] = b[i - 1]; i--; }
-        pos[i] = p; a[i] = (uint8_t)sa; b[i] = (uint8_t)sb; n++;
+    // Pairing of one chromosome end (Individual.getPairing, Individual.java:483-523): the lowest free
+    // position takes, with probability `pref` and if one is free, a partner of its own genome,
+    // otherwise any free position; uniformly in both cases.
+    PSIM_HD_NOINLINE void pair_end(PhiloxStream& rng, int side, double pref) {
+        uint32_t free_mask = (1u << P) - 1u;
+        Nib16 pw; pw.v = 0;
+        while (free_mask) {
+            const int first = lowest_bit(free_mask);
+            free_mask &= free_mask - 1;
+            const uint32_t same = genome_mask(side, genpos[side].get(first)) & free_mask;
+            const int second = (same && rng.next_unit() < pref) ? pick_bit(rng, same) : pick_bit(rng, free_mask);
+            free_mask &= ~(1u << second);
+            pw.set(first, second);
+            pw.set(second, first);
+        }
+        partner[side] = pw;
     }
-    // Multivalent.java:587-603
-    __device__ __forceinline__ bool all_chrom_recomb(int k) const {
-        if (k == 2) return n > 0;
-        unsigned seen = 0;
-        for (int e = 0; e < n; e++) seen |= (1u << (a[e] >> 1)) | (1u << (b[e] >> 1));
-        return seen == 0xFu;
+    PSIM_HD void put_bivalent(int a, int b) {   // Individual.addBivalent, :672-677
+        n_bi++;
+        seq.set(P - 2 * n_bi, order.get(a));
+        seq.set(P - 2 * n_bi + 1, order.get(b));
+        done |= (1u << a) | (1u << b);
+    }
+    // Individual.addQuadrivalent, :679-703: a-b and c-d are paired at the secondary end, a-d and b-c
+    // at the primary end; stored so that 1st-4th & 2nd-3rd pair at the head, 1st-2nd & 3rd-4th at the tail
+    PSIM_HD void put_quadrivalent(int a, int b, int c, int d) {
+        const int base = 4 * n_quad;
+        if (primary == 0) { seq.set(base, order.get(a)); seq.set(base + 1, order.get(b)); seq.set(base + 2, order.get(c)); seq.set(base + 3, order.get(d)); }
+        else { seq.set(base, order.get(b)); seq.set(base + 1, order.get(c)); seq.set(base + 2, order.get(d)); seq.set(base + 3, order.get(a)); }
+        n_quad++;
+        done |= (1u << a) | (1u << b) | (1u << c) | (1u << d);
+    }
+    PSIM_HD uint32_t two_cycles() const {   // free positions with the same partner at both ends
+        uint32_t m = 0;
+        for (int p = 0; p < P; p++) m |= (uint32_t)(partner[0].get(p) == partner[1].get(p)) << p;
+        return m & ~done;
+    }
+    // pairs that chose each other at both ends (getSpontaneousBivalents, :705-725), lowest position first
+    PSIM_HD_NOINLINE void take_two_cycles(int limit) {
+        uint32_t cand = two_cycles();
+        while (cand && n_bi < limit) {
+            const int a = lowest_bit(cand), b = partner[primary].get(a);
+            put_bivalent(a, b);
+            cand &= ~done;
+        }
+    }
+    // closed rings of four (getSpontaneousQuadrivalents, :727-787); pairs of a two-cycle are not rings
+    PSIM_HD_NOINLINE void take_four_cycles(int limit) {
+        uint32_t cand = ~(done | two_cycles()) & ((1u << P) - 1u);
+        const int sec = 1 - primary;
+        while (cand && n_quad < limit) {
+            const int a = lowest_bit(cand);
+            cand &= cand - 1;
+            if (a >= P - 3) break;
+            const int b = partner[sec].get(a), c = partner[primary].get(b), d = partner[primary].get(a);
+            if (partner[sec].get(c) == d) { put_quadrivalent(a, b, c, d); cand &= ~done; }
+        }
+    }
+    PSIM_HD void force_bivalent() {   // getForcedBivalent, :789-799: the lowest free position and its primary partner
+        const int a = lowest_bit(~done);
+        put_bivalent(a, partner[primary].get(a));
+    }
+    // A ring longer than four is cut (getForcedBiOrQuadri, :822-904): the lowest free position a and its
+    // primary partner d (the one with more free positions of its own genome at the secondary end leads)
+    // get a new secondary partner b for a - of a's genome with probability `pref` when one is
+    // available, else any free position - and close either as the bivalent a-d (b == d, if allowed)
+    // or as the quadrivalent a, b, c = primary partner of b, d.
+    PSIM_HD_NOINLINE void force_cut(PhiloxStream& rng, bool bivalent_allowed, double pref) {
+        const int sec = 1 - primary;
+        const uint32_t all = (1u << P) - 1u;
+        int a = lowest_bit(~done), d = partner[primary].get(a);
+        {
+            const int na = popc32(genome_mask(sec, genpos[sec].get(a)) & ~done), nd = popc32(genome_mask(sec, genpos[sec].get(d)) & ~done);
+            if (nd > na) { const int t = a; a = d; d = t; }
+        }
+        done |= 1u << a;
+        const uint32_t free_mask = ~done & all;                                    // still holds d
+        const uint32_t own = genome_mask(sec, genpos[sec].get(a)) & free_mask;     // a's genome, may hold d
+        const uint32_t banned = bivalent_allowed ? 0u : (1u << d);
+        int b;
+        if ((bivalent_allowed ? own != 0 : popc32(own) > 1) && rng.next_unit() < pref) b = pick_bit(rng, own & ~banned);
+        else b = pick_bit(rng, free_mask & ~banned);
+        if (b == d) { done &= ~(1u << a); put_bivalent(a, d); }
+        else { done &= ~(1u << a); put_quadrivalent(a, b, partner[primary].get(b), d); }
     }
 };
 
-// Multivalent.java:139-182 — bivalent (k = 2) and parallel quadrivalent (k = 4)
-__device__ inline void parallel_crossing_over(Chiasmata& x, PhiloxStream& rng, const ModelParams& m,
-                                              const ChromParams& ch, int k) {
-    const int slotcount = 2 * k;
-    double recomb_dist = k == 2 ? RECOMBDIST : RECOMBDIST * 2 / (double)k;
-    if (!m.allow_no_recomb) recomb_dist = recomb_dist / 0.5 * ch.recomb_dist_noempty;
-    do {
-        x.clear();
-        double p = ch.head + dist_to_first_recomb(rng, m, recomb_dist);
-        while (p < ch.tail) {
-            rng.prefetch();
-            const int i0 = rng.next_int(slotcount);
-            int i1;
-            do { i1 = rng.next_int(slotcount); } while (i1 / 2 == i0 / 2);
-            x.append(p, i0, i1);
-            p += dist_to_next_recomb(rng, m, recomb_dist);
-            if (x.overflow) return;
-        }
-    } while (!(m.allow_no_recomb || x.all_chrom_recomb(k)));
-}
-
-// Quadrivalent.java:371-424 (quadriMethod 2, quadriEachArm false). Returns exchangeLim[1].
-__device__ inline double quadrivalent_crossing_over(Chiasmata& x, PhiloxStream& rng, const ModelParams& m,
-                                                    const ChromParams& ch) {
-    const bool paral = m.parallel_multivalents == 0.0 ? false
-                     : m.parallel_multivalents == 1.0 ? true
-                     : rng.next_double() < m.parallel_multivalents;
-    if (paral) { parallel_crossing_over(x, rng, m, ch, 4); return 0.0; }  // fresh object: exchangeLim = {0,0}
-    // Quadrivalent.java:14-19: chromatids with their head in arm 0 / tail in arm 1 / head in arm 2 / tail in arm 3
-    const int ARM[4][4] = {{0, 1, 6, 7}, {0, 1, 2, 3}, {2, 3, 4, 5}, {4, 5, 6, 7}};
-    double exchange_lim[2];
-    do {
-        const double recomb_dist = m.allow_no_recomb ? RECOMBDIST : ch.recomb_dist_noempty;
-        x.clear();
-        double lastpos[4];
-        bool arm_finished[4];
-        for (int a = 0; a < 4; a++) { lastpos[a] = CUDART_NAN; arm_finished[a] = false; }
-        bool finished = false;
-        exchange_lim[0] = ch.head;
-        exchange_lim[1] = ch.tail;
-        do {
-            rng.prefetch();
-            const int a = rng.next_int(4);
-            if (arm_finished[a]) continue;
-            // generateRecombination, Quadrivalent.java:108-139
-            const int c0 = ARM[a][rng.next_int(2)];
-            const int c1 = ARM[a][2 + rng.next_int(2)];
-            const int side = a & 1;
-            const double sf = side == 0 ? 1.0 : -1.0;
-            const double side_pos = side == 1 ? ch.tail : ch.head;
-            const double oppo_pos = side == 1 ? ch.head : ch.tail;
-            double pos;
-            if (isnan(lastpos[a])) pos = side_pos + sf * dist_to_first_recomb(rng, m, recomb_dist);
-            else pos = lastpos[a] + sf * dist_to_next_recomb(rng, m, recomb_dist);
-            const int oa0 = side == 0 ? 1 : 0, oa1 = side == 0 ? 3 : 2;  // oppoArms
-            double mindist = CUDART_NAN;
-            int nearest = -1;
-            if (!isnan(lastpos[oa0])) { mindist = sf * (lastpos[oa0] - pos); nearest = oa0; }
-            if (!isnan(lastpos[oa1]) && (isnan(mindist) || mindist > sf * (lastpos[oa1] - pos))) {
-                mindist = sf * (lastpos[oa1] - pos);
-                nearest = oa1;
-            }
-            // testRecomb2, Quadrivalent.java:141-243
-            double temp_lim = exchange_lim[side];
-            const double dist_exchangelim = sf * (pos - exchange_lim[1 - side]);
-            bool reject = dist_exchangelim >= 0.0;
-            if (!reject && !isnan(mindist)) {
-                // Multivalent.rejectDist :216-220
-                reject = mindist <= 0 || (m.chiasma_interference && mindist < 0.5 &&
-                                          rng.next_double() < pow(1.0 - 2 * mindist, 2.25));
-            }
-            if (reject) {
-                arm_finished[a] = true;
-                if (dist_exchangelim >= 0.0) {
-                    temp_lim = exchange_lim[1 - side];
-                    for (int oa = 0; oa < 2; oa++) {
-                        const int arm_o = oa == 0 ? oa0 : oa1;
-                        const double lpoa = lastpos[arm_o];
-                        if (temp_lim == oppo_pos || (!isnan(lpoa) && (sf * (lpoa - temp_lim)) <= 0)) arm_finished[arm_o] = true;
-                    }
-                } else {
-                    if (sf * (pos - temp_lim) > 0) temp_lim = pos;
-                    arm_finished[nearest] = true;
-                }
-                finished = arm_finished[0] && arm_finished[1] && arm_finished[2] && arm_finished[3];
-            } else {
-                lastpos[a] = pos;
-                if ((sf * (pos - temp_lim)) > 0) temp_lim = pos;
-            }
-            exchange_lim[side] = temp_lim;
-            if (!arm_finished[a]) {  // makeRecombination :276-284
-                x.insert_sorted(pos, c0, c1);
-                lastpos[a] = pos;
-                if (x.overflow) return exchange_lim[1];
-            }
-        } while (!finished);
-    } while (!(m.allow_no_recomb || x.all_chrom_recomb(4)));
-    return exchange_lim[1];
-}
-
-// Chromosome (0..k-1) carried at `position` by the chromatid that starts in slot p
-// (Multivalent.slotsToPatterns :332-357 followed by getFounderAtCentromere).
-__device__ __forceinline__ int pattern_chrom_at(const Chiasmata& x, int p, double position) {
-    int cur = p;
-    for (int e = 0; e < x.n && x.pos[e] <= position; e++) {
-        if (x.a[e] == cur) cur = x.b[e];
-        else if (x.b[e] == cur) cur = x.a[e];
+// Individual.calcChromConfig (:601-670) for ploidy > 2.
+PSIM_HD_NOINLINE PairingResult draw_pairing(PhiloxStream& rng, const ModelParams& m, const ChromParams& ch, Nib16 genome_head, Nib16 genome_tail) {
+    PairingWork w;
+    const int P = m.ploidy;
+    if (P == 2) {   // one bivalent; which homolog comes first is a coin (Individual.java:603-608)
+        PairingResult r2;
+        r2.seq = nib_identity();
+        shuffle_nib(rng, r2.seq, 2);
+        r2.quad = 0;
+        return r2;
     }
-    return cur >> 1;
-}
-
-// Multivalent.getCentromereSortOrder :397-437 (k = 2 or parallel / unpaired quadrivalent)
-__device__ inline void multivalent_centromere_order(PhiloxStream& rng, int k, int8_t* centro) {
-    if (k == 2) {
-        if (rng.next_bool()) { centro[0] = 0; centro[1] = 0; centro[2] = 1; centro[3] = 1; }
-        else { centro[0] = 1; centro[1] = 1; centro[2] = 0; centro[3] = 0; }
-        return;
+    w.P = P;
+    w.order = nib_identity();
+    shuffle_nib(rng, w.order, P);
+    w.genpos[0].v = 0; w.genpos[1].v = 0;
+    for (int p = 0; p < P; p++) { w.genpos[0].set(p, genome_head.get(w.order.get(p))); w.genpos[1].set(p, genome_tail.get(w.order.get(p))); }
+    w.pair_end(rng, 0, ch.pref_pairing);
+    w.pair_end(rng, 1, ch.pref_pairing);
+    {   // the end with more same-genome pairs to offer is more often the primary one (getPrimarySide, :536-542)
+        int c0 = 0, c1 = 0;
+        for (int g = 0; g < P / 2; g++) { c0 += popc32(w.genome_mask(0, g)) >> 1; c1 += popc32(w.genome_mask(1, g)) >> 1; }
+        const double p0 = c0 == c1 ? 0.5 : (double)c0 / (double)(c0 + c1);
+        w.primary = rng.next_unit() < p0 ? 0 : 1;
     }
-    int8_t chr[4] = {0, 1, 2, 3};
-    shuffle_small(rng, chr, 4);
-    int8_t gam[4][2] = {{chr[0], chr[1]}, {chr[0], chr[1]}, {chr[2], chr[3]}, {chr[2], chr[3]}};
-    for (int g = 0; g < 4; g++) { shuffle_small(rng, gam[g], 2); centro[2 * g] = gam[g][0]; centro[2 * g + 1] = gam[g][1]; }
-}
-// Quadrivalent.getCentromereSortOrder :465-510
-__device__ inline void quadrivalent_centromere_order(PhiloxStream& rng, const ModelParams& m, const ChromParams& ch,
-                                                     double exchange_lim1, int8_t* centro) {
-    const bool paired = m.paired_centromeres == 0.0 ? false
-                      : m.paired_centromeres == 1.0 ? true
-                      : rng.next_double() < m.paired_centromeres;
-    if (!paired) { multivalent_centromere_order(rng, 4, centro); return; }
-    int8_t top[2], bot[2];
-    if (rng.next_bool()) {
-        const bool head_arm = ch.centro <= exchange_lim1;
-        if (head_arm) {
-            if (rng.next_bool()) { top[0] = 0; top[1] = 1; bot[0] = 2; bot[1] = 3; }
-            else { top[0] = 2; top[1] = 3; bot[0] = 0; bot[1] = 1; }
-        } else {
-            if (rng.next_bool()) { top[0] = 0; top[1] = 3; bot[0] = 1; bot[1] = 2; }
-            else { top[0] = 1; top[1] = 2; bot[0] = 0; bot[1] = 3; }
+    w.done = 0; w.n_bi = 0; w.n_quad = 0; w.seq.v = 0;
+    if (m.natural_pairing) {
+        w.take_two_cycles(P / 2);
+        w.take_four_cycles((P - 2 * w.n_bi) / 4);
+        while (2 * w.n_bi + 4 * w.n_quad < P) {
+            if (2 * w.n_bi + 4 * w.n_quad == P - 2) w.force_bivalent();
+            else w.force_cut(rng, true, ch.pref_pairing);
         }
     } else {
-        if (rng.next_bool()) { top[0] = 0; top[1] = 2; bot[0] = 1; bot[1] = 3; }
-        else { top[0] = 1; top[1] = 3; bot[0] = 0; bot[1] = 2; }
+        // number of quadrivalents ~ Binomial(P/4, fraction) (TetraploidChromosome.ranQuadri, :122-128)
+        const double u = rng.next_unit();
+        int want_quad = 0;
+        while (want_quad < P / 4 && ch.cumul_binomial[want_quad] < u) want_quad++;
+        const int want_bi = (P - 4 * want_quad) / 2;
+        w.take_two_cycles(want_bi);
+        w.take_four_cycles(want_quad);
+        while (w.n_bi < want_bi) w.force_bivalent();
+        while (w.n_quad < want_quad) w.force_cut(rng, false, ch.pref_pairing);
     }
-    int8_t gam[4][2] = {{top[0], top[1]}, {top[0], top[1]}, {bot[0], bot[1]}, {bot[0], bot[1]}};
-    for (int g = 0; g < 4; g++) { shuffle_small(rng, gam[g], 2); centro[2 * g] = gam[g][0]; centro[2 * g + 1] = gam[g][1]; }
+    PairingResult r;
+    r.seq = w.seq;
+    r.quad = w.n_quad;
+    return r;
 }
 
-// Multivalent.patternsToGametes :486-518 on indices: idx[s] = the starting slot of the chromatid
-// that ends up as output pattern s. Gamete g receives pattern g of a bivalent, patterns 2g and
-// 2g+1 of a quadrivalent.
-__device__ inline void select_gametes(const Chiasmata& x, PhiloxStream& rng, int k, const ChromParams& ch,
-                                      const int8_t* centro, int8_t* idx) {
-    const int n = 2 * k;
-    int8_t fac[8];
-    for (int p = 0; p < n; p++) { idx[p] = (int8_t)p; fac[p] = (int8_t)pattern_chrom_at(x, p, ch.centro); }
-    for (int s = 0; s < n - 1; s++) {
-        if (fac[idx[s]] != centro[s]) {
-            int t = s + 1;
-            while (fac[idx[t]] != centro[s]) t++;
-            const int8_t tmp = idx[s]; idx[s] = idx[t]; idx[t] = tmp;
-        }
+// ---------------------------------------------------------------- chiasmata of one multivalent
+// All chiasmata of a multivalent as one position-sorted list in per-thread global scratch
+// (entry e of thread slot t at [e * stride + t], like local memory but sized at run time from the
+// longest chromosome): position and the two chromatid strands that exchange (strand s belongs to
+// chromosome s / 2 of the multivalent).
+struct ChiasmaList {
+    double* pos;
+    uint8_t* ab;
+    int64_t stride;
+    int cap, n;
+    bool overflow;
+    PSIM_HD double p(int e) const { return pos[e * stride]; }
+    PSIM_HD int a(int e) const { return ab[e * stride] >> 4; }
+    PSIM_HD int b(int e) const { return ab[e * stride] & 15; }
+    PSIM_HD void append(double x, int sa, int sb) {
+        if (n >= cap) { overflow = true; return; }
+        pos[n * stride] = x; ab[n * stride] = (uint8_t)((sa << 4) | sb); n++;
     }
-    if (n > 4) {
-        for (int all = 0; all < 4; all++) {
-            if (rng.next_bool()) {
-                int first = 0; while (centro[first] != all) first++;
-                int second = first + 1; while (centro[second] != all) second++;
-                const int8_t tmp = idx[first]; idx[first] = idx[second]; idx[second] = tmp;
+    // keeps the list sorted; among equal positions the later chiasma comes last (HaploStruct.insertSegment, :129-133)
+    PSIM_HD void insert(double x, int sa, int sb) {
+        if (n >= cap) { overflow = true; return; }
+        int i = n;
+        while (i > 0 && pos[(i - 1) * stride] > x) { pos[i * stride] = pos[(i - 1) * stride]; ab[i * stride] = ab[(i - 1) * stride]; i--; }
+        pos[i * stride] = x; ab[i * stride] = (uint8_t)((sa << 4) | sb); n++;
+    }
+    PSIM_HD uint32_t chromosomes_hit() const {
+        uint32_t seen = 0;
+        for (int e = 0; e < n; e++) seen |= (1u << (a(e) >> 1)) | (1u << (b(e) >> 1));
+        return seen;
+    }
+};
+
+// Bivalent (K = 2) or parallel quadrivalent (K = 4): one renewal process along the bundle of 2K
+// chromatids, every chiasma between two chromatids of different chromosomes chosen uniformly
+// (Multivalent.doCrossingOver, Multivalent.java:139-182).
+template <int K, bool KOS, bool ANR>
+PSIM_HD_NOINLINE void chiasmata_parallel(ChiasmaList& x, PhiloxStream& rng, const ChromParams& ch) {
+    double mean = RECOMBDIST * 2.0 / K;
+    if (!ANR) mean = mean / 0.5 * ch.recomb_dist_noempty;
+    for (;;) {
+        x.n = 0;
+        double at = ch.head + draw_gap<KOS, true>(rng, mean);
+        while (at < ch.tail) {
+            int s0, s1;
+            if (K == 2) {
+                const uint32_t bits = rng.next_bits(3);
+                s0 = (int)(bits >> 1);                        // any of the four chromatids
+                s1 = (int)((((bits >> 2) ^ 1u) << 1) | (bits & 1u));   // either chromatid of the other chromosome
+            } else {
+                s0 = (int)rng.next_bits(3);
+                const int r = rng.next_below(6);              // the six chromatids of the three other chromosomes
+                s1 = r + (r >= (s0 & ~1) ? 2 : 0);
             }
+            x.append(at, s0, s1);
+            if (x.overflow) return;
+            at += draw_gap<KOS, false>(rng, mean);
+        }
+        if (ANR || x.chromosomes_hit() == (1u << K) - 1u) return;   // ALLOWNORECOMBINATION=0: every chromosome exchanges at least once
+    }
+}
+
+// Cross-type quadrivalent (Quadrivalent.doCrossingOver with quadriMethod 2, Quadrivalent.java:371-424 and
+// generateRecombination / testRecomb2 / makeRecombination, :108-284). Chromosomes 0-3 and 1-2 are
+// paired at the head, 0-1 and 2-3 at the tail: four arms, arm a growing from the head (a even) or the
+// tail (a odd) towards the other end, each a renewal process of its own. A candidate chiasma of an
+// arm is refused when it passes the point the arms of the other end have reached (the exchange limit)
+// or meets their last chiasma (with interference: comes too close to it); a refusal finishes the arm
+// and, depending on the case, the arms it ran into. Returns the exchange limit of the tail end.
+template <bool KOS, bool ANR>
+PSIM_HD_NOINLINE double chiasmata_cross(ChiasmaList& x, PhiloxStream& rng, const ChromParams& ch) {
+    const double mean = ANR ? RECOMBDIST : ch.recomb_dist_noempty;
+    double lim_head, lim_tail;
+    for (;;) {
+        x.n = 0;
+        double last0 = 0.0, last1 = 0.0, last2 = 0.0, last3 = 0.0;   // last chiasma of each arm
+        uint32_t has = 0, open = 0xFu;                              // arms that have a chiasma / can still get one
+        lim_head = ch.head;
+        lim_tail = ch.tail;
+        while (open) {
+            const int a = pick_bit(rng, open);
+            const uint32_t bits = rng.next_bits(2);
+            // arm 0 joins chromosomes 0 and 3, arm a > 0 chromosomes a-1 and a: one chromatid of each
+            const int s0 = 2 * (a == 0 ? 0 : a - 1) + (int)(bits >> 1), s1 = 2 * (a == 0 ? 3 : a) + (int)(bits & 1u);
+            const bool from_tail = a & 1;
+            const double dir = from_tail ? -1.0 : 1.0;
+            const double mine = a == 0 ? last0 : a == 1 ? last1 : a == 2 ? last2 : last3;
+            const double at = (has >> a) & 1u ? mine + dir * draw_gap<KOS, false>(rng, mean)
+                                              : (from_tail ? ch.tail : ch.head) + dir * draw_gap<KOS, true>(rng, mean);
+            // the two arms growing from the other end, and how far ahead of `at` their nearest last chiasma lies
+            const int o0 = from_tail ? 0 : 1, o1 = o0 + 2;
+            const double lo0 = from_tail ? last0 : last1, lo1 = from_tail ? last2 : last3;
+            bool met = false;
+            double ahead = 0.0;
+            int nearest = -1;
+            if ((has >> o0) & 1u) { ahead = dir * (lo0 - at); nearest = o0; met = true; }
+            if (((has >> o1) & 1u) && (!met || ahead > dir * (lo1 - at))) { ahead = dir * (lo1 - at); nearest = o1; met = true; }
+            const double my_lim = from_tail ? lim_tail : lim_head, other_lim = from_tail ? lim_head : lim_tail;
+            const bool passed = dir * (at - other_lim) >= 0.0;
+            bool refused = passed;
+            if (!refused && met)   // Multivalent.rejectDist, Multivalent.java:216-220
+                refused = ahead <= 0.0 || (KOS && ahead < 0.5 && rng.next_unit() < pow(1.0 - 2.0 * ahead, 2.25));
+            double new_lim = my_lim;
+            if (refused) {
+                open &= ~(1u << a);
+                if (passed) {
+                    // this end's limit jumps to the other end's; arms of the other end that stand at or behind it
+                    // (or all of them while that limit is still the chromosome end) are finished too
+                    new_lim = other_lim;
+                    const bool at_end = other_lim == (from_tail ? ch.head : ch.tail);
+                    if (at_end || (((has >> o0) & 1u) && dir * (lo0 - other_lim) <= 0.0)) open &= ~(1u << o0);
+                    if (at_end || (((has >> o1) & 1u) && dir * (lo1 - other_lim) <= 0.0)) open &= ~(1u << o1);
+                } else {
+                    if (dir * (at - my_lim) > 0.0) new_lim = at;
+                    open &= ~(1u << nearest);
+                }
+            } else {
+                if (dir * (at - my_lim) > 0.0) new_lim = at;
+                if (a == 0) last0 = at; else if (a == 1) last1 = at; else if (a == 2) last2 = at; else last3 = at;
+                has |= 1u << a;
+                x.insert(at, s0, s1);
+                if (x.overflow) return lim_tail;
+            }
+            if (from_tail) lim_tail = new_lim; else lim_head = new_lim;
+        }
+        if (ANR || x.chromosomes_hit() == 0xFu) return lim_tail;
+    }
+}
+
+// ---------------------------------------------------------------- segregation
+// Which chromosome each of the 2K chromatids (numbered by the strand they start on at the head)
+// carries at the centromere: the strands are walked once, swapping the two chromatids of every
+// chiasma at or before the centromere (Multivalent.slotsToPatterns :332-357 + getFounderAtCentromere).
+template <int K>
+PSIM_HD uint32_t centromere_chromosomes(const ChiasmaList& x, double centro) {
+    uint32_t on_strand = 0x76543210u;   // nibble s = chromatid currently on strand s
+    for (int e = 0; e < x.n && x.p(e) <= centro; e++) {
+        const int a = x.a(e), b = x.b(e);
+        const uint32_t ca = (on_strand >> (4 * a)) & 15u, cb = (on_strand >> (4 * b)) & 15u;
+        on_strand = (on_strand & ~((15u << (4 * a)) | (15u << (4 * b)))) | (cb << (4 * a)) | (ca << (4 * b));
+    }
+    uint32_t chrom_of = 0;              // nibble c = chromosome chromatid c carries at the centromere
+    for (int s = 0; s < 2 * K; s++) chrom_of |= (uint32_t)(s >> 1) << (4 * ((on_strand >> (4 * s)) & 15u));
+    return chrom_of;
+}
+PSIM_HD uint32_t nib8_swap(uint32_t v, int i, int j) {
+    const uint32_t a = (v >> (4 * i)) & 15u, b = (v >> (4 * j)) & 15u;
+    return (v & ~((15u << (4 * i)) | (15u << (4 * j)))) | (b << (4 * i)) | (a << (4 * j));
+}
+// The centromeres the gametes receive: nibble 2g, 2g+1 (K = 4) or g (K = 2) = chromosome whose centromere goes to
+// gamete g. Bivalent: first division separates the two chromosomes (Multivalent.getCentromereSortOrder :397-437).
+PSIM_HD uint32_t centromeres_bivalent(PhiloxStream& rng) { return rng.next_bits(1) ? 0x1100u : 0x0011u; }
+// Quadrivalent: two chromosomes go to each pole - a random two without centromere pairing (Multivalent.java:407-436),
+// with pairing adjacent or alternate segregation of the ring (Quadrivalent.getCentromereSortOrder, :465-510); the two
+// centromeres of a gamete in random order.
+PSIM_HD_NOINLINE uint32_t centromeres_quadrivalent(PhiloxStream& rng, const ModelParams& m, const ChromParams& ch, double lim_tail) {
+    const bool paired = m.paired_centromeres == 0.0 ? false : m.paired_centromeres == 1.0 ? true : rng.next_unit() < m.paired_centromeres;
+    int top0, top1, bot0, bot1;
+    if (!paired) {
+        Nib16 c = nib_identity();
+        shuffle_nib(rng, c, 4);
+        top0 = c.get(0); top1 = c.get(1); bot0 = c.get(2); bot1 = c.get(3);
+    } else {
+        const uint32_t bits = rng.next_bits(2);
+        const bool flip = bits & 1u;
+        if (bits >> 1) {   // adjacent: the partners of the arm that holds the centromeres go together
+            if (ch.centro <= lim_tail) { top0 = 0; top1 = 1; bot0 = 2; bot1 = 3; }
+            else { top0 = 0; top1 = 3; bot0 = 1; bot1 = 2; }
+        } else { top0 = 0; top1 = 2; bot0 = 1; bot1 = 3; }   // alternate
+        if (!flip) { int t = top0; top0 = bot0; bot0 = t; t = top1; top1 = bot1; bot1 = t; }
+    }
+    const uint32_t coins = rng.next_bits(4);
+    uint32_t out = 0;
+    for (int g = 0; g < 4; g++) {
+        const int u = g < 2 ? top0 : bot0, v = g < 2 ? top1 : bot1;
+        const bool sw = (coins >> g) & 1u;
+        out |= (uint32_t)(sw ? v : u) << (8 * g) | (uint32_t)(sw ? u : v) << (8 * g + 4);
+    }
+    return out;
+}
+// Chromatids to gametes (Multivalent.patternsToGametes :486-518): position s of the result takes the first chromatid
+// not yet placed whose centromere is the one position s receives; in a quadrivalent the two chromatids of every
+// centromere then change places with probability 1/2. Returns nibble s = chromatid at position s
+// (gamete g = position g of a bivalent, positions 2g, 2g+1 of a quadrivalent).
+template <int K>
+PSIM_HD_NOINLINE uint32_t assign_chromatids(PhiloxStream& rng, uint32_t chrom_of, uint32_t centro) {
+    constexpr int n = 2 * K;
+    uint32_t at = 0x76543210u;
+    for (int s = 0; s < n - 1; s++) {
+        const uint32_t want = (centro >> (4 * s)) & 15u;
+        int t = s;
+        while (((chrom_of >> (4 * ((at >> (4 * t)) & 15u))) & 15u) != want) t++;
+        if (t != s) at = nib8_swap(at, s, t);
+    }
+    if (K == 4) {
+        const uint32_t coins = rng.next_bits(4);
+        for (int c = 0; c < 4; c++) {
+            if (!((coins >> c) & 1u)) continue;
+            int first = 0; while (((centro >> (4 * first)) & 15u) != (uint32_t)c) first++;
+            int second = first + 1; while (((centro >> (4 * second)) & 15u) != (uint32_t)c) second++;
+            at = nib8_swap(at, first, second);
         }
     }
+    return at;
+}
+
+// ---------------------------------------------------------------- one multivalent, start to end
+// Chiasmata, centromere segregation and the assignment of the 2K chromatids to the gametes.
+// Returns nibble s = chromatid (numbered by the strand it starts on at the head) at gamete position s:
+// gamete g is position g of a bivalent, positions 2g and 2g+1 of a quadrivalent.
+template <bool QUAD, bool KOS, bool ANR>
+PSIM_HD_NOINLINE uint32_t draw_multivalent(ChiasmaList& x, PhiloxStream& rng, const ModelParams& m, const ChromParams& ch) {
+    if (!QUAD) {
+        chiasmata_parallel<2, KOS, ANR>(x, rng, ch);
+        if (x.overflow) return 0;
+        const uint32_t chrom_of = centromere_chromosomes<2>(x, ch.centro);
+        return assign_chromatids<2>(rng, chrom_of, centromeres_bivalent(rng));
+    }
+    // a quadrivalent pairs as a cross (four arms) or, with probability PARALLELMULTIVALENTS, as one
+    // parallel bundle (Quadrivalent.doCrossingOver, Quadrivalent.java:371-378)
+    const bool parallel = m.parallel_multivalents == 0.0 ? false : m.parallel_multivalents == 1.0 ? true : rng.next_unit() < m.parallel_multivalents;
+    double lim_tail = 0.0;   // a parallel quadrivalent has no exchange limits (they stay 0, Quadrivalent.java:42)
+    if (parallel) chiasmata_parallel<4, KOS, ANR>(x, rng, ch);
+    else lim_tail = chiasmata_cross<KOS, ANR>(x, rng, ch);
+    if (x.overflow) return 0;
+    const uint32_t chrom_of = centromere_chromosomes<4>(x, ch.centro);
+    return assign_chromatids<4>(rng, chrom_of, centromeres_quadrivalent(rng, m, ch, lim_tail));
+}
+
+// ---------------------------------------------------------------- which gametes are kept, and their homolog order
+// Gamete 0 of a meiosis makes the individual (Individual.java:258-259). With 2NGAMETES the unreduced
+// gamete is gamete 0 plus gamete 1 (SDR) or plus one of the two gametes of the other pole (FDR, one
+// coin per meiosis shared by its chromosomes; Individual.java:341-383). The P/2 homologs of every
+// gamete are put in random order (Individual.java:325-335): dest[k].get(s) = position, inside kept
+// gamete k, of the chromatid that segregation left at slot s.
+struct Transmission {
+    int n_gametes;
+    int gamete[2];
+    Nib16 dest[2];
+};
+PSIM_HD_NOINLINE Transmission draw_transmission(PhiloxStream& rng, const ModelParams& m, uint32_t child, uint32_t chrom, uint32_t parent) {
+    Transmission t;
+    t.n_gametes = m.unreduced ? 2 : 1;
+    t.gamete[0] = 0;
+    t.gamete[1] = 1;
+    if (m.unreduced == 1) {
+        rng.seek(child, 0u, parent, STAGE_UNREDUCED);
+        t.gamete[1] = rng.next_bits(1) ? 3 : 2;
+    }
+    rng.seek(child, chrom, parent, STAGE_ORDER);
+    const int p2 = m.ploidy / 2;
+    for (int k = 0; k < t.n_gametes; k++) {
+        Nib16 from = nib_identity();        // from.get(position) = slot
+        shuffle_nib(rng, from, p2);
+        t.dest[k].v = 0;
+        for (int h = 0; h < p2; h++) t.dest[k].set(from.get(h), h);
+    }
+    return t;
 }
 
 }  // namespace psim
