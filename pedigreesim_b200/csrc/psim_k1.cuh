@@ -56,14 +56,20 @@ __global__ void k_slab_mark(unsigned long long* cursor, unsigned long long* mark
 //      bivalents from the next warp boundary - and every thread takes one: chiasmata (into its
 //      column of the chiasma scratch), segregation, the chromatids of the kept gamete(s) traced
 //      once to count the segments they will have;
-//   3. the block reserves its segments in the slab with one atomic, and the same threads trace
+//   3. every warp reserves its segments in the slab with one atomic, and the same threads trace
 //      again, writing the segments (Multivalent.fillGamete :539-577) and the child's descriptors
 //      (Gamete.fertilization, Gamete.java:95-116: homologs 0..P/2-1 from parent 0's gamete,
 //      P/2..P-1 from parent 1's).
 // Warps therefore run one kind of multivalent, no task list goes through global memory, and a
 // generation is one launch. Every multivalent owns a Philox stream, so results do not depend on the
 // block size or on how the units are batched.
-constexpr int MEI_THREADS = 256;
+#ifndef PSIM_MEI_THREADS
+#define PSIM_MEI_THREADS 256
+#endif
+constexpr int MEI_THREADS = PSIM_MEI_THREADS;
+#ifndef PSIM_MEI_MIN_BLOCKS
+#define PSIM_MEI_MIN_BLOCKS 4
+#endif
 
 struct MeiosisArgs {
     ModelParams model;
@@ -146,13 +152,12 @@ __device__ __forceinline__ int trace_chromatid(const MeiosisArgs& a, const Chias
 // KOS / ANR: MAPFUNCTION=KOSAMBI and ALLOWNORECOMBINATION as compile-time constants, so that the code
 // of the other model (gamma sampler, pow, retry loop) is not in the kernel at all.
 template <bool KOS, bool ANR>
-__global__ void __launch_bounds__(MEI_THREADS) k_meiosis(const MeiosisArgs a) {
+__global__ void __launch_bounds__(MEI_THREADS, PSIM_MEI_MIN_BLOCKS) k_meiosis(const MeiosisArgs a) {
     typedef cub::BlockScan<int, MEI_THREADS> Scan;
     __shared__ typename Scan::TempStorage scan_tmp;
     __shared__ uint64_t s_seq[MEI_THREADS];
     __shared__ uint8_t s_nquad[MEI_THREADS];
     __shared__ uint16_t s_task[MEI_THREADS + 32];
-    __shared__ long long s_base;
     __shared__ int s_stop;
     const int tid = threadIdx.x;
     if (tid == 0) s_stop = *(volatile int*)a.status != 0;   // an earlier batch failed: the host runs this one again
@@ -201,6 +206,7 @@ __global__ void __launch_bounds__(MEI_THREADS) k_meiosis(const MeiosisArgs a) {
     for (int v = 0; v < nb; v++) s_task[bi0 + (before >> 16) + v] = (uint16_t)((tid << 3) | (nq + v));
     __syncthreads();
     const bool is_quad = tid < n_quad, is_bi = tid >= bi0 && tid < bi0 + n_bi;
+    bool live = is_quad || is_bi;
     ChiasmaList x;
     x.stride = (int64_t)gridDim.x * MEI_THREADS;
     x.pos = a.x_pos + (int64_t)blockIdx.x * MEI_THREADS + tid;
@@ -209,45 +215,56 @@ __global__ void __launch_bounds__(MEI_THREADS) k_meiosis(const MeiosisArgs a) {
     int n_out = 0;            // chromatids this thread delivers (<= 4: two per quadrivalent, twice with 2NGAMETES)
     int strand[4], dest[4], count[4];
     Nib16 seq; seq.v = 0;
-    int base = 0;
+    int base = 0, v = 0, quad = 0;
     int64_t phid0 = 0, chid0 = 0;
-    double head = 0.0, tail = 0.0;
-    if (is_quad || is_bi) {
-        const int code = s_task[tid], i = code >> 3, v = code & 7;
-        int par, j, r, c;
+    double head = 0.0, tail = 0.0, lim_tail = 0.0;
+    int32_t child = 0;
+    int par = 0, c = 0;
+    PhiloxStream rng;
+    rng.init(a.model.seed, a.replicate_first);
+    const ChromParams* ch = a.chrom;
+    // the chiasmata: loops whose trip counts differ from thread to thread ...
+    if (live) {
+        const int code = s_task[tid], i = code >> 3;
+        v = code & 7;
+        int j, r;
         unit_decode(a, unit0 + i, par, j, r, c);
-        const int32_t child = a.lev_ind[j];
+        child = a.lev_ind[j];
         const int32_t parent = par == 0 ? a.par0[child] : a.par1[child];
-        const ChromParams& ch = a.chrom[c];
-        head = ch.head; tail = ch.tail;
+        ch = a.chrom + c;
+        head = ch->head; tail = ch->tail;
         phid0 = (((int64_t)c * a.R + r) * a.N + parent) * P;
         chid0 = (((int64_t)c * a.R + r) * a.N + child) * P + (int64_t)par * p2;
         seq.v = s_seq[i];
-        const int quad = s_nquad[i];
-        PhiloxStream rng;
+        quad = s_nquad[i];
         rng.init(a.model.seed, a.replicate_first + (uint32_t)r);
         rng.seek((uint32_t)child, (uint32_t)c, (uint32_t)par, STAGE_MULTIVALENT + (uint32_t)v);
-        uint32_t at;
-        if (is_quad) at = draw_multivalent<true, KOS, ANR>(x, rng, a.model, ch);
-        else at = draw_multivalent<false, KOS, ANR>(x, rng, a.model, ch);
+        if (is_quad) lim_tail = draw_chiasmata<true, KOS, ANR>(x, rng, a.model, *ch);
+        else draw_chiasmata<false, KOS, ANR>(x, rng, a.model, *ch);
         if (x.overflow) {
             atomicExch(a.status, PSIM_ECAPACITY);
             atomicMin(a.status + 1, a.batch);
-        } else {
-            const Transmission tr = draw_transmission(rng, a.model, (uint32_t)child, (uint32_t)c, (uint32_t)par);
-            // Individual.java:297-321: quadrivalent v fills gamete slots 2v, 2v+1; bivalent v' slot 2 * quad + v'
-            base = is_quad ? 4 * v : 4 * quad + 2 * (v - quad);
-            const int per_gamete = is_quad ? 2 : 1;
-            for (int k = 0; k < tr.n_gametes; k++)
-                for (int o = 0; o < per_gamete; o++) {
-                    const int g = tr.gamete[k];
-                    const int slot = is_quad ? 2 * v + o : 2 * quad + (v - quad);
-                    strand[n_out] = (int)((at >> (4 * (is_quad ? 2 * g + o : g))) & 15u);
-                    dest[n_out] = k * p2 + tr.dest[k].get(slot);
-                    n_out++;
-                }
+            live = false;
         }
     }
+    __syncwarp();
+    // ... then the warp runs together again: segregation and the kept gametes are branch-free bit work
+    if (live) {
+        const uint32_t at = is_quad ? draw_segregation<true>(x, rng, a.model, *ch, lim_tail) : draw_segregation<false>(x, rng, a.model, *ch, lim_tail);
+        const Transmission tr = draw_transmission(rng, a.model, (uint32_t)child, (uint32_t)c, (uint32_t)par);
+        // Individual.java:297-321: quadrivalent v fills gamete slots 2v, 2v+1; bivalent v' slot 2 * quad + v'
+        base = is_quad ? 4 * v : 4 * quad + 2 * (v - quad);
+        const int per_gamete = is_quad ? 2 : 1;
+        for (int k = 0; k < tr.n_gametes; k++)
+            for (int o = 0; o < per_gamete; o++) {
+                const int g = tr.gamete[k];
+                const int slot = is_quad ? 2 * v + o : 2 * quad + (v - quad);
+                strand[n_out] = (int)((at >> (4 * (is_quad ? 2 * g + o : g))) & 15u);
+                dest[n_out] = k * p2 + tr.dest[k].get(slot);
+                n_out++;
+            }
+    }
+    __syncwarp();
     int mine = 0;
 #pragma unroll
     for (int o = 0; o < 4; o++) {
@@ -255,21 +272,25 @@ __global__ void __launch_bounds__(MEI_THREADS) k_meiosis(const MeiosisArgs a) {
         if (o < n_out) count[o] = trace_chromatid<false>(a, x, strand[o], seq, base, phid0, head, tail, 0);
         mine += count[o];
     }
-    // ---- 3. the block's segments: one reservation, then the same traces write
-    __syncthreads();
-    int offset, block_total;
-    Scan(scan_tmp).ExclusiveSum(mine, offset, block_total);
-    if (tid == 0) {
-        const long long at = (long long)atomicAdd(a.cursor, (unsigned long long)block_total);
-        if (at + block_total > a.slab_cap) {
+    // ---- 3. the warp's segments: one reservation, then the same traces write (no block-wide barrier
+    // here: the threads of a block finish at very different times)
+    int offset = mine;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const int y = __shfl_up_sync(0xFFFFFFFFu, offset, o); if ((tid & 31) >= o) offset += y; }
+    const int warp_total = __shfl_sync(0xFFFFFFFFu, offset, 31);
+    offset -= mine;
+    long long warp_base = 0;
+    if ((tid & 31) == 0 && warp_total > 0) {
+        warp_base = (long long)atomicAdd(a.cursor, (unsigned long long)warp_total);
+        if (warp_base + warp_total > a.slab_cap) {
             atomicCAS(a.status, 0, STATUS_SLAB_FULL);
             atomicMin(a.status + 1, a.batch);
-            s_base = -1;
-        } else s_base = at;
+            warp_base = -1;
+        }
     }
-    __syncthreads();
-    if (s_base < 0) return;
-    int64_t w = s_base + offset;
+    warp_base = __shfl_sync(0xFFFFFFFFu, warp_base, 0);
+    if (warp_base < 0) return;
+    int64_t w = warp_base + offset;
 #pragma unroll
     for (int o = 0; o < 4; o++) {
         if (o < n_out) {

@@ -447,50 +447,61 @@ PSIM_HD_NOINLINE uint32_t centromeres_quadrivalent(PhiloxStream& rng, const Mode
 // Chromatids to gametes (Multivalent.patternsToGametes :486-518): position s of the result takes the first chromatid
 // not yet placed whose centromere is the one position s receives; in a quadrivalent the two chromatids of every
 // centromere then change places with probability 1/2. Returns nibble s = chromatid at position s
-// (gamete g = position g of a bivalent, positions 2g, 2g+1 of a quadrivalent).
+// (gamete g = position g of a bivalent, positions 2g, 2g+1 of a quadrivalent). No data-dependent branch: the
+// searches are nibble matches (a zero nibble of x ^ pattern), so a warp stays converged.
+PSIM_HD uint32_t nib8_match(uint32_t v, uint32_t want) {   // bit 4t set where nibble t of v equals `want`
+    const uint32_t x = v ^ (want * 0x11111111u);
+    return ~(x | (x >> 1) | (x >> 2) | (x >> 3)) & 0x11111111u;
+}
 template <int K>
-PSIM_HD_NOINLINE uint32_t assign_chromatids(PhiloxStream& rng, uint32_t chrom_of, uint32_t centro) {
+PSIM_HD uint32_t assign_chromatids(PhiloxStream& rng, uint32_t chrom_of, uint32_t centro) {
     constexpr int n = 2 * K;
-    uint32_t at = 0x76543210u;
+    constexpr uint32_t used = n == 8 ? 0xFFFFFFFFu : 0x0000FFFFu;
+    uint32_t at = 0x76543210u & used;
+    uint32_t cof = chrom_of & used;                 // nibble t = centromere of the chromatid now at position t
     for (int s = 0; s < n - 1; s++) {
         const uint32_t want = (centro >> (4 * s)) & 15u;
-        int t = s;
-        while (((chrom_of >> (4 * ((at >> (4 * t)) & 15u))) & 15u) != want) t++;
-        if (t != s) at = nib8_swap(at, s, t);
+        const uint32_t hit = nib8_match(cof, want) & used & (0xFFFFFFFFu << (4 * s));
+        const int t = lowest_bit(hit) >> 2;         // a chromatid with that centromere is always left
+        at = nib8_swap(at, s, t);
+        cof = nib8_swap(cof, s, t);
     }
     if (K == 4) {
         const uint32_t coins = rng.next_bits(4);
         for (int c = 0; c < 4; c++) {
-            if (!((coins >> c) & 1u)) continue;
-            int first = 0; while (((centro >> (4 * first)) & 15u) != (uint32_t)c) first++;
-            int second = first + 1; while (((centro >> (4 * second)) & 15u) != (uint32_t)c) second++;
-            at = nib8_swap(at, first, second);
+            const uint32_t hit = nib8_match(centro, (uint32_t)c);           // the two positions that receive centromere c
+            const int first = lowest_bit(hit) >> 2, second = lowest_bit(hit & (hit - 1)) >> 2;
+            if ((coins >> c) & 1u) at = nib8_swap(at, first, second);
         }
     }
     return at;
 }
 
 // ---------------------------------------------------------------- one multivalent, start to end
-// Chiasmata, centromere segregation and the assignment of the 2K chromatids to the gametes.
-// Returns nibble s = chromatid (numbered by the strand it starts on at the head) at gamete position s:
-// gamete g is position g of a bivalent, positions 2g and 2g+1 of a quadrivalent.
+// Two steps, so that a kernel can let its warp reconverge between them: the chiasmata (loops whose
+// trip counts differ from thread to thread), then centromere segregation and the assignment of the
+// 2K chromatids to the gametes. draw_segregation returns nibble s = chromatid (numbered by the strand
+// it starts on at the head) at gamete position s: gamete g is position g of a bivalent, positions
+// 2g and 2g+1 of a quadrivalent.
 template <bool QUAD, bool KOS, bool ANR>
-PSIM_HD_NOINLINE uint32_t draw_multivalent(ChiasmaList& x, PhiloxStream& rng, const ModelParams& m, const ChromParams& ch) {
-    if (!QUAD) {
-        chiasmata_parallel<2, KOS, ANR>(x, rng, ch);
-        if (x.overflow) return 0;
-        const uint32_t chrom_of = centromere_chromosomes<2>(x, ch.centro);
-        return assign_chromatids<2>(rng, chrom_of, centromeres_bivalent(rng));
-    }
+PSIM_HD_NOINLINE double draw_chiasmata(ChiasmaList& x, PhiloxStream& rng, const ModelParams& m, const ChromParams& ch) {
+    if (!QUAD) { chiasmata_parallel<2, KOS, ANR>(x, rng, ch); return 0.0; }
     // a quadrivalent pairs as a cross (four arms) or, with probability PARALLELMULTIVALENTS, as one
     // parallel bundle (Quadrivalent.doCrossingOver, Quadrivalent.java:371-378)
     const bool parallel = m.parallel_multivalents == 0.0 ? false : m.parallel_multivalents == 1.0 ? true : rng.next_unit() < m.parallel_multivalents;
-    double lim_tail = 0.0;   // a parallel quadrivalent has no exchange limits (they stay 0, Quadrivalent.java:42)
-    if (parallel) chiasmata_parallel<4, KOS, ANR>(x, rng, ch);
-    else lim_tail = chiasmata_cross<KOS, ANR>(x, rng, ch);
+    if (parallel) { chiasmata_parallel<4, KOS, ANR>(x, rng, ch); return 0.0; }   // no exchange limits: they stay 0 (Quadrivalent.java:42)
+    return chiasmata_cross<KOS, ANR>(x, rng, ch);
+}
+template <bool QUAD>
+PSIM_HD_NOINLINE uint32_t draw_segregation(const ChiasmaList& x, PhiloxStream& rng, const ModelParams& m, const ChromParams& ch, double lim_tail) {
+    if (!QUAD) return assign_chromatids<2>(rng, centromere_chromosomes<2>(x, ch.centro), centromeres_bivalent(rng));
+    return assign_chromatids<4>(rng, centromere_chromosomes<4>(x, ch.centro), centromeres_quadrivalent(rng, m, ch, lim_tail));
+}
+template <bool QUAD, bool KOS, bool ANR>
+PSIM_HD_NOINLINE uint32_t draw_multivalent(ChiasmaList& x, PhiloxStream& rng, const ModelParams& m, const ChromParams& ch) {
+    const double lim_tail = draw_chiasmata<QUAD, KOS, ANR>(x, rng, m, ch);
     if (x.overflow) return 0;
-    const uint32_t chrom_of = centromere_chromosomes<4>(x, ch.centro);
-    return assign_chromatids<4>(rng, chrom_of, centromeres_quadrivalent(rng, m, ch, lim_tail));
+    return draw_segregation<QUAD>(x, rng, m, ch, lim_tail);
 }
 
 // ---------------------------------------------------------------- which gametes are kept, and their homolog order

@@ -16,7 +16,7 @@
 
 #ifdef __CUDACC__
 #define PSIM_HD __host__ __device__ __forceinline__
-#define PSIM_HD_NOINLINE __host__ __device__
+#define PSIM_HD_NOINLINE __host__ __device__ __forceinline__
 #else
 #define PSIM_HD inline
 #define PSIM_HD_NOINLINE inline
