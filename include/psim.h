@@ -36,7 +36,7 @@
 extern "C" {
 #endif
 
-#define PSIM_ABI_VERSION 1
+#define PSIM_ABI_VERSION 2
 
 typedef struct psim_ctx psim_ctx;
 
@@ -50,7 +50,7 @@ enum {
 
 /* The model flags of PopulationData (PopulationData.java:187-222) plus the RNG identity. */
 typedef struct psim_config {
-    int32_t ploidy;                /* PLOIDY: positive, even, <= 16 */
+    int32_t ploidy;                /* PLOIDY: positive, even, <= 16 (4-bit homolog numbers on the device) */
     int32_t chiasma_interference;  /* MAPFUNCTION: 0 = HALDANE, 1 = KOSAMBI */
     int32_t natural_pairing;       /* NATURALPAIRING */
     int32_t allow_no_recomb;       /* ALLOWNORECOMBINATION */
@@ -98,6 +98,13 @@ int psim_set_haplostructs(psim_ctx* ctx, uint32_t replicate, int64_t first, int6
  * other individual without one, one pedigree generation per kernel batch, in every replicate.
  * max_founder_allele is what readHaploStructFiles returned (-1 for a fresh simulation). */
 int psim_simulate(psim_ctx* ctx, int32_t max_founder_allele);
+
+/* psim_simulate without the final wait: the whole simulation (founders, then one kernel launch per generation) is
+ * enqueued on the context's stream and the call returns. psim_wait - or the next call on the context that needs the
+ * population - completes it and reports its status. Lets one host thread keep several contexts (replicate populations,
+ * GPUs) busy: simulate population k+1 while population k is being emitted. */
+int psim_simulate_async(psim_ctx* ctx, int32_t max_founder_allele);
+int psim_wait(psim_ctx* ctx);
 
 /* Same, but only the listed non-founders are simulated (their parents must already have a
  * haplostruct or be listed too). For drivers that shard the individuals of a generation over
@@ -150,8 +157,23 @@ typedef struct psim_emit_targets {
     void* dose;            /* u8 dose per individual: _alleledose.dat, Main.writeAlleledoseFile */
     int64_t dose_pitch;
     int32_t dose_which;    /* with codes: MAX/MIN_ALLELE or the name of founder allele `which`; */
-    int32_t reserved;      /*   without codes: founder allele `which` (Main.java:402-418,987-1015) */
+    int32_t flags;         /*   without codes: founder allele `which` (Main.java:402-418,987-1015). flags: PSIM_EMIT_* */
 } psim_emit_targets;
+
+/* psim_emit_targets.flags (0 = u8 / u16 tables, the call returns when the tables are complete). */
+#define PSIM_EMIT_ASYNC 0x1   /* device targets: return once the work is enqueued on the context's stream; the tables are
+                                 complete after psim_wait (or any later call on the context that waits for the stream) */
+#define PSIM_EMIT_PACKED4 0x2 /* founder and dose tables hold TWO 4-bit cells per byte (cell 2k in the low, 2k+1 in the high
+                                 nibble; pitches in bytes; a row's last byte is zero-padded when the cell count is odd):
+                                 needs <= 16 founder alleles, ploidy <= 14 and no allele table. Halves the bytes written
+                                 to HBM and sent over PCIe for the same genotype calls */
+/* Which emission kernels serve the call: PSIM_PATH_AUTO picks; the others are for tests and measurements (a request
+ * the chosen kernels cannot serve falls through to the generic ones). */
+#define PSIM_PATH_AUTO 0
+#define PSIM_PATH_ROWS 1
+#define PSIM_PATH_TILES 2
+#define PSIM_PATH_GENERIC 3
+#define PSIM_EMIT_PATH(p) ((p) << 8)
 
 int psim_emit(psim_ctx* ctx, int64_t ind_first, int64_t ind_count, int64_t locus_first,
               int64_t locus_count, const psim_emit_targets* targets);

@@ -3,8 +3,9 @@
 The product is the C-ABI CUDA library libpsim.so (include/psim.h); this package is its thin
 Python binding plus the sharding helpers the benchmark uses. No CPU fallback exists.
 """
-from ._lib import (DOSE_MAX_ALLELE, DOSE_MIN_ALLELE, MEM_DEVICE, MEM_HOST, PSIM_ECAPACITY, PSIM_ECUDA, PSIM_EINVAL, PSIM_ESTATE,
-                   EmitTargets, PsimContext, PsimError, TextTargets, load)
+from ._lib import (DOSE_MAX_ALLELE, DOSE_MIN_ALLELE, EMIT_ASYNC, EMIT_PACKED4, MEM_DEVICE, MEM_HOST, PATH_AUTO, PATH_GENERIC,
+                   PATH_ROWS, PATH_TILES, PSIM_ECAPACITY, PSIM_ECUDA, PSIM_EINVAL, PSIM_ESTATE, EmitTargets, PsimContext,
+                   PsimError, TextTargets, emit_path, load)
 
 __all__ = ["PsimContext", "PsimError", "EmitTargets", "load", "DOSE_MAX_ALLELE", "DOSE_MIN_ALLELE", "MEM_HOST",
-           "MEM_DEVICE"]
+           "MEM_DEVICE", "EMIT_ASYNC", "EMIT_PACKED4", "PATH_AUTO", "PATH_ROWS", "PATH_TILES", "PATH_GENERIC", "emit_path"]

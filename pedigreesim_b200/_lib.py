@@ -9,11 +9,19 @@ import os
 import numpy as np
 
 PKG = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.environ.get("PSIM_LIB", os.path.join(PKG, "libpsim.so"))  # PSIM_LIB: tuning builds only
+LIB_PATH = os.path.join(PKG, "libpsim.so")
+if os.environ.get("PSIM_TUNING_LIB"):   # experiments under tools/ only: a differently built library (profiles/README.md)
+    LIB_PATH = os.environ["PSIM_TUNING_LIB"]
 
 PSIM_OK, PSIM_EINVAL, PSIM_ECUDA, PSIM_ECAPACITY, PSIM_ESTATE = 0, 1, 2, 3, 4
 DOSE_MIN_ALLELE, DOSE_MAX_ALLELE = -1, -2
 MEM_HOST, MEM_DEVICE = 0, 1
+EMIT_ASYNC, EMIT_PACKED4 = 0x1, 0x2
+PATH_AUTO, PATH_ROWS, PATH_TILES, PATH_GENERIC = 0, 1, 2, 3
+
+
+def emit_path(p):
+    return p << 8
 
 
 class PsimError(RuntimeError):
@@ -35,7 +43,7 @@ class EmitTargets(C.Structure):
     _fields_ = [
         ("founder", C.c_void_p), ("founder_pitch", C.c_int64), ("founder_bytes", C.c_int32), ("memory", C.c_int32),
         ("allele", C.c_void_p), ("allele_pitch", C.c_int64),
-        ("dose", C.c_void_p), ("dose_pitch", C.c_int64), ("dose_which", C.c_int32), ("reserved", C.c_int32),
+        ("dose", C.c_void_p), ("dose_pitch", C.c_int64), ("dose_which", C.c_int32), ("flags", C.c_int32),
     ]
 
 
@@ -71,7 +79,7 @@ EXPORTS = [
     "psim_set_map", "psim_set_allele_codes", "psim_emit", "psim_all_dose_rows", "psim_emit_all_dose", "psim_get_stats",
     "psim_export_haplostructs_device", "psim_import_haplostructs_device", "psim_reset", "psim_set_stream", "psim_simulate_subset",
     "psim_alloc_host", "psim_free_host", "psim_set_locus_names", "psim_set_allele_names", "psim_emit_text",
-    "psim_gamete_stats_run", "psim_emit_all_dose_text",
+    "psim_gamete_stats_run", "psim_emit_all_dose_text", "psim_simulate_async", "psim_wait",
 ]
 
 _lib = None
@@ -98,6 +106,8 @@ def load():
     L.psim_set_haplostructs.argtypes = [vp, u32, i64, i64, vp, vp, vp]
     L.psim_simulate.argtypes = [vp, i32]
     L.psim_simulate_subset.argtypes = [vp, i32, vp, i64]
+    L.psim_simulate_async.argtypes = [vp, i32]
+    L.psim_wait.argtypes = [vp]
     L.psim_segment_count.argtypes = [vp, u32, i64, i64, C.POINTER(i64)]
     L.psim_get_haplostructs.argtypes = [vp, u32, i64, i64, vp, vp, vp]
     L.psim_get_meiotic_configs.argtypes = [vp, u32, i64, i64, vp, vp]
@@ -212,6 +222,13 @@ class PsimContext:
     def simulate(self, maxfounderallele=-1):
         self._chk(self.L.psim_simulate(self.h, maxfounderallele))
 
+    def simulate_async(self, maxfounderallele=-1):
+        """Enqueue the simulation and return; wait() (or the next call that needs the population) completes it."""
+        self._chk(self.L.psim_simulate_async(self.h, maxfounderallele))
+
+    def wait(self):
+        self._chk(self.L.psim_wait(self.h))
+
     def simulate_subset(self, individuals, maxfounderallele=-1):
         ind = np.ascontiguousarray(individuals, dtype=np.int32)
         self._chk(self.L.psim_simulate_subset(self.h, maxfounderallele, _p(ind), len(ind)))
@@ -237,8 +254,9 @@ class PsimContext:
 
     # --- seam B
     def emit(self, founder=False, allele=False, dose=False, dose_which=0, ind_first=0, ind_count=None, loc_first=0,
-             loc_count=None, founder_bytes=1):
-        """Emit into fresh host arrays; returns a dict of the requested tables ([loci][columns])."""
+             loc_count=None, founder_bytes=1, packed=False, path=PATH_AUTO):
+        """Emit into fresh host arrays; returns a dict of the requested tables ([loci][columns]).
+        packed: two 4-bit cells per byte (EMIT_PACKED4), rows of ceil(columns / 2) bytes."""
         ind_count = self.N - ind_first if ind_count is None else ind_count
         loc_count = self.Ltot - loc_first if loc_count is None else loc_count
         q = self.R * ind_count
@@ -247,18 +265,21 @@ class PsimContext:
         t.memory = MEM_HOST
         t.dose_which = dose_which
         t.founder_bytes = founder_bytes
+        t.flags = (EMIT_PACKED4 if packed else 0) | emit_path(path)
         if founder:
-            out["founder"] = np.zeros((loc_count, q * self.P), dtype=np.uint8 if founder_bytes == 1 else np.uint16)
+            cols = (q * self.P + 1) // 2 if packed else q * self.P
+            out["founder"] = np.zeros((loc_count, cols), dtype=np.uint8 if founder_bytes == 1 else np.uint16)
             t.founder = out["founder"].ctypes.data
-            t.founder_pitch = q * self.P * founder_bytes
+            t.founder_pitch = cols * founder_bytes
         if allele:
             out["allele"] = np.zeros((loc_count, q * self.P), dtype=np.uint8)
             t.allele = out["allele"].ctypes.data
             t.allele_pitch = q * self.P
         if dose:
-            out["dose"] = np.zeros((loc_count, q), dtype=np.uint8)
+            cols = (q + 1) // 2 if packed else q
+            out["dose"] = np.zeros((loc_count, cols), dtype=np.uint8)
             t.dose = out["dose"].ctypes.data
-            t.dose_pitch = q
+            t.dose_pitch = cols
         self._chk(self.L.psim_emit(self.h, ind_first, ind_count, loc_first, loc_count, C.byref(t)))
         return out
 

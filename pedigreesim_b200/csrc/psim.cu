@@ -149,6 +149,7 @@ struct psim_ctx_impl {
         int units_per_block = 0;
         bool pending = false;
     } run;
+    bool emit_pending = false, emit_pending_device = false;   // an asynchronous psim_emit has not been waited for
     bool fresh = false;   // no individual has a haplostruct (after psim_set_pedigree / psim_reset)
     bool check_reps = false;            // psim_set_haplostructs was called: replicate coverage to be verified
     std::vector<int32_t> founder_idx;   // founders of the pedigree, ascending
@@ -160,6 +161,7 @@ struct psim_ctx_impl {
 #define CTX ((psim_ctx_impl*)ctx)
 
 int fail(psim_ctx_impl* c, int code, const std::string& msg) { c->err = msg; return code; }
+int settle(psim_ctx_impl* c);
 
 #define CUDA_TRY(call)                                                                         \
     do {                                                                                       \
@@ -265,50 +267,58 @@ void launch_tiles(psim_ctx_impl* c, const EmitArgs& ea, int blocks, int mode) {
     cudaEventRecord(next_kev(c), c->stream);
     k_emit_dense<P, G><<<c->sm_count * 4, EMIT_THREADS, 0, c->stream>>>(ea);
 }
-// Row-image emission (k_band_plan + k_emit_rows) of loci [l_begin, l_end). Returns PSIM_OK and sets
-// `done` when the request fits the path; otherwise leaves `done` false for the tiled / generic paths.
+// Row-image emission (k_band_plan + k_emit_rows) of loci [l_begin, l_end). Sets `done` when the request
+// fits the path; otherwise leaves it false for the tiled / generic paths. Nothing is read back: units
+// whose run-start list overflows are listed on the device and redone by k_emit_rows_overflow.
 template <int DK>
-static void launch_rows(psim_ctx_impl* c, const RowsArgs& ra, int blocks, int threads, size_t smem) {
+static void launch_rows(psim_ctx_impl* c, const RowsArgs& ra, int blocks, size_t smem) {
     cudaFuncSetAttribute(k_emit_rows<DK>, cudaFuncAttributeMaxDynamicSharedMemorySize, ROWS_SMEM);
-    k_emit_rows<DK><<<blocks, threads, smem, c->stream>>>(ra);
+    k_emit_rows<DK><<<blocks, ROWS_THREADS, smem, c->stream>>>(ra);
 }
+#ifdef PSIM_TUNING
+static int tuning_int(const char* name) { const char* v = getenv(name); return v ? atoi(v) : 0; }
+#else
+static int tuning_int(const char*) { return 0; }   // the knobs exist in tuning builds only (-DPSIM_TUNING)
+#endif
 
 static int emit_rows_path(psim_ctx_impl* c, int64_t ind_first, int64_t ind_count, int64_t l_begin, int64_t l_end, int64_t row0_locus,
-                          uint8_t* founder, int64_t founder_pitch, uint8_t* dose, int64_t dose_pitch, int dose_which, int mode,
-                          bool& done) {
+                          uint8_t* founder, int64_t founder_pitch, uint8_t* dose, int64_t dose_pitch, int dose_mode, int dose_which, int mode,
+                          int path, bool& done) {
     done = false;
-    static const bool disabled = getenv("PSIM_NO_ROWS") != nullptr;
     const int P = c->P;
-    if (disabled || !(mode == 0 || (mode == 1 && (P == 2 || P == 4)))) return PSIM_OK;
+    if (path == PSIM_PATH_TILES || path == PSIM_PATH_GENERIC || !(mode == 0 || (mode == 1 && (P == 2 || P == 4)))) return PSIM_OK;
     const int DK = !dose ? 0 : mode == 0 ? 1 : P == 4 ? 2 : 3;
     const int64_t n_cols_ind = (int64_t)c->R * ind_count, n_cols = n_cols_ind * P;
-    // tuning knobs (experiments only): list capacity, threads per block, widest row segment
-    static const int env_cap = getenv("PSIM_ROWS_CAP") ? atoi(getenv("PSIM_ROWS_CAP")) : 0;
-    static const int env_thr = getenv("PSIM_ROWS_THREADS") ? atoi(getenv("PSIM_ROWS_THREADS")) : 0;
-    static const int64_t env_seg = getenv("PSIM_SEG_MAX") ? atoll(getenv("PSIM_SEG_MAX")) : 0;
+    static const int env_cap = tuning_int("PSIM_ROWS_CAP");
+    static const int64_t env_seg = tuning_int("PSIM_SEG_MAX");
+    static const int env_band = tuning_int("PSIM_BAND_ROWS");
+    static const int env_units = tuning_int("PSIM_ROWS_UNITS");
     const int cap = env_cap > 0 ? env_cap : 8192;
-    const int threads = env_thr >= 64 && env_thr <= ROWS_THREADS ? env_thr / 32 * 32 : ROWS_THREADS;
     const double per_cell = (double)ROWS_NBUF + (DK >= 2 ? 0.5 : 0.0) + (DK >= 1 ? (double)ROWS_NBUF : 0.0) / P;
     const int64_t budget = ROWS_SMEM - 2 * (ROWS_MAX_BAND + 2) * 4 - cap * 4;
     const int64_t quantum = 16 * P;
     int64_t seg_max = (int64_t)(budget / per_cell) / quantum * quantum;
     seg_max = std::min<int64_t>(seg_max, 65535 / quantum * quantum);
     if (env_seg > 0) seg_max = std::max<int64_t>(quantum, std::min<int64_t>(seg_max, env_seg / quantum * quantum));
-    const int n_seg = (int)((n_cols + seg_max - 1) / seg_max);
-    const int64_t seg_cells = ((n_cols + n_seg - 1) / n_seg + quantum - 1) / quantum * quantum;
     // run starts per cell and row, from the resident haplostructs (as in the tiled path)
     const double seg_per_hom = c->n_hom > 0 ? (double)c->slab_used / (double)c->n_hom : 1.0;
     const double loci_per_chrom = std::max(1.0, (double)c->L / c->C);
     const double starts_per_cell = std::max(0.0, seg_per_hom - 1.0) / loci_per_chrom;
-    static const int env_band = getenv("PSIM_BAND_ROWS") ? atoi(getenv("PSIM_BAND_ROWS")) : 0;
-    static const int env_bps = getenv("PSIM_ROWS_BLOCKS_PER_SM") ? atoi(getenv("PSIM_ROWS_BLOCKS_PER_SM")) : 0;
-    const int n_blocks = c->sm_count * (env_bps > 0 ? env_bps : 1);
-    // band height: one unit per resident block when the request is large, never so tall that a unit's
-    // expected run starts come near the list capacity
+    // A coarse map over many columns has many run starts per row: the row segment is then made
+    // narrower, so that a band of at least 16 rows keeps its expected run starts within half the list
+    // (a narrow segment still leaves the SM as one bulk store per row; below 4 KB the path is not taken).
+    // PSIM_PATH_ROWS takes the path as it is: lists that overflow are redone per cell.
+    const int min_band = 16;
+    if (path != PSIM_PATH_ROWS && starts_per_cell * (double)seg_max * min_band > cap / 2) {
+        const int64_t fit = (int64_t)((cap / 2) / (starts_per_cell * min_band)) / quantum * quantum;
+        if (fit < 4096) return PSIM_OK;   // sparse map: tiled / dense path
+        seg_max = std::min(seg_max, fit);
+    }
+    const int n_seg = (int)((n_cols + seg_max - 1) / seg_max);
+    const int64_t seg_cells = ((n_cols + n_seg - 1) / n_seg + quantum - 1) / quantum * quantum;
+    const int n_blocks = c->sm_count;
     // tallest band whose expected run starts stay within half the list capacity
     const double per_row = starts_per_cell * (double)seg_cells;
-    const bool forced = getenv("PSIM_ROWS_FORCE") != nullptr;   // test knob: take this path even if lists will overflow
-    if (!forced && per_row * 8.0 > cap / 2) return PSIM_OK;      // sparse map: tiled / dense path
     const int64_t band_cap = env_band > 0 ? std::min(env_band, ROWS_MAX_BAND)
                            : std::max<int64_t>(8, std::min<int64_t>(ROWS_MAX_BAND, per_row > 0 ? (int64_t)((cap / 2) / per_row) : ROWS_MAX_BAND));
 
@@ -325,6 +335,8 @@ static int emit_rows_path(psim_ctx_impl* c, int64_t ind_first, int64_t ind_count
     ra.unit_counter = c->tile_counter_d;
     const size_t smem = ROWS_NBUF * (size_t)seg_cells + (DK >= 2 ? seg_cells / 2 : 0) + (size_t)(DK >= 1 ? ROWS_NBUF : 0) * (seg_cells / P) +
                         (size_t)cap * 4 + 2 * (ROWS_MAX_BAND + 2) * 4;
+    RowsOverflowArgs oa{};
+    oa.dose_mode = dose_mode; oa.code = c->code_d; oa.match_code = c->match_d; oa.A = c->A;
     int k0 = 0;
     while (k0 < c->C && c->locus_off_h[k0 + 1] <= l_begin) k0++;
     while (k0 < c->C && c->locus_off_h[k0] < l_end) {
@@ -341,7 +353,10 @@ static int emit_rows_path(psim_ctx_impl* c, int64_t ind_first, int64_t ind_count
         if (ra.n_chunks == 0) break;
         {   // Bands per chromosome piece: proportional to its rows, largest remainders get the extra
             // band. The total is the smallest one (tallest bands) whose units fill whole waves of
-            // resident blocks; no band is taller than band_cap.
+            // resident blocks; no band is taller than band_cap. (Handing the last rows out in many short
+            // bands so that fast blocks take more was tried - tools/exp_tail.sh - and does not pay: the
+            // blocks of a launch end 163-216 us after its start, but their sum is what the memory system
+            // takes; a block that ends early only leaves its share to the others.)
             int64_t total = 0;
             for (int q = 0; q < ra.n_chunks; q++) total += ra.chunk_l1[q] - ra.chunk_l0[q];
             auto allocate = [&](int64_t target) -> int64_t {
@@ -377,7 +392,6 @@ static int emit_rows_path(psim_ctx_impl* c, int64_t ind_first, int64_t ind_count
                 if (eff > best_eff + 1e-9) { best_eff = eff; best_t = tg; }
                 if (env_band > 0 || (best_eff >= 0.97 && tg >= best_t + 8)) break;   // good enough; look a little further for a full wave
             }
-            static const int env_units = getenv("PSIM_ROWS_UNITS") ? atoi(getenv("PSIM_ROWS_UNITS")) : 0;   // tuning knob: bands per launch
             if (env_units > 0) best_t = std::max<int64_t>(t_min, env_units);
             allocate(best_t);
             for (int q = 0; q < ra.n_chunks; q++) ra.chunk_unit_base[q + 1] = ra.chunk_unit_base[q] + ra.chunk_bands[q] * n_seg;
@@ -390,50 +404,18 @@ static int emit_rows_path(psim_ctx_impl* c, int64_t ind_first, int64_t ind_count
         // list counters, overflow count and ticket: one small kernel (a 2-D memset is a copy-engine job
         // and queues behind the PCIe copy of the previous chunk)
         k_rows_reset<<<grid_for(ra.n_units + 2, 256), 256, 0, c->stream>>>(ra.plan, ra.plan_stride, ra.n_units, ra.overflow, c->tile_counter_d);
-        c->stats.kernel_launches++;
         k_band_plan<<<dim3((unsigned)((n_cols + 255) / 256), (unsigned)ra.n_chunks), 256, 0, c->stream>>>(ra);
         cudaEventRecord(next_kev(c), c->stream);
         const int blocks = std::min(ra.n_units, n_blocks);
-        if (DK == 0) launch_rows<0>(c, ra, blocks, threads, smem);
-        else if (DK == 1) launch_rows<1>(c, ra, blocks, threads, smem);
-        else if (DK == 2) launch_rows<2>(c, ra, blocks, threads, smem);
-        else launch_rows<3>(c, ra, blocks, threads, smem);
+        if (DK == 0) launch_rows<0>(c, ra, blocks, smem);
+        else if (DK == 1) launch_rows<1>(c, ra, blocks, smem);
+        else if (DK == 2) launch_rows<2>(c, ra, blocks, smem);
+        else launch_rows<3>(c, ra, blocks, smem);
         cudaEventRecord(next_kev(c), c->stream);
-        c->stats.kernel_launches += 2;
+        k_emit_rows_overflow<<<dim3((unsigned)c->sm_count, 8), 256, 0, c->stream>>>(ra, oa);
+        c->stats.kernel_launches += 4;
         c->stats.emit_kernel_launches++;
         CUDA_TRY(cudaGetLastError());
-        // units whose run-start list overflowed (not expected with the band heuristic): searched per cell
-        c->scalars_h[2] = 0;
-        k_publish<<<1, 32, 0, c->stream>>>(c->scalars_dev, nullptr, nullptr, ra.overflow);
-        c->stats.kernel_launches++;
-        CUDA_TRY(cudaStreamSynchronize(c->stream));
-        const int n_over = (int)c->scalars_h[2];
-        if (n_over > 0) {
-            std::vector<int> units((size_t)n_over);
-            CUDA_TRY(cudaMemcpy(units.data(), ra.overflow + 1, (size_t)n_over * sizeof(int), cudaMemcpyDeviceToHost));
-            for (int u : units) {
-                int k = 0;
-                while (u >= ra.chunk_unit_base[k + 1]) k++;
-                const int j = (u - ra.chunk_unit_base[k]) / n_seg, sg = (u - ra.chunk_unit_base[k]) % n_seg;
-                const int64_t len = ra.chunk_l1[k] - ra.chunk_l0[k];
-                const int64_t g0 = ra.chunk_l0[k] + len * j / ra.chunk_bands[k], g1 = ra.chunk_l0[k] + len * (j + 1) / ra.chunk_bands[k];
-                EmitGenericArgs ga{};
-                ga.C = c->C; ga.R = c->R; ga.P = P; ga.N = c->N;
-                ga.run_desc = c->run_desc_d; ga.run_lb = c->run_lb_d; ga.run_founder = c->run_founder_d;
-                ga.locus_off = c->locus_off_d;
-                ga.ind_first = ind_first; ga.ind_count = ind_count; ga.n_cols_ind = n_cols_ind;
-                ga.locus_first = row0_locus; ga.l_begin = g0; ga.l_count = g1 - g0;
-                ga.q_first = (int64_t)sg * (seg_cells / P);
-                ga.q_count = std::min<int64_t>(seg_cells / P, n_cols_ind - ga.q_first);
-                ga.founder = founder; ga.founder_pitch = founder_pitch; ga.founder_bytes = 1;
-                ga.dose = dose; ga.dose_pitch = dose_pitch;
-                ga.dose_mode = mode == 0 ? 0 : 1; ga.dose_which = dose_which;
-                ga.code = c->code_d; ga.match_code = c->match_d; ga.A = c->A;
-                k_emit_generic<<<grid_for(ga.l_count * ga.q_count, 256), 256, 0, c->stream>>>(ga);
-                c->stats.kernel_launches++;
-                CUDA_TRY(cudaGetLastError());
-            }
-        }
     }
     done = true;
     return PSIM_OK;
@@ -581,6 +563,7 @@ int psim_set_pedigree(psim_ctx* ctx, int64_t n_ind, const int32_t* parent0, cons
     if (c->C == 0) return fail(c, PSIM_ESTATE, "psim_set_chromosomes must be called first");
     if (n_ind > INT32_MAX) return fail(c, PSIM_EINVAL, "more than 2^31-1 individuals");
     cudaSetDevice(c->cfg.device);
+    if (int rc = settle(c)) return rc;
     int nf = 0;
     for (int64_t i = 0; i < n_ind; i++) {
         const bool f0 = parent0[i] < 0, f1 = parent1[i] < 0;
@@ -638,6 +621,7 @@ int psim_set_haplostructs(psim_ctx* ctx, uint32_t replicate, int64_t first, int6
     if (replicate < c->cfg.replicate_first || replicate >= c->cfg.replicate_first + c->cfg.replicate_count)
         return fail(c, PSIM_EINVAL, "replicate not held by this context");
     cudaSetDevice(c->cfg.device);
+    if (int rc = settle(c)) return rc;
     const int r = (int)(replicate - c->cfg.replicate_first);
     const int64_t nh = count * c->C * c->P;
     const int64_t nseg = seg_off[nh];
@@ -927,7 +911,7 @@ static int sim_finish(psim_ctx_impl* c) {
 }
 
 static int simulate_impl(psim_ctx_impl* c, int32_t max_founder_allele, const int32_t* subset, int64_t n_subset) {
-    if (int rc = sim_finish(c)) return rc;
+    if (int rc = settle(c)) return rc;
     if (int rc = sim_begin(c, max_founder_allele, subset, n_subset)) return rc;
     return sim_finish(c);
 }
@@ -936,6 +920,20 @@ int psim_simulate(psim_ctx* ctx, int32_t max_founder_allele) {
     psim_ctx_impl* c = CTX;
     if (!c) return PSIM_EINVAL;
     return simulate_impl(c, max_founder_allele, nullptr, 0);
+}
+
+int psim_simulate_async(psim_ctx* ctx, int32_t max_founder_allele) {
+    psim_ctx_impl* c = CTX;
+    if (!c) return PSIM_EINVAL;
+    if (int rc = settle(c)) return rc;
+    return sim_begin(c, max_founder_allele, nullptr, 0);
+}
+
+int psim_wait(psim_ctx* ctx) {
+    psim_ctx_impl* c = CTX;
+    if (!c) return PSIM_EINVAL;
+    cudaSetDevice(c->cfg.device);
+    return settle(c);
 }
 
 int psim_simulate_subset(psim_ctx* ctx, int32_t max_founder_allele, const int32_t* individuals, int64_t count) {
@@ -947,6 +945,7 @@ int psim_simulate_subset(psim_ctx* ctx, int32_t max_founder_allele, const int32_
 }
 
 static int check_range(psim_ctx_impl* c, uint32_t replicate, int64_t first, int64_t count, int& r) {
+    if (int rc = settle(c)) return rc;
     if (c->N == 0) return fail(c, PSIM_ESTATE, "psim_set_pedigree must be called first");
     if (first < 0 || count <= 0 || first + count > c->N) return fail(c, PSIM_EINVAL, "individual range out of bounds");
     if (replicate < c->cfg.replicate_first || replicate >= c->cfg.replicate_first + c->cfg.replicate_count)
@@ -1018,6 +1017,7 @@ int psim_get_meiotic_configs(psim_ctx* ctx, uint32_t replicate, int64_t first, i
     psim_ctx_impl* c = CTX;
     if (!c || !quad || !chromseq) return PSIM_EINVAL;
     cudaSetDevice(c->cfg.device);
+    if (int rc = settle(c)) return rc;
     if (c->N == 0) return fail(c, PSIM_ESTATE, "psim_set_pedigree must be called first");
     if (first < 0 || count <= 0 || first + count > c->N) return fail(c, PSIM_EINVAL, "individual range out of bounds");
     if (replicate < c->cfg.replicate_first || replicate >= c->cfg.replicate_first + c->cfg.replicate_count)
@@ -1039,6 +1039,7 @@ int psim_set_map(psim_ctx* ctx, const int64_t* locus_off, const double* pos) {
     if (!c || !locus_off || !pos) return PSIM_EINVAL;
     if (c->C == 0) return fail(c, PSIM_ESTATE, "psim_set_chromosomes must be called first");
     cudaSetDevice(c->cfg.device);
+    if (int rc = settle(c)) return rc;
     if (locus_off[0] != 0) return fail(c, PSIM_EINVAL, "locus_off[0] must be 0");
     for (int k = 0; k < c->C; k++) {
         if (locus_off[k + 1] < locus_off[k]) return fail(c, PSIM_EINVAL, "locus_off must be non-decreasing");
@@ -1068,6 +1069,7 @@ int psim_set_allele_codes(psim_ctx* ctx, int32_t n_alleles, const uint8_t* code)
     if (!c) return PSIM_EINVAL;
     if (c->L == 0) return fail(c, PSIM_ESTATE, "psim_set_map must be called first");
     cudaSetDevice(c->cfg.device);
+    if (int rc = settle(c)) return rc;
     cudaFree(c->code_d); cudaFree(c->match_d); cudaFree(c->code16_d); cudaFree(c->nibmask_d); cudaFree(c->mtab_d);
     c->code_d = nullptr; c->match_d = nullptr; c->code16_d = nullptr; c->nibmask_d = nullptr; c->mtab_d = nullptr;
     c->A = 0; c->code_h.clear(); c->match_which = 12345678;
@@ -1113,7 +1115,7 @@ static int ensure_staging(psim_ctx_impl* c, size_t bytes) {
 // Emit loci [l_begin, l_end) (global) into device tables whose row 0 is locus `row0_locus`.
 static int emit_device(psim_ctx_impl* c, int64_t ind_first, int64_t ind_count, int64_t l_begin, int64_t l_end, int64_t row0_locus,
                        void* founder, int64_t founder_pitch, int founder_bytes, uint8_t* allele, int64_t allele_pitch,
-                       uint8_t* dose, int64_t dose_pitch, int dose_mode, int dose_which) {
+                       uint8_t* dose, int64_t dose_pitch, int dose_mode, int dose_which, int path = PSIM_PATH_AUTO) {
     const int P = c->P;
     const int64_t n_cols_ind = (int64_t)c->R * ind_count;
     int G = 0;
@@ -1123,15 +1125,16 @@ static int emit_device(psim_ctx_impl* c, int64_t ind_first, int64_t ind_count, i
                          (!dose || ((uintptr_t)dose % 16 == 0 && dose_pitch % 16 == 0));
     const int64_t max_pitch = (int64_t)1 << 25;   // row offsets inside a tile are 32-bit (64 rows)
     const bool small_pitch = founder_pitch < max_pitch && allele_pitch < max_pitch && dose_pitch < max_pitch;
-    const bool tiled = G != 0 && aligned && small_pitch && founder_bytes == 1 && c->founder_allele_count <= 256 &&
-                       c->run_cap < (int64_t)0xFFFFFFFF;
+    bool tiled = G != 0 && aligned && small_pitch && founder_bytes == 1 && c->founder_allele_count <= 256 &&
+                 c->run_cap < (int64_t)0xFFFFFFFF;
     if (tiled && !allele && (founder || dose)) {
         bool done = false;
         const int mode0 = !c->code_d ? 0 : c->A <= 8 ? 1 : c->A <= 16 ? 2 : 3;
         if (int rc = emit_rows_path(c, ind_first, ind_count, l_begin, l_end, row0_locus, (uint8_t*)founder, founder_pitch, dose, dose_pitch,
-                                    dose_which, mode0, done)) return rc;
+                                    dose_mode, dose_which, mode0, path, done)) return rc;
         if (done) return PSIM_OK;
     }
+    if (path == PSIM_PATH_GENERIC) tiled = false;
     if (tiled) {
         EmitArgs ea{};
         ea.C = c->C; ea.R = c->R; ea.P = P; ea.N = c->N;
@@ -1139,8 +1142,8 @@ static int emit_device(psim_ctx_impl* c, int64_t ind_first, int64_t ind_count, i
         ea.locus_off = c->locus_off_d;
         ea.ind_first = ind_first; ea.ind_count = ind_count; ea.n_cols_ind = n_cols_ind;
         ea.locus_first = row0_locus;
-        static const int env_tile = getenv("PSIM_TILE_LOCI") ? atoi(getenv("PSIM_TILE_LOCI")) : 0;       // tuning knobs
-        static const int env_bps = getenv("PSIM_BLOCKS_PER_SM") ? atoi(getenv("PSIM_BLOCKS_PER_SM")) : 0;
+        static const int env_tile = tuning_int("PSIM_TILE_LOCI");
+        static const int env_bps = tuning_int("PSIM_BLOCKS_PER_SM");
         {   // rows per tile: as tall as possible (the plan is read once per tile) while a warp's expected
             // number of run starts per tile stays far below EMIT_EV
             const double seg_per_hom = c->n_hom > 0 ? (double)c->slab_used / (double)c->n_hom : 1.0;
@@ -1220,7 +1223,38 @@ static int emit_device(psim_ctx_impl* c, int64_t ind_first, int64_t ind_count, i
     return PSIM_OK;
 }
 
+// device times of the last emission from the events recorded around its kernels (after the stream has been waited for)
+static void emit_times(psim_ctx_impl* c, bool device_targets) {
+    float ms_total = 0.f, ms_kernel = 0.f;
+    cudaEventElapsedTime(&ms_total, c->ev0, c->ev1);
+    for (int i = device_targets ? 0 : 2; i + 1 < c->kev_used; i += 2) {
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, c->kev[i], c->kev[i + 1]);
+        ms_kernel += ms;
+    }
+    c->stats.ms_emit_kernel = ms_kernel;
+    c->stats.ms_emit_total = ms_total;
+    c->stats.ms_emit_plan = 0.0;
+}
+}  // extern "C"
+namespace {
+// Completes what psim_simulate_async / an asynchronous psim_emit left running. Every entry point that
+// reads or changes the population calls it first.
+int settle(psim_ctx_impl* c) {
+    int rc = sim_finish(c);
+    if (c->emit_pending) {
+        cudaError_t e = cudaStreamSynchronize(c->stream);
+        c->emit_pending = false;
+        if (e != cudaSuccess) return fail(c, PSIM_ECUDA, std::string("asynchronous emission: ") + cudaGetErrorString(e));
+        emit_times(c, c->emit_pending_device);
+    }
+    return rc;
+}
+}  // namespace
+extern "C" {
+
 static int emit_prepare(psim_ctx_impl* c, int64_t ind_first, int64_t ind_count, int64_t locus_first, int64_t locus_count) {
+    if (int rc = settle(c)) return rc;
     if (c->N == 0) return fail(c, PSIM_ESTATE, "psim_set_pedigree must be called first");
     if (c->L == 0) return fail(c, PSIM_ESTATE, "psim_set_map must be called first");
     if (ind_first < 0 || ind_count <= 0 || ind_first + ind_count > c->N) return fail(c, PSIM_EINVAL, "individual range out of bounds");
@@ -1262,13 +1296,16 @@ int psim_emit(psim_ctx* ctx, int64_t ind_first, int64_t ind_count, int64_t locus
     c->stats.emit_kernel_launches = 0;
     c->kev_used = 0;
     CUDA_TRY(cudaEventRecord(c->ev0, c->stream));
+    const int path = (t->flags >> 8) & 3;
     if (t->memory == PSIM_MEM_DEVICE) {
         if (int rc = emit_device(c, ind_first, ind_count, locus_first, locus_first + locus_count, locus_first, t->founder,
                                  t->founder_pitch, fb, (uint8_t*)t->allele, t->allele_pitch, (uint8_t*)t->dose, t->dose_pitch,
-                                 dose_mode, dose_which)) return rc;
+                                 dose_mode, dose_which, path)) return rc;
         CUDA_TRY(cudaEventRecord(c->ev1, c->stream));
+        if (t->flags & PSIM_EMIT_ASYNC) { c->emit_pending = true; c->emit_pending_device = true; return PSIM_OK; }
         CUDA_TRY(cudaStreamSynchronize(c->stream));
     } else {
+        if (t->flags & PSIM_EMIT_ASYNC) return fail(c, PSIM_EINVAL, "PSIM_EMIT_ASYNC needs device targets (PSIM_MEM_DEVICE)");
         // Host targets: locus chunks are emitted into one of two device slots and copied out on a
         // second stream while the next chunk is computed. A table whose host pitch is not 16-byte
         // aligned is written with an aligned pitch and repacked on the device (2-D device copy),
@@ -1300,7 +1337,7 @@ int psim_emit(psim_ctx* ctx, int64_t ind_first, int64_t ind_count, int64_t locus
         if (int rc = ensure_staging(c, (size_t)(2 * slot_bytes))) return rc;
         cudaEvent_t ready[2] = {c->ev2, c->ev3};
         cudaEvent_t freed[2] = {next_kev(c), next_kev(c)};
-        static const bool trace = getenv("PSIM_TRACE") != nullptr;
+        static const bool trace = tuning_int("PSIM_TRACE") != 0;
         std::vector<cudaEvent_t> tev;
         int k = 0;
         // the first chunk is short so that the PCIe link starts early
@@ -1322,7 +1359,7 @@ int psim_emit(psim_ctx* ctx, int64_t ind_first, int64_t ind_count, int64_t locus
             if (k >= 2) CUDA_TRY(cudaStreamWaitEvent(c->stream, freed[sl], 0));   // slot copied out
             if (trace) { timespec ts; clock_gettime(CLOCK_MONOTONIC, &ts); fprintf(stderr, "psim_emit chunk %d begins at host %.3f ms\n", k, ts.tv_sec * 1e3 + ts.tv_nsec * 1e-6); }
             if (int rc = emit_device(c, ind_first, ind_count, l0, l1, l0, sp[0], tab[0].spitch, fb, sp[1], tab[1].spitch,
-                                     sp[2], tab[2].spitch, dose_mode, dose_which)) return rc;
+                                     sp[2], tab[2].spitch, dose_mode, dose_which, path)) return rc;
             for (int q = 0; q < 3; q++)
                 if (dn[q]) {   // (a 2-D device copy with an unaligned pitch runs at a fraction of this kernel's pace)
                     k_repack_dense<<<c->sm_count * 8, 256, 0, c->stream>>>(sp[q], tab[q].spitch, dn[q], tab[q].width, nr);
@@ -1356,17 +1393,7 @@ int psim_emit(psim_ctx* ctx, int64_t ind_first, int64_t ind_count, int64_t locus
             for (cudaEvent_t e : tev) cudaEventDestroy(e);
         }
     }
-    float ms_total = 0.f, ms_kernel = 0.f;
-    cudaEventElapsedTime(&ms_total, c->ev0, c->ev1);
-    const int first_pair = t->memory == PSIM_MEM_DEVICE ? 0 : 2;
-    for (int i = first_pair; i + 1 < c->kev_used; i += 2) {
-        float ms = 0.f;
-        cudaEventElapsedTime(&ms, c->kev[i], c->kev[i + 1]);
-        ms_kernel += ms;
-    }
-    c->stats.ms_emit_kernel = ms_kernel;
-    c->stats.ms_emit_total = ms_total;
-    c->stats.ms_emit_plan = 0.0;
+    emit_times(c, t->memory == PSIM_MEM_DEVICE);
     return PSIM_OK;
 }
 
@@ -1753,6 +1780,7 @@ int psim_reset(psim_ctx* ctx, int64_t seed, uint32_t replicate_first) {
     if (!c) return PSIM_EINVAL;
     if (c->N == 0) return fail(c, PSIM_ESTATE, "psim_set_pedigree must be called first");
     cudaSetDevice(c->cfg.device);
+    if (int rc = settle(c)) return rc;
     c->cfg.seed = seed;
     c->cfg.replicate_first = replicate_first;
     c->model.seed = (uint64_t)seed;
@@ -1773,6 +1801,7 @@ int psim_set_stream(psim_ctx* ctx, uint64_t cuda_stream) {
     psim_ctx_impl* c = CTX;
     if (!c) return PSIM_EINVAL;
     cudaSetDevice(c->cfg.device);
+    if (int rc = settle(c)) return rc;
     cudaStreamSynchronize(c->stream);
     c->stream = cuda_stream ? (cudaStream_t)(uintptr_t)cuda_stream : c->own_stream;
     return PSIM_OK;
@@ -1825,6 +1854,7 @@ int psim_import_haplostructs_device(psim_ctx* ctx, int64_t first, int64_t count,
     psim_ctx_impl* c = CTX;
     if (!c || !in) return PSIM_EINVAL;
     cudaSetDevice(c->cfg.device);
+    if (int rc = settle(c)) return rc;
     if (c->R != 1) return fail(c, PSIM_EINVAL, "device import supports replicate_count == 1");
     if (c->N == 0) return fail(c, PSIM_ESTATE, "psim_set_pedigree must be called first");
     if (first < 0 || count <= 0 || first + count > c->N) return fail(c, PSIM_EINVAL, "individual range out of bounds");

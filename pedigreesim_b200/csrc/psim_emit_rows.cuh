@@ -69,6 +69,9 @@ __global__ void __launch_bounds__(256) k_band_plan(const RowsArgs a) {
     uint32_t f = n ? __ldg(a.run_founder + b + lo) : 0;
     uint32_t kx = lo + 1;
     uint32_t nxt = kx < n ? __ldg(a.run_lb + b + kx) : NO_EVENT;
+#ifdef PSIM_ROWS_PROFILE
+    if (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) { unsigned long long g; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(g)); printf("band plan block 0 at %llu\n", g); }
+#endif
     for (int j = 0; j < a.chunk_bands[k]; j++) {
         int64_t g0, g1;
         band_rows(a, k, j, g0, g1);
@@ -99,29 +102,38 @@ __global__ void k_rows_reset(uint8_t* plan, int64_t plan_stride, int n_units, in
     else if (u == n_units + 1) *ticket = 0;
 }
 
-constexpr int ROWS_THREADS = 512;
+constexpr int ROWS_COMPUTE = 512;                 // threads that make the rows
 constexpr int ROWS_MAX_BAND = 255;     // the row of a run start inside its band is 8 bits
 constexpr int ROWS_SMEM = 220 * 1024;  // one block per SM
 #ifndef PSIM_ROWS_NBUF
-#define PSIM_ROWS_NBUF 2
+#define PSIM_ROWS_NBUF 3
 #endif
-constexpr int ROWS_NBUF = PSIM_ROWS_NBUF;   // row buffers: NBUF-1 rows can be queued at the bulk engine while the next is made
+constexpr int ROWS_NBUF = PSIM_ROWS_NBUF;   // row buffers in flight
+constexpr int ROWS_THREADS = ROWS_COMPUTE + 32 * ROWS_NBUF;   // + one warp per row buffer that hands its rows to the bulk-copy engine
 
 __device__ __forceinline__ void bulk_store(void* gdst, const void* ssrc, uint32_t bytes) {
     asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst),
                  "r"((uint32_t)__cvta_generic_to_shared(ssrc)), "r"(bytes) : "memory");
 }
+// named barriers (0 is __syncthreads): FULL + b / EMPTY + b for row buffer b, WORK among the compute threads
+constexpr int BAR_FULL = 1, BAR_EMPTY = 1 + ROWS_NBUF, BAR_WORK = 1 + 2 * ROWS_NBUF;
+__device__ __forceinline__ void bar_sync(int id, int n) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory"); }
+__device__ __forceinline__ void bar_arrive(int id, int n) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(n) : "memory"); }
 
 // DK: how the dose row is made. 0 = no dose table, 1 = no genotypes (count of one founder allele:
 // patched like the founder row), 2 = genotypes, A <= 8, ploidy 4, 3 = genotypes, A <= 8, ploidy 2.
-// Founder and dose rows are double-buffered: while the bulk engine streams row r-1 out of one
-// buffer, row r is made in the other (copy + patch, or recomputed), so the engine always has a
-// row queued and the block never waits for the row it has just issued.
+// Warp-specialised: 512 threads make row r in buffer r % NBUF (patch the run starts of the rows the
+// buffer missed, recompute the dose row); every buffer has a warp of its own that hands its rows to
+// the bulk-copy engine and waits until they have been read. Issuing a bulk store keeps the issuing
+// WARP busy for 800-1600 cycles whatever the size of the store (measured with clock64: 10 KB dose
+// rows alone take as long to issue as 40 KB founder rows), so stores issued from one warp never
+// overlap; issued from NBUF warps they do, and none of it sits in the path of the threads that make
+// the next row.
 template <int DK>
 __global__ void __launch_bounds__(ROWS_THREADS, 1) k_emit_rows(const RowsArgs a) {
     extern __shared__ __align__(128) uint8_t smem[];
     const int tid = threadIdx.x;
-    const int NT = blockDim.x;   // ROWS_THREADS, or fewer when several narrow-segment blocks share an SM
+    const int NT = ROWS_THREADS;
     const int P = a.P;
     const int seg_cells = a.seg_cells, seg_ind = seg_cells / P;
     constexpr int NB = ROWS_NBUF;
@@ -135,8 +147,15 @@ __global__ void __launch_bounds__(ROWS_THREADS, 1) k_emit_rows(const RowsArgs a)
     const int64_t n_cols = a.n_cols_ind * P;
     const bool count_ok = a.dose_which >= 0 && a.dose_which < 256;           // DK 1: a founder allele that exists
 
+#ifdef PSIM_ROWS_PROFILE
+    long long pt[6] = {0, 0, 0, 0, 0, 0}; long long pc = clock64(); const long long p_begin = pc;
+    unsigned long long g_begin; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(g_begin));
+#define PT(k) do { if ((tid & 511) == 0) { const long long now = clock64(); pt[k] += now - pc; pc = now; } } while (0)
+#else
+#define PT(k)
+#endif
     for (;;) {
-        __syncthreads();
+        __syncthreads();   // (the issuing warp gets here only after the engine has read the last rows of the previous unit)
         if (tid == 0) s_unit = atomicAdd(a.unit_counter, 1);
         __syncthreads();
         const int u = s_unit;
@@ -153,15 +172,12 @@ __global__ void __launch_bounds__(ROWS_THREADS, 1) k_emit_rows(const RowsArgs a)
         const int n_ind = n_cell / P;
         const uint8_t* pu = a.plan + (int64_t)u * a.plan_stride;
         const uint32_t n_ev = *reinterpret_cast<const uint32_t*>(pu);
-        if (n_ev > (uint32_t)a.cap) {   // sparse map: searched per cell afterwards (k_emit_generic)
+        if (n_ev > (uint32_t)a.cap) {   // more run starts than the list holds: k_emit_rows_overflow searches per cell
             if (tid == 0) a.overflow[1 + atomicAdd(a.overflow, 1)] = u;
             continue;
         }
-        // the bulk engine must be done reading the previous unit's rows out of shared memory
-        if (tid == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
-        __syncthreads();
 
-        // ---- start state of the band, run starts bucketed by row
+        // ---- start state of the band, run starts bucketed by row (all threads)
         for (int i = tid * 16; i < seg_cells; i += NT * 16)
             *reinterpret_cast<uint4*>(img0 + i) = __ldg(reinterpret_cast<const uint4*>(pu + 16 + i));
         for (int i = tid; i <= n_rows; i += NT) start[i] = 0;
@@ -200,8 +216,6 @@ __global__ void __launch_bounds__(ROWS_THREADS, 1) k_emit_rows(const RowsArgs a)
                 dose0[i] = (uint8_t)(count_ok ? dsum : 0);
             }
         }
-        uint4 Tn = make_uint4(0, 0, 0, 0);
-        if (DK >= 2) Tn = __ldg(a.mtab + g0);
         __syncthreads();
         // the other buffers start from the same state (they become rows 1 .. NB-1)
         for (int b = 1; b < NB; b++) {
@@ -211,10 +225,45 @@ __global__ void __launch_bounds__(ROWS_THREADS, 1) k_emit_rows(const RowsArgs a)
                 for (int i = tid; i < seg_ind / 16; i += NT)
                     reinterpret_cast<uint4*>(dose0 + (size_t)b * seg_ind)[i] = reinterpret_cast<const uint4*>(dose0)[i];
         }
+        __syncthreads();
+
+        if (tid >= ROWS_COMPUTE) {
+            // ---- the issuing warp of buffer b: lane 0 sends the founder row, lane 1 the dose row, lanes 2.. the ragged ends
+            const int lane = tid & 31, b = (tid - ROWS_COMPUTE) >> 5;
+            const uint8_t* const img = img0 + (size_t)b * seg_cells;
+            const uint8_t* const drow = dose0 + (size_t)b * seg_ind;
+            for (int r = b; r < n_rows; r += NB) {
+                uint8_t* const gf = a.founder ? a.founder + (out_row0 + r) * a.founder_pitch + c0 : nullptr;
+                uint8_t* const gd = a.dose ? a.dose + (out_row0 + r) * a.dose_pitch + c0 / P : nullptr;
+                PT(0);
+                bar_sync(BAR_FULL + b, ROWS_COMPUTE + 32);
+                PT(1);
+                if (lane == 0) {
+                    if (gf && (n_cell & ~15)) bulk_store(gf, img, (uint32_t)(n_cell & ~15));
+                    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                } else if (lane == 1) {
+                    if (DK >= 1 && gd && (n_ind & ~15)) bulk_store(gd, drow, (uint32_t)(n_ind & ~15));
+                    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                } else {   // a bulk store moves multiples of 16 bytes
+                    const int t = lane - 2;
+                    if (gf && t < 15 && t < (n_cell & 15)) gf[(n_cell & ~15) + t] = img[(n_cell & ~15) + t];
+                    if (DK >= 1 && gd && t >= 15 && t - 15 < (n_ind & 15)) gd[(n_ind & ~15) + t - 15] = drow[(n_ind & ~15) + t - 15];
+                }
+                PT(2);
+                if (lane < 2) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // the engine has read the row
+                PT(3);
+                __syncwarp();
+                if (r + NB < n_rows) bar_arrive(BAR_EMPTY + b, ROWS_COMPUTE + 32);
+            }
+            continue;
+        }
 
         // ---- the rows. Buffer r % NB holds row r-NB when row r begins: it takes the run starts of rows r-NB+1 .. r.
+        constexpr int CT = ROWS_COMPUTE;
+        uint4 Tn = make_uint4(0, 0, 0, 0);
+        if (DK >= 2) Tn = __ldg(a.mtab + g0);
         auto patch = [&](uint8_t* img, uint8_t* drow, uint32_t e0, uint32_t e1) {
-            for (uint32_t e = e0 + tid; e < e1; e += NT) {
+            for (uint32_t e = e0 + tid; e < e1; e += CT) {
                 const uint32_t w = evs[e], cs = (w >> 8) & 0xFFFF, f = w & 0xFF;
                 if (DK == 1) {
                     const int delta = (int)(f == (uint32_t)a.dose_which) - (int)(count_ok && img[cs] == (uint8_t)a.dose_which);
@@ -228,33 +277,34 @@ __global__ void __launch_bounds__(ROWS_THREADS, 1) k_emit_rows(const RowsArgs a)
             const uint32_t e0 = start[r], e1 = start[r + 1];   // this row's run starts (row 0 has none: they are the state)
             uint8_t* const img = img0 + (size_t)(r % NB) * seg_cells;
             uint8_t* const drow = dose0 + (size_t)(r % NB) * seg_ind;
-            // buffers of row r were last read by the bulk stores of row r-NB
-            if (r >= NB && tid == 0) asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(NB - 1) : "memory");
-            if (DK >= 2) {
-                for (uint32_t e = e0 + tid; e < e1; e += NT) {
+            if (DK >= 2) {   // (the 4-bit image is not a store source: it can be brought to row r before the buffer is free)
+                for (uint32_t e = e0 + tid; e < e1; e += CT) {
                     const uint32_t w = evs[e], cs = (w >> 8) & 0xFFFF, sh = (cs & 7) * 4;
                     atomicAnd(&nib[cs >> 3], ~(0xFu << sh));
                     atomicOr(&nib[cs >> 3], (w & 7) << sh);
                 }
             }
-            __syncthreads();
+            PT(0);
+            if (r >= NB) bar_sync(BAR_EMPTY + r % NB, ROWS_COMPUTE + 32);   // the engine has read row r-NB out of this buffer
+            else if (DK >= 2) bar_sync(BAR_WORK, CT);
+            PT(1);
             // catch up with the rows this buffer missed, oldest first (a cell may change on two of them)
             for (int m = NB - 1; m >= 1; m--) {
                 if (r - m >= 1) patch(img, drow, start[r - m], start[r - m + 1]);
-                if (m > 1) __syncthreads();
+                bar_sync(BAR_WORK, CT);
             }
             if (DK >= 2) {
                 const uint4 T = Tn;
                 if (r + 1 < n_rows) Tn = __ldg(a.mtab + g0 + r + 1);
                 if (DK == 2) {   // 8 individuals per step: 4 words of the 4-bit image in, 8 dose bytes out
-                    for (int i = tid; i < seg_ind / 8; i += NT) {
+                    for (int i = tid; i < seg_ind / 8; i += CT) {
                         const uint4 v = reinterpret_cast<const uint4*>(nib)[i];
                         auto two = [&](uint32_t w) { return __dp4a(prmt(T.x, T.y, w) + prmt(T.z, T.w, w >> 16), 0x01010101u, 0u); };
                         const uint32_t lo = two(v.x) | (two(v.y) << 8), hi = two(v.z) | (two(v.w) << 8);   // dose nibbles
                         reinterpret_cast<uint2*>(drow)[i] = make_uint2(prmt(0x03020100u, 0x07060504u, lo), prmt(0x03020100u, 0x07060504u, hi));
                     }
                 } else {         // ploidy 2: 16 individuals per step
-                    for (int i = tid; i < seg_ind / 16; i += NT) {
+                    for (int i = tid; i < seg_ind / 16; i += CT) {
                         const uint4 v = reinterpret_cast<const uint4*>(nib)[i];
                         auto four = [&](uint32_t w) {
                             const uint32_t xl = prmt(T.x, T.y, w), xh = prmt(T.x, T.y, w >> 16);
@@ -264,22 +314,65 @@ __global__ void __launch_bounds__(ROWS_THREADS, 1) k_emit_rows(const RowsArgs a)
                     }
                 }
             }
-            __syncthreads();
+            PT(2);
             patch(img, drow, e0, e1);
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-            __syncthreads();
-            uint8_t* const gf = a.founder ? a.founder + (out_row0 + r) * a.founder_pitch + c0 : nullptr;
-            uint8_t* const gd = a.dose ? a.dose + (out_row0 + r) * a.dose_pitch + c0 / P : nullptr;
-            if (tid == 0) {
-                if (gf && (n_cell & ~15)) bulk_store(gf, img, (uint32_t)(n_cell & ~15));
-                if (DK >= 1 && gd && (n_ind & ~15)) bulk_store(gd, drow, (uint32_t)(n_ind & ~15));
-                asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-            }
-            // ragged ends (a bulk store moves multiples of 16 bytes)
-            if (gf && tid < (n_cell & 15)) gf[(n_cell & ~15) + tid] = img[(n_cell & ~15) + tid];
-            if (DK >= 1 && gd && tid >= 32 && tid - 32 < (n_ind & 15)) gd[(n_ind & ~15) + tid - 32] = drow[(n_ind & ~15) + tid - 32];
+            PT(3);
+            bar_arrive(BAR_FULL + r % NB, ROWS_COMPUTE + 32);
+            if (DK >= 2) bar_sync(BAR_WORK, CT);   // the dose row was read from the 4-bit image: the next row's patches wait for that
         }
     }
-    if (tid == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+    if (tid >= ROWS_COMPUTE && (tid & 31) < 2) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+#ifdef PSIM_ROWS_PROFILE
+    unsigned long long g_end; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(g_end));
+    if (tid == 0) printf("block %d compute: nib-patch %lld  EMPTY wait %lld  catchup+dose %lld  patch+fence %lld  rest %lld, whole %lld cycles in %llu ns (from %llu to %llu)\n", blockIdx.x, pt[0], pt[1], pt[2], pt[3], 0LL, clock64() - p_begin, g_end - g_begin, g_begin, g_end);
+    if ((blockIdx.x % 49) == 0 && tid == 512) printf("block %d issuer: loop %lld  FULL wait %lld  issue %lld  wait.read %lld, whole %lld\n", blockIdx.x, pt[0], pt[1], pt[2], pt[3], clock64() - p_begin);
+#endif
 }
 
+// Units whose run-start list overflowed (not expected with the band heuristic; the list is filled by
+// k_emit_rows on the device, so no host round trip): every cell searched in its homolog's runs.
+struct RowsOverflowArgs {
+    int dose_mode;                // 0: count founder allele dose_which; 1: count the locus' matched allele code
+    const uint8_t* code; const uint8_t* match_code; int A;
+};
+__global__ void __launch_bounds__(256) k_emit_rows_overflow(const RowsArgs a, const RowsOverflowArgs o) {
+#ifdef PSIM_ROWS_PROFILE
+    if (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) { unsigned long long g; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(g)); printf("overflow kernel starts at %llu\n", g); }
+#endif
+    const int n_over = a.overflow[0];
+    const int P = a.P;
+    const int64_t n_cols = a.n_cols_ind * P;
+    for (int x = blockIdx.y; x < n_over; x += gridDim.y) {
+        const int u = a.overflow[1 + x];
+        int k = 0;
+        while (u >= a.chunk_unit_base[k + 1]) k++;
+        const int j = (u - a.chunk_unit_base[k]) / a.n_seg, s = (u - a.chunk_unit_base[k]) % a.n_seg;
+        int64_t g0, g1;
+        band_rows(a, k, j, g0, g1);
+        const int64_t c0 = (int64_t)s * a.seg_cells;
+        const int64_t n_ind = min((int64_t)a.seg_cells, n_cols - c0) / P, q0 = c0 / P;
+        const int c = a.chunk_chrom[k];
+        for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < (g1 - g0) * n_ind; t += (int64_t)gridDim.x * blockDim.x) {
+            const int64_t gl = g0 + t / n_ind, q = q0 + t % n_ind;
+            const uint32_t l = (uint32_t)(gl - a.chunk_coff[k]);
+            const int64_t r = q / a.ind_count, i = a.ind_first + q % a.ind_count;
+            const int64_t hid0 = (((int64_t)c * a.R + r) * a.N + i) * P;
+            const int64_t row = gl - a.locus_first;
+            const uint8_t* codes = o.code ? o.code + gl * o.A : nullptr;
+            const int match = o.dose_mode == 1 ? (int)o.match_code[gl] : a.dose_which;
+            int dose = 0;
+            for (int h = 0; h < P; h++) {
+                const uint64_t d = a.run_desc[hid0 + h];
+                const uint64_t b = desc_begin(d);
+                const uint32_t n = desc_count(d);
+                uint32_t lo = 0, hi = n;
+                while (hi - lo > 1) { const uint32_t mid = (lo + hi) >> 1; if (a.run_lb[b + mid] <= l) lo = mid; else hi = mid; }
+                const int f = a.run_founder[b + lo];
+                if (a.founder) a.founder[row * a.founder_pitch + q * P + h] = (uint8_t)f;
+                if ((codes ? (int)codes[f] : f) == match) dose++;
+            }
+            if (a.dose) a.dose[row * a.dose_pitch + q] = (uint8_t)dose;
+        }
+    }
+}

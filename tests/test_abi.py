@@ -30,7 +30,7 @@ def test_library_exports_every_declared_symbol(psim_lib):
     for name in declared_functions():
         assert hasattr(psim_lib, name), name
     assert sorted(lib.EXPORTS) == declared_functions()
-    assert psim_lib.psim_abi_version() == 1
+    assert psim_lib.psim_abi_version() == 2
 
 
 def test_header_compiles_as_plain_c(tmp_path):

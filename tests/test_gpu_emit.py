@@ -193,14 +193,14 @@ def test_many_run_starts_per_row_fall_back_cleanly():
     assert np.array_equal(got["dose"], o.emit(_oracle.EMIT_DOSE, which=2))
 
 
-def test_overflowing_units_are_redone_per_cell(monkeypatch):
-    """Force the row-image path onto a map where the run-start lists overflow: those units go to
-    the overflow list and are redone by the per-cell kernel; the tables must still be exact."""
-    monkeypatch.setenv("PSIM_ROWS_FORCE", "1")
+def test_overflowing_units_are_redone_per_cell():
+    """Force the row-image path (PSIM_PATH_ROWS) onto a map where the run-start lists overflow: those
+    units go to the overflow list and are redone by the per-cell kernel; the tables must still be exact."""
+    import pedigreesim_b200 as ps
     for ploidy, codes in ((4, 0), (4, 2), (2, 2)):
         o, g = _both(ploidy, [6.0, 1.0], 3000, ploidy * 2, [24, 40], seed=21 + ploidy, codes=codes, max_segments=40, grid_breaks=False)
         which = _oracle.MAX_ALLELE if codes else 3
-        got = g.emit(founder=True, dose=True, dose_which=which)
+        got = g.emit(founder=True, dose=True, dose_which=which, path=ps.PATH_ROWS)
         assert np.array_equal(got["founder"], o.emit(_oracle.EMIT_FOUNDER))
         assert np.array_equal(got["dose"], o.emit(_oracle.EMIT_DOSE, which=which))
 

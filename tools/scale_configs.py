@@ -23,9 +23,10 @@ import _cases  # noqa: E402
 import pedigreesim_b200 as ps  # noqa: E402
 
 
-def emit_block(ctx, P, n_ind_first, n_ind, l0, nl, founder, dose, which):
+def emit_block(ctx, P, n_ind_first, n_ind, l0, nl, founder, dose, which, path=0):
     fp, dp = founder.shape[1], dose.shape[1]
     t = ps.EmitTargets()
+    t.flags = ps.emit_path(path)
     t.founder, t.founder_pitch, t.founder_bytes = founder.data_ptr(), fp, 1
     t.dose, t.dose_pitch, t.dose_which = dose.data_ptr(), dp, which
     t.memory = ps.MEM_DEVICE
@@ -42,6 +43,8 @@ def run(name, P, p0, p1, lengths, centro, pref, fq, loci_per_chrom, emit_first, 
     ctx.set_chromosomes(lengths, centro, pref, fq)
     ctx.set_pedigree(p0, p1)
     out["setup_s"] = round(time.perf_counter() - t0, 3)
+    ctx.simulate()          # cold: kernels are loaded on first use, scratch and slab are allocated
+    ctx.reset(12345, 0)
     t0 = time.perf_counter()
     ctx.simulate()
     torch.cuda.synchronize()
@@ -74,14 +77,10 @@ def run(name, P, p0, p1, lengths, centro, pref, fq, loci_per_chrom, emit_first, 
     # cross-check the last block against the tiled kernel and against invariants
     f_rows = founder[:, :cols].clone()
     d_rows = dose[:, :R * emit_count].clone()
-    os.environ["PSIM_NO_ROWS"] = "1"
-    try:
-        founder.zero_()
-        dose.zero_()
-        torch.cuda.synchronize()   # torch's stream is not the library's
-        emit_block(ctx, P, emit_first, emit_count, int(starts[-1]), block_loci, founder, dose, 0)
-    finally:
-        del os.environ["PSIM_NO_ROWS"]
+    founder.zero_()
+    dose.zero_()
+    torch.cuda.synchronize()   # torch's stream is not the library's
+    emit_block(ctx, P, emit_first, emit_count, int(starts[-1]), block_loci, founder, dose, 0, path=ps.PATH_TILES)
     same = bool(torch.equal(f_rows, founder[:, :cols]) and torch.equal(d_rows, dose[:, :R * emit_count]))
     n_found = int((p0 < 0).sum())
     in_range = bool(int(f_rows.max()) < n_found * P)
