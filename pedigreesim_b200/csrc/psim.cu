@@ -294,8 +294,9 @@ static int emit_rows_path(psim_ctx_impl* c, int64_t ind_first, int64_t ind_count
     static const int env_band = tuning_int("PSIM_BAND_ROWS");
     static const int env_units = tuning_int("PSIM_ROWS_UNITS");
     const int cap = env_cap > 0 ? env_cap : 8192;
-    const double per_cell = (double)ROWS_NBUF + (DK >= 2 ? 0.5 : 0.0) + (DK >= 1 ? (double)ROWS_NBUF : 0.0) / P;
-    const int64_t budget = ROWS_SMEM - 2 * (ROWS_MAX_BAND + 2) * 4 - cap * 4;
+    const bool dose_rows = DK == 1 || (DK >= 2 && !ROWS_DOSE_DIRECT);
+    const double per_cell = (double)ROWS_NBUF + (DK >= 2 ? 1.0 : 0.0) + (dose_rows ? (double)ROWS_NBUF : 0.0) / P;
+    const int64_t budget = ROWS_SMEM - 2 * (ROWS_MAX_BAND + 2) * 4 - cap * 5;
     const int64_t quantum = 16 * P;
     int64_t seg_max = (int64_t)(budget / per_cell) / quantum * quantum;
     seg_max = std::min<int64_t>(seg_max, 65535 / quantum * quantum);
@@ -328,13 +329,13 @@ static int emit_rows_path(psim_ctx_impl* c, int64_t ind_first, int64_t ind_count
     ra.ind_first = ind_first; ra.ind_count = ind_count; ra.n_cols_ind = n_cols_ind;
     ra.locus_first = row0_locus;
     ra.n_seg = n_seg; ra.seg_cells = (int)seg_cells; ra.cap = cap;
-    ra.plan_stride = (16 + seg_cells + (int64_t)cap * 4 + 127) / 128 * 128;
+    ra.plan_stride = (16 + seg_cells + (int64_t)cap * 5 + 127) / 128 * 128;
     ra.founder = founder; ra.founder_pitch = founder_pitch;
     ra.dose = dose; ra.dose_pitch = dose_pitch;
     ra.dose_which = dose_which; ra.mtab = c->mtab_d;
     ra.unit_counter = c->tile_counter_d;
-    const size_t smem = ROWS_NBUF * (size_t)seg_cells + (DK >= 2 ? seg_cells / 2 : 0) + (size_t)(DK >= 1 ? ROWS_NBUF : 0) * (seg_cells / P) +
-                        (size_t)cap * 4 + 2 * (ROWS_MAX_BAND + 2) * 4;
+    const size_t smem = ROWS_NBUF * (size_t)seg_cells + (DK >= 2 ? seg_cells : 0) + (size_t)(dose_rows ? ROWS_NBUF : 0) * (seg_cells / P) +
+                        (size_t)cap * 5 + 2 * (ROWS_MAX_BAND + 2) * 4;
     RowsOverflowArgs oa{};
     oa.dose_mode = dose_mode; oa.code = c->code_d; oa.match_code = c->match_d; oa.A = c->A;
     int k0 = 0;

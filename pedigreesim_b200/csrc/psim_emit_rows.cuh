@@ -30,7 +30,7 @@ struct RowsArgs {
     int chunk_unit_base[65];
     int n_seg, seg_cells;         // segments per row; cells per segment (a multiple of 16 * P)
     int n_units, cap;             // units = sum(bands) * n_seg; run starts a unit's list can hold
-    uint8_t* plan;                // per unit: [count u32, 12 bytes pad][seg_cells state bytes][cap run starts]
+    uint8_t* plan;                // per unit: [count u32, 12 bytes pad][seg_cells state bytes][cap run starts u32][cap distances u8]
     int64_t plan_stride;
     int* unit_counter;            // ticket
     int* overflow;                // [0] = number of units whose list overflowed, then their ids
@@ -69,9 +69,6 @@ __global__ void __launch_bounds__(256) k_band_plan(const RowsArgs a) {
     uint32_t f = n ? __ldg(a.run_founder + b + lo) : 0;
     uint32_t kx = lo + 1;
     uint32_t nxt = kx < n ? __ldg(a.run_lb + b + kx) : NO_EVENT;
-#ifdef PSIM_ROWS_PROFILE
-    if (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) { unsigned long long g; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(g)); printf("band plan block 0 at %llu\n", g); }
-#endif
     for (int j = 0; j < a.chunk_bands[k]; j++) {
         int64_t g0, g1;
         band_rows(a, k, j, g0, g1);
@@ -86,10 +83,15 @@ __global__ void __launch_bounds__(256) k_band_plan(const RowsArgs a) {
         while (nxt < tl1) {
             f = __ldg(a.run_founder + b + kx);
             const uint32_t idx = atomicAdd(reinterpret_cast<uint32_t*>(pu), 1u);
-            if (idx < (uint32_t)a.cap)
-                reinterpret_cast<uint32_t*>(pu + 16 + a.seg_cells)[idx] = ((nxt - tl0) << 24) | (cs << 8) | f;
+            const uint32_t row = nxt - tl0;
             kx++;
             nxt = kx < n ? __ldg(a.run_lb + b + kx) : NO_EVENT;
+            if (idx < (uint32_t)a.cap) {
+                reinterpret_cast<uint32_t*>(pu + 16 + a.seg_cells)[idx] = (row << 24) | (cs << 8) | f;
+                // rows until the same cell changes again (255: not soon): a row buffer that takes the run starts
+                // of several rows in one pass skips those that are overwritten inside its window
+                (pu + 16 + a.seg_cells + (size_t)a.cap * 4)[idx] = (uint8_t)min(nxt - (row + tl0), 255u);
+            }
         }
     }
 }
@@ -109,6 +111,10 @@ constexpr int ROWS_SMEM = 220 * 1024;  // one block per SM
 #define PSIM_ROWS_NBUF 3
 #endif
 constexpr int ROWS_NBUF = PSIM_ROWS_NBUF;   // row buffers in flight
+#ifndef PSIM_DOSE_DIRECT
+#define PSIM_DOSE_DIRECT 0
+#endif
+constexpr bool ROWS_DOSE_DIRECT = PSIM_DOSE_DIRECT != 0;   // recomputed dose rows go from registers to global memory, not through a row buffer
 constexpr int ROWS_THREADS = ROWS_COMPUTE + 32 * ROWS_NBUF;   // + one warp per row buffer that hands its rows to the bulk-copy engine
 
 __device__ __forceinline__ void bulk_store(void* gdst, const void* ssrc, uint32_t bytes) {
@@ -122,13 +128,18 @@ __device__ __forceinline__ void bar_arrive(int id, int n) { asm volatile("bar.ar
 
 // DK: how the dose row is made. 0 = no dose table, 1 = no genotypes (count of one founder allele:
 // patched like the founder row), 2 = genotypes, A <= 8, ploidy 4, 3 = genotypes, A <= 8, ploidy 2.
-// Warp-specialised: 512 threads make row r in buffer r % NBUF (patch the run starts of the rows the
-// buffer missed, recompute the dose row); every buffer has a warp of its own that hands its rows to
-// the bulk-copy engine and waits until they have been read. Issuing a bulk store keeps the issuing
-// WARP busy for 800-1600 cycles whatever the size of the store (measured with clock64: 10 KB dose
-// rows alone take as long to issue as 40 KB founder rows), so stores issued from one warp never
-// overlap; issued from NBUF warps they do, and none of it sits in the path of the threads that make
-// the next row.
+// Warp-specialised: 512 threads make row r in buffer r % NBUF; every buffer has a warp of its own that
+// hands its rows to the bulk-copy engine and waits until they have been read (issuing a bulk store
+// keeps the issuing warp busy for 800-1600 cycles whatever the size of the store).
+// Making a row is latency, not arithmetic: every phase that ends in a block-wide barrier costs
+// 300-500 cycles (dependent shared-memory loads, then the slowest of 16 warps), and a row may take
+// ~2100 cycles before HBM is the limit. So a row has as few phases as possible:
+//   1. when the engine has read the buffer's previous row: ONE pass patches the run starts of all the
+//      rows the buffer missed (k_band_plan marks the starts that are overwritten again inside such a
+//      window, so the pass touches every cell at most once and needs no order);
+//   2. with genotypes: barrier, then the dose row is recomputed from a 4-bit image of the row (kept
+//      twice, for even and odd rows, patched the same way) and goes from registers straight to global
+//      memory; without genotypes the dose row is patched like the founder row and leaves as a bulk store.
 template <int DK>
 __global__ void __launch_bounds__(ROWS_THREADS, 1) k_emit_rows(const RowsArgs a) {
     extern __shared__ __align__(128) uint8_t smem[];
@@ -138,24 +149,19 @@ __global__ void __launch_bounds__(ROWS_THREADS, 1) k_emit_rows(const RowsArgs a)
     const int seg_cells = a.seg_cells, seg_ind = seg_cells / P;
     constexpr int NB = ROWS_NBUF;
     uint8_t* const img0 = smem;                                              // founder byte of every cell on the current row (x NB)
-    uint32_t* const nib = reinterpret_cast<uint32_t*>(img0 + (size_t)NB * seg_cells);   // DK >= 2: the same, 4 bits per cell
-    uint8_t* const dose0 = reinterpret_cast<uint8_t*>(nib) + (DK >= 2 ? seg_cells / 2 : 0);
-    uint32_t* const evs = reinterpret_cast<uint32_t*>(dose0 + (DK >= 1 ? (size_t)NB * seg_ind : 0));   // the unit's run starts sorted by row
+    uint32_t* const nib0 = reinterpret_cast<uint32_t*>(img0 + (size_t)NB * seg_cells);   // DK >= 2: the same, 4 bits per cell (x 2)
+    constexpr bool DSM = DK == 1 || (DK >= 2 && !ROWS_DOSE_DIRECT);          // dose rows in shared memory, sent as bulk stores
+    uint8_t* const dose0 = reinterpret_cast<uint8_t*>(nib0) + (DK >= 2 ? seg_cells : 0);   // dose rows (x NB)
+    uint32_t* const evs = reinterpret_cast<uint32_t*>(dose0 + (DSM ? (size_t)NB * seg_ind : 0));   // the unit's run starts sorted by row
     uint32_t* const start = evs + a.cap;                                     // [band rows + 1] first run start of each row
     uint32_t* const cursor = start + ROWS_MAX_BAND + 2;
+    uint8_t* const evd = reinterpret_cast<uint8_t*>(cursor + ROWS_MAX_BAND + 2);   // rows until the run start's cell changes again
     __shared__ int s_unit;
     const int64_t n_cols = a.n_cols_ind * P;
     const bool count_ok = a.dose_which >= 0 && a.dose_which < 256;           // DK 1: a founder allele that exists
 
-#ifdef PSIM_ROWS_PROFILE
-    long long pt[6] = {0, 0, 0, 0, 0, 0}; long long pc = clock64(); const long long p_begin = pc;
-    unsigned long long g_begin; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(g_begin));
-#define PT(k) do { if ((tid & 511) == 0) { const long long now = clock64(); pt[k] += now - pc; pc = now; } } while (0)
-#else
-#define PT(k)
-#endif
     for (;;) {
-        __syncthreads();   // (the issuing warp gets here only after the engine has read the last rows of the previous unit)
+        __syncthreads();   // (an issuing warp gets here only after the engine has read its last row of the previous unit)
         if (tid == 0) s_unit = atomicAdd(a.unit_counter, 1);
         __syncthreads();
         const int u = s_unit;
@@ -183,6 +189,7 @@ __global__ void __launch_bounds__(ROWS_THREADS, 1) k_emit_rows(const RowsArgs a)
         for (int i = tid; i <= n_rows; i += NT) start[i] = 0;
         __syncthreads();
         const uint32_t* ev_g = reinterpret_cast<const uint32_t*>(pu + 16 + seg_cells);
+        const uint8_t* evd_g = pu + 16 + seg_cells + (size_t)a.cap * 4;
         for (uint32_t e = tid; e < n_ev; e += NT) atomicAdd(&start[__ldg(ev_g + e) >> 24], 1u);
         __syncthreads();
         if (tid < 32) {   // exclusive scan of the row histogram (<= 256 bins) by one warp
@@ -200,13 +207,17 @@ __global__ void __launch_bounds__(ROWS_THREADS, 1) k_emit_rows(const RowsArgs a)
         __syncthreads();
         for (uint32_t e = tid; e < n_ev; e += NT) {
             const uint32_t w = __ldg(ev_g + e);
-            evs[atomicAdd(&cursor[w >> 24], 1u)] = w;
+            const uint32_t at = atomicAdd(&cursor[w >> 24], 1u);
+            evs[at] = w;
+            evd[at] = __ldg(evd_g + e);
         }
         if (DK >= 2) {   // 4-bit image: low 3 bits of every cell, the PRMT selectors of the dose lookup
             for (int i = tid; i < seg_cells / 16; i += NT) {
                 const uint4 v = reinterpret_cast<const uint4*>(img0)[i];
                 auto pack = [](uint32_t x) { return (x & 0x7) | ((x >> 4) & 0x70) | ((x >> 8) & 0x700) | ((x >> 12) & 0x7000); };
-                reinterpret_cast<uint2*>(nib)[i] = make_uint2(pack(v.x) | (pack(v.y) << 16), pack(v.z) | (pack(v.w) << 16));
+                const uint2 pk = make_uint2(pack(v.x) | (pack(v.y) << 16), pack(v.z) | (pack(v.w) << 16));
+                reinterpret_cast<uint2*>(nib0)[i] = pk;
+                reinterpret_cast<uint2*>(nib0 + seg_cells / 8)[i] = pk;
             }
         }
         if (DK == 1) {   // dose of one founder allele on the band's first row
@@ -235,99 +246,93 @@ __global__ void __launch_bounds__(ROWS_THREADS, 1) k_emit_rows(const RowsArgs a)
             for (int r = b; r < n_rows; r += NB) {
                 uint8_t* const gf = a.founder ? a.founder + (out_row0 + r) * a.founder_pitch + c0 : nullptr;
                 uint8_t* const gd = a.dose ? a.dose + (out_row0 + r) * a.dose_pitch + c0 / P : nullptr;
-                PT(0);
                 bar_sync(BAR_FULL + b, ROWS_COMPUTE + 32);
-                PT(1);
                 if (lane == 0) {
                     if (gf && (n_cell & ~15)) bulk_store(gf, img, (uint32_t)(n_cell & ~15));
                     asm volatile("cp.async.bulk.commit_group;" ::: "memory");
                 } else if (lane == 1) {
-                    if (DK >= 1 && gd && (n_ind & ~15)) bulk_store(gd, drow, (uint32_t)(n_ind & ~15));
+                    if (DSM && gd && (n_ind & ~15)) bulk_store(gd, drow, (uint32_t)(n_ind & ~15));
                     asm volatile("cp.async.bulk.commit_group;" ::: "memory");
                 } else {   // a bulk store moves multiples of 16 bytes
                     const int t = lane - 2;
                     if (gf && t < 15 && t < (n_cell & 15)) gf[(n_cell & ~15) + t] = img[(n_cell & ~15) + t];
-                    if (DK >= 1 && gd && t >= 15 && t - 15 < (n_ind & 15)) gd[(n_ind & ~15) + t - 15] = drow[(n_ind & ~15) + t - 15];
+                    if (DSM && gd && t >= 15 && t - 15 < (n_ind & 15)) gd[(n_ind & ~15) + t - 15] = drow[(n_ind & ~15) + t - 15];
                 }
-                PT(2);
                 if (lane < 2) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // the engine has read the row
-                PT(3);
                 __syncwarp();
                 if (r + NB < n_rows) bar_arrive(BAR_EMPTY + b, ROWS_COMPUTE + 32);
             }
             continue;
         }
 
-        // ---- the rows. Buffer r % NB holds row r-NB when row r begins: it takes the run starts of rows r-NB+1 .. r.
+        // ---- the rows. Buffer r % NB holds row r-NB when row r begins and takes the run starts of rows r-NB+1 .. r;
+        // the 4-bit image of row parity r & 1 holds row r-2 and takes those of rows r-1 and r.
         constexpr int CT = ROWS_COMPUTE;
         uint4 Tn = make_uint4(0, 0, 0, 0);
         if (DK >= 2) Tn = __ldg(a.mtab + g0);
-        auto patch = [&](uint8_t* img, uint8_t* drow, uint32_t e0, uint32_t e1) {
+        for (int r = 0; r < n_rows; r++) {
+            const int b = r % NB;
+            uint8_t* const img = img0 + (size_t)b * seg_cells;
+            uint8_t* const drow = dose0 + (size_t)b * seg_ind;
+            uint32_t* const nib = nib0 + (size_t)(r & 1) * (seg_cells / 8);
+            const int w0 = max(1, r - NB + 1);                    // first row of the buffer's window (row 0 has no run starts: they are the state)
+            const uint32_t e0 = start[w0], en = start[max(1, r - 1)], e1 = start[r + 1];
+            if (r >= NB) bar_sync(BAR_EMPTY + b, ROWS_COMPUTE + 32);   // the engine has read row r-NB out of this buffer
             for (uint32_t e = e0 + tid; e < e1; e += CT) {
                 const uint32_t w = evs[e], cs = (w >> 8) & 0xFFFF, f = w & 0xFF;
+                if ((int)(w >> 24) + (int)evd[e] <= r) continue;   // the cell changes again inside the window
                 if (DK == 1) {
                     const int delta = (int)(f == (uint32_t)a.dose_which) - (int)(count_ok && img[cs] == (uint8_t)a.dose_which);
                     const uint32_t ind = cs / P;
                     if (delta) atomicAdd(reinterpret_cast<uint32_t*>(drow) + (ind >> 2), (uint32_t)delta << (8 * (ind & 3)));
                 }
                 img[cs] = (uint8_t)f;
-            }
-        };
-        for (int r = 0; r < n_rows; r++) {
-            const uint32_t e0 = start[r], e1 = start[r + 1];   // this row's run starts (row 0 has none: they are the state)
-            uint8_t* const img = img0 + (size_t)(r % NB) * seg_cells;
-            uint8_t* const drow = dose0 + (size_t)(r % NB) * seg_ind;
-            if (DK >= 2) {   // (the 4-bit image is not a store source: it can be brought to row r before the buffer is free)
-                for (uint32_t e = e0 + tid; e < e1; e += CT) {
-                    const uint32_t w = evs[e], cs = (w >> 8) & 0xFFFF, sh = (cs & 7) * 4;
+                if (DK >= 2 && e >= en) {
+                    const uint32_t sh = (cs & 7) * 4;
                     atomicAnd(&nib[cs >> 3], ~(0xFu << sh));
                     atomicOr(&nib[cs >> 3], (w & 7) << sh);
                 }
             }
-            PT(0);
-            if (r >= NB) bar_sync(BAR_EMPTY + r % NB, ROWS_COMPUTE + 32);   // the engine has read row r-NB out of this buffer
-            else if (DK >= 2) bar_sync(BAR_WORK, CT);
-            PT(1);
-            // catch up with the rows this buffer missed, oldest first (a cell may change on two of them)
-            for (int m = NB - 1; m >= 1; m--) {
-                if (r - m >= 1) patch(img, drow, start[r - m], start[r - m + 1]);
-                bar_sync(BAR_WORK, CT);
-            }
             if (DK >= 2) {
+                bar_sync(BAR_WORK, CT);
                 const uint4 T = Tn;
                 if (r + 1 < n_rows) Tn = __ldg(a.mtab + g0 + r + 1);
+                // the dose row is recomputed from the 4-bit image and goes from registers straight to global memory
+                // (16 / 8 bytes per thread, consecutive threads consecutive bytes): no shared-memory row, no second
+                // bulk store per table row
+                uint8_t* const gd = a.dose ? a.dose + (out_row0 + r) * a.dose_pitch + c0 / P : nullptr;
                 if (DK == 2) {   // 8 individuals per step: 4 words of the 4-bit image in, 8 dose bytes out
-                    for (int i = tid; i < seg_ind / 8; i += CT) {
+                    for (int i = tid; i < (n_ind + 7) / 8; i += CT) {
                         const uint4 v = reinterpret_cast<const uint4*>(nib)[i];
                         auto two = [&](uint32_t w) { return __dp4a(prmt(T.x, T.y, w) + prmt(T.z, T.w, w >> 16), 0x01010101u, 0u); };
                         const uint32_t lo = two(v.x) | (two(v.y) << 8), hi = two(v.z) | (two(v.w) << 8);   // dose nibbles
-                        reinterpret_cast<uint2*>(drow)[i] = make_uint2(prmt(0x03020100u, 0x07060504u, lo), prmt(0x03020100u, 0x07060504u, hi));
+                        const uint2 out = make_uint2(prmt(0x03020100u, 0x07060504u, lo), prmt(0x03020100u, 0x07060504u, hi));
+                        if (DSM) reinterpret_cast<uint2*>(drow)[i] = out;
+                        else if (i * 8 + 8 <= n_ind) *reinterpret_cast<uint2*>(gd + i * 8) = out;
+                        else for (int q = 0; i * 8 + q < n_ind; q++) gd[i * 8 + q] = (uint8_t)((q < 4 ? out.x : out.y) >> (8 * (q & 3)));
                     }
                 } else {         // ploidy 2: 16 individuals per step
-                    for (int i = tid; i < seg_ind / 16; i += CT) {
+                    for (int i = tid; i < (n_ind + 15) / 16; i += CT) {
                         const uint4 v = reinterpret_cast<const uint4*>(nib)[i];
                         auto four = [&](uint32_t w) {
                             const uint32_t xl = prmt(T.x, T.y, w), xh = prmt(T.x, T.y, w >> 16);
                             return prmt(xl + (xl >> 8), xh + (xh >> 8), 0x6420u);
                         };
-                        reinterpret_cast<uint4*>(drow)[i] = make_uint4(four(v.x), four(v.y), four(v.z), four(v.w));
+                        const uint4 out = make_uint4(four(v.x), four(v.y), four(v.z), four(v.w));
+                        if (DSM) reinterpret_cast<uint4*>(drow)[i] = out;
+                        else if (i * 16 + 16 <= n_ind) *reinterpret_cast<uint4*>(gd + i * 16) = out;
+                        else {
+                            const uint32_t w4[4] = {out.x, out.y, out.z, out.w};
+                            for (int q = 0; i * 16 + q < n_ind; q++) gd[i * 16 + q] = (uint8_t)(w4[q >> 2] >> (8 * (q & 3)));
+                        }
                     }
                 }
             }
-            PT(2);
-            patch(img, drow, e0, e1);
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-            PT(3);
-            bar_arrive(BAR_FULL + r % NB, ROWS_COMPUTE + 32);
-            if (DK >= 2) bar_sync(BAR_WORK, CT);   // the dose row was read from the 4-bit image: the next row's patches wait for that
+            bar_arrive(BAR_FULL + b, ROWS_COMPUTE + 32);
         }
     }
     if (tid >= ROWS_COMPUTE && (tid & 31) < 2) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
-#ifdef PSIM_ROWS_PROFILE
-    unsigned long long g_end; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(g_end));
-    if (tid == 0) printf("block %d compute: nib-patch %lld  EMPTY wait %lld  catchup+dose %lld  patch+fence %lld  rest %lld, whole %lld cycles in %llu ns (from %llu to %llu)\n", blockIdx.x, pt[0], pt[1], pt[2], pt[3], 0LL, clock64() - p_begin, g_end - g_begin, g_begin, g_end);
-    if ((blockIdx.x % 49) == 0 && tid == 512) printf("block %d issuer: loop %lld  FULL wait %lld  issue %lld  wait.read %lld, whole %lld\n", blockIdx.x, pt[0], pt[1], pt[2], pt[3], clock64() - p_begin);
-#endif
 }
 
 // Units whose run-start list overflowed (not expected with the band heuristic; the list is filled by
@@ -337,9 +342,6 @@ struct RowsOverflowArgs {
     const uint8_t* code; const uint8_t* match_code; int A;
 };
 __global__ void __launch_bounds__(256) k_emit_rows_overflow(const RowsArgs a, const RowsOverflowArgs o) {
-#ifdef PSIM_ROWS_PROFILE
-    if (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) { unsigned long long g; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(g)); printf("overflow kernel starts at %llu\n", g); }
-#endif
     const int n_over = a.overflow[0];
     const int P = a.P;
     const int64_t n_cols = a.n_cols_ind * P;
