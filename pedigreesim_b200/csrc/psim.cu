@@ -275,6 +275,11 @@ static void launch_rows(psim_ctx_impl* c, const RowsArgs& ra, int blocks, size_t
     cudaFuncSetAttribute(k_emit_rows<DK>, cudaFuncAttributeMaxDynamicSharedMemorySize, ROWS_SMEM);
     k_emit_rows<DK><<<blocks, ROWS_THREADS, smem, c->stream>>>(ra);
 }
+template <int DK>
+static void launch_rows_packed(psim_ctx_impl* c, const RowsArgs& ra, int blocks, size_t smem) {
+    cudaFuncSetAttribute(k_emit_rows_packed<DK>, cudaFuncAttributeMaxDynamicSharedMemorySize, ROWS_SMEM);
+    k_emit_rows_packed<DK><<<blocks, ROWS_THREADS, smem, c->stream>>>(ra);
+}
 #ifdef PSIM_TUNING
 static int tuning_int(const char* name) { const char* v = getenv(name); return v ? atoi(v) : 0; }
 #else
@@ -283,9 +288,10 @@ static int tuning_int(const char*) { return 0; }   // the knobs exist in tuning 
 
 static int emit_rows_path(psim_ctx_impl* c, int64_t ind_first, int64_t ind_count, int64_t l_begin, int64_t l_end, int64_t row0_locus,
                           uint8_t* founder, int64_t founder_pitch, uint8_t* dose, int64_t dose_pitch, int dose_mode, int dose_which, int mode,
-                          int path, bool& done) {
+                          int path, bool packed, bool& done) {
     done = false;
     const int P = c->P;
+    if (packed && P > 8) return PSIM_OK;
     if (path == PSIM_PATH_TILES || path == PSIM_PATH_GENERIC || !(mode == 0 || (mode == 1 && (P == 2 || P == 4)))) return PSIM_OK;
     const int DK = !dose ? 0 : mode == 0 ? 1 : P == 4 ? 2 : 3;
     const int64_t n_cols_ind = (int64_t)c->R * ind_count, n_cols = n_cols_ind * P;
@@ -295,9 +301,10 @@ static int emit_rows_path(psim_ctx_impl* c, int64_t ind_first, int64_t ind_count
     static const int env_units = tuning_int("PSIM_ROWS_UNITS");
     const int cap = env_cap > 0 ? env_cap : 8192;
     const bool dose_rows = DK == 1 || (DK >= 2 && !ROWS_DOSE_DIRECT);
-    const double per_cell = (double)ROWS_NBUF + (DK >= 2 ? 1.0 : 0.0) + (dose_rows ? (double)ROWS_NBUF : 0.0) / P;
+    const double per_cell = packed ? 0.5 * ROWS_NBUF + (DK >= 1 ? 0.5 * ROWS_NBUF : 0.0) / P
+                                   : (double)ROWS_NBUF + (DK >= 2 ? 1.0 : 0.0) + (dose_rows ? (double)ROWS_NBUF : 0.0) / P;
     const int64_t budget = ROWS_SMEM - 2 * (ROWS_MAX_BAND + 2) * 4 - cap * 5;
-    const int64_t quantum = 16 * P;
+    const int64_t quantum = (packed ? 32 : 16) * P;
     int64_t seg_max = (int64_t)(budget / per_cell) / quantum * quantum;
     seg_max = std::min<int64_t>(seg_max, 65535 / quantum * quantum);
     if (env_seg > 0) seg_max = std::max<int64_t>(quantum, std::min<int64_t>(seg_max, env_seg / quantum * quantum));
@@ -334,7 +341,8 @@ static int emit_rows_path(psim_ctx_impl* c, int64_t ind_first, int64_t ind_count
     ra.dose = dose; ra.dose_pitch = dose_pitch;
     ra.dose_which = dose_which; ra.mtab = c->mtab_d;
     ra.unit_counter = c->tile_counter_d;
-    const size_t smem = ROWS_NBUF * (size_t)seg_cells + (DK >= 2 ? seg_cells : 0) + (size_t)(dose_rows ? ROWS_NBUF : 0) * (seg_cells / P) +
+    const size_t smem = (packed ? ROWS_NBUF * (size_t)seg_cells / 2 + (size_t)(DK >= 1 ? ROWS_NBUF : 0) * (seg_cells / P / 2)
+                                : ROWS_NBUF * (size_t)seg_cells + (DK >= 2 ? seg_cells : 0) + (size_t)(dose_rows ? ROWS_NBUF : 0) * (seg_cells / P)) +
                         (size_t)cap * 5 + 2 * (ROWS_MAX_BAND + 2) * 4;
     RowsOverflowArgs oa{};
     oa.dose_mode = dose_mode; oa.code = c->code_d; oa.match_code = c->match_d; oa.A = c->A;
@@ -408,12 +416,20 @@ static int emit_rows_path(psim_ctx_impl* c, int64_t ind_first, int64_t ind_count
         k_band_plan<<<dim3((unsigned)((n_cols + 255) / 256), (unsigned)ra.n_chunks), 256, 0, c->stream>>>(ra);
         cudaEventRecord(next_kev(c), c->stream);
         const int blocks = std::min(ra.n_units, n_blocks);
-        if (DK == 0) launch_rows<0>(c, ra, blocks, smem);
-        else if (DK == 1) launch_rows<1>(c, ra, blocks, smem);
-        else if (DK == 2) launch_rows<2>(c, ra, blocks, smem);
-        else launch_rows<3>(c, ra, blocks, smem);
+        if (packed) {
+            if (DK == 0) launch_rows_packed<0>(c, ra, blocks, smem);
+            else if (DK == 1) launch_rows_packed<1>(c, ra, blocks, smem);
+            else if (DK == 2) launch_rows_packed<2>(c, ra, blocks, smem);
+            else launch_rows_packed<3>(c, ra, blocks, smem);
+        } else {
+            if (DK == 0) launch_rows<0>(c, ra, blocks, smem);
+            else if (DK == 1) launch_rows<1>(c, ra, blocks, smem);
+            else if (DK == 2) launch_rows<2>(c, ra, blocks, smem);
+            else launch_rows<3>(c, ra, blocks, smem);
+        }
         cudaEventRecord(next_kev(c), c->stream);
-        k_emit_rows_overflow<<<dim3((unsigned)c->sm_count, 8), 256, 0, c->stream>>>(ra, oa);
+        if (packed) k_emit_rows_overflow_packed<<<dim3((unsigned)c->sm_count, 8), 256, 0, c->stream>>>(ra, oa, c->locus_off_d);
+        else k_emit_rows_overflow<<<dim3((unsigned)c->sm_count, 8), 256, 0, c->stream>>>(ra, oa);
         c->stats.kernel_launches += 4;
         c->stats.emit_kernel_launches++;
         CUDA_TRY(cudaGetLastError());
@@ -1116,9 +1132,35 @@ static int ensure_staging(psim_ctx_impl* c, size_t bytes) {
 // Emit loci [l_begin, l_end) (global) into device tables whose row 0 is locus `row0_locus`.
 static int emit_device(psim_ctx_impl* c, int64_t ind_first, int64_t ind_count, int64_t l_begin, int64_t l_end, int64_t row0_locus,
                        void* founder, int64_t founder_pitch, int founder_bytes, uint8_t* allele, int64_t allele_pitch,
-                       uint8_t* dose, int64_t dose_pitch, int dose_mode, int dose_which, int path = PSIM_PATH_AUTO) {
+                       uint8_t* dose, int64_t dose_pitch, int dose_mode, int dose_which, int path = PSIM_PATH_AUTO, bool packed = false) {
     const int P = c->P;
     const int64_t n_cols_ind = (int64_t)c->R * ind_count;
+    if (packed) {   // two 4-bit cells per byte: the row-image kernels, else one thread per pair of individuals
+        const bool aligned16 = (!founder || ((uintptr_t)founder % 16 == 0 && founder_pitch % 16 == 0)) &&
+                               (!dose || ((uintptr_t)dose % 16 == 0 && dose_pitch % 16 == 0));
+        if (aligned16 && c->run_cap < (int64_t)0xFFFFFFFF && path != PSIM_PATH_GENERIC) {
+            bool done = false;
+            const int mode0 = !c->code_d ? 0 : c->A <= 8 ? 1 : 2;
+            if (int rc = emit_rows_path(c, ind_first, ind_count, l_begin, l_end, row0_locus, (uint8_t*)founder, founder_pitch, dose, dose_pitch,
+                                        dose_mode, dose_which, mode0, path, true, done)) return rc;
+            if (done) return PSIM_OK;
+        }
+        EmitPackedArgs pa{};
+        pa.C = c->C; pa.R = c->R; pa.P = P; pa.N = c->N;
+        pa.run_desc = c->run_desc_d; pa.run_lb = c->run_lb_d; pa.run_founder = c->run_founder_d; pa.locus_off = c->locus_off_d;
+        pa.ind_first = ind_first; pa.ind_count = ind_count; pa.n_cols_ind = n_cols_ind;
+        pa.locus_first = row0_locus; pa.l_begin = l_begin; pa.l_count = l_end - l_begin;
+        pa.q_first = 0; pa.q_count = n_cols_ind;
+        pa.founder = (uint8_t*)founder; pa.founder_pitch = founder_pitch; pa.dose = dose; pa.dose_pitch = dose_pitch;
+        pa.dose_mode = dose_mode; pa.dose_which = dose_which; pa.code = c->code_d; pa.match_code = c->match_d; pa.A = c->A;
+        cudaEventRecord(next_kev(c), c->stream);
+        k_emit_generic_packed<<<grid_for(pa.l_count * ((n_cols_ind + 1) / 2), 256), 256, 0, c->stream>>>(pa);
+        cudaEventRecord(next_kev(c), c->stream);
+        c->stats.kernel_launches++;
+        c->stats.emit_kernel_launches++;
+        CUDA_TRY(cudaGetLastError());
+        return PSIM_OK;
+    }
     int G = 0;
     if (P == 2) G = 8; else if (P == 4) G = 4; else if (P == 6) G = 8; else if (P == 8) G = 2;
     const bool aligned = (!founder || ((uintptr_t)founder % 16 == 0 && founder_pitch % 16 == 0)) &&
@@ -1132,7 +1174,7 @@ static int emit_device(psim_ctx_impl* c, int64_t ind_first, int64_t ind_count, i
         bool done = false;
         const int mode0 = !c->code_d ? 0 : c->A <= 8 ? 1 : c->A <= 16 ? 2 : 3;
         if (int rc = emit_rows_path(c, ind_first, ind_count, l_begin, l_end, row0_locus, (uint8_t*)founder, founder_pitch, dose, dose_pitch,
-                                    dose_mode, dose_which, mode0, path, done)) return rc;
+                                    dose_mode, dose_which, mode0, path, false, done)) return rc;
         if (done) return PSIM_OK;
     }
     if (path == PSIM_PATH_GENERIC) tiled = false;
@@ -1278,9 +1320,17 @@ int psim_emit(psim_ctx* ctx, int64_t ind_first, int64_t ind_count, int64_t locus
     if (t->allele && !c->code_d) return fail(c, PSIM_ESTATE, "allele table requested but no allele codes set");
     const int64_t n_cols_ind = (int64_t)c->R * ind_count;
     const int64_t n_cols = n_cols_ind * c->P;
-    if (t->founder && t->founder_pitch < n_cols * fb) return fail(c, PSIM_EINVAL, "founder_pitch too small");
+    const bool packed = (t->flags & PSIM_EMIT_PACKED4) != 0;
+    if (packed) {
+        if (t->allele) return fail(c, PSIM_EINVAL, "PSIM_EMIT_PACKED4 has no allele table");
+        if (fb != 1) return fail(c, PSIM_EINVAL, "PSIM_EMIT_PACKED4 needs founder_bytes = 1");
+        if (c->founder_allele_count > 16) return fail(c, PSIM_EINVAL, "PSIM_EMIT_PACKED4 needs at most 16 founder alleles");
+        if (c->P > 14) return fail(c, PSIM_EINVAL, "PSIM_EMIT_PACKED4 needs ploidy <= 14");
+    }
+    const int64_t w_founder = packed ? (n_cols + 1) / 2 : n_cols * fb, w_dose = packed ? (n_cols_ind + 1) / 2 : n_cols_ind;
+    if (t->founder && t->founder_pitch < w_founder) return fail(c, PSIM_EINVAL, "founder_pitch too small");
     if (t->allele && t->allele_pitch < n_cols) return fail(c, PSIM_EINVAL, "allele_pitch too small");
-    if (t->dose && t->dose_pitch < n_cols_ind) return fail(c, PSIM_EINVAL, "dose_pitch too small");
+    if (t->dose && t->dose_pitch < w_dose) return fail(c, PSIM_EINVAL, "dose_pitch too small");
     int dose_mode = 0, dose_which = t->dose_which;
     if (c->code_d) {
         dose_mode = 1;
@@ -1301,7 +1351,7 @@ int psim_emit(psim_ctx* ctx, int64_t ind_first, int64_t ind_count, int64_t locus
     if (t->memory == PSIM_MEM_DEVICE) {
         if (int rc = emit_device(c, ind_first, ind_count, locus_first, locus_first + locus_count, locus_first, t->founder,
                                  t->founder_pitch, fb, (uint8_t*)t->allele, t->allele_pitch, (uint8_t*)t->dose, t->dose_pitch,
-                                 dose_mode, dose_which, path)) return rc;
+                                 dose_mode, dose_which, path, packed)) return rc;
         CUDA_TRY(cudaEventRecord(c->ev1, c->stream));
         if (t->flags & PSIM_EMIT_ASYNC) { c->emit_pending = true; c->emit_pending_device = true; return PSIM_OK; }
         CUDA_TRY(cudaStreamSynchronize(c->stream));
@@ -1315,9 +1365,9 @@ int psim_emit(psim_ctx* ctx, int64_t ind_first, int64_t ind_count, int64_t locus
         // unaligned; strided: padded host rows (a view into a wider table) are copied row by row
         struct Tab { void* host; int64_t hpitch, width; bool direct; int64_t spitch; bool strided; };
         auto up = [](int64_t x, int64_t m) { return (x + m - 1) / m * m; };
-        Tab tab[3] = {{t->founder, t->founder_pitch, n_cols * fb, false, 0, false},
+        Tab tab[3] = {{t->founder, t->founder_pitch, w_founder, false, 0, false},
                       {t->allele, t->allele_pitch, n_cols, false, 0, false},
-                      {t->dose, t->dose_pitch, n_cols_ind, false, 0, false}};
+                      {t->dose, t->dose_pitch, w_dose, false, 0, false}};
         int64_t row_bytes = 0;
         for (Tab& x : tab) {
             if (!x.host) continue;
@@ -1360,7 +1410,7 @@ int psim_emit(psim_ctx* ctx, int64_t ind_first, int64_t ind_count, int64_t locus
             if (k >= 2) CUDA_TRY(cudaStreamWaitEvent(c->stream, freed[sl], 0));   // slot copied out
             if (trace) { timespec ts; clock_gettime(CLOCK_MONOTONIC, &ts); fprintf(stderr, "psim_emit chunk %d begins at host %.3f ms\n", k, ts.tv_sec * 1e3 + ts.tv_nsec * 1e-6); }
             if (int rc = emit_device(c, ind_first, ind_count, l0, l1, l0, sp[0], tab[0].spitch, fb, sp[1], tab[1].spitch,
-                                     sp[2], tab[2].spitch, dose_mode, dose_which, path)) return rc;
+                                     sp[2], tab[2].spitch, dose_mode, dose_which, path, packed)) return rc;
             for (int q = 0; q < 3; q++)
                 if (dn[q]) {   // (a 2-D device copy with an unaligned pitch runs at a fraction of this kernel's pace)
                     k_repack_dense<<<c->sm_count * 8, 256, 0, c->stream>>>(sp[q], tab[q].spitch, dn[q], tab[q].width, nr);

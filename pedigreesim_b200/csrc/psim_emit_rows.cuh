@@ -378,3 +378,275 @@ __global__ void __launch_bounds__(256) k_emit_rows_overflow(const RowsArgs a, co
         }
     }
 }
+
+// ------------------------------------------------------------------------------------------
+// PSIM_EMIT_PACKED4: the same tables with two 4-bit cells per byte (cell 2k in the low nibble). The row
+// image IS the packed founder row (4 bits per cell), so there is no byte image at all: a buffer is
+// patched with one atomicXor per run start (cells that share a word are patched by different threads),
+// the dose nibbles come straight out of the PRMT / IDP.4A lookup, and a table row leaves the SM as
+// half the bytes. Same plan, same issuing warps, same barriers as k_emit_rows.
+template <int DK>
+__global__ void __launch_bounds__(ROWS_THREADS, 1) k_emit_rows_packed(const RowsArgs a) {
+    extern __shared__ __align__(128) uint8_t smem[];
+    const int tid = threadIdx.x;
+    const int NT = ROWS_THREADS;
+    const int P = a.P;
+    const int seg_cells = a.seg_cells, seg_ind = seg_cells / P;   // seg_cells is a multiple of 32 * P
+    constexpr int NB = ROWS_NBUF;
+    const int img_bytes = seg_cells / 2, dose_bytes = seg_ind / 2;
+    uint8_t* const img0 = smem;                                              // 4-bit founder of every cell on the buffer's row (x NB)
+    uint8_t* const dose0 = img0 + (size_t)NB * img_bytes;                    // DK >= 1: 4-bit dose rows (x NB)
+    uint32_t* const evs = reinterpret_cast<uint32_t*>(dose0 + (DK >= 1 ? (size_t)NB * dose_bytes : 0));
+    uint32_t* const start = evs + a.cap;
+    uint32_t* const cursor = start + ROWS_MAX_BAND + 2;
+    uint8_t* const evd = reinterpret_cast<uint8_t*>(cursor + ROWS_MAX_BAND + 2);
+    __shared__ int s_unit;
+    const int64_t n_cols = a.n_cols_ind * P;
+    const bool count_ok = a.dose_which >= 0 && a.dose_which < 16;            // DK 1: a founder allele that exists
+
+    for (;;) {
+        __syncthreads();
+        if (tid == 0) s_unit = atomicAdd(a.unit_counter, 1);
+        __syncthreads();
+        const int u = s_unit;
+        if (u >= a.n_units) break;
+        int k = 0;
+        while (u >= a.chunk_unit_base[k + 1]) k++;
+        const int j = (u - a.chunk_unit_base[k]) / a.n_seg, s = (u - a.chunk_unit_base[k]) % a.n_seg;
+        int64_t g0, g1;
+        band_rows(a, k, j, g0, g1);
+        const int n_rows = (int)(g1 - g0);
+        const int64_t out_row0 = g0 - a.locus_first;
+        const int64_t c0 = (int64_t)s * seg_cells;
+        const int n_cell = (int)min((int64_t)seg_cells, n_cols - c0);
+        const int n_ind = n_cell / P;
+        const int row_bytes = (n_cell + 1) / 2, drow_bytes = (n_ind + 1) / 2;   // (cells past the end are zero)
+        const uint8_t* pu = a.plan + (int64_t)u * a.plan_stride;
+        const uint32_t n_ev = *reinterpret_cast<const uint32_t*>(pu);
+        if (n_ev > (uint32_t)a.cap) {
+            if (tid == 0) a.overflow[1 + atomicAdd(a.overflow, 1)] = u;
+            continue;
+        }
+        // ---- start state of the band packed to 4 bits, run starts bucketed by row (all threads)
+        for (int i = tid; i < seg_cells / 16; i += NT) {
+            uint4 v = __ldg(reinterpret_cast<const uint4*>(pu + 16) + i);
+            if (i * 16 + 16 > n_cell) {   // the plan's state bytes beyond the last column were never written
+                uint32_t w4[4] = {v.x, v.y, v.z, v.w};
+                for (int q = 0; q < 16; q++) if (i * 16 + q >= n_cell) w4[q >> 2] &= ~(0xFFu << (8 * (q & 3)));
+                v = make_uint4(w4[0], w4[1], w4[2], w4[3]);
+            }
+            auto pack = [](uint32_t x) { return (x & 0xF) | ((x >> 4) & 0xF0) | ((x >> 8) & 0xF00) | ((x >> 12) & 0xF000); };
+            reinterpret_cast<uint2*>(img0)[i] = make_uint2(pack(v.x) | (pack(v.y) << 16), pack(v.z) | (pack(v.w) << 16));
+        }
+        for (int i = tid; i <= n_rows; i += NT) start[i] = 0;
+        __syncthreads();
+        const uint32_t* ev_g = reinterpret_cast<const uint32_t*>(pu + 16 + seg_cells);
+        const uint8_t* evd_g = pu + 16 + seg_cells + (size_t)a.cap * 4;
+        for (uint32_t e = tid; e < n_ev; e += NT) atomicAdd(&start[__ldg(ev_g + e) >> 24], 1u);
+        __syncthreads();
+        if (tid < 32) {
+            uint32_t carry = 0;
+            for (int base = 0; base <= n_rows; base += 32) {
+                const int i = base + tid;
+                const uint32_t v = i <= n_rows ? start[i] : 0;
+                uint32_t x = v;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) { const uint32_t y = __shfl_up_sync(0xFFFFFFFFu, x, o); if (tid >= o) x += y; }
+                if (i <= n_rows) { start[i] = carry + x - v; cursor[i] = carry + x - v; }
+                carry += __shfl_sync(0xFFFFFFFFu, x, 31);
+            }
+        }
+        __syncthreads();
+        for (uint32_t e = tid; e < n_ev; e += NT) {
+            const uint32_t w = __ldg(ev_g + e);
+            const uint32_t at = atomicAdd(&cursor[w >> 24], 1u);
+            evs[at] = w;
+            evd[at] = __ldg(evd_g + e);
+        }
+        if (DK == 1) {   // dose of one founder allele on the band's first row, 4 bits per individual
+            for (int i = tid; i < seg_ind / 8; i += NT) {   // 8 individuals = one word of dose nibbles
+                uint32_t out = 0;
+                for (int q = 0; q < 8; q++) {
+                    const int ind = i * 8 + q;
+                    int dsum = 0;
+                    for (int h = 0; h < P; h++) {
+                        const int cell = ind * P + h;
+                        dsum += ((img0[cell >> 1] >> (4 * (cell & 1))) & 15) == a.dose_which;
+                    }
+                    if (count_ok && ind < n_ind) out |= (uint32_t)dsum << (4 * q);
+                }
+                reinterpret_cast<uint32_t*>(dose0)[i] = out;
+            }
+        }
+        __syncthreads();
+        for (int b = 1; b < NB; b++) {
+            for (int i = tid; i < img_bytes / 16; i += NT)
+                reinterpret_cast<uint4*>(img0 + (size_t)b * img_bytes)[i] = reinterpret_cast<const uint4*>(img0)[i];
+            if (DK == 1)
+                for (int i = tid; i < dose_bytes / 16; i += NT)
+                    reinterpret_cast<uint4*>(dose0 + (size_t)b * dose_bytes)[i] = reinterpret_cast<const uint4*>(dose0)[i];
+        }
+        __syncthreads();
+
+        if (tid >= ROWS_COMPUTE) {
+            const int lane = tid & 31, b = (tid - ROWS_COMPUTE) >> 5;
+            const uint8_t* const img = img0 + (size_t)b * img_bytes;
+            const uint8_t* const drow = dose0 + (size_t)b * dose_bytes;
+            for (int r = b; r < n_rows; r += NB) {
+                uint8_t* const gf = a.founder ? a.founder + (out_row0 + r) * a.founder_pitch + c0 / 2 : nullptr;
+                uint8_t* const gd = a.dose ? a.dose + (out_row0 + r) * a.dose_pitch + c0 / P / 2 : nullptr;
+                bar_sync(BAR_FULL + b, ROWS_COMPUTE + 32);
+                if (lane == 0) {
+                    if (gf && (row_bytes & ~15)) bulk_store(gf, img, (uint32_t)(row_bytes & ~15));
+                    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                } else if (lane == 1) {
+                    if (DK >= 1 && gd && (drow_bytes & ~15)) bulk_store(gd, drow, (uint32_t)(drow_bytes & ~15));
+                    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                } else {
+                    const int t = lane - 2;
+                    if (gf && t < 15 && t < (row_bytes & 15)) gf[(row_bytes & ~15) + t] = img[(row_bytes & ~15) + t];
+                    if (DK >= 1 && gd && t >= 15 && t - 15 < (drow_bytes & 15)) gd[(drow_bytes & ~15) + t - 15] = drow[(drow_bytes & ~15) + t - 15];
+                }
+                if (lane < 2) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+                __syncwarp();
+                if (r + NB < n_rows) bar_arrive(BAR_EMPTY + b, ROWS_COMPUTE + 32);
+            }
+            continue;
+        }
+
+        constexpr int CT = ROWS_COMPUTE;
+        uint4 Tn = make_uint4(0, 0, 0, 0);
+        if (DK >= 2) Tn = __ldg(a.mtab + g0);
+        for (int r = 0; r < n_rows; r++) {
+            const int b = r % NB;
+            uint32_t* const img = reinterpret_cast<uint32_t*>(img0 + (size_t)b * img_bytes);
+            uint32_t* const drow = reinterpret_cast<uint32_t*>(dose0 + (size_t)b * dose_bytes);
+            const int w0 = max(1, r - NB + 1);
+            const uint32_t e0 = start[w0], e1 = start[r + 1];
+            if (r >= NB) bar_sync(BAR_EMPTY + b, ROWS_COMPUTE + 32);
+            for (uint32_t e = e0 + tid; e < e1; e += CT) {
+                const uint32_t w = evs[e], cs = (w >> 8) & 0xFFFF, f = w & 0xF;
+                if ((int)(w >> 24) + (int)evd[e] <= r) continue;   // the cell changes again inside the window
+                const uint32_t sh = (cs & 7) * 4;
+                const uint32_t old = (img[cs >> 3] >> sh) & 15u;   // (only this thread changes this nibble)
+                if (DK == 1) {
+                    const int delta = (int)(f == (uint32_t)a.dose_which) - (int)(count_ok && old == (uint32_t)a.dose_which);
+                    const uint32_t ind = cs / P;
+                    if (delta) atomicAdd(drow + (ind >> 3), (uint32_t)delta << (4 * (ind & 7)));
+                }
+                atomicXor(&img[cs >> 3], (old ^ f) << sh);
+            }
+            if (DK >= 2) {
+                bar_sync(BAR_WORK, CT);
+                const uint4 T = Tn;
+                if (r + 1 < n_rows) Tn = __ldg(a.mtab + g0 + r + 1);
+                if (DK == 2) {   // 8 individuals per step: 4 words of the image in, 8 dose nibbles out
+                    for (int i = tid; i < seg_ind / 8; i += CT) {
+                        const uint4 v = reinterpret_cast<const uint4*>(img)[i];
+                        auto two = [&](uint32_t w) { return __dp4a(prmt(T.x, T.y, w) + prmt(T.z, T.w, w >> 16), 0x01010101u, 0u); };
+                        uint32_t out = two(v.x) | (two(v.y) << 8) | (two(v.z) << 16) | (two(v.w) << 24);
+                        if (i * 8 + 8 > n_ind) out &= i * 8 >= n_ind ? 0u : 0xFFFFFFFFu >> (4 * (i * 8 + 8 - n_ind));   // nibbles past the last individual are zero
+                        drow[i] = out;
+                    }
+                } else {         // ploidy 2: 16 individuals per step
+                    for (int i = tid; i < seg_ind / 16; i += CT) {
+                        const uint4 v = reinterpret_cast<const uint4*>(img)[i];
+                        auto four = [&](uint32_t w) {   // 4 individuals of one word -> 16 bits of dose nibbles
+                            const uint32_t xl = prmt(T.x, T.y, w), xh = prmt(T.x, T.y, w >> 16);
+                            const uint32_t d = prmt(xl + (xl >> 8), xh + (xh >> 8), 0x6420u);
+                            return (d & 0xF) | ((d >> 4) & 0xF0) | ((d >> 8) & 0xF00) | ((d >> 12) & 0xF000);
+                        };
+                        uint32_t o0 = four(v.x) | (four(v.y) << 16), o1 = four(v.z) | (four(v.w) << 16);
+                        if (i * 16 + 8 > n_ind) o0 &= i * 16 >= n_ind ? 0u : 0xFFFFFFFFu >> (4 * (i * 16 + 8 - n_ind));
+                        if (i * 16 + 16 > n_ind) o1 &= i * 16 + 8 >= n_ind ? 0u : 0xFFFFFFFFu >> (4 * (i * 16 + 16 - n_ind));
+                        reinterpret_cast<uint2*>(drow)[i] = make_uint2(o0, o1);
+                    }
+                }
+            }
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            bar_arrive(BAR_FULL + b, ROWS_COMPUTE + 32);
+        }
+    }
+    if (tid >= ROWS_COMPUTE && (tid & 31) < 2) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+}
+
+// per-cell kernels for packed tables: one thread per (row, pair of emitted individuals)
+struct EmitPackedArgs {
+    int C, R, P;
+    int64_t N;
+    const uint64_t* run_desc;
+    const uint32_t* run_lb;
+    const uint16_t* run_founder;
+    const int64_t* locus_off;
+    int64_t ind_first, ind_count, n_cols_ind;
+    int64_t locus_first, l_begin, l_count;
+    int64_t q_first, q_count;     // emitted individuals of this launch; q_first even
+    uint8_t* founder; int64_t founder_pitch;
+    uint8_t* dose; int64_t dose_pitch;
+    int dose_mode, dose_which;
+    const uint8_t* code; const uint8_t* match_code; int A;
+};
+__device__ __forceinline__ void emit_packed_pair(const EmitPackedArgs& a, int c, uint32_t l, int64_t gl, int64_t q) {
+    const int P = a.P;
+    const int64_t row = gl - a.locus_first;
+    const uint8_t* codes = a.code ? a.code + gl * a.A : nullptr;
+    const int match = a.dose_mode == 1 ? (int)a.match_code[gl] : a.dose_which;
+    uint8_t fl[32];       // founder alleles of the pair's 2 * P cells
+    for (int k = 0; k < 2 * P; k++) fl[k] = 0;
+    int dose2 = 0;
+    for (int x = 0; x < 2; x++) {
+        if (q + x >= a.q_first + a.q_count) break;
+        const int64_t r = (q + x) / a.ind_count, i = a.ind_first + (q + x) % a.ind_count;
+        const int64_t hid0 = (((int64_t)c * a.R + r) * a.N + i) * P;
+        int dose = 0;
+        for (int h = 0; h < P; h++) {
+            const uint64_t d = a.run_desc[hid0 + h];
+            const uint64_t b = desc_begin(d);
+            const uint32_t n = desc_count(d);
+            uint32_t lo = 0, hi = n;
+            while (hi - lo > 1) { const uint32_t mid = (lo + hi) >> 1; if (a.run_lb[b + mid] <= l) lo = mid; else hi = mid; }
+            const int f = a.run_founder[b + lo];
+            fl[x * P + h] = (uint8_t)(f & 15);
+            if ((codes ? (int)codes[f] : f) == match) dose++;
+        }
+        dose2 |= dose << (4 * x);
+    }
+    if (a.founder) for (int k = 0; k < P; k++) a.founder[row * a.founder_pitch + (q / 2) * P + k] = (uint8_t)(fl[2 * k] | (fl[2 * k + 1] << 4));
+    if (a.dose) a.dose[row * a.dose_pitch + q / 2] = (uint8_t)dose2;
+}
+__global__ void __launch_bounds__(256) k_emit_generic_packed(const EmitPackedArgs a) {
+    const int64_t pairs = (a.q_count + 1) / 2;
+    const int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (t >= a.l_count * pairs) return;
+    const int64_t gl = a.l_begin + t / pairs, q = a.q_first + 2 * (t % pairs);
+    int c = 0;
+    while (gl >= a.locus_off[c + 1]) c++;
+    emit_packed_pair(a, c, (uint32_t)(gl - a.locus_off[c]), gl, q);
+}
+__global__ void __launch_bounds__(256) k_emit_rows_overflow_packed(const RowsArgs a, const RowsOverflowArgs o, const int64_t* locus_off) {
+    const int n_over = a.overflow[0];
+    const int P = a.P;
+    const int64_t n_cols = a.n_cols_ind * P;
+    for (int x = blockIdx.y; x < n_over; x += gridDim.y) {
+        const int u = a.overflow[1 + x];
+        int k = 0;
+        while (u >= a.chunk_unit_base[k + 1]) k++;
+        const int j = (u - a.chunk_unit_base[k]) / a.n_seg, s = (u - a.chunk_unit_base[k]) % a.n_seg;
+        int64_t g0, g1;
+        band_rows(a, k, j, g0, g1);
+        const int64_t c0 = (int64_t)s * a.seg_cells;
+        EmitPackedArgs e{};
+        e.C = a.C; e.R = a.R; e.P = P; e.N = a.N;
+        e.run_desc = a.run_desc; e.run_lb = a.run_lb; e.run_founder = a.run_founder; e.locus_off = locus_off;
+        e.ind_first = a.ind_first; e.ind_count = a.ind_count; e.n_cols_ind = a.n_cols_ind;
+        e.locus_first = a.locus_first;
+        e.q_first = c0 / P; e.q_count = min((int64_t)a.seg_cells, n_cols - c0) / P;
+        e.founder = a.founder; e.founder_pitch = a.founder_pitch; e.dose = a.dose; e.dose_pitch = a.dose_pitch;
+        e.dose_mode = o.dose_mode; e.dose_which = a.dose_which; e.code = o.code; e.match_code = o.match_code; e.A = o.A;
+        const int64_t pairs = (e.q_count + 1) / 2;
+        for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < (g1 - g0) * pairs; t += (int64_t)gridDim.x * blockDim.x) {
+            const int64_t gl = g0 + t / pairs;
+            emit_packed_pair(e, a.chunk_chrom[k], (uint32_t)(gl - a.chunk_coff[k]), gl, e.q_first + 2 * (t % pairs));
+        }
+    }
+}

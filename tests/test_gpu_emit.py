@@ -233,3 +233,60 @@ def test_more_than_64_chromosomes_and_replicates():
     g.set_locus_names(["L%d" % l for l in range(sum(loci))])
     text = g.emit_text(founder=True)["founder"].split(b"\n")
     assert text[10].split(b"\t")[1:] == [str(int(v)).encode() for v in got["founder"][10]]
+
+
+def _pack4(table):
+    """Two 4-bit cells per byte, cell 2k in the low nibble; an odd last cell is padded with zero (PSIM_EMIT_PACKED4)."""
+    t = np.asarray(table, dtype=np.uint8)
+    if t.shape[1] % 2:
+        t = np.concatenate([t, np.zeros((t.shape[0], 1), np.uint8)], axis=1)
+    return (t[:, 0::2] & 15) | ((t[:, 1::2] & 15) << 4)
+
+
+@pytest.mark.parametrize("ploidy,n_ind,loci,codes,which", [
+    (4, 700, [257, 64], 2, _oracle.MAX_ALLELE), (4, 701, [257, 64], 2, 1), (2, 1233, [300, 7, 129], 2, _oracle.MIN_ALLELE),
+    (4, 333, [150, 33], 0, 3), (2, 77, [90], 0, 0), (6, 301, [130, 20], 0, 5), (6, 90, [77], 3, _oracle.MAX_ALLELE), (8, 41, [40], 0, 9),
+])
+def test_packed_tables_are_the_oracle_tables_packed(ploidy, n_ind, loci, codes, which):
+    import pedigreesim_b200 as ps
+    lengths = [1.0 + 0.25 * k for k in range(len(loci))]
+    n_alleles = min(16, ploidy * 2)
+    o, g = _both(ploidy, lengths, n_ind, n_alleles, loci, seed=ploidy * 100 + n_ind, codes=codes)
+    ref_f, ref_d = _pack4(o.emit(_oracle.EMIT_FOUNDER)), _pack4(o.emit(_oracle.EMIT_DOSE, which=which))
+    for path in (ps.PATH_AUTO, ps.PATH_ROWS, ps.PATH_GENERIC):
+        got = g.emit(founder=True, dose=True, dose_which=which, packed=True, path=path)
+        assert np.array_equal(got["founder"], ref_f), path
+        assert np.array_equal(got["dose"], ref_d), path
+    got = g.emit(founder=True, packed=True)
+    assert np.array_equal(got["founder"], ref_f)
+    got = g.emit(dose=True, dose_which=which, packed=True)
+    assert np.array_equal(got["dose"], ref_d)
+    # a sub-range starts its own packing at its first individual
+    i0, ni, l0, nl = 3, n_ind // 2 | 1, 5, loci[0] - 9
+    got = g.emit(founder=True, dose=True, dose_which=which, packed=True, ind_first=i0, ind_count=ni, loc_first=l0, loc_count=nl)
+    assert np.array_equal(got["founder"], _pack4(o.emit(_oracle.EMIT_FOUNDER)[l0:l0 + nl, i0 * ploidy:(i0 + ni) * ploidy]))
+    assert np.array_equal(got["dose"], _pack4(o.emit(_oracle.EMIT_DOSE, which=which)[l0:l0 + nl, i0:i0 + ni]))
+
+
+def test_packed_rows_wider_than_one_segment_and_overflowing_lists():
+    import pedigreesim_b200 as ps
+    # 60 000 individuals x 4: several row segments per table row
+    o, g = _both(4, [1.0], 60000, 8, [21], seed=3, codes=2, max_segments=3)
+    got = g.emit(founder=True, dose=True, dose_which=_oracle.MAX_ALLELE, packed=True)
+    assert np.array_equal(got["founder"], _pack4(o.emit(_oracle.EMIT_FOUNDER)))
+    assert np.array_equal(got["dose"], _pack4(o.emit(_oracle.EMIT_DOSE, which=_oracle.MAX_ALLELE)))
+    # a sparse map forced onto the row-image kernels: the lists overflow, the units are redone per pair
+    for ploidy, codes in ((4, 0), (4, 2), (2, 2)):
+        o, g = _both(ploidy, [6.0, 1.0], 3001, ploidy * 2, [24, 40], seed=41 + ploidy, codes=codes, max_segments=40, grid_breaks=False)
+        which = _oracle.MAX_ALLELE if codes else 3
+        got = g.emit(founder=True, dose=True, dose_which=which, packed=True, path=ps.PATH_ROWS)
+        assert np.array_equal(got["founder"], _pack4(o.emit(_oracle.EMIT_FOUNDER)))
+        assert np.array_equal(got["dose"], _pack4(o.emit(_oracle.EMIT_DOSE, which=which)))
+
+
+def test_packed_requests_that_cannot_be_served_are_refused():
+    import pedigreesim_b200 as ps
+    o, g = _both(4, [1.0], 10, 20, [9], seed=1)          # 20 founder alleles do not fit 4 bits
+    with pytest.raises(ps.PsimError) as e:
+        g.emit(founder=True, packed=True)
+    assert e.value.code == ps.PSIM_EINVAL and "16 founder alleles" in str(e.value)

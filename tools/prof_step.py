@@ -23,6 +23,7 @@ def main():
     ap.add_argument("--no-dose", action="store_true")
     ap.add_argument("--no-founder", action="store_true")
     ap.add_argument("--no-codes", action="store_true", help="no founder genotypes: dose of founder allele 0")
+    ap.add_argument("--packed", action="store_true", help="PSIM_EMIT_PACKED4 tables")
     ap.add_argument("--scale", type=float, default=1.0, help="scale chromosome lengths (1e-4: no crossovers at all)")
     args = ap.parse_args()
     w = bench.workload(args.popsize)
@@ -35,8 +36,8 @@ def main():
     ctx.set_map(w["off"], w["pos"])
     if not args.no_codes:
         ctx.set_allele_codes(w["code"])
-    fp = (N * P + 127) // 128 * 128
-    dp = (N + 127) // 128 * 128
+    fp = (N * P // (2 if args.packed else 1) + 127) // 128 * 128
+    dp = ((N + 1) // (2 if args.packed else 1) + 127) // 128 * 128
     d_founder = torch.empty((L, fp), dtype=torch.uint8, device="cuda")
     d_dose = torch.empty((L, dp), dtype=torch.uint8, device="cuda")
     d_allele = torch.empty((L, fp), dtype=torch.uint8, device="cuda") if args.alleles else None
@@ -48,6 +49,8 @@ def main():
     if args.alleles:
         tgt.allele, tgt.allele_pitch = d_allele.data_ptr(), fp
     tgt.memory = ps.MEM_DEVICE
+    tgt.flags = ps.EMIT_PACKED4 if args.packed else 0
+    div = 2 if args.packed else 1
     for k in range(args.steps):
         t0 = time.perf_counter()
         ctx.reset(bench.SEED, k + 1)
@@ -60,7 +63,7 @@ def main():
         st = ctx.stats()
         print("step %d: reset %.2f ms, simulate %.2f ms (device %.2f), emit %.2f ms (kernel %.3f ms = %.0f GB/s)" % (
             k, (t1 - t0) * 1e3, (t2 - t1) * 1e3, st["ms_simulate"], (t3 - t2) * 1e3, st["ms_emit_kernel"],
-            N * L * ((0 if args.no_founder else P) + (0 if args.no_dose else 1) + (P if args.alleles else 0)) / st["ms_emit_kernel"] / 1e6))
+            N * L * ((0 if args.no_founder else P) + (0 if args.no_dose else 1) + (P if args.alleles else 0)) / div / st["ms_emit_kernel"] / 1e6))
     ctx.close()
 
 
