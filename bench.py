@@ -12,8 +12,12 @@ the HBM-write-bound kernel; N*L*(P+1) algorithmic bytes). With N > 1 GPUs every 
 emits its own replicate population of that size (weak scaling, no data-path collective).
 
 Prints ONE JSON line (rank 0). `value` is measured with inputs resident in HBM and outputs written
-to HBM; `e2e` is the same metric through the C ABI with host buffers (pedigree / map / allele-code
-uploads and the device->host copy of both tables inside the timed region).
+to HBM (u8 tables): two contexts alternate, the next replicate's meioses (psim_simulate_async) run
+while the current one is emitted (PSIM_EMIT_ASYNC), one host wait per step. `e2e` is the same metric
+through the C ABI with host buffers (pedigree / map / allele-code uploads and the device->host copy of
+both tables inside the timed region), with PSIM_EMIT_PACKED4 tables (two 4-bit cells per byte: the 8
+founder alleles and the doses 0..4 of this workload fit; SURVEY.md 8(d) counts a packed format at its
+packed size); `e2e.u8` is the same leg with one byte per cell.
 """
 import argparse
 import json
@@ -29,6 +33,7 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 SEED = 12345
+CPU_SAMPLE_POPSIZE = 1000   # offspring per CPU population: the one sample size of cpu_baseline, --impl reference and DESIGN.md
 
 
 # ------------------------------------------------------------------------------------ workload
@@ -149,44 +154,80 @@ def _reference_worker(job):
     return v, t, ws["M"]
 
 
+def find_jar():
+    """The reference's own jar and a JVM to run it, if this box has both. The jar is copied (unmodified) to
+    baseline/_ref/ by __graft_entry__.build() where /root/reference exists; no JVM ships in this image."""
+    import shutil
+    java = shutil.which("java")
+    jar = os.path.join(ROOT, "baseline", "_ref", "PedigreeSim.jar")
+    return (java, jar) if java and os.path.exists(jar) else (None, None)
+
+
+def _jar_worker(job):
+    """One population = one JVM run of PedigreeSim.jar on its own .par (SEED = 12345 + replicate)."""
+    java, jar, offspring, steps, warmup, k = job
+    import tempfile
+    times = []
+    for s in range(warmup + steps):
+        with tempfile.TemporaryDirectory() as d:
+            subprocess.check_call([sys.executable, os.path.join(ROOT, "tools", "make_config.py"), "2", d, "--popsize", str(offspring)],
+                                  stdout=subprocess.DEVNULL)
+            par = os.path.join(d, "x.par")
+            txt = open(par).read().replace("SEED = 12345", "SEED = %d" % (SEED + 1000 * k + s))
+            open(par, "w").write(txt)
+            t0 = time.perf_counter()
+            subprocess.check_call([java, "-jar", jar, "x.par"], cwd=d, stdout=subprocess.DEVNULL)
+            if s >= warmup:
+                times.append(time.perf_counter() - t0)
+    ws = workload(offspring)
+    t = float(np.mean(times))
+    return ws["N"] * ws["L"] * ws["P"] / t / 1e9, t, ws["M"]
+
+
 def run_reference(args):
     """The reference's CPU path on this job. One population is one single-threaded run (the jar shares
     one java.util.Random and cannot be threaded), but the job is a sequence of independent replicate
     populations (one per step and rank), so the host runs one population per core side by side on
-    every core it has - the way PedigreeSim is run for a Monte Carlo sweep (one JVM per core)."""
+    every core it has - the way PedigreeSim is run for a Monte Carlo sweep (one JVM per core).
+    With a JVM on the box this is PedigreeSim.jar itself (kind "jar", file output included, as the
+    reference has no other sink); otherwise the oracle port of the same path (kind "port")."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     w = workload()
-    total = args.steps + args.warmup
-    # about 2 minutes for the whole run at ~0.013 G allele-loci/s on one core (measured at 10000
-    # offspring; smaller samples stay in cache and run up to 4x faster per cell)
-    offspring = int(max(100, min(10000, 120.0 / total * 0.013e9 / (w["L"] * w["P"]))))
     try:
         n_cpu = len(os.sched_getaffinity(0))
     except AttributeError:
         n_cpu = os.cpu_count() or 1
     procs = max(1, n_cpu)
-    offspring = int(max(100, min(offspring, 16e9 / (procs * w["L"] * (w["P"] + 1)))))   # tables of all populations within 16 GB
-    if procs == 1:
-        v, t, ws = cpu_port_run(w, offspring, args.steps, args.warmup)
-        meioses_per_s = ws["M"] / t
+    offspring = CPU_SAMPLE_POPSIZE
+    java, jar = find_jar()
+    import multiprocessing as mp
+    if java:
+        with mp.get_context("fork").Pool(procs) as pool:
+            res = pool.map(_jar_worker, [(java, jar, offspring, args.steps, args.warmup, k) for k in range(procs)])
+        kind, note = "jar", "PedigreeSim.jar, one JVM per core, its own output files written"
+    elif procs == 1:
+        v1, t1, ws = cpu_port_run(w, offspring, args.steps, args.warmup)
+        res = [(v1, t1, ws["M"])]
+        kind, note = "port", None
     else:
-        import multiprocessing as mp
         with mp.get_context("fork").Pool(procs) as pool:
             res = pool.map(_reference_worker, [(offspring, args.steps, args.warmup, k) for k in range(procs)])
-        t = max(r[1] for r in res)                       # the slowest population closes the step
-        v = sum(r[0] * r[1] for r in res) / t            # cells of all populations / that time
-        meioses_per_s = sum(r[2] for r in res) / t
+        kind, note = "port", None
+    if kind == "port":
+        note = ("no JVM on this box: the reference jar cannot run; this is the oracle restatement (one thread per "
+                "population like the jar), without the jar's text formatting")
+    t = max(r[1] for r in res)                       # the slowest population closes the step
+    v = sum(r[0] * r[1] for r in res) / t            # cells of all populations / that time
+    meioses_per_s = sum(r[2] for r in res) / t
     sample = "%d replicate population(s) side by side, each the same workload with POPSIZE=%d of 10000 offspring per step (all 24000 loci)" % (procs, offspring)
     out = {
         "impl": "reference", "metric": "genotype calls/sec (G allele-loci/s)", "value": v, "unit": "G allele-loci/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": t * 1e3,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
         "config": {"workload": WORKLOAD_NAME, "sample": sample},
-        "cpu_baseline": {"value": v, "unit": "G allele-loci/s", "cores": procs, "kind": "port", "sample": sample,
-                         "note": "no JVM in the image: the reference jar cannot run; this is the oracle restatement "
-                                 "(one thread per population like the jar), without the jar's text formatting"},
+        "cpu_baseline": {"value": v, "unit": "G allele-loci/s", "cores": procs, "kind": kind, "sample": sample, "note": note},
         "e2e": {"value": v, "unit": "G allele-loci/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "meioses_per_s": meioses_per_s,
     }
@@ -212,6 +253,50 @@ def bind_to_gpu_numa_node(index):
         pass
 
 
+def replicate_sweep(ps, torch, local, rank, R=2000):
+    """BASELINE.json configs[4] on this GPU: R independent replicate tetraploid pedigrees (F1 of 200, natural pairing,
+    prefPairing 0.25, 5 chromosomes x 100 loci) side by side in one context; simulate, then emit the founder-allele and
+    founder-allele-0 dose tables of all replicates (u8, device). Reports the emission against the HBM roofline end to
+    end (every emission kernel, not only the streaming one)."""
+    P, C, n, loci = 4, 5, 200, 100
+    p0 = np.array([-1, -1] + [0] * n, np.int32)
+    p1 = np.array([-1, -1] + [1] * n, np.int32)
+    N = n + 2
+    off = np.arange(C + 1, dtype=np.int64) * loci
+    pos = np.concatenate([(np.arange(loci) + 0.5) / loci for _ in range(C)])
+    ctx = ps.PsimContext(P, seed=SEED, replicate_first=1000000 + rank * R, replicate_count=R, device=local, natural_pairing=True)
+    ctx.set_chromosomes([1.0] * C, [0.5] * C, [0.25] * C, [0.0] * C)
+    ctx.set_pedigree(p0, p1)
+    ctx.set_map(off, pos)
+    L = C * loci
+    cols = R * N * P
+    fp, dp = (cols + 127) // 128 * 128, (R * N + 127) // 128 * 128
+    f = torch.empty((L, fp), dtype=torch.uint8, device="cuda")
+    d = torch.empty((L, dp), dtype=torch.uint8, device="cuda")
+    t = ps.EmitTargets()
+    t.founder, t.founder_pitch, t.founder_bytes = f.data_ptr(), fp, 1
+    t.dose, t.dose_pitch, t.dose_which = d.data_ptr(), dp, 0
+    t.memory = ps.MEM_DEVICE
+    sim, ek, et = [], [], []
+    for k in range(4):
+        ctx.reset(SEED + k, 1000000 + rank * R)
+        ctx.simulate()
+        ctx.emit_into(t, 0, N, 0, L)
+        st = ctx.stats()
+        if k:
+            sim.append(st["ms_simulate"]); ek.append(st["ms_emit_kernel"]); et.append(st["ms_emit_total"])
+    ctx.close()
+    bytes_ = L * R * N * (P + 1)
+    peak, _ = measured_peak()
+    ms_sim, ms_k, ms_all = float(np.mean(sim)), float(np.mean(ek)), float(np.mean(et))
+    return {"workload": "configs[4]: %d replicate tetraploid F1(200) pedigrees in one context, 5 chromosomes x 100 loci" % R,
+            "meioses_per_s": R * 2 * n / (ms_sim * 1e-3), "simulate_ms": ms_sim,
+            "emit_kernel_ms": ms_k, "emit_all_kernels_ms": ms_all, "bytes": bytes_,
+            "G_allele_loci_per_s": L * cols / (ms_all * 1e-3) / 1e9,
+            "roofline": {"bound": "hbm", "scope": "all emission kernels of the call (index, band plan, rows)", "achieved": bytes_ / (ms_all * 1e-3) / 1e9,
+                         "peak": peak, "unit": "GB/s", "frac": bytes_ / (ms_all * 1e-3) / 1e9 / peak}}
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
@@ -228,68 +313,110 @@ def run_ours(args):
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     w = workload()
     P, L, N, M = w["P"], w["L"], w["N"], w["M"]
-    ctx = ps.PsimContext(P, seed=SEED, replicate_first=rank, device=local, **w["model"])
-    stream = torch.cuda.Stream()
-    ctx.set_stream(stream.cuda_stream)
-    ctx.set_chromosomes(w["lengths"], w["centro"], w["pref"], w["fq"])
-    ctx.set_pedigree(w["p0"], w["p1"])
-    ctx.set_map(w["off"], w["pos"])
-    ctx.set_allele_codes(w["code"])
     fp = (N * P + 127) // 128 * 128
     dp = (N + 127) // 128 * 128
-    d_founder = torch.empty((L, fp), dtype=torch.uint8, device="cuda")
-    d_dose = torch.empty((L, dp), dtype=torch.uint8, device="cuda")
-    tgt = ps.EmitTargets()
-    tgt.founder, tgt.founder_pitch, tgt.founder_bytes = d_founder.data_ptr(), fp, 1
-    tgt.dose, tgt.dose_pitch, tgt.dose_which = d_dose.data_ptr(), dp, ps.DOSE_MAX_ALLELE
-    tgt.memory = ps.MEM_DEVICE
+
+    # three contexts = three device-resident populations in rotation: while population k is emitted, population k+1 is
+    # simulated, and the context that takes population k+1 finished its last emission a whole step ago (no wait)
+    NCTX = 3
+    ctxs, streams, tgts, keep = [], [], [], []
+    for k in range(NCTX):
+        ctx = ps.PsimContext(P, seed=SEED, replicate_first=rank, device=local, **w["model"])
+        stream = torch.cuda.Stream()
+        ctx.set_stream(stream.cuda_stream)
+        ctx.set_chromosomes(w["lengths"], w["centro"], w["pref"], w["fq"])
+        ctx.set_pedigree(w["p0"], w["p1"])
+        ctx.set_map(w["off"], w["pos"])
+        ctx.set_allele_codes(w["code"])
+        d_founder = torch.empty((L, fp), dtype=torch.uint8, device="cuda")
+        d_dose = torch.empty((L, dp), dtype=torch.uint8, device="cuda")
+        tgt = ps.EmitTargets()
+        tgt.founder, tgt.founder_pitch, tgt.founder_bytes = d_founder.data_ptr(), fp, 1
+        tgt.dose, tgt.dose_pitch, tgt.dose_which = d_dose.data_ptr(), dp, ps.DOSE_MAX_ALLELE
+        tgt.memory = ps.MEM_DEVICE
+        tgt.flags = ps.EMIT_ASYNC
+        ctxs.append(ctx); streams.append(stream); tgts.append(tgt); keep.append((d_founder, d_dose))
+    ctx = ctxs[0]
 
     def barrier():
         if world > 1:
             dist.barrier()
 
-    acc = {"sim": 0.0, "emit": 0.0, "emit_total": 0.0, "launches": 0, "emit_launches": 0}
+    acc = {"sim": 0.0, "emit": 0.0, "emit_total": 0.0, "emit_launches": 0, "n": 0}
 
-    def step(k, timed):
-        ctx.reset(SEED, rank + world * (k + 1))  # a fresh replicate every step: nothing is cached
+    def collect(c):   # device times of the context's last simulate + emit (both complete)
+        c.wait()
+        st = c.stats()
+        acc["sim"] += st["ms_simulate"]
+        acc["emit"] += st["ms_emit_kernel"]
+        acc["emit_total"] += st["ms_emit_total"]
+        acc["emit_launches"] += st["emit_kernel_launches"]
+        acc["n"] += 1
+
+    def replicate_id(k):
+        return rank + world * (k + 1)   # a fresh replicate every step: nothing is cached
+
+    def run_steps(first, count, timed):
+        # step k: population k is emitted (its simulation was enqueued one step earlier) while population k+1 is simulated
+        ctxs[first % NCTX].reset(SEED, replicate_id(first))
+        ctxs[first % NCTX].simulate_async()
+        for k in range(first, first + count):
+            a, b = k % NCTX, (k + 1) % NCTX
+            if timed and k - (NCTX - 1) >= first:
+                collect(ctxs[b])                       # its emission of step k - 2 finished long ago: no wait
+            ctxs[b].reset(SEED, replicate_id(k + 1))
+            ctxs[b].simulate_async()
+            ctxs[a].emit_into(tgts[a], 0, N, 0, L)     # the one host wait of the step: population k's simulation; then K0 + K2 are enqueued
+        for c in ctxs:
+            c.wait()
+
+    run_steps(0, args.warmup, False)
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    l0 = sum(c.stats()["kernel_launches"] for c in ctxs)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    torch.cuda.synchronize()
+    e0.record(streams[0])
+    for st_ in streams[1:]:
+        st_.wait_event(e0)
+    run_steps(args.warmup, args.steps, True)
+    for st_ in streams[1:]:
+        streams[0].wait_stream(st_)
+    e1.record(streams[0])
+    torch.cuda.synchronize()
+    barrier()
+    ms = e0.elapsed_time(e1)
+    launches = sum(c.stats()["kernel_launches"] for c in ctxs) - l0
+    clocks = sampler.stop() if rank == 0 else None
+    # the simulation of the population after the last one was enqueued too (it is part of the timed work: K steps emit K
+    # populations and simulate K + 1); kernel times of the roofline kernel, alone on the device:
+    solo = {"emit": 0.0, "launches": 0, "sim": 0.0, "total": 0.0}
+    tgts[0].flags = 0
+    for k in range(3):
+        ctx.reset(SEED, replicate_id(100000 + k))
         ctx.simulate()
-        ctx.emit_into(tgt, 0, N, 0, L)
-        if timed:
-            st = ctx.stats()
-            acc["sim"] += st["ms_simulate"]
-            acc["emit"] += st["ms_emit_kernel"]
-            acc["emit_total"] += st["ms_emit_total"]
-            acc["emit_launches"] += st["emit_kernel_launches"]
+        ctx.emit_into(tgts[0], 0, N, 0, L)
+        st = ctx.stats()
+        solo["emit"] += st["ms_emit_kernel"]; solo["launches"] += st["emit_kernel_launches"]
+        solo["sim"] += st["ms_simulate"]; solo["total"] += st["ms_emit_total"]
+    tgts[0].flags = ps.EMIT_ASYNC
 
-    with torch.cuda.stream(stream):
-        for k in range(args.warmup):
-            step(k, False)
-        sampler = ClockSampler(local)
-        if rank == 0:
-            sampler.start()
-        l0 = ctx.stats()["kernel_launches"]
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        barrier()
-        torch.cuda.synchronize()
-        e0.record(stream)
-        for k in range(args.steps):
-            step(args.warmup + k, True)
-        e1.record(stream)
-        torch.cuda.synchronize()
-        barrier()
-        ms = e0.elapsed_time(e1)
-        launches = ctx.stats()["kernel_launches"] - l0
-        clocks = sampler.stop() if rank == 0 else None
+    # ---- end to end through the C ABI with host buffers
+    stream = streams[0]
+    e2e_steps = max(1, min(args.steps, 5))
+    trace = bool(os.environ.get("PSIM_BENCH_TRACE"))
 
-        # end to end through the C ABI with host buffers
-        h_founder = torch.empty((L, N * P), dtype=torch.uint8, pin_memory=True)
-        h_dose = torch.empty((L, N), dtype=torch.uint8, pin_memory=True)
+    def e2e_leg(packed):
+        wf, wd = ((N * P + 1) // 2, (N + 1) // 2) if packed else (N * P, N)
+        h_founder = torch.empty((L, wf), dtype=torch.uint8, pin_memory=True)
+        h_dose = torch.empty((L, wd), dtype=torch.uint8, pin_memory=True)
         ht = ps.EmitTargets()
-        ht.founder, ht.founder_pitch, ht.founder_bytes = h_founder.data_ptr(), N * P, 1
-        ht.dose, ht.dose_pitch, ht.dose_which = h_dose.data_ptr(), N, ps.DOSE_MAX_ALLELE
+        ht.founder, ht.founder_pitch, ht.founder_bytes = h_founder.data_ptr(), wf, 1
+        ht.dose, ht.dose_pitch, ht.dose_which = h_dose.data_ptr(), wd, ps.DOSE_MAX_ALLELE
         ht.memory = ps.MEM_HOST
-
-        trace = bool(os.environ.get("PSIM_BENCH_TRACE"))
+        ht.flags = ps.EMIT_PACKED4 if packed else 0
 
         def e2e_step(k):
             ts = [time.perf_counter()]
@@ -307,8 +434,7 @@ def run_ours(args):
                 print("e2e step %d: set_pedigree %.2f inputs %.2f simulate %.2f emit %.2f ms" % (
                     (k,) + tuple((b - a) * 1e3 for a, b in zip(ts, ts[1:]))), file=sys.stderr)
 
-        e2e_steps = max(1, min(args.steps, 5))
-        for k in range(max(3, min(args.warmup, 3))):   # W >= 3 also here: a fresh box's first pinned D2H copies are slow
+        for k in range(3):   # W >= 3 also here: a fresh box's first pinned D2H copies are slow
             e2e_step(-1 - k)
         barrier()
         torch.cuda.synchronize()
@@ -318,55 +444,75 @@ def run_ours(args):
         e1.record(stream)
         torch.cuda.synchronize()
         barrier()
-        ms_e2e = e0.elapsed_time(e1)
+        return e0.elapsed_time(e1), int(L * wf + L * wd)
+
+    ms_e2e, d2h = e2e_leg(True)
+    ms_e2e_u8, d2h_u8 = e2e_leg(False)
 
     if world > 1:
-        t = torch.tensor([ms, ms_e2e], device="cuda", dtype=torch.float64)
+        t = torch.tensor([ms, ms_e2e, ms_e2e_u8], device="cuda", dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms, ms_e2e = float(t[0]), float(t[1])
+        ms, ms_e2e, ms_e2e_u8 = float(t[0]), float(t[1]), float(t[2])
     cells = N * L * P
     value = world * cells * args.steps / (ms * 1e-3) / 1e9
     e2e_value = world * cells * e2e_steps / (ms_e2e * 1e-3) / 1e9
     peak, peak_src = measured_peak()
-    k2_ms = acc["emit"] / max(1, acc["emit_launches"])
+    k2_ms = solo["emit"] / max(1, solo["launches"])
     algo_bytes = N * L * (P + 1)
     achieved = algo_bytes / (k2_ms * 1e-3) / 1e9 if k2_ms > 0 else 0.0
+    h2d = int(w["p0"].nbytes * 2 + w["off"].nbytes + w["pos"].nbytes + w["code"].nbytes)
     if rank == 0:
         out = {
             "metric": "genotype calls/sec (G allele-loci/s)", "value": value, "unit": "G allele-loci/s",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
-            "config": {"workload": WORKLOAD_NAME, "per_gpu": "one replicate population per rank, no collective",
+            "config": {"workload": WORKLOAD_NAME, "per_gpu": "one replicate population per rank and step, no collective",
                        "tables": "founder-allele u8 [L][N*P] + MAX-allele dose u8 [L][N]",
+                       "pipeline": "three contexts per rank in rotation: population k+1 is simulated (psim_simulate_async) while population k is "
+                                   "emitted (PSIM_EMIT_ASYNC); one host wait per step (K steps emit K populations and simulate K + 1)",
                        "l2": "1.2 GB of output per step exceeds the 126 MB L2; a new replicate is simulated every step",
+                       "e2e_tables": "PSIM_EMIT_PACKED4: founder-allele and dose tables with two 4-bit cells per byte (e2e.u8: one byte per cell)",
                        "positions": "fp64 Morgan"},
             "meioses_per_s": world * M * args.steps / (ms * 1e-3),
-            "kernel_ms": {"simulate_per_step": acc["sim"] / args.steps, "emit_kernel_per_launch": k2_ms,
-                          "emit_all_kernels_per_step": acc["emit_total"] / args.steps,
-                          "emit_kernel_share_of_step": acc["emit"] / ms if ms > 0 else None},
-            "roofline": {"bound": "hbm", "kernel": "k_emit_rows<2> (row-image emission: shared-memory row + TMA bulk store per table row; the band-plan helper kernels are reported under kernel_ms)", "achieved": achieved, "peak": peak, "unit": "GB/s",
+            "kernel_ms": {"simulate_per_step_overlapped": acc["sim"] / max(1, acc["n"]),
+                          "emit_all_kernels_per_step_overlapped": acc["emit_total"] / max(1, acc["n"]),
+                          "simulate_alone": solo["sim"] / 3, "emit_all_kernels_alone": solo["total"] / 3,
+                          "emit_kernel_per_launch": k2_ms,
+                          "emit_kernel_share_of_step": k2_ms / (ms / args.steps) if ms > 0 else None},
+            "roofline": {"bound": "hbm", "kernel": "k_emit_rows<2> (row-image emission: shared-memory row + TMA bulk store per table row; "
+                                                   "timed alone on the device, 3 launches after the pipelined steps; the band-plan helper kernels are reported under kernel_ms)",
+                         "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": None, "algorithmic_bytes_per_launch": algo_bytes,
                          "peak_source": peak_src},
             "e2e": {"value": e2e_value, "unit": "G allele-loci/s", "steps": e2e_steps, "ms_per_step": ms_e2e / e2e_steps,
-                    "h2d_bytes_per_step": int(w["p0"].nbytes * 2 + w["off"].nbytes + w["pos"].nbytes + w["code"].nbytes),
-                    "d2h_bytes_per_step": int(L * N * P + L * N)},
+                    "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "tables": "PSIM_EMIT_PACKED4",
+                    "u8": {"value": world * cells * e2e_steps / (ms_e2e_u8 * 1e-3) / 1e9, "ms_per_step": ms_e2e_u8 / e2e_steps,
+                           "d2h_bytes_per_step": d2h_u8}},
             "gpu_launches": int(launches),
             "clocks": clocks,
         }
+        if world == 1:
+            try:
+                out["replicate_sweep"] = replicate_sweep(ps, torch, local, rank)
+            except Exception as e:   # (never let the extra block take the line down)
+                out["replicate_sweep"] = {"error": str(e)}
         if world == 1 and not args.no_cpu:
-            v, t, ws = cpu_port_run(w, 2500, 1, 0)
+            v, t, ws = cpu_port_run(w, CPU_SAMPLE_POPSIZE, 1, 0)
             out["cpu_baseline"] = {"value": v, "unit": "G allele-loci/s", "cores": 1, "kind": "port",
-                                   "sample": "same workload with POPSIZE=2500 of 10000 offspring, all 24000 loci, "
-                                             "once: %.1f s" % t,
+                                   "sample": "same workload with POPSIZE=%d of 10000 offspring, all 24000 loci, "
+                                             "once: %.1f s" % (CPU_SAMPLE_POPSIZE, t),
                                    "meioses_per_s": ws["M"] / t}
         prof = os.path.join(ROOT, "profiles", "k2_traffic.json")
         if os.path.exists(prof):
             try:
-                out["roofline"]["traffic"] = json.load(open(prof)).get("dram_bytes_per_launch")
+                tr = json.load(open(prof))
+                out["roofline"]["traffic"] = tr.get("dram_bytes_per_launch")
+                out["roofline"]["traffic_source"] = "not measured in this run: " + tr.get("source", "profiles/k2_traffic.json")
             except Exception:
                 pass
         print(json.dumps(out))
-    ctx.close()
+    for c in ctxs:
+        c.close()
     if world > 1:
         dist.destroy_process_group()
 

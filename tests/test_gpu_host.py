@@ -248,3 +248,26 @@ def test_small_blocks_give_the_same_files(host_bin, tmp_path):
     da, db = scenario(tmp_path, files, par)
     assert run_host(host_bin, da, "x.par") == run_host(host_bin, db, "x.par", "--block-mib", "1")
     assert_same_files(da, db, "o", DAT + (".hsa", ".hsb", "_meioticconfigs.dat"), must_exist=("_founderalleles.dat", "_allAlleledose.dat"))
+
+
+# ------------------------------------------------------------------------------------ jar-recorded goldens
+JAR_GOLDEN = os.path.join(ROOT, "tests", "golden", "jar")
+JAR_CASES = sorted(os.listdir(JAR_GOLDEN)) if os.path.isdir(JAR_GOLDEN) else []
+
+
+@pytest.mark.skipif(not JAR_CASES, reason="no jar-recorded goldens: run tests/golden/make_jar_goldens.sh on a machine with a JVM")
+@pytest.mark.parametrize("case", JAR_CASES or ["none"])
+def test_replay_of_jar_recorded_haplostructs(host_bin, tmp_path, case):
+    """north_star's first correctness leg: the replay mode consumes the reference's OWN recorded
+    out.hsa / out.hsb (written by PedigreeSim.jar, Main.writeHaploStructFiles Main.java:1100-1136) and
+    must reproduce the jar's genotype, dose and founder-allele files byte for byte."""
+    g = os.path.join(JAR_GOLDEN, case)
+    par = dict(l.strip().split(" = ") for l in open(os.path.join(g, "case.par")) if " = " in l)
+    for n in ("case.chrom", "case.map", "case.gen", "out.ped", "out.hsa", "out.hsb"):
+        shutil.copy(os.path.join(g, n), tmp_path / n)
+    write(tmp_path, "replay.par", par_text(PLOIDY=par["PLOIDY"], CHROMFILE="case.chrom", PEDFILE="out.ped", HAPLOSTRUCT="out",
+                                           MAPFILE="case.map", FOUNDERFILE="case.gen", OUTPUT="again", MISSING=par.get("MISSING", "NA")))
+    run_host(host_bin, tmp_path, "replay.par")
+    for n in DAT:
+        if os.path.exists(os.path.join(g, "out" + n)):
+            assert read(tmp_path / ("again" + n)) == read(os.path.join(g, "out" + n)), n

@@ -224,3 +224,28 @@ def test_unreduced_tetraploid_gametes_carry_every_centromere_once_under_fdr():
             assert (F == np.arange(4)).all()
         else:
             assert (F[:, 0] == F[:, 1]).all() and (F[:, 2] == F[:, 3]).all() and (F[:, 1] != F[:, 2]).all()
+
+
+# ---------------------------------------------------------------- the jar itself (recorded where a JVM exists)
+JAR_GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "jar")
+JAR_CASES = sorted(os.listdir(JAR_GOLDEN)) if os.path.isdir(JAR_GOLDEN) else []
+
+
+@pytest.mark.skipif(not JAR_CASES, reason="no jar-recorded goldens: run tests/golden/make_jar_goldens.sh on a machine with a JVM")
+@pytest.mark.parametrize("case", JAR_CASES or ["none"])
+def test_oracle_java_mode_reproduces_the_jar(tmp_path, case):
+    """Draw-for-draw equality of the restatement with PedigreeSim.jar: same SEED, same files
+    (.ped, .hsa, _meioticconfigs.dat and the four .dat tables byte for byte; .hsb to 1e-12, Math.log ulps)."""
+    import shutil
+    g = os.path.join(JAR_GOLDEN, case)
+    for n in ("case.par", "case.chrom", "case.map", "case.gen"):
+        shutil.copy(os.path.join(g, n), tmp_path / n)
+    _oracle.run_parameter_file("case.par", cwd=str(tmp_path))
+    for n in (".ped", ".hsa", "_meioticconfigs.dat", "_founderalleles.dat", "_genotypes.dat", "_alleledose.dat", "_allAlleledose.dat"):
+        if os.path.exists(os.path.join(g, "out" + n)):
+            assert open(tmp_path / ("out" + n), "rb").read() == open(os.path.join(g, "out" + n), "rb").read(), n
+    a, b = open(tmp_path / "out.hsb").read().split(), open(os.path.join(g, "out.hsb")).read().split()
+    assert len(a) == len(b)
+    for x, y in zip(a, b):
+        if x != y:
+            assert abs(float(x) - float(y)) <= 1e-12 * max(1.0, abs(float(y))), (x, y)
