@@ -297,6 +297,69 @@ def replicate_sweep(ps, torch, local, rank, R=2000):
                          "peak": peak, "unit": "GB/s", "frac": bytes_ / (ms_all * 1e-3) / 1e9 / peak}}
 
 
+def sharded_block(ps, torch, dist, rank, world, local, lines, generations=8, chromosomes=10):
+    """BASELINE.json configs[3]: ONE pedigree over the GPUs of the box. Diploid RIL chain P1 x P2 -> F1 -> `lines` F2 plants
+    selfed to F<generations>, 10 chromosomes of 150 cM: psim_simulate_sharded (generation loop and NCCL exchange inside
+    libpsim) with both partitions, against psim_simulate of the whole pedigree on one GPU (rank 0's). Every timing is a
+    second pass after psim_reset (slab and exchange buffers at their final size), max over ranks; the last generation is
+    compared bit for bit with the one-GPU run on rank 0."""
+    p0 = np.empty(3 + lines * (generations - 1), np.int32)
+    p0[:3] = (-1, -1, 0)
+    p1 = p0.copy()
+    p1[2] = 1
+    p0[3:3 + lines] = 2
+    p0[3 + lines:] = np.arange(3, 3 + lines * (generations - 2), dtype=np.int32)
+    p1[3:] = p0[3:]
+    n = len(p0)
+    lengths, centro = [1.5] * chromosomes, [0.75] * chromosomes
+    ctx = ps.PsimContext(2, seed=SEED, device=local)
+    ctx.set_chromosomes(lengths, centro)
+    ctx.set_pedigree(p0, p1)
+    uid = torch.zeros(128, dtype=torch.uint8, device="cuda")
+    if rank == 0:
+        uid = torch.frombuffer(bytearray(ps.shard_unique_id()), dtype=torch.uint8).cuda()
+    dist.broadcast(uid, 0)
+    ctx.shard_init(rank, world, uid.cpu().numpy().tobytes())
+    sample_first, sample_count = n - 4096, 4096
+    ref = None
+    out = {"workload": "configs[3]: diploid RIL chain, %d F2 lines selfed to F%d = %d individuals, %d chromosomes x 150 cM, one pedigree over %d GPUs"
+                       % (lines, generations, n, chromosomes, world), "meioses": 2 * (n - 2)}
+    if rank == 0:
+        ctx.simulate()
+        ctx.reset(SEED, 0)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        ctx.simulate()
+        torch.cuda.synchronize()
+        out["one_gpu_seconds"] = time.perf_counter() - t0
+        ref = ctx.get_haplostructs(sample_first, sample_count)
+        out["segments"] = int(ctx.stats()["n_segments"])
+    for name, part in (("block", ps.PARTITION_BLOCK), ("lineage", ps.PARTITION_LINEAGE)):
+        ctx.reset(SEED, 0)
+        ctx.simulate_sharded(partition=part)
+        ctx.reset(SEED, 0)
+        dist.barrier()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        ctx.simulate_sharded(partition=part)
+        torch.cuda.synchronize()
+        t = torch.tensor([time.perf_counter() - t0], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        st = ctx.shard_stats()
+        if part == ps.PARTITION_LINEAGE:   # outside the timed region: bring the sample together for the check
+            ctx.shard_gather(np.arange(sample_first, sample_first + sample_count, dtype=np.int32))
+        same = None
+        if rank == 0:
+            got = ctx.get_haplostructs(sample_first, sample_count)
+            same = all(np.array_equal(a, b) for a, b in zip(ref, got))
+        out[name] = {"seconds": float(t[0]), "meioses_per_s": 2 * (n - 2) / float(t[0]),
+                     "speedup_vs_one_gpu": None if rank else out["one_gpu_seconds"] / float(t[0]),
+                     "segments_received_rank0": int(st["segments_received"]), "bytes_sent_rank0": int(st["bytes_sent"]),
+                     "exchange_steps": int(st["collectives"]), "sample_bit_identical_to_one_gpu": same}
+    ctx.close()
+    return out
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
@@ -453,6 +516,12 @@ def run_ours(args):
         t = torch.tensor([ms, ms_e2e, ms_e2e_u8], device="cuda", dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms, ms_e2e, ms_e2e_u8 = float(t[0]), float(t[1]), float(t[2])
+    sharded = None
+    if world > 1 and args.sharded_lines > 0:   # every rank takes part; rank 0 reports
+        try:
+            sharded = sharded_block(ps, torch, dist, rank, world, local, args.sharded_lines)
+        except Exception as e:   # (never let the extra block take the line down)
+            sharded = {"error": str(e)}
     cells = N * L * P
     value = world * cells * args.steps / (ms * 1e-3) / 1e9
     e2e_value = world * cells * e2e_steps / (ms_e2e * 1e-3) / 1e9
@@ -491,6 +560,8 @@ def run_ours(args):
             "gpu_launches": int(launches),
             "clocks": clocks,
         }
+        if sharded is not None:
+            out["sharded"] = sharded
         if world == 1:
             try:
                 out["replicate_sweep"] = replicate_sweep(ps, torch, local, rank)
@@ -524,6 +595,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--sharded-lines", type=int, default=1000000,
+                    help="N > 1: F2 lines of the one-pedigree-over-all-GPUs block (configs[3]: 1 000 000); 0 skips it")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 0)
     if args.impl == "reference":

@@ -285,6 +285,53 @@ typedef struct psim_device_hs {
 int psim_export_haplostructs_device(psim_ctx* ctx, int64_t first, int64_t count, psim_device_hs* out);
 int psim_import_haplostructs_device(psim_ctx* ctx, int64_t first, int64_t count, const psim_device_hs* in);
 
+/* ---- One pedigree over the GPUs of a box, inside the library. The dependency is the reference's own
+ * (Main.simulateIndividuals, Main.java:1504-1520: an individual needs its parents' haplostructs): every rank holds the whole
+ * pedigree in its context (same psim_set_chromosomes / psim_set_pedigree / seed and the same individuals simulated so far
+ * on all ranks, replicate_count 1), simulates its share of every generation, and after a generation the ranks hand each
+ * other the new haplostructs that another rank needs: the sizes first (one 8-byte all-gather, the one host wait of the
+ * exchange), then every sharing rank's packed haplostructs straight into the other ranks' segment slabs (grouped
+ * ncclBroadcast = an all-gather of ragged parts); no exchange at all in generations where nobody shares. Results are
+ * bit-identical to psim_simulate on one GPU (counter-based streams keyed by individual).
+ *   PSIM_PARTITION_BLOCK    every generation is cut into equal blocks and every new haplostruct is shared: any pedigree,
+ *                           every rank ends with the whole population;
+ *   PSIM_PARTITION_LINEAGE  an individual lives on the rank that owns its parents where possible; parents with children on
+ *                           other ranks (or with a large progeny in one generation) are shared: a selfing chain or an F1
+ *                           exchanges next to nothing, and every rank ends with its own lines (psim_shard_owner), which it
+ *                           emits itself; psim_shard_gather brings listed individuals together when somebody needs them.
+ * Transports: psim_shard_init - one process per GPU over NCCL (libnccl.so.2 is loaded at run time, by psim_shard_unique_id
+ * / psim_shard_init only; rank 0 calls psim_shard_unique_id and hands the bytes to the other ranks by any means it has);
+ * psim_shard_init_local - several contexts of ONE process (one per GPU, or several on one GPU), every context driven by its
+ * own thread making the same calls, exchanging by peer copies. The communicator belongs to the context. */
+#define PSIM_UNIQUE_ID_BYTES 128
+#define PSIM_SHARD_MAX_WORLD 16
+#define PSIM_PARTITION_BLOCK 0
+#define PSIM_PARTITION_LINEAGE 1
+int psim_shard_unique_id(uint8_t* id /* [PSIM_UNIQUE_ID_BYTES] */);
+int psim_shard_init(psim_ctx* ctx, int32_t rank, int32_t world, const uint8_t* id);
+typedef struct psim_shard_group psim_shard_group;
+int psim_shard_group_create(int32_t world, psim_shard_group** out);
+void psim_shard_group_destroy(psim_shard_group* group);   /* after the contexts that joined it */
+int psim_shard_init_local(psim_ctx* ctx, int32_t rank, psim_shard_group* group);
+int psim_simulate_sharded(psim_ctx* ctx, int32_t max_founder_allele, int32_t partition);
+/* owner[i] = rank that holds individual i after psim_simulate_sharded, -1 = every rank (founders, shared individuals,
+ * everybody with PSIM_PARTITION_BLOCK) */
+int psim_shard_owner(psim_ctx* ctx, int32_t* owner /* [n_ind] */);
+/* collective: the listed individuals go from their owners to every rank (the same list on all ranks) */
+int psim_shard_gather(psim_ctx* ctx, const int32_t* individuals, int64_t count);
+typedef struct psim_shard_stats {
+    int64_t collectives;         /* exchanges steps of the last psim_simulate_sharded (sizes + payloads) */
+    int64_t bytes_sent;          /* payload bytes this rank contributed */
+    int64_t segments_received;   /* segments imported from other ranks */
+    double  ms_total;            /* wall time of the call on this rank */
+} psim_shard_stats;
+int psim_shard_get_stats(psim_ctx* ctx, psim_shard_stats* out);
+/* The partition on its own (pure host, no context, no device): generation, owner rank and shared mark of every individual
+ * of a parents-first pedigree; has_haplostruct (may be NULL) marks individuals that need no simulation. */
+int psim_shard_plan(int64_t n_ind, const int32_t* parent0, const int32_t* parent1, const uint8_t* has_haplostruct, int32_t world,
+                    int32_t partition, int32_t* level /* [n_ind] or NULL */, int32_t* owner /* [n_ind] or NULL */,
+                    uint8_t* share /* [n_ind] or NULL */);
+
 #ifdef __cplusplus
 }
 #endif

@@ -18,6 +18,8 @@ DOSE_MIN_ALLELE, DOSE_MAX_ALLELE = -1, -2
 MEM_HOST, MEM_DEVICE = 0, 1
 EMIT_ASYNC, EMIT_PACKED4 = 0x1, 0x2
 PATH_AUTO, PATH_ROWS, PATH_TILES, PATH_GENERIC = 0, 1, 2, 3
+PARTITION_BLOCK, PARTITION_LINEAGE = 0, 1
+UNIQUE_ID_BYTES = 128
 
 
 def emit_path(p):
@@ -68,6 +70,10 @@ class GameteStats(C.Structure):
                 ("quadrivalent_hist", C.c_void_p)]
 
 
+class ShardStats(C.Structure):
+    _fields_ = [("collectives", C.c_int64), ("bytes_sent", C.c_int64), ("segments_received", C.c_int64), ("ms_total", C.c_double)]
+
+
 class DeviceHS(C.Structure):
     _fields_ = [("n_homologs", C.c_int64), ("n_segments", C.c_int64), ("seg_off", C.c_void_p),
                 ("founder", C.c_void_p), ("pos", C.c_void_p)]
@@ -80,6 +86,8 @@ EXPORTS = [
     "psim_export_haplostructs_device", "psim_import_haplostructs_device", "psim_reset", "psim_set_stream", "psim_simulate_subset",
     "psim_alloc_host", "psim_free_host", "psim_set_locus_names", "psim_set_allele_names", "psim_emit_text",
     "psim_gamete_stats_run", "psim_emit_all_dose_text", "psim_simulate_async", "psim_wait",
+    "psim_shard_unique_id", "psim_shard_init", "psim_shard_group_create", "psim_shard_group_destroy", "psim_shard_init_local",
+    "psim_simulate_sharded", "psim_shard_owner", "psim_shard_gather", "psim_shard_get_stats", "psim_shard_plan",
 ]
 
 _lib = None
@@ -128,6 +136,17 @@ def load():
     L.psim_get_stats.argtypes = [vp, C.POINTER(Stats)]
     L.psim_export_haplostructs_device.argtypes = [vp, i64, i64, C.POINTER(DeviceHS)]
     L.psim_import_haplostructs_device.argtypes = [vp, i64, i64, C.POINTER(DeviceHS)]
+    L.psim_shard_unique_id.argtypes = [vp]
+    L.psim_shard_init.argtypes = [vp, i32, i32, vp]
+    L.psim_shard_group_create.argtypes = [i32, C.POINTER(vp)]
+    L.psim_shard_group_destroy.argtypes = [vp]
+    L.psim_shard_group_destroy.restype = None
+    L.psim_shard_init_local.argtypes = [vp, i32, vp]
+    L.psim_simulate_sharded.argtypes = [vp, i32, i32]
+    L.psim_shard_owner.argtypes = [vp, vp]
+    L.psim_shard_gather.argtypes = [vp, vp, i64]
+    L.psim_shard_get_stats.argtypes = [vp, C.POINTER(ShardStats)]
+    L.psim_shard_plan.argtypes = [i64, vp, vp, vp, i32, i32, vp, vp, vp]
     _lib = L
     return L
 
@@ -383,3 +402,73 @@ class PsimContext:
 
     def import_device(self, first, count, d):
         self._chk(self.L.psim_import_haplostructs_device(self.h, first, count, C.byref(d)))
+
+    # ---- one pedigree over several GPUs (psim_simulate_sharded)
+    def shard_init(self, rank, world, unique_id):
+        """One process per GPU over NCCL; `unique_id` = shard_unique_id() of rank 0, handed to every rank."""
+        uid = np.frombuffer(bytes(unique_id), dtype=np.uint8).copy()
+        assert len(uid) == UNIQUE_ID_BYTES
+        self._chk(self.L.psim_shard_init(self.h, rank, world, _p(uid)))
+
+    def shard_init_local(self, rank, group):
+        """Several contexts of one process (ShardGroup), each driven by its own thread."""
+        self._chk(self.L.psim_shard_init_local(self.h, rank, group.h))
+        self._group = group   # (the group outlives the contexts that joined it)
+
+    def simulate_sharded(self, maxfounderallele=-1, partition=PARTITION_BLOCK):
+        self._chk(self.L.psim_simulate_sharded(self.h, maxfounderallele, partition))
+
+    def shard_owner(self):
+        out = np.empty(self.N, np.int32)
+        self._chk(self.L.psim_shard_owner(self.h, _p(out)))
+        return out
+
+    def shard_gather(self, individuals):
+        ind = np.ascontiguousarray(individuals, dtype=np.int32)
+        self._chk(self.L.psim_shard_gather(self.h, _p(ind), len(ind)))
+
+    def shard_stats(self):
+        s = ShardStats()
+        self._chk(self.L.psim_shard_get_stats(self.h, C.byref(s)))
+        return {k: getattr(s, k) for k, _ in ShardStats._fields_}
+
+
+def shard_unique_id():
+    """The NCCL unique id of a new communicator (rank 0 makes it, every rank passes it to shard_init)."""
+    L = load()
+    uid = np.zeros(UNIQUE_ID_BYTES, np.uint8)
+    rc = L.psim_shard_unique_id(_p(uid))
+    if rc != PSIM_OK:
+        raise PsimError(rc, (L.psim_last_error(None) or b"").decode())
+    return uid.tobytes()
+
+
+class ShardGroup:
+    """Rendezvous of the contexts of one process that share a pedigree (psim_shard_init_local)."""
+
+    def __init__(self, world):
+        self.L = load()
+        h = C.c_void_p()
+        rc = self.L.psim_shard_group_create(world, C.byref(h))
+        if rc != PSIM_OK:
+            raise PsimError(rc, "psim_shard_group_create failed")
+        self.h, self.world = h, world
+
+    def close(self):
+        if self.h:
+            self.L.psim_shard_group_destroy(self.h)
+            self.h = None
+
+
+def shard_plan(parent0, parent1, world, partition, has_haplostruct=None):
+    """(level, owner, share) of every individual: the partition psim_simulate_sharded uses (pure host)."""
+    L = load()
+    p0 = np.ascontiguousarray(parent0, dtype=np.int32)
+    p1 = np.ascontiguousarray(parent1, dtype=np.int32)
+    n = len(p0)
+    has = None if has_haplostruct is None else np.ascontiguousarray(has_haplostruct, dtype=np.uint8)
+    level, owner, share = np.empty(n, np.int32), np.empty(n, np.int32), np.empty(n, np.uint8)
+    rc = L.psim_shard_plan(n, _p(p0), _p(p1), None if has is None else _p(has), world, partition, _p(level), _p(owner), _p(share))
+    if rc != PSIM_OK:
+        raise PsimError(rc, "psim_shard_plan: invalid pedigree or arguments")
+    return level, owner, share.astype(bool)

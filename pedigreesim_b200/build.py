@@ -9,7 +9,7 @@ CSRC = os.path.join(PKG, "csrc")
 LIB = os.path.join(PKG, "libpsim.so")
 SOURCES = ["psim.cu"]
 HEADERS = ["psim_meiosis.cuh", "psim_rng.cuh", "psim_k1.cuh", "psim_k0.cuh", "psim_emit_tiles.cuh", "psim_emit_rows.cuh",
-           "psim_emit_generic.cuh", "psim_text.cuh", "psim_stats.cuh", "psim_misc.cuh", os.path.join("..", "..", "include", "psim.h")]
+           "psim_emit_generic.cuh", "psim_text.cuh", "psim_stats.cuh", "psim_misc.cuh", "psim_shard.inl", os.path.join("..", "..", "include", "psim.h")]
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
@@ -49,7 +49,7 @@ def build(force=False, verbose=False):
         build_host()
         return LIB
     nvcc = os.environ.get("NVCC", "nvcc")
-    cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB] + [os.path.join(CSRC, f) for f in SOURCES]
+    cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB] + [os.path.join(CSRC, f) for f in SOURCES] + ["-ldl"]
     subprocess.check_call(cmd)
     build_host(force=True)
     return LIB

@@ -62,6 +62,8 @@ namespace {
 
 std::string g_create_error;
 
+struct ShardState;   // psim_shard.inl
+
 struct psim_ctx_impl {
     psim_config cfg{};
     std::string err;
@@ -156,7 +158,10 @@ struct psim_ctx_impl {
     std::vector<int32_t> level_scratch; // N zeros between calls (simulate_impl)
     psim_stats stats{};
     int sm_count = 148;
+    uint64_t ped_version = 0;           // counts psim_set_pedigree calls
+    ShardState* shard = nullptr;        // psim_shard_init / psim_shard_init_local
 };
+void shard_free(psim_ctx_impl* c);
 
 #define CTX ((psim_ctx_impl*)ctx)
 
@@ -341,6 +346,11 @@ static int emit_rows_path(psim_ctx_impl* c, int64_t ind_first, int64_t ind_count
     ra.dose = dose; ra.dose_pitch = dose_pitch;
     ra.dose_which = dose_which; ra.mtab = c->mtab_d;
     ra.unit_counter = c->tile_counter_d;
+    {   // tuning builds: PSIM_ROWS_PACE = aggregate GB/s the SMs together hand to the bulk-copy engines at most
+        static const int env_pace = tuning_int("PSIM_ROWS_PACE");
+        const double row_bytes = (packed ? 0.5 : 1.0) * ((founder ? (double)seg_cells : 0.0) + (dose ? (double)seg_cells / P : 0.0));
+        ra.pace = env_pace > 0 ? (int)(row_bytes * 1.965 * c->sm_count / env_pace) : 0;
+    }
     const size_t smem = (packed ? ROWS_NBUF * (size_t)seg_cells / 2 + (size_t)(DK >= 1 ? ROWS_NBUF : 0) * (seg_cells / P / 2)
                                 : ROWS_NBUF * (size_t)seg_cells + (DK >= 2 ? seg_cells : 0) + (size_t)(dose_rows ? ROWS_NBUF : 0) * (seg_cells / P)) +
                         (size_t)cap * 5 + 2 * (ROWS_MAX_BAND + 2) * 4;
@@ -502,6 +512,7 @@ void psim_destroy(psim_ctx* ctx) {
     psim_ctx_impl* c = CTX;
     cudaSetDevice(c->cfg.device);
     cudaDeviceSynchronize();
+    shard_free(c);
     free_population(c);
     cudaFree(c->chrom_d); cudaFree(c->seg_pos_d); cudaFree(c->seg_founder_d);
     cudaFree(c->run_lb_d); cudaFree(c->run_founder_d);
@@ -581,6 +592,7 @@ int psim_set_pedigree(psim_ctx* ctx, int64_t n_ind, const int32_t* parent0, cons
     if (n_ind > INT32_MAX) return fail(c, PSIM_EINVAL, "more than 2^31-1 individuals");
     cudaSetDevice(c->cfg.device);
     if (int rc = settle(c)) return rc;
+    c->ped_version++;
     int nf = 0;
     for (int64_t i = 0; i < n_ind; i++) {
         const bool f0 = parent0[i] < 0, f1 = parent1[i] < 0;
@@ -646,8 +658,9 @@ int psim_set_haplostructs(psim_ctx* ctx, uint32_t replicate, int64_t first, int6
         if (seg_off[t + 1] <= seg_off[t]) return fail(c, PSIM_EINVAL, "every homolog needs at least one segment");
         if (seg_off[t + 1] - seg_off[t] >= (1 << 24)) return fail(c, PSIM_ECAPACITY, "more than 2^24 segments in one homolog");
     }
-    for (int64_t s = 0; s < nseg; s++)
-        if (founder[s] < 0 || founder[s] > 65535) return fail(c, PSIM_EINVAL, "invalid founder allele '" + std::to_string(founder[s]) + "'");
+    for (int64_t s = 0; s < nseg; s++)   // founder alleles are numbered 0 .. founderAlleleCount-1 (Main.java:1235)
+        if (founder[s] < 0 || founder[s] >= c->founder_allele_count || founder[s] > 65535)
+            return fail(c, PSIM_EINVAL, "invalid founder allele '" + std::to_string(founder[s]) + "'");
     if (int rc = ensure_slab(c, c->slab_used + nseg)) return rc;
     int64_t* off_d = nullptr;
     CUDA_TRY(dev_alloc(&off_d, (size_t)nh + 1));
@@ -824,7 +837,10 @@ static int sim_begin(psim_ctx_impl* c, int32_t max_founder_allele, const int32_t
     psim_ctx_impl::SimRun& run = c->run;
     run.plan = &plan;
     run.batches.clear();
-    run.units_per_block = P == 2 ? MEI_THREADS : (MEI_THREADS - 32) / (P / 2);
+    {   // a unit per thread; its multivalents go round by round (tuning builds: PSIM_MEI_UPB units per block)
+        static const int env_upb = tuning_int("PSIM_MEI_UPB");
+        run.units_per_block = env_upb > 0 ? std::min(env_upb, MEI_THREADS) : env_upb < 0 ? (P == 2 ? MEI_THREADS : (MEI_THREADS - 32) / (P / 2)) : MEI_THREADS;
+    }
     const int64_t max_blocks = std::max<int64_t>(1, (int64_t)(1LL << 30) / ((int64_t)MEI_THREADS * c->chiasma_cap * 9));
     const int64_t max_batch = std::max<int64_t>(1, max_blocks * run.units_per_block / ((int64_t)C * R * 2));
     if (!plan.f_ind.empty()) run.batches.push_back({0, 0, (int64_t)plan.f_ind.size()});
@@ -1091,7 +1107,9 @@ int psim_set_allele_codes(psim_ctx* ctx, int32_t n_alleles, const uint8_t* code)
     c->code_d = nullptr; c->match_d = nullptr; c->code16_d = nullptr; c->nibmask_d = nullptr; c->mtab_d = nullptr;
     c->A = 0; c->code_h.clear(); c->match_which = 12345678;
     if (!code) return PSIM_OK;
-    if (n_alleles <= 0 || n_alleles > 256) return fail(c, PSIM_EINVAL, "allele codes need 1..256 founder alleles");
+    // (up to 256 unique allele NAMES per locus - the codes are bytes - for any number of founder alleles: tables
+    // with more than 256 founder alleles are emitted by the per-cell kernels, which index code[l][founder])
+    if (n_alleles <= 0 || n_alleles > 65536) return fail(c, PSIM_EINVAL, "allele codes need 1..65536 founder alleles");
     c->A = n_alleles;
     c->code_h.assign(code, code + (size_t)c->L * n_alleles);
     CUDA_TRY(dev_alloc(&c->code_d, (size_t)c->L * n_alleles));
@@ -1915,9 +1933,12 @@ int psim_import_haplostructs_device(psim_ctx* ctx, int64_t first, int64_t count,
     CUDA_TRY(cudaMemcpyAsync(c->seg_pos_d + c->slab_used, in->pos, in->n_segments * sizeof(double), cudaMemcpyDeviceToDevice, c->stream));
     CUDA_TRY(cudaMemcpyAsync(c->seg_founder_d + c->slab_used, in->founder, in->n_segments * sizeof(int32_t), cudaMemcpyDeviceToDevice, c->stream));
     k_scatter_desc<<<grid_for(nh, 256), 256, 0, c->stream>>>(nh, first, 0, c->C, c->R, c->N, c->P, in->seg_off, c->slab_used, c->desc_d);
-    c->stats.kernel_launches++;
+    c->scalars_h[0] = 0;
+    k_check_founders<<<grid_for(in->n_segments, 256), 256, 0, c->stream>>>(in->founder, in->n_segments, c->founder_allele_count, c->scalars_dev);
+    c->stats.kernel_launches += 2;
     CUDA_TRY(cudaGetLastError());
     CUDA_TRY(cudaStreamSynchronize(c->stream));
+    if (c->scalars_h[0] != 0) return fail(c, PSIM_EINVAL, "invalid founder allele '" + std::to_string(c->scalars_h[0] - 1) + "'");
     c->slab_used += in->n_segments;
     c->stats.n_segments = c->slab_used;
     for (int64_t i = first; i < first + count; i++) c->hs_reps[i] = c->R;
@@ -1927,3 +1948,5 @@ int psim_import_haplostructs_device(psim_ctx* ctx, int64_t first, int64_t count,
 }
 
 }  // extern "C"
+
+#include "psim_shard.inl"

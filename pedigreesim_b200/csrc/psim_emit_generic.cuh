@@ -38,7 +38,8 @@ __global__ void __launch_bounds__(256) k_emit_generic(const EmitGenericArgs a) {
     const int match = a.dose_mode == 1 ? (int)a.match_code[gl] : a.dose_which;
     for (int h = 0; h < a.P; h++) {
         const uint64_t d = a.run_desc[hid0 + h];
-        const uint32_t b = (uint32_t)desc_begin(d), n = desc_count(d);
+        const uint64_t b = desc_begin(d);   // (40 bits: the slab may hold more than 2^32 segments)
+        const uint32_t n = desc_count(d);
         uint32_t lo = 0, hi = n;
         while (hi - lo > 1) { const uint32_t mid = (lo + hi) >> 1; if (a.run_lb[b + mid] <= l) lo = mid; else hi = mid; }
         const int f = a.run_founder[b + lo];
@@ -85,7 +86,8 @@ __global__ void __launch_bounds__(256) k_emit_all_dose(const AllDoseArgs a) {
     const uint8_t* codes = a.code ? a.code + gl * a.A : nullptr;
     for (int h = 0; h < a.P; h++) {
         const uint64_t d = a.run_desc[hid0 + h];
-        const uint32_t b = (uint32_t)desc_begin(d), n = desc_count(d);
+        const uint64_t b = desc_begin(d);   // (40 bits: the slab may hold more than 2^32 segments)
+        const uint32_t n = desc_count(d);
         uint32_t lo = 0, hi = n;
         while (hi - lo > 1) { const uint32_t mid = (lo + hi) >> 1; if (a.run_lb[b + mid] <= l) lo = mid; else hi = mid; }
         int f = a.run_founder[b + lo];

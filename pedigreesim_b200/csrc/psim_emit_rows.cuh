@@ -38,7 +38,15 @@ struct RowsArgs {
     uint8_t* dose;    int64_t dose_pitch;
     int dose_which;               // without genotypes: founder allele to count
     const uint4* mtab;            // with genotypes: per-locus byte tables of the counted allele (k_match_codes)
+    int pace;                     // tuning builds: least SM cycles between two rows handed to the bulk-copy engine (0: none)
 };
+// Tuning builds (PSIM_ROWS_PACE): an SM hands a row to the bulk-copy engine no sooner than `pace` cycles after the previous one.
+__device__ __forceinline__ void pace_rows(long long* next, int pace) {
+    const long long now = clock64();
+    long long mine = (long long)atomicAdd((unsigned long long*)next, (unsigned long long)pace);
+    if (mine < now) { atomicMax(next, now + pace); mine = now; }
+    while (clock64() < mine) __nanosleep(20);
+}
 
 __device__ __forceinline__ void band_rows(const RowsArgs& a, int k, int j, int64_t& g0, int64_t& g1) {
     const int64_t len = a.chunk_l1[k] - a.chunk_l0[k];
@@ -115,14 +123,36 @@ constexpr int ROWS_NBUF = PSIM_ROWS_NBUF;   // row buffers in flight
 #define PSIM_DOSE_DIRECT 0
 #endif
 constexpr bool ROWS_DOSE_DIRECT = PSIM_DOSE_DIRECT != 0;   // recomputed dose rows go from registers to global memory, not through a row buffer
-constexpr int ROWS_THREADS = ROWS_COMPUTE + 32 * ROWS_NBUF;   // + one warp per row buffer that hands its rows to the bulk-copy engine
+#ifndef PSIM_ROWS_INFLIGHT
+#define PSIM_ROWS_INFLIGHT 0
+#endif
+// 0: one issuing warp per row buffer (every buffer's row is handed to the bulk-copy engine as soon as it is made);
+// k > 0: ONE issuing warp that keeps at most k rows in the engine (it hands over row r when row r - k has been read)
+constexpr int ROWS_INFLIGHT = PSIM_ROWS_INFLIGHT;
+static_assert(ROWS_INFLIGHT <= ROWS_NBUF, "a row in the engine occupies a buffer");
+constexpr int ROWS_ISSUE_WARPS = ROWS_INFLIGHT > 0 ? 1 : ROWS_NBUF;
+constexpr int ROWS_THREADS = ROWS_COMPUTE + 32 * ROWS_ISSUE_WARPS;   // + the warps that hand rows to the bulk-copy engine
+#ifndef PSIM_ROWS_GROUPS
+#define PSIM_ROWS_GROUPS 2
+#endif
+// The compute threads work as ROWS_GROUPS independent groups, group g making rows g, g + GROUPS, ...: making a row is
+// a chain of latencies (wait for the buffer, dependent shared-memory patches, a barrier, the dose pass, a fence), so
+// two groups half a row apart keep the bulk-copy engine fed where one group of twice the threads leaves it idle
+// between rows. A group owns the 4-bit image of its row parity; the row buffers go round all groups.
+constexpr int ROWS_GROUPS = PSIM_ROWS_GROUPS;
+static_assert(ROWS_GROUPS == 1 || ROWS_GROUPS == 2, "the 4-bit image is kept per row parity");
+constexpr int ROWS_GROUP_THREADS = ROWS_COMPUTE / ROWS_GROUPS;
 
 __device__ __forceinline__ void bulk_store(void* gdst, const void* ssrc, uint32_t bytes) {
     asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst),
                  "r"((uint32_t)__cvta_generic_to_shared(ssrc)), "r"(bytes) : "memory");
 }
 // named barriers (0 is __syncthreads): FULL + b / EMPTY + b for row buffer b, WORK among the compute threads
-constexpr int BAR_FULL = 1, BAR_EMPTY = 1 + ROWS_NBUF, BAR_WORK = 1 + 2 * ROWS_NBUF;
+// (EMPTY + b + NBUF * g: group g waits for buffer b - two groups may wait for the same buffer at the same time, for rows
+// NBUF apart; WORK + g among the threads of group g)
+constexpr int BAR_FULL = 1, BAR_EMPTY = 1 + ROWS_NBUF, BAR_WORK = 1 + ROWS_NBUF + ROWS_NBUF * ROWS_GROUPS;
+static_assert(BAR_WORK + ROWS_GROUPS <= 16, "named barriers");
+__device__ __forceinline__ int bar_empty(int row) { return BAR_EMPTY + row % ROWS_NBUF + ROWS_NBUF * (row % ROWS_GROUPS); }   // waited for by the group that makes `row`
 __device__ __forceinline__ void bar_sync(int id, int n) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory"); }
 __device__ __forceinline__ void bar_arrive(int id, int n) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(n) : "memory"); }
 
@@ -157,6 +187,8 @@ __global__ void __launch_bounds__(ROWS_THREADS, 1) k_emit_rows(const RowsArgs a)
     uint32_t* const cursor = start + ROWS_MAX_BAND + 2;
     uint8_t* const evd = reinterpret_cast<uint8_t*>(cursor + ROWS_MAX_BAND + 2);   // rows until the run start's cell changes again
     __shared__ int s_unit;
+    __shared__ long long s_pace;
+    if (tid == 0) s_pace = 0;
     const int64_t n_cols = a.n_cols_ind * P;
     const bool count_ok = a.dose_which >= 0 && a.dose_which < 256;           // DK 1: a founder allele that exists
 
@@ -240,45 +272,49 @@ __global__ void __launch_bounds__(ROWS_THREADS, 1) k_emit_rows(const RowsArgs a)
 
         if (tid >= ROWS_COMPUTE) {
             // ---- the issuing warp of buffer b: lane 0 sends the founder row, lane 1 the dose row, lanes 2.. the ragged ends
-            const int lane = tid & 31, b = (tid - ROWS_COMPUTE) >> 5;
-            const uint8_t* const img = img0 + (size_t)b * seg_cells;
-            const uint8_t* const drow = dose0 + (size_t)b * seg_ind;
-            for (int r = b; r < n_rows; r += NB) {
+            const int lane = tid & 31, b0 = (tid - ROWS_COMPUTE) >> 5;
+            for (int r = b0; r < n_rows; r += ROWS_ISSUE_WARPS) {
+                const int b = r % NB;
+                const uint8_t* const img = img0 + (size_t)b * seg_cells;
+                const uint8_t* const drow = dose0 + (size_t)b * seg_ind;
                 uint8_t* const gf = a.founder ? a.founder + (out_row0 + r) * a.founder_pitch + c0 : nullptr;
                 uint8_t* const gd = a.dose ? a.dose + (out_row0 + r) * a.dose_pitch + c0 / P : nullptr;
-                bar_sync(BAR_FULL + b, ROWS_COMPUTE + 32);
-                if (lane == 0) {
-                    if (gf && (n_cell & ~15)) bulk_store(gf, img, (uint32_t)(n_cell & ~15));
+                bar_sync(BAR_FULL + b, ROWS_GROUP_THREADS + 32);
+                if (a.pace > 0) { if (lane == 0) pace_rows(&s_pace, a.pace); __syncwarp(); }
+                if (ROWS_INFLIGHT > 0 ? lane == 0 : lane < 2) {
+                    if ((ROWS_INFLIGHT > 0 || lane == 0) && gf && (n_cell & ~15)) bulk_store(gf, img, (uint32_t)(n_cell & ~15));
+                    if ((ROWS_INFLIGHT > 0 || lane == 1) && DSM && gd && (n_ind & ~15)) bulk_store(gd, drow, (uint32_t)(n_ind & ~15));
                     asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-                } else if (lane == 1) {
-                    if (DSM && gd && (n_ind & ~15)) bulk_store(gd, drow, (uint32_t)(n_ind & ~15));
-                    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-                } else {   // a bulk store moves multiples of 16 bytes
+                } else if (lane >= 2) {   // a bulk store moves multiples of 16 bytes
                     const int t = lane - 2;
                     if (gf && t < 15 && t < (n_cell & 15)) gf[(n_cell & ~15) + t] = img[(n_cell & ~15) + t];
                     if (DSM && gd && t >= 15 && t - 15 < (n_ind & 15)) gd[(n_ind & ~15) + t - 15] = drow[(n_ind & ~15) + t - 15];
                 }
-                if (lane < 2) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // the engine has read the row
+                // the engine has read the row (one warp per buffer) / row r - INFLIGHT + 1 (one issuing warp)
+                if (lane < 2) asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(ROWS_INFLIGHT > 0 ? ROWS_INFLIGHT - 1 : 0) : "memory");
                 __syncwarp();
-                if (r + NB < n_rows) bar_arrive(BAR_EMPTY + b, ROWS_COMPUTE + 32);
+                const int rr = r - (ROWS_INFLIGHT > 0 ? ROWS_INFLIGHT - 1 : 0);
+                if (rr >= 0 && rr + NB < n_rows) bar_arrive(bar_empty(rr + NB), ROWS_GROUP_THREADS + 32);
             }
+            if (ROWS_INFLIGHT > 1 && lane < 2) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
             continue;
         }
 
         // ---- the rows. Buffer r % NB holds row r-NB when row r begins and takes the run starts of rows r-NB+1 .. r;
         // the 4-bit image of row parity r & 1 holds row r-2 and takes those of rows r-1 and r.
-        constexpr int CT = ROWS_COMPUTE;
+        constexpr int CT = ROWS_GROUP_THREADS;
+        const int grp = tid / CT, lt = tid % CT;
         uint4 Tn = make_uint4(0, 0, 0, 0);
-        if (DK >= 2) Tn = __ldg(a.mtab + g0);
-        for (int r = 0; r < n_rows; r++) {
+        if (DK >= 2 && grp < n_rows) Tn = __ldg(a.mtab + g0 + grp);
+        for (int r = grp; r < n_rows; r += ROWS_GROUPS) {
             const int b = r % NB;
             uint8_t* const img = img0 + (size_t)b * seg_cells;
             uint8_t* const drow = dose0 + (size_t)b * seg_ind;
             uint32_t* const nib = nib0 + (size_t)(r & 1) * (seg_cells / 8);
             const int w0 = max(1, r - NB + 1);                    // first row of the buffer's window (row 0 has no run starts: they are the state)
             const uint32_t e0 = start[w0], en = start[max(1, r - 1)], e1 = start[r + 1];
-            if (r >= NB) bar_sync(BAR_EMPTY + b, ROWS_COMPUTE + 32);   // the engine has read row r-NB out of this buffer
-            for (uint32_t e = e0 + tid; e < e1; e += CT) {
+            if (r >= NB) bar_sync(bar_empty(r), ROWS_GROUP_THREADS + 32);   // the engine has read row r-NB out of this buffer
+            for (uint32_t e = e0 + lt; e < e1; e += CT) {
                 const uint32_t w = evs[e], cs = (w >> 8) & 0xFFFF, f = w & 0xFF;
                 if ((int)(w >> 24) + (int)evd[e] <= r) continue;   // the cell changes again inside the window
                 if (DK == 1) {
@@ -294,15 +330,15 @@ __global__ void __launch_bounds__(ROWS_THREADS, 1) k_emit_rows(const RowsArgs a)
                 }
             }
             if (DK >= 2) {
-                bar_sync(BAR_WORK, CT);
+                bar_sync(BAR_WORK + grp, CT);
                 const uint4 T = Tn;
-                if (r + 1 < n_rows) Tn = __ldg(a.mtab + g0 + r + 1);
+                if (r + ROWS_GROUPS < n_rows) Tn = __ldg(a.mtab + g0 + r + ROWS_GROUPS);
                 // the dose row is recomputed from the 4-bit image and goes from registers straight to global memory
                 // (16 / 8 bytes per thread, consecutive threads consecutive bytes): no shared-memory row, no second
                 // bulk store per table row
                 uint8_t* const gd = a.dose ? a.dose + (out_row0 + r) * a.dose_pitch + c0 / P : nullptr;
                 if (DK == 2) {   // 8 individuals per step: 4 words of the 4-bit image in, 8 dose bytes out
-                    for (int i = tid; i < (n_ind + 7) / 8; i += CT) {
+                    for (int i = lt; i < (n_ind + 7) / 8; i += CT) {
                         const uint4 v = reinterpret_cast<const uint4*>(nib)[i];
                         auto two = [&](uint32_t w) { return __dp4a(prmt(T.x, T.y, w) + prmt(T.z, T.w, w >> 16), 0x01010101u, 0u); };
                         const uint32_t lo = two(v.x) | (two(v.y) << 8), hi = two(v.z) | (two(v.w) << 8);   // dose nibbles
@@ -312,7 +348,7 @@ __global__ void __launch_bounds__(ROWS_THREADS, 1) k_emit_rows(const RowsArgs a)
                         else for (int q = 0; i * 8 + q < n_ind; q++) gd[i * 8 + q] = (uint8_t)((q < 4 ? out.x : out.y) >> (8 * (q & 3)));
                     }
                 } else {         // ploidy 2: 16 individuals per step
-                    for (int i = tid; i < (n_ind + 15) / 16; i += CT) {
+                    for (int i = lt; i < (n_ind + 15) / 16; i += CT) {
                         const uint4 v = reinterpret_cast<const uint4*>(nib)[i];
                         auto four = [&](uint32_t w) {
                             const uint32_t xl = prmt(T.x, T.y, w), xh = prmt(T.x, T.y, w >> 16);
@@ -329,7 +365,7 @@ __global__ void __launch_bounds__(ROWS_THREADS, 1) k_emit_rows(const RowsArgs a)
                 }
             }
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-            bar_arrive(BAR_FULL + b, ROWS_COMPUTE + 32);
+            bar_arrive(BAR_FULL + b, ROWS_GROUP_THREADS + 32);
         }
     }
     if (tid >= ROWS_COMPUTE && (tid & 31) < 2) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
@@ -401,6 +437,8 @@ __global__ void __launch_bounds__(ROWS_THREADS, 1) k_emit_rows_packed(const Rows
     uint32_t* const cursor = start + ROWS_MAX_BAND + 2;
     uint8_t* const evd = reinterpret_cast<uint8_t*>(cursor + ROWS_MAX_BAND + 2);
     __shared__ int s_unit;
+    __shared__ long long s_pace;
+    if (tid == 0) s_pace = 0;
     const int64_t n_cols = a.n_cols_ind * P;
     const bool count_ok = a.dose_which >= 0 && a.dose_which < 16;            // DK 1: a founder allele that exists
 
@@ -489,42 +527,45 @@ __global__ void __launch_bounds__(ROWS_THREADS, 1) k_emit_rows_packed(const Rows
         __syncthreads();
 
         if (tid >= ROWS_COMPUTE) {
-            const int lane = tid & 31, b = (tid - ROWS_COMPUTE) >> 5;
-            const uint8_t* const img = img0 + (size_t)b * img_bytes;
-            const uint8_t* const drow = dose0 + (size_t)b * dose_bytes;
-            for (int r = b; r < n_rows; r += NB) {
+            const int lane = tid & 31, b0 = (tid - ROWS_COMPUTE) >> 5;
+            for (int r = b0; r < n_rows; r += ROWS_ISSUE_WARPS) {
+                const int b = r % NB;
+                const uint8_t* const img = img0 + (size_t)b * img_bytes;
+                const uint8_t* const drow = dose0 + (size_t)b * dose_bytes;
                 uint8_t* const gf = a.founder ? a.founder + (out_row0 + r) * a.founder_pitch + c0 / 2 : nullptr;
                 uint8_t* const gd = a.dose ? a.dose + (out_row0 + r) * a.dose_pitch + c0 / P / 2 : nullptr;
-                bar_sync(BAR_FULL + b, ROWS_COMPUTE + 32);
-                if (lane == 0) {
-                    if (gf && (row_bytes & ~15)) bulk_store(gf, img, (uint32_t)(row_bytes & ~15));
+                bar_sync(BAR_FULL + b, ROWS_GROUP_THREADS + 32);
+                if (a.pace > 0) { if (lane == 0) pace_rows(&s_pace, a.pace); __syncwarp(); }
+                if (ROWS_INFLIGHT > 0 ? lane == 0 : lane < 2) {
+                    if ((ROWS_INFLIGHT > 0 || lane == 0) && gf && (row_bytes & ~15)) bulk_store(gf, img, (uint32_t)(row_bytes & ~15));
+                    if ((ROWS_INFLIGHT > 0 || lane == 1) && DK >= 1 && gd && (drow_bytes & ~15)) bulk_store(gd, drow, (uint32_t)(drow_bytes & ~15));
                     asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-                } else if (lane == 1) {
-                    if (DK >= 1 && gd && (drow_bytes & ~15)) bulk_store(gd, drow, (uint32_t)(drow_bytes & ~15));
-                    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-                } else {
+                } else if (lane >= 2) {
                     const int t = lane - 2;
                     if (gf && t < 15 && t < (row_bytes & 15)) gf[(row_bytes & ~15) + t] = img[(row_bytes & ~15) + t];
                     if (DK >= 1 && gd && t >= 15 && t - 15 < (drow_bytes & 15)) gd[(drow_bytes & ~15) + t - 15] = drow[(drow_bytes & ~15) + t - 15];
                 }
-                if (lane < 2) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+                if (lane < 2) asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(ROWS_INFLIGHT > 0 ? ROWS_INFLIGHT - 1 : 0) : "memory");
                 __syncwarp();
-                if (r + NB < n_rows) bar_arrive(BAR_EMPTY + b, ROWS_COMPUTE + 32);
+                const int rr = r - (ROWS_INFLIGHT > 0 ? ROWS_INFLIGHT - 1 : 0);
+                if (rr >= 0 && rr + NB < n_rows) bar_arrive(bar_empty(rr + NB), ROWS_GROUP_THREADS + 32);
             }
+            if (ROWS_INFLIGHT > 1 && lane < 2) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
             continue;
         }
 
-        constexpr int CT = ROWS_COMPUTE;
+        constexpr int CT = ROWS_GROUP_THREADS;
+        const int grp = tid / CT, lt = tid % CT;
         uint4 Tn = make_uint4(0, 0, 0, 0);
-        if (DK >= 2) Tn = __ldg(a.mtab + g0);
-        for (int r = 0; r < n_rows; r++) {
+        if (DK >= 2 && grp < n_rows) Tn = __ldg(a.mtab + g0 + grp);
+        for (int r = grp; r < n_rows; r += ROWS_GROUPS) {
             const int b = r % NB;
             uint32_t* const img = reinterpret_cast<uint32_t*>(img0 + (size_t)b * img_bytes);
             uint32_t* const drow = reinterpret_cast<uint32_t*>(dose0 + (size_t)b * dose_bytes);
             const int w0 = max(1, r - NB + 1);
             const uint32_t e0 = start[w0], e1 = start[r + 1];
-            if (r >= NB) bar_sync(BAR_EMPTY + b, ROWS_COMPUTE + 32);
-            for (uint32_t e = e0 + tid; e < e1; e += CT) {
+            if (r >= NB) bar_sync(bar_empty(r), ROWS_GROUP_THREADS + 32);
+            for (uint32_t e = e0 + lt; e < e1; e += CT) {
                 const uint32_t w = evs[e], cs = (w >> 8) & 0xFFFF, f = w & 0xF;
                 if ((int)(w >> 24) + (int)evd[e] <= r) continue;   // the cell changes again inside the window
                 const uint32_t sh = (cs & 7) * 4;
@@ -537,11 +578,11 @@ __global__ void __launch_bounds__(ROWS_THREADS, 1) k_emit_rows_packed(const Rows
                 atomicXor(&img[cs >> 3], (old ^ f) << sh);
             }
             if (DK >= 2) {
-                bar_sync(BAR_WORK, CT);
+                bar_sync(BAR_WORK + grp, CT);
                 const uint4 T = Tn;
-                if (r + 1 < n_rows) Tn = __ldg(a.mtab + g0 + r + 1);
+                if (r + ROWS_GROUPS < n_rows) Tn = __ldg(a.mtab + g0 + r + ROWS_GROUPS);
                 if (DK == 2) {   // 8 individuals per step: 4 words of the image in, 8 dose nibbles out
-                    for (int i = tid; i < seg_ind / 8; i += CT) {
+                    for (int i = lt; i < seg_ind / 8; i += CT) {
                         const uint4 v = reinterpret_cast<const uint4*>(img)[i];
                         auto two = [&](uint32_t w) { return __dp4a(prmt(T.x, T.y, w) + prmt(T.z, T.w, w >> 16), 0x01010101u, 0u); };
                         uint32_t out = two(v.x) | (two(v.y) << 8) | (two(v.z) << 16) | (two(v.w) << 24);
@@ -549,7 +590,7 @@ __global__ void __launch_bounds__(ROWS_THREADS, 1) k_emit_rows_packed(const Rows
                         drow[i] = out;
                     }
                 } else {         // ploidy 2: 16 individuals per step
-                    for (int i = tid; i < seg_ind / 16; i += CT) {
+                    for (int i = lt; i < seg_ind / 16; i += CT) {
                         const uint4 v = reinterpret_cast<const uint4*>(img)[i];
                         auto four = [&](uint32_t w) {   // 4 individuals of one word -> 16 bits of dose nibbles
                             const uint32_t xl = prmt(T.x, T.y, w), xh = prmt(T.x, T.y, w >> 16);
@@ -564,7 +605,7 @@ __global__ void __launch_bounds__(ROWS_THREADS, 1) k_emit_rows_packed(const Rows
                 }
             }
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-            bar_arrive(BAR_FULL + b, ROWS_COMPUTE + 32);
+            bar_arrive(BAR_FULL + b, ROWS_GROUP_THREADS + 32);
         }
     }
     if (tid >= ROWS_COMPUTE && (tid & 31) < 2) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");

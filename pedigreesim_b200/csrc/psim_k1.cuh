@@ -53,7 +53,7 @@ __global__ void k_slab_mark(unsigned long long* cursor, unsigned long long* mark
 //   1. one thread per unit draws the pairing configuration (bit masks in registers) and leaves it in
 //      shared memory and in the configuration tables;
 //   2. the multivalents of all the block's units are compacted by kind - quadrivalents first,
-//      bivalents from the next warp boundary - and every thread takes one: chiasmata (into its
+//      bivalents from the next warp boundary - and every thread takes one per round: chiasmata (into its
 //      column of the chiasma scratch), segregation, the chromatids of the kept gamete(s) traced
 //      once to count the segments they will have;
 //   3. every warp reserves its segments in the slab with one atomic, and the same threads trace
@@ -157,7 +157,7 @@ __global__ void __launch_bounds__(MEI_THREADS, PSIM_MEI_MIN_BLOCKS) k_meiosis(co
     __shared__ typename Scan::TempStorage scan_tmp;
     __shared__ uint64_t s_seq[MEI_THREADS];
     __shared__ uint8_t s_nquad[MEI_THREADS];
-    __shared__ uint16_t s_task[MEI_THREADS + 32];
+    __shared__ uint16_t s_task[MEI_THREADS * (MAXP / 2) + 32];
     __shared__ int s_stop;
     const int tid = threadIdx.x;
     if (tid == 0) s_stop = *(volatile int*)a.status != 0;   // an earlier batch failed: the host runs this one again
@@ -205,7 +205,12 @@ __global__ void __launch_bounds__(MEI_THREADS, PSIM_MEI_MIN_BLOCKS) k_meiosis(co
     for (int v = 0; v < nq; v++) s_task[(before & 0xFFFF) + v] = (uint16_t)((tid << 3) | v);
     for (int v = 0; v < nb; v++) s_task[bi0 + (before >> 16) + v] = (uint16_t)((tid << 3) | (nq + v));
     __syncthreads();
-    const bool is_quad = tid < n_quad, is_bi = tid >= bi0 && tid < bi0 + n_bi;
+    // (a block takes as many units as it has threads, so the multivalents may need several rounds: the warps go
+    // round by round on their own - there is no block-wide barrier below)
+    const int n_slots = bi0 + n_bi;
+    for (int slot0 = tid & ~31; slot0 < n_slots; slot0 += MEI_THREADS) {
+    const int slot = slot0 + (tid & 31);
+    const bool is_quad = slot < n_quad, is_bi = slot >= bi0 && slot < bi0 + n_bi;
     bool live = is_quad || is_bi;
     ChiasmaList x;
     x.stride = (int64_t)gridDim.x * MEI_THREADS;
@@ -225,7 +230,7 @@ __global__ void __launch_bounds__(MEI_THREADS, PSIM_MEI_MIN_BLOCKS) k_meiosis(co
     const ChromParams* ch = a.chrom;
     // the chiasmata: loops whose trip counts differ from thread to thread ...
     if (live) {
-        const int code = s_task[tid], i = code >> 3;
+        const int code = s_task[slot], i = code >> 3;
         v = code & 7;
         int j, r;
         unit_decode(a, unit0 + i, par, j, r, c);
@@ -289,7 +294,7 @@ __global__ void __launch_bounds__(MEI_THREADS, PSIM_MEI_MIN_BLOCKS) k_meiosis(co
         }
     }
     warp_base = __shfl_sync(0xFFFFFFFFu, warp_base, 0);
-    if (warp_base < 0) return;
+    if (warp_base < 0) return;   // (the whole warp)
     int64_t w = warp_base + offset;
 #pragma unroll
     for (int o = 0; o < 4; o++) {
@@ -298,5 +303,6 @@ __global__ void __launch_bounds__(MEI_THREADS, PSIM_MEI_MIN_BLOCKS) k_meiosis(co
             a.desc[chid0 + dest[o]] = make_desc((uint64_t)w, (uint64_t)count[o]);
             w += count[o];
         }
+    }
     }
 }

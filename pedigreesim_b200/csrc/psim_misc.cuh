@@ -110,6 +110,12 @@ __global__ void __launch_bounds__(256) k_repack_dense(const uint8_t* __restrict_
     }
 }
 
+// Founder alleles of imported segments must be 0 .. founderAlleleCount-1 (Main.java:1235); host[0] = 1 + an offender.
+__global__ void k_check_founders(const int32_t* __restrict__ founder, int64_t n, int count, volatile int64_t* host) {
+    const int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (t < n && (founder[t] < 0 || founder[t] >= count)) host[0] = (int64_t)founder[t] + 1;
+}
+
 // Small device values the host needs after the next stream synchronisation, stored straight into
 // mapped page-locked memory (see psim_ctx_impl::scalars_h).
 __global__ void k_publish(volatile int64_t* host, const int64_t* v0, const int* v1, const int* v2) {
@@ -119,4 +125,47 @@ __global__ void k_publish(volatile int64_t* host, const int64_t* v0, const int* 
         if (v2) host[2] = *v2;
         __threadfence_system();
     }
+}
+
+// ------------------------------------------------------------------------------------------
+// One pedigree over several GPUs (psim_simulate_sharded): the haplostructs a rank shares after a
+// generation travel as one byte payload
+//   [first segment of every homolog, and the total: u32 x (n_h + 1)] [founder: i32 x n_seg] [pos: f64 x n_seg]
+// (each part padded to 8 bytes) with the homologs in the order [individual of the list][chromosome][homolog]
+// (replicate_count is 1). The receiver needs no scan: a homolog's segments start at slab base + offset.
+__device__ __forceinline__ int64_t listed_hid(int64_t t, const int32_t* __restrict__ list, int C, int64_t N, int P) {
+    const int h = (int)(t % P);
+    const int c = (int)((t / P) % C);
+    const int64_t i = list[t / ((int64_t)P * C)];
+    return ((int64_t)c * N + i) * P + h;
+}
+__global__ void k_pack_counts(int64_t n_h, const int32_t* __restrict__ list, int C, int64_t N, int P, const uint64_t* __restrict__ desc,
+                              int64_t* __restrict__ cnt64) {
+    const int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (t > n_h) return;
+    cnt64[t] = t < n_h ? desc_count(desc[listed_hid(t, list, C, N, P)]) : 0;   // (entry n_h: the scan leaves the total there)
+}
+__global__ void k_pack_segments(int64_t n_h, const int32_t* __restrict__ list, int C, int64_t N, int P, const uint64_t* __restrict__ desc,
+                                const int64_t* __restrict__ off, const double* __restrict__ seg_pos, const int32_t* __restrict__ seg_founder,
+                                uint32_t* __restrict__ out_off, int32_t* __restrict__ out_founder, double* __restrict__ out_pos) {
+    const int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (t > n_h) return;
+    int64_t w = off[t];
+    out_off[t] = (uint32_t)w;
+    if (t == n_h) return;
+    const uint64_t d = desc[listed_hid(t, list, C, N, P)];
+    const int64_t b = (int64_t)desc_begin(d);
+    const int n = (int)desc_count(d);
+    for (int s = 0; s < n; s++, w++) { out_pos[w] = seg_pos[b + s]; out_founder[w] = seg_founder[b + s]; }
+}
+__global__ void k_unpack_desc(int64_t n_h, const int32_t* __restrict__ list, int C, int64_t N, int P, const uint32_t* __restrict__ in_off,
+                              int64_t slab_base, uint64_t* __restrict__ desc) {
+    const int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (t >= n_h) return;
+    desc[listed_hid(t, list, C, N, P)] = make_desc((uint64_t)(slab_base + in_off[t]), (uint64_t)(in_off[t + 1] - in_off[t]));
+}
+// (device value -> mapped page-locked host memory, like k_publish)
+__global__ void k_publish_i64(volatile int64_t* host, const int64_t* v, int n) {
+    if ((int)threadIdx.x < n) host[threadIdx.x] = v[threadIdx.x];
+    __threadfence_system();
 }

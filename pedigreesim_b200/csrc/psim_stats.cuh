@@ -25,7 +25,8 @@ struct StatsArgs {
 
 __device__ __forceinline__ uint32_t founder_at_row(const StatsArgs& a, int64_t hid, uint32_t l) {
     const uint64_t d = a.run_desc[hid];
-    const uint32_t b = (uint32_t)desc_begin(d), n = desc_count(d);
+    const uint64_t b = desc_begin(d);   // (40 bits: the slab may hold more than 2^32 segments)
+        const uint32_t n = desc_count(d);
     uint32_t lo = 0, hi = n;
     while (hi - lo > 1) { const uint32_t mid = (lo + hi) >> 1; if (a.run_lb[b + mid] <= l) lo = mid; else hi = mid; }
     return a.run_founder[b + lo];
@@ -92,7 +93,8 @@ __global__ void __launch_bounds__(256) k_stats_homolog(const StatsArgs a) {
     }
     if (!a.diff) return;
     const uint64_t d = a.run_desc[hid];
-    const uint32_t b = (uint32_t)desc_begin(d), n = desc_count(d);
+    const uint64_t b = desc_begin(d);   // (40 bits: the slab may hold more than 2^32 segments)
+        const uint32_t n = desc_count(d);
     const size_t W = (size_t)a.Lc + 1;
     for (uint32_t j = 1; j < n; j++) {
         const uint32_t j0 = a.run_lb[b + j], j1 = j + 1 < n ? a.run_lb[b + j + 1] : a.Lc;

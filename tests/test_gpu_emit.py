@@ -290,3 +290,36 @@ def test_packed_requests_that_cannot_be_served_are_refused():
     with pytest.raises(ps.PsimError) as e:
         g.emit(founder=True, packed=True)
     assert e.value.code == ps.PSIM_EINVAL and "16 founder alleles" in str(e.value)
+
+
+def test_founder_genotypes_with_more_than_256_founder_alleles():
+    """75 tetraploid founders own 300 founder alleles: the founder table needs 16 bits, the allele codes
+    are still bytes (at most 256 unique names per locus) indexed by the 16-bit founder allele."""
+    o, g = _both(4, [1.0, 0.7], 150, 300, [60, 45], seed=12, codes=5)
+    for which in (_oracle.MAX_ALLELE, _oracle.MIN_ALLELE, 280):
+        got = g.emit(founder=True, allele=True, dose=True, dose_which=which, founder_bytes=2)
+        assert np.array_equal(got["founder"], o.emit(_oracle.EMIT_FOUNDER_U16))
+        assert np.array_equal(got["allele"], o.emit(_oracle.EMIT_ALLELE))
+        assert np.array_equal(got["dose"], o.emit(_oracle.EMIT_DOSE, which=which))
+    ro, ad = g.emit_all_dose()
+    assert ad.sum(axis=0).min() >= 0 and int(ro[-1]) == ad.shape[0]
+
+
+def test_preset_founder_alleles_must_exist_in_the_pedigree():
+    import pedigreesim_b200 as ps
+    g = ps.PsimContext(2)
+    g.set_chromosomes([1.0], [0.5])
+    g.set_pedigree([-1, -1, 0], [-1, -1, 1])            # 2 founders x 2 = founder alleles 0..3 (Main.java:1235)
+    seg_off = np.arange(0, 5, dtype=np.int64)
+    with pytest.raises(ps.PsimError) as e:
+        g.set_haplostructs(0, seg_off, np.array([0, 1, 2, 4], np.int32), np.zeros(4))
+    assert e.value.code == ps.PSIM_EINVAL and "invalid founder allele '4'" in str(e.value)
+    g.set_haplostructs(0, seg_off, np.array([0, 1, 2, 3], np.int32), np.zeros(4))
+    g.simulate(3)
+    # a pedigree whose founders would be numbered past its own founder allele count
+    h = ps.PsimContext(2)
+    h.set_chromosomes([1.0], [0.5])
+    h.set_pedigree([-1, -1, 0], [-1, -1, 1])
+    with pytest.raises(ps.PsimError) as e:
+        h.simulate(300)
+    assert e.value.code == ps.PSIM_EINVAL and "invalid founder allele" in str(e.value)

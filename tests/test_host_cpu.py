@@ -197,6 +197,36 @@ def test_large_pedigree_loads_fast(host_bin, tmp_path):
     assert head[1].split() == ["P1", "NA", "NA"] and head[2].split() == ["P2", "NA", "NA"] and head[3].split()[0] == "F1"
 
 
+def test_configs3_pedigree_of_seven_million_rows_is_ingested(host_bin, tmp_path):
+    """BASELINE.json configs[3] at full size: the RIL chain P1 x P2 -> F1 -> 1 000 000 F2 lines selfed to F8 is a .ped of
+    7 000 003 rows (PopulationData.java:244-252 reads it, sortPedigree :309-464 orders it). The file lists the youngest
+    generation first and the founders last, every generation in reverse line order: every row has to wait for its
+    parents (the reference's rotation takes one pass per generation) and names are looked up far from where they are
+    defined. Reading, name resolution, parents-first ordering and writing out.ped back must stay linear per pass."""
+    import time
+    lines, gens = 1_000_000, 8
+    with open(tmp_path / "x.ped", "w") as f:
+        f.write("Name\tParent1\tParent2\n")
+        for g in range(gens, 2, -1):
+            f.write("".join("F%d_%d\tF%d_%d\tF%d_%d\n" % (g, k, g - 1, k, g - 1, k) for k in range(lines - 1, -1, -1)))
+        f.write("".join("F2_%d\tF1\tF1\n" % k for k in range(lines - 1, -1, -1)))
+        f.write("F1\tP1\tP2\nP1\tNA\tNA\nP2\tNA\tNA\n")
+    write(tmp_path, "x.chrom", CHROM2)
+    write(tmp_path, "x.map", MAP2)
+    write(tmp_path, "x.par", base_par(PEDFILE="x.ped"))
+    t = time.time()
+    log = run_host(host_bin, str(tmp_path), "x.par", "--parse-only")
+    took = time.time() - t
+    assert "parse-only: 7000003 individuals" in log
+    assert took < 120, took                                   # (measured: about 10 s, of which the 170 MB out.ped about 3)
+    with open(tmp_path / "out.ped") as f:
+        head = [f.readline().split() for _ in range(5)]
+        assert head[1] == ["P1", "NA", "NA"] and head[2] == ["P2", "NA", "NA"] and head[3] == ["F1", "P1", "P2"]
+        assert head[4] == ["F2_999999", "F1", "F1"]
+        n = 5 + sum(1 for _ in f)
+    assert n == 7000004
+
+
 def test_map_is_position_sorted_with_stable_ties_and_clamped(host_bin, tmp_path):
     # unsorted map with ties and a position a hair outside the chromosome: the .gen row order the
     # reference demands is the sorted one (Main.java:863-867), so a .gen in that order must load

@@ -1,7 +1,9 @@
 #!/usr/bin/env python
 """One large pedigree sharded over the GPUs of a box (BASELINE.json configs[3] at reduced size):
-diploid RIL chain F2 -> F<g> by selfing, individuals of each generation split over the ranks,
-NCCL all-gather of the new HaploStructs after every generation.
+diploid RIL chain F2 -> F<g> by selfing, individuals of each generation split over the ranks, the new
+HaploStructs that another rank needs exchanged after every generation. --impl library
+(default) is psim_simulate_sharded: the generation loop and the NCCL exchange inside libpsim; --impl
+python is the same partition driven from pedigreesim_b200/sharded.py over torch.distributed.
 
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 \
         --master-port 29511 tools/run_sharded.py --lines 200000 --generations 8
@@ -43,7 +45,9 @@ def main():
     ap.add_argument("--lines", type=int, default=100000)
     ap.add_argument("--generations", type=int, default=8)
     ap.add_argument("--chromosomes", type=int, default=10)
-    ap.add_argument("--check", type=int, default=1)
+    ap.add_argument("--check", type=int, nargs="?", const=1, default=1)
+    ap.add_argument("--impl", default="library", choices=["library", "python"])
+    ap.add_argument("--out", default=None, help="append the JSON line to this file as well")
     ap.add_argument("--partition", default="block", choices=["block", "lineage"],
                     help="lineage: a rank keeps its lines, only individuals with a child on another rank are shared")
     args = ap.parse_args()
@@ -58,29 +62,47 @@ def main():
     ctx = ps.PsimContext(2, seed=12345, device=local)
     ctx.set_chromosomes(lengths, centro)
     ctx.set_pedigree(p0, p1)
-    drv = sharded.ShardedPedigree(sharded.PsimShard(ctx), p0, p1, partition=args.partition)
+    part = ps.PARTITION_BLOCK if args.partition == "block" else ps.PARTITION_LINEAGE
+    if args.impl == "library":
+        uid = torch.zeros(128, dtype=torch.uint8, device="cuda")
+        if rank == 0:
+            uid = torch.frombuffer(bytearray(ps.shard_unique_id()), dtype=torch.uint8).cuda()
+        dist.broadcast(uid, 0)
+        ctx.shard_init(rank, world, uid.cpu().numpy().tobytes())
+        run = lambda: ctx.simulate_sharded(partition=part)   # noqa: E731
+    else:
+        drv = sharded.ShardedPedigree(sharded.PsimShard(ctx), p0, p1, partition=args.partition)
+        run = drv.simulate
     # first pass: the slab and the exchange buffers grow to their final size (cudaMalloc / cudaFree of
     # gigabytes); the timed pass re-simulates the same pedigree after psim_reset into that memory
-    drv.simulate()
+    run()
     torch.cuda.synchronize()
     ctx.reset(12345, 0)
-    drv.exchanged_segments = 0
-    drv.collectives = 0
+    if args.impl == "python":
+        drv.exchanged_segments = 0
+        drv.collectives = 0
     dist.barrier()
     torch.cuda.synchronize()
     t0 = time.perf_counter()
-    drv.simulate()
+    run()
     torch.cuda.synchronize()
     dist.barrier()
     dt = time.perf_counter() - t0
     n = len(p0)
     ok = True
     unsharded_dt = None
-    exchanged, collectives = drv.exchanged_segments, drv.collectives
+    if args.impl == "python":
+        exchanged, collectives = drv.exchanged_segments, drv.collectives
+    else:
+        st = ctx.shard_stats()
+        exchanged, collectives = st["segments_received"], st["collectives"]
     if args.check:
         last = n - args.lines
         if args.partition == "lineage":   # outside the timed region: bring the last generation together for the check
-            drv.gather(np.arange(last, n))
+            if args.impl == "python":
+                drv.gather(np.arange(last, n))
+            else:
+                ctx.shard_gather(np.arange(last, n, dtype=np.int32))
         so, fo, po = ctx.get_haplostructs(first=last, count=args.lines)
         if rank == 0:
             ref = ps.PsimContext(2, seed=12345, device=local)
@@ -109,10 +131,16 @@ def main():
         ok = ok and same
     if rank == 0:
         meioses = 2 * (n - 2)
-        print(json.dumps({"n_gpus": world, "individuals": n, "meioses": meioses, "seconds": dt, "meioses_per_s": meioses / dt,
-                          "partition": args.partition, "exchanged_segments_per_rank": exchanged, "collectives": collectives,
-                          "bit_identical_to_unsharded": ok,
-                          "unsharded_seconds_one_gpu": unsharded_dt}))
+        line = json.dumps({"n_gpus": world, "world": world, "impl": args.impl, "transport": "nccl", "individuals": n, "meioses": meioses,
+                           "seconds": dt, "meioses_per_s": meioses / dt,
+                           "partition": args.partition, "exchanged_segments_per_rank": exchanged, "collectives": collectives,
+                           "bit_identical_to_unsharded": ok, "identical": ok,
+                           "unsharded_seconds_one_gpu": unsharded_dt,
+                           "speedup_vs_one_gpu": None if not unsharded_dt else unsharded_dt / dt})
+        print(line)
+        if args.out:
+            with open(args.out, "a") as f:
+                f.write(line + "\n")
     ctx.close()
     dist.destroy_process_group()
     if not ok:
