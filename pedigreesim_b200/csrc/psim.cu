@@ -69,7 +69,8 @@ struct psim_ctx_impl {
     std::string err;
     int C = 0, P = 0, R = 1;
     int64_t N = 0;
-    cudaStream_t stream = nullptr, own_stream = nullptr, copy_stream = nullptr, aux_stream = nullptr;   // aux: second compute stream of psim_simulate
+    cudaStream_t stream = nullptr, own_stream = nullptr, copy_stream = nullptr, aux_stream = nullptr;   // aux: lowest-priority stream of the meiosis kernels
+    cudaEvent_t ev_aux0 = nullptr, ev_aux1 = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev2 = nullptr, ev3 = nullptr, ev4 = nullptr;
     std::vector<cudaEvent_t> kev;   // event pool: triples (before plan, before stream, after stream) per launch
     int kev_used = 0;
@@ -304,11 +305,12 @@ static int emit_rows_path(psim_ctx_impl* c, int64_t ind_first, int64_t ind_count
     static const int64_t env_seg = tuning_int("PSIM_SEG_MAX");
     static const int env_band = tuning_int("PSIM_BAND_ROWS");
     static const int env_units = tuning_int("PSIM_ROWS_UNITS");
-    const int cap = env_cap > 0 ? env_cap : 8192;
+    int cap = env_cap > 0 ? env_cap : 8192;
     const bool dose_rows = DK == 1 || (DK >= 2 && !ROWS_DOSE_DIRECT);
     const double per_cell = packed ? 0.5 * ROWS_NBUF + (DK >= 1 ? 0.5 * ROWS_NBUF : 0.0) / P
                                    : (double)ROWS_NBUF + (DK >= 2 ? 1.0 : 0.0) + (dose_rows ? (double)ROWS_NBUF : 0.0) / P;
-    const int64_t budget = ROWS_SMEM - 2 * (ROWS_MAX_BAND + 2) * 4 - cap * 5;
+    const int64_t smem_lists = ROWS_SMEM - 2 * (ROWS_MAX_BAND + 2) * 4;   // what the row buffers and the run-start list share
+    const int64_t budget = smem_lists - cap * 5;
     const int64_t quantum = (packed ? 32 : 16) * P;
     int64_t seg_max = (int64_t)(budget / per_cell) / quantum * quantum;
     seg_max = std::min<int64_t>(seg_max, 65535 / quantum * quantum);
@@ -321,20 +323,31 @@ static int emit_rows_path(psim_ctx_impl* c, int64_t ind_first, int64_t ind_count
     // narrower, so that a band of at least 16 rows keeps its expected run starts within half the list
     // (a narrow segment still leaves the SM as one bulk store per row; below 4 KB the path is not taken).
     // PSIM_PATH_ROWS takes the path as it is: lists that overflow are redone per cell.
-    const int min_band = 16;
-    if (path != PSIM_PATH_ROWS && starts_per_cell * (double)seg_max * min_band > cap / 2) {
-        const int64_t fit = (int64_t)((cap / 2) / (starts_per_cell * min_band)) / quantum * quantum;
+    // The list then takes the shared memory the narrower row buffers leave (5 bytes per run start): the segment is
+    // the widest one whose band of `min_band` rows keeps its expected run starts within half of THAT list, because
+    // what a short band costs is its start (state load, counting sort, buffer copies: ~5 us) against ~0.6 us per row.
+    const int min_band = 32;
+    bool coarse = false;
+    if (path != PSIM_PATH_ROWS && env_cap <= 0 && starts_per_cell * (double)seg_max * min_band > cap / 2) {
+        const int64_t fit = (int64_t)((double)smem_lists / (per_cell + 10.0 * starts_per_cell * min_band)) / quantum * quantum;
         if (fit < 4096) return PSIM_OK;   // sparse map: tiled / dense path
         seg_max = std::min(seg_max, fit);
+        coarse = true;
     }
     const int n_seg = (int)((n_cols + seg_max - 1) / seg_max);
     const int64_t seg_cells = ((n_cols + n_seg - 1) / n_seg + quantum - 1) / quantum * quantum;
+    if (coarse) cap = (int)std::min<int64_t>(1 << 20, std::max<int64_t>(cap, (smem_lists - (int64_t)(per_cell * (double)seg_cells) - 64) / 5));
     const int n_blocks = c->sm_count;
     // tallest band whose expected run starts stay within half the list capacity
     const double per_row = starts_per_cell * (double)seg_cells;
     const int64_t band_cap = env_band > 0 ? std::min(env_band, ROWS_MAX_BAND)
                            : std::max<int64_t>(8, std::min<int64_t>(ROWS_MAX_BAND, per_row > 0 ? (int64_t)((cap / 2) / per_row) : ROWS_MAX_BAND));
 
+    if (n_cols >= (int64_t)1 << 31) return PSIM_OK;   // (k_band_plan does its column arithmetic in 32 bits)
+    for (int k = 0; k < c->C; k++) {                  // (and keeps the band bounds of a chromosome piece in shared memory)
+        const int64_t a0 = std::max(l_begin, c->locus_off_h[k]), a1 = std::min(l_end, c->locus_off_h[k + 1]);
+        if (a1 > a0 && (a1 - a0 + band_cap - 1) / band_cap > ROWS_MAX_PLAN_BANDS / 2) return PSIM_OK;
+    }
     RowsArgs ra{};
     ra.C = c->C; ra.R = c->R; ra.P = P; ra.N = c->N;
     ra.run_desc = c->run_desc_d; ra.run_lb = c->run_lb_d; ra.run_founder = c->run_founder_d;
@@ -386,7 +399,7 @@ static int emit_rows_path(psim_ctx_impl* c, int64_t ind_first, int64_t ind_count
                     const double ideal = (double)len * (double)target / (double)total;
                     int64_t nb = std::max<int64_t>(1, (int64_t)ideal);
                     nb = std::max(nb, (len + band_cap - 1) / band_cap);
-                    nb = std::min(nb, len);
+                    nb = std::min(nb, std::min<int64_t>(len, ROWS_MAX_PLAN_BANDS));
                     ra.chunk_bands[q] = (int)nb;
                     rem[q] = ideal - (double)nb;
                     given += nb;
@@ -394,7 +407,7 @@ static int emit_rows_path(psim_ctx_impl* c, int64_t ind_first, int64_t ind_count
                 while (given < target) {
                     int best = -1;
                     for (int q = 0; q < ra.n_chunks; q++)
-                        if (ra.chunk_bands[q] < ra.chunk_l1[q] - ra.chunk_l0[q] && (best < 0 || rem[q] > rem[best])) best = q;
+                        if (ra.chunk_bands[q] < std::min<int64_t>(ra.chunk_l1[q] - ra.chunk_l0[q], ROWS_MAX_PLAN_BANDS) && (best < 0 || rem[q] > rem[best])) best = q;
                     if (best < 0) break;
                     ra.chunk_bands[best]++;
                     rem[best] -= 1.0;
@@ -405,17 +418,27 @@ static int emit_rows_path(psim_ctx_impl* c, int64_t ind_first, int64_t ind_count
             const int64_t t_min = std::max<int64_t>(1, (total + band_cap - 1) / band_cap);
             int64_t best_t = t_min;
             double best_eff = 0.0;
+            // (a band's start - state load, counting sort, buffer copies, while the previous band's last rows drain - costs
+            // about as much as eight of its rows: a fuller last wave does not pay for bands that are much shorter)
+            const double start_rows = 8.0;
             for (int64_t tg = t_min; tg < t_min + 4 * n_blocks && tg <= std::max<int64_t>(t_min, total / (env_band > 0 ? 1 : 16)); tg++) {
-                const int64_t units = allocate(tg) * n_seg;
-                const double eff = (double)units / (double)((units + n_blocks - 1) / n_blocks * n_blocks);
+                const int64_t bands = allocate(tg), units = bands * n_seg;
+                const double rows_per_band = (double)total / (double)bands;
+                const double eff = (double)units / (double)((units + n_blocks - 1) / n_blocks * n_blocks) * rows_per_band / (rows_per_band + start_rows);
                 if (eff > best_eff + 1e-9) { best_eff = eff; best_t = tg; }
-                if (env_band > 0 || (best_eff >= 0.97 && tg >= best_t + 8)) break;   // good enough; look a little further for a full wave
+                if (env_band > 0) break;
             }
             if (env_units > 0) best_t = std::max<int64_t>(t_min, env_units);
             allocate(best_t);
             for (int q = 0; q < ra.n_chunks; q++) ra.chunk_unit_base[q + 1] = ra.chunk_unit_base[q] + ra.chunk_bands[q] * n_seg;
         }
         ra.n_units = ra.chunk_unit_base[ra.n_chunks];
+        {
+            static const int env_trace = tuning_int("PSIM_ROWS_TRACE");
+            if (env_trace) fprintf(stderr, "[rows] cols %lld x %d segments of %lld cells, list %d, starts/cell/row %.5f, tallest band %lld rows, %d pieces, %d units (first piece: %lld rows in %d bands)\n",
+                                   (long long)n_cols, n_seg, (long long)seg_cells, cap, starts_per_cell, (long long)band_cap, ra.n_chunks, ra.n_units,
+                                   (long long)(ra.chunk_l1[0] - ra.chunk_l0[0]), ra.chunk_bands[0]);
+        }
         if (int rc = ensure_buf(c, c->b_plan, (size_t)ra.n_units * ra.plan_stride)) return rc;
         if (int rc = ensure_buf(c, c->b_dense_list, ((size_t)ra.n_units + 1) * sizeof(int))) return rc;
         ra.plan = (uint8_t*)c->b_plan.p;
@@ -491,7 +514,10 @@ int psim_create(const psim_config* cfg, psim_ctx** out) {
     if (cudaGetDeviceProperties(&prop, cfg->device) == cudaSuccess) c->sm_count = prop.multiProcessorCount;
     bool ok = cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking) == cudaSuccess &&
               cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking) == cudaSuccess &&
-              cudaStreamCreateWithFlags(&c->aux_stream, cudaStreamNonBlocking) == cudaSuccess &&
+              [&] { int least = 0, greatest = 0; cudaDeviceGetStreamPriorityRange(&least, &greatest);
+                    return cudaStreamCreateWithPriority(&c->aux_stream, cudaStreamNonBlocking, least); }() == cudaSuccess &&
+              cudaEventCreateWithFlags(&c->ev_aux0, cudaEventDisableTiming) == cudaSuccess &&
+              cudaEventCreateWithFlags(&c->ev_aux1, cudaEventDisableTiming) == cudaSuccess &&
               cudaHostAlloc((void**)&c->scalars_h, 8 * sizeof(int64_t), cudaHostAllocMapped) == cudaSuccess &&
               cudaHostGetDevicePointer((void**)&c->scalars_dev, c->scalars_h, 0) == cudaSuccess &&
               cudaEventCreate(&c->ev0) == cudaSuccess && cudaEventCreate(&c->ev1) == cudaSuccess &&
@@ -532,6 +558,8 @@ void psim_destroy(psim_ctx* ctx) {
     if (c->own_stream) cudaStreamDestroy(c->own_stream);
     if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
     if (c->aux_stream) cudaStreamDestroy(c->aux_stream);
+    if (c->ev_aux0) cudaEventDestroy(c->ev_aux0);
+    if (c->ev_aux1) cudaEventDestroy(c->ev_aux1);
     if (c->scalars_h) cudaFreeHost(c->scalars_h);
     delete c;
 }
@@ -690,6 +718,21 @@ static int sim_enqueue(psim_ctx_impl* c, int from_batch, int64_t cursor_at) {
     const int C = c->C, P = c->P, R = c->R;
     const int64_t N = c->N;
     int32_t* const lev_all_d = (int32_t*)c->b_lev.p;
+    // The meiosis kernels run on a stream of the lowest priority (between two events of the context's stream): when
+    // another context of the process emits at the same time, the blocks of ITS streaming kernel - one per SM, bound by
+    // HBM - are placed first, and the meiosis blocks (bound by latency, next to no memory traffic) fill what is left.
+    static const int env_prio = tuning_int("PSIM_SIM_PRIO");
+    cudaStream_t const ctx_stream = c->stream;
+    const bool low = env_prio >= 0 && c->aux_stream;
+    if (low) {
+        CUDA_TRY(cudaEventRecord(c->ev_aux0, ctx_stream));
+        CUDA_TRY(cudaStreamWaitEvent(c->aux_stream, c->ev_aux0, 0));
+    }
+    struct Swap {   // (the launches below name c->stream)
+        psim_ctx_impl* c; cudaStream_t keep;
+        ~Swap() { c->stream = keep; }
+    } swap{c, ctx_stream};
+    if (low) c->stream = c->aux_stream;
     for (int b = from_batch; b < (int)run.batches.size(); b++) {
         const psim_ctx_impl::SimRun::Batch& bt = run.batches[b];
         const long long restart = b == from_batch ? (long long)cursor_at : -1;
@@ -726,6 +769,11 @@ static int sim_enqueue(psim_ctx_impl* c, int from_batch, int64_t cursor_at) {
         c->stats.kernel_launches += 2;
     }
     CUDA_TRY(cudaGetLastError());
+    if (low) {
+        CUDA_TRY(cudaEventRecord(c->ev_aux1, c->aux_stream));
+        c->stream = ctx_stream;
+        CUDA_TRY(cudaStreamWaitEvent(ctx_stream, c->ev_aux1, 0));
+    }
     CUDA_TRY(cudaEventRecord(c->ev1, c->stream));
     k_publish<<<1, 32, 0, c->stream>>>(c->scalars_dev, (const int64_t*)c->cursor_d, c->status_d, c->status_d + 1);
     c->stats.kernel_launches++;

@@ -48,6 +48,7 @@ __device__ __forceinline__ void pace_rows(long long* next, int pace) {
     while (clock64() < mine) __nanosleep(20);
 }
 
+constexpr int ROWS_MAX_PLAN_BANDS = 4096;   // bands of one chromosome piece in one launch (more: the launch is cut)
 __device__ __forceinline__ void band_rows(const RowsArgs& a, int k, int j, int64_t& g0, int64_t& g1) {
     const int64_t len = a.chunk_l1[k] - a.chunk_l0[k];
     g0 = a.chunk_l0[k] + len * j / a.chunk_bands[k];
@@ -55,33 +56,44 @@ __device__ __forceinline__ void band_rows(const RowsArgs& a, int k, int j, int64
 }
 
 // One thread per (chromosome piece, emitted cell column): walks the homolog's runs once down the
-// piece and leaves the state byte of every band plus the run starts inside it.
+// piece and leaves the state byte of every band plus the run starts inside it. (The band bounds are computed once per
+// block, and the column arithmetic is 32-bit: 64-bit divisions per thread and band were most of this kernel's time.
+// One counter atomic per warp and band instead of one per run start was tried and is slower.)
 __global__ void __launch_bounds__(256) k_band_plan(const RowsArgs a) {
+    __shared__ uint32_t s_tl[ROWS_MAX_PLAN_BANDS + 1];   // first row of every band, relative to the chromosome
     const int k = blockIdx.y;
+    const int n_bands = a.chunk_bands[k];
+    const int64_t c_off = a.chunk_coff[k];
+    for (int j = threadIdx.x; j <= n_bands; j += blockDim.x) {
+        int64_t g0, g1;
+        band_rows(a, k, min(j, n_bands - 1), g0, g1);
+        s_tl[j] = (uint32_t)((j < n_bands ? g0 : g1) - c_off);
+    }
+    __syncthreads();
     const int64_t col = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-    const int P = a.P;
+    const uint32_t P = (uint32_t)a.P;
     if (col >= a.n_cols_ind * P) return;
     const int c = a.chunk_chrom[k];
-    const int64_t q = col / P;
-    const int h = (int)(col % P);
-    const int64_t r = q / a.ind_count, i = a.ind_first + q % a.ind_count;
+    const uint32_t col32 = (uint32_t)col;   // (the row-image path is taken for fewer than 2^31 cell columns)
+    const uint32_t q = col32 / P, h = col32 - q * P;
+    const uint32_t r = q / (uint32_t)a.ind_count;
+    const int64_t i = a.ind_first + (q - r * (uint32_t)a.ind_count);
     const int64_t hid = (((int64_t)c * a.R + r) * a.N + i) * P + h;
-    const int s = (int)(col / a.seg_cells);
-    const uint32_t cs = (uint32_t)(col % a.seg_cells);
+    const uint32_t s = col32 / (uint32_t)a.seg_cells;
+    const uint32_t cs = col32 - s * (uint32_t)a.seg_cells;
     const uint64_t d = __ldg(a.run_desc + hid);
-    const uint32_t b = (uint32_t)desc_begin(d), n = desc_count(d);
-    const int64_t c_off = a.chunk_coff[k];
-    const uint32_t l_begin = (uint32_t)(a.chunk_l0[k] - c_off);
+    const uint64_t b = desc_begin(d);   // (40 bits: the slab may hold more than 2^32 segments)
+    const uint32_t n = desc_count(d);
+    const uint32_t l_begin = s_tl[0];
     uint32_t lo = 0, hi = n;   // last run with lb <= l_begin
     while (hi - lo > 1) { const uint32_t mid = (lo + hi) >> 1; if (__ldg(a.run_lb + b + mid) <= l_begin) lo = mid; else hi = mid; }
     uint32_t f = n ? __ldg(a.run_founder + b + lo) : 0;
     uint32_t kx = lo + 1;
     uint32_t nxt = kx < n ? __ldg(a.run_lb + b + kx) : NO_EVENT;
-    for (int j = 0; j < a.chunk_bands[k]; j++) {
-        int64_t g0, g1;
-        band_rows(a, k, j, g0, g1);
-        const uint32_t tl0 = (uint32_t)(g0 - c_off), tl1 = (uint32_t)(g1 - c_off);
-        uint8_t* pu = a.plan + (int64_t)(a.chunk_unit_base[k] + j * a.n_seg + s) * a.plan_stride;
+    uint8_t* pu = a.plan + (int64_t)(a.chunk_unit_base[k] + s) * a.plan_stride;
+    const int64_t band_stride = (int64_t)a.n_seg * a.plan_stride;
+    for (int j = 0; j < n_bands; j++, pu += band_stride) {
+        const uint32_t tl0 = s_tl[j], tl1 = s_tl[j + 1];
         while (nxt <= tl0) {   // a run starting exactly on the band's first row is its start state
             f = __ldg(a.run_founder + b + kx);
             kx++;
@@ -112,7 +124,10 @@ __global__ void k_rows_reset(uint8_t* plan, int64_t plan_stride, int n_units, in
     else if (u == n_units + 1) *ticket = 0;
 }
 
-constexpr int ROWS_COMPUTE = 512;                 // threads that make the rows
+#ifndef PSIM_ROWS_COMPUTE
+#define PSIM_ROWS_COMPUTE 512
+#endif
+constexpr int ROWS_COMPUTE = PSIM_ROWS_COMPUTE;   // threads that make the rows
 constexpr int ROWS_MAX_BAND = 255;     // the row of a run start inside its band is 8 bits
 constexpr int ROWS_SMEM = 220 * 1024;  // one block per SM
 #ifndef PSIM_ROWS_NBUF
@@ -155,6 +170,39 @@ static_assert(BAR_WORK + ROWS_GROUPS <= 16, "named barriers");
 __device__ __forceinline__ int bar_empty(int row) { return BAR_EMPTY + row % ROWS_NBUF + ROWS_NBUF * (row % ROWS_GROUPS); }   // waited for by the group that makes `row`
 __device__ __forceinline__ void bar_sync(int id, int n) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory"); }
 __device__ __forceinline__ void bar_arrive(int id, int n) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(n) : "memory"); }
+
+// The run starts of a unit, bucketed by row (counting sort by all threads of the block): evs / evd sorted by row,
+// start[i] = first entry of row i. (A histogram per warp instead of one for the block - fewer threads on a bin - was
+// tried for bands of few rows and many run starts and is slower: profiles/README.md, round 2.)
+__device__ __forceinline__ void bucket_run_starts(const uint8_t* pu, int seg_cells, int cap, uint32_t n_ev, int n_rows, uint32_t* evs, uint8_t* evd,
+                                                  uint32_t* start, uint32_t* cursor) {
+    const int tid = threadIdx.x, NT = blockDim.x;
+    const uint32_t* ev_g = reinterpret_cast<const uint32_t*>(pu + 16 + seg_cells);
+    const uint8_t* evd_g = pu + 16 + seg_cells + (size_t)cap * 4;
+    for (int i = tid; i <= n_rows; i += NT) start[i] = 0;
+    __syncthreads();
+    for (uint32_t e = tid; e < n_ev; e += NT) atomicAdd(&start[__ldg(ev_g + e) >> 24], 1u);
+    __syncthreads();
+    if (tid < 32) {   // exclusive scan of the row histogram (<= 256 bins) by one warp
+        uint32_t carry = 0;
+        for (int base = 0; base <= n_rows; base += 32) {
+            const int i = base + tid;
+            const uint32_t v = i <= n_rows ? start[i] : 0;
+            uint32_t x = v;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) { const uint32_t y = __shfl_up_sync(0xFFFFFFFFu, x, o); if (tid >= o) x += y; }
+            if (i <= n_rows) { start[i] = carry + x - v; cursor[i] = carry + x - v; }
+            carry += __shfl_sync(0xFFFFFFFFu, x, 31);
+        }
+    }
+    __syncthreads();
+    for (uint32_t e = tid; e < n_ev; e += NT) {
+        const uint32_t w = __ldg(ev_g + e);
+        const uint32_t at = atomicAdd(&cursor[w >> 24], 1u);
+        evs[at] = w;
+        evd[at] = __ldg(evd_g + e);
+    }
+}
 
 // DK: how the dose row is made. 0 = no dose table, 1 = no genotypes (count of one founder allele:
 // patched like the founder row), 2 = genotypes, A <= 8, ploidy 4, 3 = genotypes, A <= 8, ploidy 2.
@@ -218,31 +266,7 @@ __global__ void __launch_bounds__(ROWS_THREADS, 1) k_emit_rows(const RowsArgs a)
         // ---- start state of the band, run starts bucketed by row (all threads)
         for (int i = tid * 16; i < seg_cells; i += NT * 16)
             *reinterpret_cast<uint4*>(img0 + i) = __ldg(reinterpret_cast<const uint4*>(pu + 16 + i));
-        for (int i = tid; i <= n_rows; i += NT) start[i] = 0;
-        __syncthreads();
-        const uint32_t* ev_g = reinterpret_cast<const uint32_t*>(pu + 16 + seg_cells);
-        const uint8_t* evd_g = pu + 16 + seg_cells + (size_t)a.cap * 4;
-        for (uint32_t e = tid; e < n_ev; e += NT) atomicAdd(&start[__ldg(ev_g + e) >> 24], 1u);
-        __syncthreads();
-        if (tid < 32) {   // exclusive scan of the row histogram (<= 256 bins) by one warp
-            uint32_t carry = 0;
-            for (int base = 0; base <= n_rows; base += 32) {
-                const int i = base + tid;
-                const uint32_t v = i <= n_rows ? start[i] : 0;
-                uint32_t x = v;
-#pragma unroll
-                for (int o = 1; o < 32; o <<= 1) { const uint32_t y = __shfl_up_sync(0xFFFFFFFFu, x, o); if (tid >= o) x += y; }
-                if (i <= n_rows) { start[i] = carry + x - v; cursor[i] = carry + x - v; }
-                carry += __shfl_sync(0xFFFFFFFFu, x, 31);
-            }
-        }
-        __syncthreads();
-        for (uint32_t e = tid; e < n_ev; e += NT) {
-            const uint32_t w = __ldg(ev_g + e);
-            const uint32_t at = atomicAdd(&cursor[w >> 24], 1u);
-            evs[at] = w;
-            evd[at] = __ldg(evd_g + e);
-        }
+        bucket_run_starts(pu, seg_cells, a.cap, n_ev, n_rows, evs, evd, start, cursor);
         if (DK >= 2) {   // 4-bit image: low 3 bits of every cell, the PRMT selectors of the dose lookup
             for (int i = tid; i < seg_cells / 16; i += NT) {
                 const uint4 v = reinterpret_cast<const uint4*>(img0)[i];
@@ -476,31 +500,7 @@ __global__ void __launch_bounds__(ROWS_THREADS, 1) k_emit_rows_packed(const Rows
             auto pack = [](uint32_t x) { return (x & 0xF) | ((x >> 4) & 0xF0) | ((x >> 8) & 0xF00) | ((x >> 12) & 0xF000); };
             reinterpret_cast<uint2*>(img0)[i] = make_uint2(pack(v.x) | (pack(v.y) << 16), pack(v.z) | (pack(v.w) << 16));
         }
-        for (int i = tid; i <= n_rows; i += NT) start[i] = 0;
-        __syncthreads();
-        const uint32_t* ev_g = reinterpret_cast<const uint32_t*>(pu + 16 + seg_cells);
-        const uint8_t* evd_g = pu + 16 + seg_cells + (size_t)a.cap * 4;
-        for (uint32_t e = tid; e < n_ev; e += NT) atomicAdd(&start[__ldg(ev_g + e) >> 24], 1u);
-        __syncthreads();
-        if (tid < 32) {
-            uint32_t carry = 0;
-            for (int base = 0; base <= n_rows; base += 32) {
-                const int i = base + tid;
-                const uint32_t v = i <= n_rows ? start[i] : 0;
-                uint32_t x = v;
-#pragma unroll
-                for (int o = 1; o < 32; o <<= 1) { const uint32_t y = __shfl_up_sync(0xFFFFFFFFu, x, o); if (tid >= o) x += y; }
-                if (i <= n_rows) { start[i] = carry + x - v; cursor[i] = carry + x - v; }
-                carry += __shfl_sync(0xFFFFFFFFu, x, 31);
-            }
-        }
-        __syncthreads();
-        for (uint32_t e = tid; e < n_ev; e += NT) {
-            const uint32_t w = __ldg(ev_g + e);
-            const uint32_t at = atomicAdd(&cursor[w >> 24], 1u);
-            evs[at] = w;
-            evd[at] = __ldg(evd_g + e);
-        }
+        bucket_run_starts(pu, seg_cells, a.cap, n_ev, n_rows, evs, evd, start, cursor);
         if (DK == 1) {   // dose of one founder allele on the band's first row, 4 bits per individual
             for (int i = tid; i < seg_ind / 8; i += NT) {   // 8 individuals = one word of dose nibbles
                 uint32_t out = 0;
