@@ -89,14 +89,22 @@ class ClockSampler:
         for line in self.proc.stdout:
             self.lines.append(line.strip())
 
-    def stop(self):
+    def mark(self):
+        """Number of samples so far (start of a window)."""
+        return len(self.lines)
+
+    def wait_for(self, n, timeout):
+        t0 = time.time()
+        while self.proc and len(self.lines) < n and time.time() - t0 < timeout:
+            time.sleep(0.01)
+
+    def stop(self, first=0):
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
         self.proc.terminate()
         sm, mx, reasons = [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for ln in self.lines:
+        for ln in self.lines[first:]:
             f = [x.strip() for x in ln.split(",")]
             if len(f) < 9:
                 continue
@@ -433,14 +441,17 @@ def run_ours(args):
         for c in ctxs:
             c.wait()
 
-    run_steps(0, args.warmup, False)
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
+    run_steps(0, args.warmup, False)
+    if rank == 0:
+        sampler.wait_for(1, 3.0)   # nvidia-smi is up and sampling every 100 ms
     l0 = sum(c.stats()["kernel_launches"] for c in ctxs)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     torch.cuda.synchronize()
+    s0 = sampler.mark()
     e0.record(streams[0])
     for st_ in streams[1:]:
         st_.wait_event(e0)
@@ -452,7 +463,16 @@ def run_ours(args):
     barrier()
     ms = e0.elapsed_time(e1)
     launches = sum(c.stats()["kernel_launches"] for c in ctxs) - l0
-    clocks = sampler.stop() if rank == 0 else None
+    clocks = None
+    if rank == 0:
+        # nvidia-smi samples every 100 ms and a step lasts half a millisecond: when the timed region was too short for
+        # three samples, the very same steps go on (untimed) right behind it until the window holds three
+        t_roll, k_roll = time.time(), args.warmup + args.steps
+        while sampler.proc and sampler.mark() - s0 < 3 and time.time() - t_roll < 2.0:
+            run_steps(k_roll, 20, False)
+            k_roll += 20
+        clocks = sampler.stop(s0)
+        clocks["window"] = "the timed region (%.1f ms) and the identical untimed steps that follow it until nvidia-smi (-lms 100) has given three samples" % ms
     # the simulation of the population after the last one was enqueued too (it is part of the timed work: K steps emit K
     # populations and simulate K + 1); kernel times of the roofline kernel, alone on the device:
     solo = {"emit": 0.0, "launches": 0, "sim": 0.0, "total": 0.0}
@@ -591,7 +611,7 @@ def run_ours(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=None, help="default: 200 (a step is half a millisecond); --impl reference: 2 (a step is seconds)")
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
@@ -599,6 +619,8 @@ def main():
                     help="N > 1: F2 lines of the one-pedigree-over-all-GPUs block (configs[3]: 1 000 000); 0 skips it")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 0)
+    if args.steps is None:
+        args.steps = 2 if args.impl == "reference" else 200
     if args.impl == "reference":
         run_reference(args)
     else:

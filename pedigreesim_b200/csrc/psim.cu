@@ -359,11 +359,6 @@ static int emit_rows_path(psim_ctx_impl* c, int64_t ind_first, int64_t ind_count
     ra.dose = dose; ra.dose_pitch = dose_pitch;
     ra.dose_which = dose_which; ra.mtab = c->mtab_d;
     ra.unit_counter = c->tile_counter_d;
-    {   // tuning builds: PSIM_ROWS_PACE = aggregate GB/s the SMs together hand to the bulk-copy engines at most
-        static const int env_pace = tuning_int("PSIM_ROWS_PACE");
-        const double row_bytes = (packed ? 0.5 : 1.0) * ((founder ? (double)seg_cells : 0.0) + (dose ? (double)seg_cells / P : 0.0));
-        ra.pace = env_pace > 0 ? (int)(row_bytes * 1.965 * c->sm_count / env_pace) : 0;
-    }
     const size_t smem = (packed ? ROWS_NBUF * (size_t)seg_cells / 2 + (size_t)(DK >= 1 ? ROWS_NBUF : 0) * (seg_cells / P / 2)
                                 : ROWS_NBUF * (size_t)seg_cells + (DK >= 2 ? seg_cells : 0) + (size_t)(dose_rows ? ROWS_NBUF : 0) * (seg_cells / P)) +
                         (size_t)cap * 5 + 2 * (ROWS_MAX_BAND + 2) * 4;
@@ -419,14 +414,21 @@ static int emit_rows_path(psim_ctx_impl* c, int64_t ind_first, int64_t ind_count
             int64_t best_t = t_min;
             double best_eff = 0.0;
             // (a band's start - state load, counting sort, buffer copies, while the previous band's last rows drain - costs
-            // about as much as eight of its rows: a fuller last wave does not pay for bands that are much shorter)
+            // about as much as eight of its rows: a fuller last wave does not pay for bands that are much shorter. The
+            // candidates are the fewest bands and the band counts next to the first few whole numbers of waves.)
             const double start_rows = 8.0;
-            for (int64_t tg = t_min; tg < t_min + 4 * n_blocks && tg <= std::max<int64_t>(t_min, total / (env_band > 0 ? 1 : 16)); tg++) {
+            auto consider = [&](int64_t tg) {
+                if (tg < t_min || tg > std::max<int64_t>(t_min, total / (env_band > 0 ? 1 : 16))) return;
                 const int64_t bands = allocate(tg), units = bands * n_seg;
                 const double rows_per_band = (double)total / (double)bands;
                 const double eff = (double)units / (double)((units + n_blocks - 1) / n_blocks * n_blocks) * rows_per_band / (rows_per_band + start_rows);
                 if (eff > best_eff + 1e-9) { best_eff = eff; best_t = tg; }
-                if (env_band > 0) break;
+            };
+            consider(t_min);
+            if (env_band <= 0) {
+                const int64_t w0 = (t_min * n_seg + n_blocks - 1) / n_blocks;
+                for (int64_t wv = w0; wv < w0 + 4; wv++)
+                    for (int64_t tg = wv * n_blocks / n_seg - 1; tg <= wv * n_blocks / n_seg + 1; tg++) consider(tg);
             }
             if (env_units > 0) best_t = std::max<int64_t>(t_min, env_units);
             allocate(best_t);

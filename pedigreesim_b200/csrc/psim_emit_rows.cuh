@@ -38,16 +38,7 @@ struct RowsArgs {
     uint8_t* dose;    int64_t dose_pitch;
     int dose_which;               // without genotypes: founder allele to count
     const uint4* mtab;            // with genotypes: per-locus byte tables of the counted allele (k_match_codes)
-    int pace;                     // tuning builds: least SM cycles between two rows handed to the bulk-copy engine (0: none)
 };
-// Tuning builds (PSIM_ROWS_PACE): an SM hands a row to the bulk-copy engine no sooner than `pace` cycles after the previous one.
-__device__ __forceinline__ void pace_rows(long long* next, int pace) {
-    const long long now = clock64();
-    long long mine = (long long)atomicAdd((unsigned long long*)next, (unsigned long long)pace);
-    if (mine < now) { atomicMax(next, now + pace); mine = now; }
-    while (clock64() < mine) __nanosleep(20);
-}
-
 constexpr int ROWS_MAX_PLAN_BANDS = 4096;   // bands of one chromosome piece in one launch (more: the launch is cut)
 __device__ __forceinline__ void band_rows(const RowsArgs& a, int k, int j, int64_t& g0, int64_t& g1) {
     const int64_t len = a.chunk_l1[k] - a.chunk_l0[k];
@@ -235,8 +226,6 @@ __global__ void __launch_bounds__(ROWS_THREADS, 1) k_emit_rows(const RowsArgs a)
     uint32_t* const cursor = start + ROWS_MAX_BAND + 2;
     uint8_t* const evd = reinterpret_cast<uint8_t*>(cursor + ROWS_MAX_BAND + 2);   // rows until the run start's cell changes again
     __shared__ int s_unit;
-    __shared__ long long s_pace;
-    if (tid == 0) s_pace = 0;
     const int64_t n_cols = a.n_cols_ind * P;
     const bool count_ok = a.dose_which >= 0 && a.dose_which < 256;           // DK 1: a founder allele that exists
 
@@ -304,7 +293,6 @@ __global__ void __launch_bounds__(ROWS_THREADS, 1) k_emit_rows(const RowsArgs a)
                 uint8_t* const gf = a.founder ? a.founder + (out_row0 + r) * a.founder_pitch + c0 : nullptr;
                 uint8_t* const gd = a.dose ? a.dose + (out_row0 + r) * a.dose_pitch + c0 / P : nullptr;
                 bar_sync(BAR_FULL + b, ROWS_GROUP_THREADS + 32);
-                if (a.pace > 0) { if (lane == 0) pace_rows(&s_pace, a.pace); __syncwarp(); }
                 if (ROWS_INFLIGHT > 0 ? lane == 0 : lane < 2) {
                     if ((ROWS_INFLIGHT > 0 || lane == 0) && gf && (n_cell & ~15)) bulk_store(gf, img, (uint32_t)(n_cell & ~15));
                     if ((ROWS_INFLIGHT > 0 || lane == 1) && DSM && gd && (n_ind & ~15)) bulk_store(gd, drow, (uint32_t)(n_ind & ~15));
@@ -461,8 +449,6 @@ __global__ void __launch_bounds__(ROWS_THREADS, 1) k_emit_rows_packed(const Rows
     uint32_t* const cursor = start + ROWS_MAX_BAND + 2;
     uint8_t* const evd = reinterpret_cast<uint8_t*>(cursor + ROWS_MAX_BAND + 2);
     __shared__ int s_unit;
-    __shared__ long long s_pace;
-    if (tid == 0) s_pace = 0;
     const int64_t n_cols = a.n_cols_ind * P;
     const bool count_ok = a.dose_which >= 0 && a.dose_which < 16;            // DK 1: a founder allele that exists
 
@@ -535,7 +521,6 @@ __global__ void __launch_bounds__(ROWS_THREADS, 1) k_emit_rows_packed(const Rows
                 uint8_t* const gf = a.founder ? a.founder + (out_row0 + r) * a.founder_pitch + c0 / 2 : nullptr;
                 uint8_t* const gd = a.dose ? a.dose + (out_row0 + r) * a.dose_pitch + c0 / P / 2 : nullptr;
                 bar_sync(BAR_FULL + b, ROWS_GROUP_THREADS + 32);
-                if (a.pace > 0) { if (lane == 0) pace_rows(&s_pace, a.pace); __syncwarp(); }
                 if (ROWS_INFLIGHT > 0 ? lane == 0 : lane < 2) {
                     if ((ROWS_INFLIGHT > 0 || lane == 0) && gf && (row_bytes & ~15)) bulk_store(gf, img, (uint32_t)(row_bytes & ~15));
                     if ((ROWS_INFLIGHT > 0 || lane == 1) && DK >= 1 && gd && (drow_bytes & ~15)) bulk_store(gd, drow, (uint32_t)(drow_bytes & ~15));

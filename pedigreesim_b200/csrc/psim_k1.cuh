@@ -218,7 +218,8 @@ __global__ void __launch_bounds__(MEI_THREADS, PSIM_MEI_MIN_BLOCKS) k_meiosis(co
     x.ab = a.x_ab + (int64_t)blockIdx.x * MEI_THREADS + tid;
     x.cap = a.x_cap; x.n = 0; x.overflow = false;
     int n_out = 0;            // chromatids this thread delivers (<= 4: two per quadrivalent, twice with 2NGAMETES)
-    int strand[4], dest[4], count[4];
+    uint32_t strands = 0, dests = 0;   // nibble o: the strand chromatid o starts on, the child's homolog it becomes
+    int count[4];
     Nib16 seq; seq.v = 0;
     int base = 0, v = 0, quad = 0;
     int64_t phid0 = 0, chid0 = 0;
@@ -264,17 +265,17 @@ __global__ void __launch_bounds__(MEI_THREADS, PSIM_MEI_MIN_BLOCKS) k_meiosis(co
             for (int o = 0; o < per_gamete; o++) {
                 const int g = tr.gamete[k];
                 const int slot = is_quad ? 2 * v + o : 2 * quad + (v - quad);
-                strand[n_out] = (int)((at >> (4 * (is_quad ? 2 * g + o : g))) & 15u);
-                dest[n_out] = k * p2 + tr.dest[k].get(slot);
+                strands |= ((at >> (4 * (is_quad ? 2 * g + o : g))) & 15u) << (4 * n_out);
+                dests |= (uint32_t)(k * p2 + tr.dest[k].get(slot)) << (4 * n_out);
                 n_out++;
             }
     }
     __syncwarp();
+    // (the traces are not unrolled: eight inlined copies of trace_chromatid were a fifth of the kernel's code)
     int mine = 0;
-#pragma unroll
-    for (int o = 0; o < 4; o++) {
-        count[o] = 0;
-        if (o < n_out) count[o] = trace_chromatid<false>(a, x, strand[o], seq, base, phid0, head, tail, 0);
+#pragma unroll 1
+    for (int o = 0; o < n_out; o++) {
+        count[o] = trace_chromatid<false>(a, x, (int)((strands >> (4 * o)) & 15u), seq, base, phid0, head, tail, 0);
         mine += count[o];
     }
     // ---- 3. the warp's segments: one reservation, then the same traces write (no block-wide barrier
@@ -296,13 +297,11 @@ __global__ void __launch_bounds__(MEI_THREADS, PSIM_MEI_MIN_BLOCKS) k_meiosis(co
     warp_base = __shfl_sync(0xFFFFFFFFu, warp_base, 0);
     if (warp_base < 0) return;   // (the whole warp)
     int64_t w = warp_base + offset;
-#pragma unroll
-    for (int o = 0; o < 4; o++) {
-        if (o < n_out) {
-            trace_chromatid<true>(a, x, strand[o], seq, base, phid0, head, tail, w);
-            a.desc[chid0 + dest[o]] = make_desc((uint64_t)w, (uint64_t)count[o]);
-            w += count[o];
-        }
+#pragma unroll 1
+    for (int o = 0; o < n_out; o++) {
+        trace_chromatid<true>(a, x, (int)((strands >> (4 * o)) & 15u), seq, base, phid0, head, tail, w);
+        a.desc[chid0 + ((dests >> (4 * o)) & 15u)] = make_desc((uint64_t)w, (uint64_t)count[o]);
+        w += count[o];
     }
     }
 }

@@ -76,7 +76,15 @@ PSIM_HD void shuffle_nib(PhiloxStream& rng, Nib16& a, int n) {   // uniform rand
 }
 
 // ---------------------------------------------------------------- distances between chiasmata
-PSIM_HD double draw_exponential(PhiloxStream& r, double mean) { return -mean * log(r.next_open()); }
+// (the logarithm is a CALL on the device, by value like philox4x32_10: the exponential draw is inlined at every gap of
+// every kind of multivalent, and fp64 log is ~100 instructions of a kernel that waits on its instruction cache)
+#if defined(__CUDACC__) && !defined(PSIM_LOG_INLINE)
+__host__ __device__ __noinline__
+#else
+PSIM_HD
+#endif
+double log_called(double x) { return log(x); }
+PSIM_HD double draw_exponential(PhiloxStream& r, double mean) { return -mean * log_called(r.next_open()); }
 // Gamma(k, theta) for k >= 1 by Cheng's GA rejection sampler (the algorithm Tools.ranGamma uses, Tools.java:294-314)
 PSIM_HD_NOINLINE double draw_gamma(PhiloxStream& rng, double k, double theta) {
     const double lam = sqrt(2.0 * k - 1.0);
