@@ -144,6 +144,7 @@ struct psim_ctx_impl {
         std::vector<int32_t> f_ind, f_allele, order;
         std::vector<int64_t> level_off;
     } plan, plan_once;   // plan: kept across psim_reset; plan_once: a simulation that starts from a partly filled population
+    SimPlan *lev_plan = nullptr, *find_plan = nullptr;   // the plans whose generation / founder lists the device buffers hold
     // the simulation that has been enqueued (sim_begin) and not yet settled (sim_finish)
     struct SimRun {
         struct Batch { int level; int64_t first, count; };   // level 0: the founders; else `count` individuals of plan->order from `first`
@@ -786,6 +787,7 @@ static int sim_enqueue(psim_ctx_impl* c, int from_batch, int64_t cursor_at) {
 // subset == nullptr: every individual without a haplostruct; otherwise only the listed non-founders
 // (founders without a haplostruct are always initialised: it is cheap and every rank of a sharded
 // pedigree needs them).
+static int sim_start(psim_ctx_impl* c, psim_ctx_impl::SimPlan& plan, bool upload, int lv_lo, int lv_hi, bool founders);
 static int sim_begin(psim_ctx_impl* c, int32_t max_founder_allele, const int32_t* subset, int64_t n_subset) {
     if (c->N == 0) return fail(c, PSIM_ESTATE, "psim_set_pedigree must be called first");
     cudaSetDevice(c->cfg.device);
@@ -880,8 +882,20 @@ static int sim_begin(psim_ctx_impl* c, int32_t max_founder_allele, const int32_t
         if (fresh) { sp = std::move(pl); sp.valid = true; }
     }
     psim_ctx_impl::SimPlan& plan = fresh ? sp : c->plan_once;
-    const bool upload = !(reuse && sp.on_device);
-    if (upload && !fresh) sp.on_device = false;   // the device copies of the lists are about to be overwritten
+    return sim_start(c, plan, !(reuse && sp.on_device), 1, plan.max_level, true);
+}
+
+// Enqueues the founders (if asked) and the generations lv_lo .. lv_hi of a plan whose lists are, or are now put, on the device.
+static int sim_start(psim_ctx_impl* c, psim_ctx_impl::SimPlan& plan, bool upload, int lv_lo, int lv_hi, bool founders) {
+    const int C = c->C, P = c->P, R = c->R;
+    if (upload && !plan.order.empty()) {   // the device copies of another plan's generation lists are about to be overwritten
+        if (c->lev_plan && c->lev_plan != &plan) c->lev_plan->on_device = false;
+        c->lev_plan = &plan;
+    }
+    if (upload && founders && !plan.f_ind.empty()) {   // ... and of its founder lists
+        if (c->find_plan && c->find_plan != &plan) c->find_plan->on_device = false;
+        c->find_plan = &plan;
+    }
     // --- batches: the founders, then every generation cut into pieces whose chiasma scratch stays
     // below about 1 GiB (a thread's column holds chiasma_cap entries of 9 bytes)
     psim_ctx_impl::SimRun& run = c->run;
@@ -893,9 +907,9 @@ static int sim_begin(psim_ctx_impl* c, int32_t max_founder_allele, const int32_t
     }
     const int64_t max_blocks = std::max<int64_t>(1, (int64_t)(1LL << 30) / ((int64_t)MEI_THREADS * c->chiasma_cap * 9));
     const int64_t max_batch = std::max<int64_t>(1, max_blocks * run.units_per_block / ((int64_t)C * R * 2));
-    if (!plan.f_ind.empty()) run.batches.push_back({0, 0, (int64_t)plan.f_ind.size()});
+    if (founders && !plan.f_ind.empty()) run.batches.push_back({0, 0, (int64_t)plan.f_ind.size()});
     int64_t most_blocks = 0;
-    for (int lv = 1; lv <= plan.max_level; lv++) {
+    for (int lv = std::max(1, lv_lo); lv <= std::min(lv_hi, (int)plan.max_level); lv++) {
         const int64_t lev_begin = plan.level_off[lv], lev_size = plan.level_off[lv + 1] - lev_begin;
         for (int64_t b0 = 0; b0 < lev_size; b0 += max_batch) {
             const int64_t n = std::min<int64_t>(max_batch, lev_size - b0);
@@ -903,7 +917,7 @@ static int sim_begin(psim_ctx_impl* c, int32_t max_founder_allele, const int32_t
             most_blocks = std::max(most_blocks, (n * C * R * 2 + run.units_per_block - 1) / run.units_per_block);
         }
     }
-    if (!plan.f_ind.empty()) {
+    if (founders && !plan.f_ind.empty()) {
         const size_t n_new = plan.f_ind.size();
         if (int rc = ensure_buf(c, c->b_find, n_new * sizeof(int32_t))) return rc;
         if (int rc = ensure_buf(c, c->b_fal, n_new * sizeof(int32_t))) return rc;
@@ -912,17 +926,17 @@ static int sim_begin(psim_ctx_impl* c, int32_t max_founder_allele, const int32_t
             CUDA_TRY(cudaMemcpyAsync(c->b_fal.p, plan.f_allele.data(), n_new * sizeof(int32_t), cudaMemcpyHostToDevice, c->stream));
         }
     }
-    if (most_blocks > 0) {
+    if (most_blocks > 0 || upload) {
         const size_t n_slots = (size_t)most_blocks * MEI_THREADS;
         if (int rc = ensure_buf(c, c->b_lev, plan.order.size() * sizeof(int32_t))) return rc;
         if (int rc = ensure_buf(c, c->b_xpos, n_slots * c->chiasma_cap * sizeof(double))) return rc;
         if (int rc = ensure_buf(c, c->b_xab, n_slots * c->chiasma_cap)) return rc;
-        if (upload)   // every generation list in one copy
+        if (upload && !plan.order.empty())   // every generation list in one copy
             CUDA_TRY(cudaMemcpyAsync(c->b_lev.p, plan.order.data(), plan.order.size() * sizeof(int32_t), cudaMemcpyHostToDevice, c->stream));
     }
     if (int rc = ensure_buf(c, c->b_mark, (run.batches.size() + 1) * sizeof(unsigned long long))) return rc;
     c->mark_d = (unsigned long long*)c->b_mark.p;
-    if (fresh) sp.on_device = true;
+    if (upload) plan.on_device = true;
     c->fresh = false;
     // room for the founders and about two segments per homolog, so that the first run of a typical
     // pedigree does not have to be repeated (a slab that is too small is grown in sim_finish)

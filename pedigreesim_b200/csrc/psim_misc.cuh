@@ -164,6 +164,21 @@ __global__ void k_unpack_desc(int64_t n_h, const int32_t* __restrict__ list, int
     if (t >= n_h) return;
     desc[listed_hid(t, list, C, N, P)] = make_desc((uint64_t)(slab_base + in_off[t]), (uint64_t)(in_off[t + 1] - in_off[t]));
 }
+// The same when a rank shares everything it has just simulated: the segments travel straight out of the slab, headed by
+// the homologs' descriptors relative to the first of them.
+__global__ void k_pack_desc(int64_t n_h, const int32_t* __restrict__ list, int C, int64_t N, int P, const uint64_t* __restrict__ desc,
+                            int64_t slab_from, uint64_t* __restrict__ out) {
+    const int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (t >= n_h) return;
+    const uint64_t d = desc[listed_hid(t, list, C, N, P)];
+    out[t] = make_desc(desc_begin(d) - (uint64_t)slab_from, desc_count(d));
+}
+__global__ void k_unpack_desc_rel(int64_t n_h, const int32_t* __restrict__ list, int C, int64_t N, int P, const uint64_t* __restrict__ in,
+                                  int64_t slab_base, uint64_t* __restrict__ desc) {
+    const int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (t >= n_h) return;
+    desc[listed_hid(t, list, C, N, P)] = make_desc(desc_begin(in[t]) + (uint64_t)slab_base, desc_count(in[t]));
+}
 // (device value -> mapped page-locked host memory, like k_publish)
 __global__ void k_publish_i64(volatile int64_t* host, const int64_t* v, int n) {
     if ((int)threadIdx.x < n) host[threadIdx.x] = v[threadIdx.x];

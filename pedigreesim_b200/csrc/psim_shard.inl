@@ -160,6 +160,8 @@ struct Nccl {
     int (*CommDestroy)(comm_t) = nullptr;
     int (*AllGather)(const void*, void*, size_t, int, comm_t, cudaStream_t) = nullptr;
     int (*Broadcast)(const void*, void*, size_t, int, int, comm_t, cudaStream_t) = nullptr;
+    int (*Send)(const void*, size_t, int, int, comm_t, cudaStream_t) = nullptr;
+    int (*Recv)(void*, size_t, int, int, comm_t, cudaStream_t) = nullptr;
     int (*GroupStart)() = nullptr;
     int (*GroupEnd)() = nullptr;
     const char* (*GetErrorString)(int) = nullptr;
@@ -176,10 +178,12 @@ struct Nccl {
         CommDestroy = (decltype(CommDestroy))sym("ncclCommDestroy");
         AllGather = (decltype(AllGather))sym("ncclAllGather");
         Broadcast = (decltype(Broadcast))sym("ncclBroadcast");
+        Send = (decltype(Send))sym("ncclSend");
+        Recv = (decltype(Recv))sym("ncclRecv");
         GroupStart = (decltype(GroupStart))sym("ncclGroupStart");
         GroupEnd = (decltype(GroupEnd))sym("ncclGroupEnd");
         GetErrorString = (decltype(GetErrorString))sym("ncclGetErrorString");
-        if (!GetUniqueId || !CommInitRank || !CommDestroy || !AllGather || !Broadcast || !GroupStart || !GroupEnd || !GetErrorString) {
+        if (!GetUniqueId || !CommInitRank || !CommDestroy || !AllGather || !Broadcast || !Send || !Recv || !GroupStart || !GroupEnd || !GetErrorString) {
             handle = nullptr;
             return false;
         }
@@ -215,12 +219,23 @@ struct NcclTransport : ShardTransport {
         return PSIM_OK;
     }
     int xfer(psim_ctx_impl* c, const XferOp* ops, int n) override {
+        // one group of point-to-point transfers: the root of a part sends it to every other rank (tuning builds,
+        // PSIM_SHARD_BCAST=1: one ncclBroadcast per part instead)
+        static const int env_bcast = tuning_int("PSIM_SHARD_BCAST");
         NCCL_TRY(g_nccl.GroupStart());
         for (int k = 0; k < n; k++) {
             if (ops[k].bytes <= 0) continue;
-            void* const dst = ops[k].root == rank ? const_cast<void*>(ops[k].src) : ops[k].dst;   // (in place on the root)
-            const int r = g_nccl.Broadcast(ops[k].src, dst, (size_t)ops[k].bytes, Nccl::kUint8, ops[k].root, comm, c->stream);
-            if (r != 0) { g_nccl.GroupEnd(); return fail(c, PSIM_ECUDA, std::string("ncclBroadcast: ") + g_nccl.GetErrorString(r)); }
+            int r = 0;
+            if (env_bcast) {
+                void* const dst = ops[k].root == rank ? const_cast<void*>(ops[k].src) : ops[k].dst;   // (in place on the root)
+                r = g_nccl.Broadcast(ops[k].src, dst, (size_t)ops[k].bytes, Nccl::kUint8, ops[k].root, comm, c->stream);
+            } else if (ops[k].root == rank) {
+                for (int p = 0; p < world && r == 0; p++)
+                    if (p != rank) r = g_nccl.Send(ops[k].src, (size_t)ops[k].bytes, Nccl::kUint8, p, comm, c->stream);
+            } else {
+                r = g_nccl.Recv(ops[k].dst, (size_t)ops[k].bytes, Nccl::kUint8, ops[k].root, comm, c->stream);
+            }
+            if (r != 0) { g_nccl.GroupEnd(); return fail(c, PSIM_ECUDA, std::string("NCCL transfer: ") + g_nccl.GetErrorString(r)); }
         }
         NCCL_TRY(g_nccl.GroupEnd());
         return PSIM_OK;
@@ -270,9 +285,11 @@ struct ShardState {
     int plan_partition = -1;
     std::vector<int32_t> lists_h;       // per (level, rank): the individuals that rank shares after that level
     std::vector<int64_t> list_off;      // [(max_level + 1) * world + 1]
-    std::vector<int32_t> mine_h;        // per level: the individuals this rank simulates
-    std::vector<int64_t> mine_off;
+    std::vector<uint8_t> level_direct;  // per level: every rank shares all it simulates (its new segments travel straight out of the slab)
+    psim_ctx_impl::SimPlan mine;        // per level: the individuals this rank simulates, as psim_simulate's generation lists
     std::vector<int32_t> owner;         // after the last run: rank that holds an individual, -1 = everybody
+    std::vector<int32_t> owner_after;   // ... as the plan leaves it
+    bool owner_current = false;         // owner == owner_after
     psim_ctx_impl::Buf lists_d, cnt, send, offs;
     psim_shard_stats stats{};
     ~ShardState() {
@@ -282,6 +299,7 @@ struct ShardState {
 };
 
 void shard_free(psim_ctx_impl* c) {
+    if (c->shard && c->lev_plan == &c->shard->mine) c->lev_plan = nullptr;
     delete c->shard;
     c->shard = nullptr;
 }
@@ -290,40 +308,63 @@ inline int64_t align8(int64_t x) { return (x + 7) / 8 * 8; }
 
 // The ranks hand each other the haplostructs of the listed individuals: lists[list_off[r] .. list_off[r + 1])
 // (device: lists_d, host: lists_h) is what rank r contributes and every other rank receives.
-int shard_exchange(psim_ctx_impl* c, ShardState* S, const int32_t* lists_d, const int32_t* lists_h, const int64_t* list_off) {
+// direct_from >= 0: every rank shares ALL it simulated in this generation (the block partition), and those segments
+// are the tail of its slab from direct_from on - they travel straight out of the slab (no pack pass, no scan), headed
+// by the homologs' descriptors relative to direct_from instead of offsets.
+int shard_exchange(psim_ctx_impl* c, ShardState* S, const int32_t* lists_d, const int32_t* lists_h, const int64_t* list_off, int64_t direct_from = -1) {
     const int world = S->world, rank = S->rank, C = c->C, P = c->P;
     const int64_t hp = (int64_t)C * P;
     int64_t any = 0;
     for (int r = 0; r < world; r++) any += list_off[r + 1] - list_off[r];
     if (any == 0 || world == 1) return PSIM_OK;
-    // ---- pack what this rank contributes
+    const bool direct = direct_from >= 0;
+    const int64_t head_unit = direct ? 8 : 4;   // bytes per homolog of a part's header (direct: + 0, else + 1 entries)
+    auto head_bytes = [&](int64_t nh_r) { return direct ? 8 * nh_r : align8(4 * (nh_r + 1)); };
+    (void)head_unit;
+    // ---- what this rank contributes
     const int64_t nh = (list_off[rank + 1] - list_off[rank]) * hp;
     if (int rc = ensure_buf(c, S->cnt, (size_t)(nh + 1) * 2 * sizeof(int64_t))) return rc;
     int64_t* const cnt = (int64_t*)S->cnt.p;
     int64_t* const off = cnt + nh + 1;
-    k_pack_counts<<<grid_for(nh + 1, 256), 256, 0, c->stream>>>(nh, lists_d + list_off[rank], C, c->N, P, c->desc_d, cnt);
-    c->stats.kernel_launches++;
-    if (int rc = exclusive_scan_i64(c, cnt, off, nh + 1)) return rc;
     int64_t nseg[PSIM_SHARD_MAX_WORLD];
+    if (direct) {
+        const int64_t mine = nh > 0 ? c->slab_used - direct_from : 0;
+        CUDA_TRY(cudaMemcpyAsync(off + nh, &mine, sizeof(mine), cudaMemcpyHostToDevice, c->stream));   // (pageable: staged before it returns)
+    } else {
+        k_pack_counts<<<grid_for(nh + 1, 256), 256, 0, c->stream>>>(nh, lists_d + list_off[rank], C, c->N, P, c->desc_d, cnt);
+        c->stats.kernel_launches++;
+        if (int rc = exclusive_scan_i64(c, cnt, off, nh + 1)) return rc;
+    }
     if (int rc = S->tr->sizes(c, off + nh, nseg)) return rc;
     S->stats.collectives++;
     if (nseg[rank] >= (1LL << 32)) return fail(c, PSIM_ECAPACITY, "more than 2^32 segments in one exchange");
-    const int64_t off_bytes = align8(4 * (nh + 1)), fo_bytes = align8(4 * nseg[rank]);
-    if (int rc = ensure_buf(c, S->send, (size_t)(off_bytes + fo_bytes + 8 * nseg[rank]))) return rc;
+    const int64_t off_bytes = head_bytes(nh), fo_bytes = align8(4 * nseg[rank]);
+    if (int rc = ensure_buf(c, S->send, (size_t)(direct ? off_bytes : off_bytes + fo_bytes + 8 * nseg[rank]))) return rc;
     uint8_t* const send = (uint8_t*)S->send.p;
-    if (nh > 0) {
+    const uint8_t* send_founder = send + off_bytes;
+    const uint8_t* send_pos = send + off_bytes + fo_bytes;
+    if (nh > 0 && direct) {
+        k_pack_desc<<<grid_for(nh, 256), 256, 0, c->stream>>>(nh, lists_d + list_off[rank], C, c->N, P, c->desc_d, direct_from, (uint64_t*)send);
+        c->stats.kernel_launches++;
+        send_founder = (const uint8_t*)(c->seg_founder_d + direct_from);
+        send_pos = (const uint8_t*)(c->seg_pos_d + direct_from);
+    } else if (nh > 0) {
         k_pack_segments<<<grid_for(nh + 1, 256), 256, 0, c->stream>>>(nh, lists_d + list_off[rank], C, c->N, P, c->desc_d, off, c->seg_pos_d, c->seg_founder_d,
                                                                       (uint32_t*)send, (int32_t*)(send + off_bytes), (double*)(send + off_bytes + fo_bytes));
         c->stats.kernel_launches++;
     }
-    // ---- where the others' parts go: offsets into a receive buffer, segments straight into the slab
+    // ---- where the others' parts go: headers into a receive buffer, segments straight into the slab
     int64_t in_seg = 0, in_off_bytes = 0;
     for (int r = 0; r < world; r++) {
         if (r == rank) continue;
         in_seg += nseg[r];
-        in_off_bytes += align8(4 * ((list_off[r + 1] - list_off[r]) * hp + 1));
+        in_off_bytes += head_bytes((list_off[r + 1] - list_off[r]) * hp);
     }
-    if (int rc = ensure_slab(c, c->slab_used + in_seg)) return rc;
+    if (int rc = ensure_slab(c, c->slab_used + in_seg)) return rc;   // (may move the slab: the pointers are taken below)
+    if (direct && nh > 0) {
+        send_founder = (const uint8_t*)(c->seg_founder_d + direct_from);
+        send_pos = (const uint8_t*)(c->seg_pos_d + direct_from);
+    }
     if (int rc = ensure_buf(c, S->offs, (size_t)in_off_bytes)) return rc;
     XferOp ops[3 * PSIM_SHARD_MAX_WORLD];
     int n_ops = 0;
@@ -332,11 +373,11 @@ int shard_exchange(psim_ctx_impl* c, ShardState* S, const int32_t* lists_d, cons
     for (int r = 0; r < world; r++) {
         const int64_t nh_r = (list_off[r + 1] - list_off[r]) * hp;
         if (nh_r == 0) continue;
-        const int64_t ob = align8(4 * (nh_r + 1));
+        const int64_t ob = head_bytes(nh_r);
         if (r == rank) {
             ops[n_ops++] = {r, send, nullptr, ob};
-            ops[n_ops++] = {r, send + off_bytes, nullptr, 4 * nseg[r]};
-            ops[n_ops++] = {r, send + off_bytes + fo_bytes, nullptr, 8 * nseg[r]};
+            ops[n_ops++] = {r, send_founder, nullptr, 4 * nseg[r]};
+            ops[n_ops++] = {r, send_pos, nullptr, 8 * nseg[r]};
             continue;
         }
         base[r] = slab_at; offs_pos[r] = offs_at;
@@ -350,8 +391,12 @@ int shard_exchange(psim_ctx_impl* c, ShardState* S, const int32_t* lists_d, cons
     for (int r = 0; r < world; r++) {
         const int64_t nh_r = (list_off[r + 1] - list_off[r]) * hp;
         if (r == rank || nh_r == 0) continue;
-        k_unpack_desc<<<grid_for(nh_r, 256), 256, 0, c->stream>>>(nh_r, lists_d + list_off[r], C, c->N, P, (const uint32_t*)((uint8_t*)S->offs.p + offs_pos[r]),
-                                                                  base[r], c->desc_d);
+        if (direct)
+            k_unpack_desc_rel<<<grid_for(nh_r, 256), 256, 0, c->stream>>>(nh_r, lists_d + list_off[r], C, c->N, P, (const uint64_t*)((uint8_t*)S->offs.p + offs_pos[r]),
+                                                                          base[r], c->desc_d);
+        else
+            k_unpack_desc<<<grid_for(nh_r, 256), 256, 0, c->stream>>>(nh_r, lists_d + list_off[r], C, c->N, P, (const uint32_t*)((uint8_t*)S->offs.p + offs_pos[r]),
+                                                                      base[r], c->desc_d);
         c->stats.kernel_launches++;
         for (int64_t k = list_off[r]; k < list_off[r + 1]; k++) c->hs_reps[lists_h[k]] = c->R;
     }
@@ -477,9 +522,14 @@ int psim_simulate_sharded(psim_ctx* ctx, int32_t max_founder_allele, int32_t par
         const ShardPlan& pl = S->plan;
         const int levels = pl.max_level;
         S->list_off.assign((size_t)(levels + 1) * world + 1, 0);
-        S->mine_off.assign((size_t)levels + 2, 0);
-        S->lists_h.clear(); S->mine_h.clear();
+        S->lists_h.clear();
+        S->mine = psim_ctx_impl::SimPlan();
+        S->mine.level_off.assign((size_t)levels + 2, 0);
+        S->level_direct.assign((size_t)levels + 1, 0);
         for (int lv = 1; lv <= levels; lv++) {
+            bool all_shared = true;
+            for (int64_t k = pl.level_off[lv]; k < pl.level_off[lv + 1] && all_shared; k++) all_shared = pl.share[pl.order[(size_t)k]] != 0;
+            S->level_direct[(size_t)lv] = all_shared;
             for (int r = 0; r < world; r++) {
                 S->list_off[(size_t)lv * world + r] = (int64_t)S->lists_h.size();
                 for (int64_t k = pl.level_off[lv]; k < pl.level_off[lv + 1]; k++) {
@@ -487,13 +537,20 @@ int psim_simulate_sharded(psim_ctx* ctx, int32_t max_founder_allele, int32_t par
                     if (pl.owner[i] == r && pl.share[i]) S->lists_h.push_back(i);
                 }
             }
-            S->mine_off[lv] = (int64_t)S->mine_h.size();
+            S->mine.level_off[lv] = (int64_t)S->mine.order.size();
             for (int64_t k = pl.level_off[lv]; k < pl.level_off[lv + 1]; k++)
-                if (pl.owner[pl.order[(size_t)k]] == rank) S->mine_h.push_back(pl.order[(size_t)k]);
+                if (pl.owner[pl.order[(size_t)k]] == rank) S->mine.order.push_back(pl.order[(size_t)k]);
         }
         S->list_off[(size_t)(levels + 1) * world] = (int64_t)S->lists_h.size();
         for (int r = 0; r < world; r++) S->list_off[(size_t)r] = 0;   // (level 0: nothing)
-        S->mine_off[(size_t)levels + 1] = (int64_t)S->mine_h.size();
+        S->mine.level_off[(size_t)levels + 1] = (int64_t)S->mine.order.size();
+        S->mine.max_level = levels;
+        S->mine.valid = true;
+        S->owner_current = false;
+        S->owner_after.assign((size_t)N, -1);   // who holds an individual after the run: its owner, everybody if it was shared
+        for (int64_t i = 0; i < N; i++)
+            if (pl.level[(size_t)i] > 0 && !pl.share[(size_t)i]) S->owner_after[(size_t)i] = pl.owner[(size_t)i];
+        if (c->lev_plan == &S->mine) c->lev_plan = nullptr;   // (a new list: the device copy is stale)
         if (int rc = ensure_buf(c, S->lists_d, S->lists_h.size() * sizeof(int32_t))) return rc;
         if (!S->lists_h.empty())
             CUDA_TRY(cudaMemcpyAsync(S->lists_d.p, S->lists_h.data(), S->lists_h.size() * sizeof(int32_t), cudaMemcpyHostToDevice, c->stream));
@@ -504,16 +561,19 @@ int psim_simulate_sharded(psim_ctx* ctx, int32_t max_founder_allele, int32_t par
     // ---- founders: every rank initialises them (counter-based streams: no exchange needed)
     static const int32_t none = 0;
     if (int rc = simulate_impl(c, max_founder_allele, &none, 0)) return rc;
+    // (the generation lists of this rank were made with the plan and stay on the device across a psim_reset loop: a
+    // generation costs its kernel, not a walk over its individuals on the host)
     for (int lv = 1; lv <= pl.max_level; lv++) {
-        const int64_t m0 = S->mine_off[lv], m1 = S->mine_off[lv + 1];
-        if (m1 > m0)
-            if (int rc = simulate_impl(c, max_founder_allele, S->mine_h.data() + m0, m1 - m0)) return rc;
-        if (int rc = shard_exchange(c, S, (const int32_t*)S->lists_d.p, S->lists_h.data(), S->list_off.data() + (size_t)lv * world)) return rc;
+        const int64_t slab_before = c->slab_used;
+        if (S->mine.level_off[lv + 1] > S->mine.level_off[lv]) {
+            if (int rc = sim_start(c, S->mine, !S->mine.on_device, lv, lv, false)) return rc;
+            if (int rc = sim_finish(c)) return rc;
+        }
+        if (int rc = shard_exchange(c, S, (const int32_t*)S->lists_d.p, S->lists_h.data(), S->list_off.data() + (size_t)lv * world,
+                                    S->level_direct[(size_t)lv] ? slab_before : -1)) return rc;
     }
     CUDA_TRY(cudaStreamSynchronize(c->stream));
-    S->owner.assign((size_t)N, -1);
-    for (int64_t i = 0; i < N; i++)
-        if (pl.level[(size_t)i] > 0 && !pl.share[(size_t)i]) S->owner[(size_t)i] = pl.owner[(size_t)i];
+    if (!S->owner_current) { S->owner = S->owner_after; S->owner_current = true; }   // (psim_shard_gather changes its copy)
     S->stats.ms_total = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
     return PSIM_OK;
 }
@@ -547,7 +607,7 @@ int psim_shard_gather(psim_ctx* ctx, const int32_t* individuals, int64_t count) 
     if (!rc) rc = shard_exchange(c, S, (const int32_t*)tmp.p, lists.data(), off.data());
     cudaStreamSynchronize(c->stream);
     cudaFree(tmp.p);
-    if (!rc) for (int32_t i : lists) S->owner[(size_t)i] = -1;
+    if (!rc) { for (int32_t i : lists) S->owner[(size_t)i] = -1; S->owner_current = false; }
     return rc;
 }
 

@@ -293,6 +293,7 @@ int run(const Options& opt) {
     // ---- libpsim context (seam A inputs)
     Lib lib;
     auto t0 = clk::now();
+    auto t_ctx = t0, t_sim = t0;   // (PSIM_HOST_TIMING: context creation, simulation, the segment files)
     try {
         psim_config cfg{};
         cfg.ploidy = P;
@@ -306,6 +307,7 @@ int run(const Options& opt) {
         cfg.replicate_count = 1;
         cfg.device = opt.device;
         if (psim_create(&cfg, &lib.ctx) != PSIM_OK) throw HostError(std::string("libpsim: ") + psim_last_error(nullptr));
+        t_ctx = clk::now();
         lib.chk(psim_set_chromosomes(lib.ctx, C, ch.length.data(), ch.centromere.data(),
                                      P == 2 ? nullptr : ch.pref_pairing.data(), P == 2 ? nullptr : ch.frac_quad.data()));
         lib.chk(psim_set_pedigree(lib.ctx, N, pd.parent0.data(), pd.parent1.data()));
@@ -343,6 +345,7 @@ int run(const Options& opt) {
     if (simulate_new) {
         try {
             lib.chk(psim_simulate(lib.ctx, preset.max_founder_allele));
+            t_sim = clk::now();
             say("write file " + out_base + ".hsa");
             say("write file " + out_base + ".hsb");
             // two passes over blocks of individuals: the widest haplostruct sets the column count
@@ -545,9 +548,11 @@ int run(const Options& opt) {
     if (std::getenv("PSIM_HOST_TIMING")) {
         psim_stats s{};
         psim_get_stats(lib.ctx, &s);
-        std::fprintf(stderr, "[pedigreesim] simulate+write %.3f s, emit+write %.3f s, %lld meioses, %lld libpsim kernel launches\n",
-                     std::chrono::duration<double>(t1 - t0).count(), std::chrono::duration<double>(t2 - t1).count(),
-                     (long long)s.n_meioses, (long long)s.kernel_launches);
+        std::fprintf(stderr, "[pedigreesim] simulate+write %.3f s (CUDA context %.3f s, inputs + psim_simulate %.3f s, .hsa/.hsb/_meioticconfigs.dat %.3f s), "
+                             "emit+write %.3f s, %lld meioses, %lld libpsim kernel launches\n",
+                     std::chrono::duration<double>(t1 - t0).count(), std::chrono::duration<double>(t_ctx - t0).count(),
+                     std::chrono::duration<double>(t_sim - t_ctx).count(), std::chrono::duration<double>(t1 - std::max(t_sim, t_ctx)).count(),
+                     std::chrono::duration<double>(t2 - t1).count(), (long long)s.n_meioses, (long long)s.kernel_launches);
     }
     return 0;
 }
