@@ -290,9 +290,10 @@ int psim_import_haplostructs_device(psim_ctx* ctx, int64_t first, int64_t count,
  * pedigree in its context (same psim_set_chromosomes / psim_set_pedigree / seed and the same individuals simulated so far
  * on all ranks, replicate_count 1), simulates its share of every generation, and after a generation the ranks hand each
  * other the new haplostructs that another rank needs: the sizes first (one 8-byte all-gather, the one host wait of the
- * exchange), then every sharing rank's packed haplostructs straight into the other ranks' segment slabs (grouped
- * ncclBroadcast = an all-gather of ragged parts); no exchange at all in generations where nobody shares. Results are
- * bit-identical to psim_simulate on one GPU (counter-based streams keyed by individual).
+ * exchange), then the haplostructs straight into the other ranks' segment slabs - packed and sent as one group of
+ * ncclBroadcast (an all-gather of ragged parts) when few are shared, or, when every rank shares all it has just
+ * simulated, straight out of its slab as three ncclAllGather of equal padded parts; no exchange at all in generations
+ * where nobody shares. Results are bit-identical to psim_simulate on one GPU (counter-based streams keyed by individual).
  *   PSIM_PARTITION_BLOCK    every generation is cut into equal blocks and every new haplostruct is shared: any pedigree,
  *                           every rank ends with the whole population;
  *   PSIM_PARTITION_LINEAGE  an individual lives on the rank that owns its parents where possible; parents with children on

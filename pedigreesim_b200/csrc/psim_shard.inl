@@ -148,6 +148,8 @@ struct ShardTransport {
     virtual int sizes(psim_ctx_impl* c, const int64_t* mine_d, int64_t* all_h) = 0;
     // every op: `bytes` bytes from the root's src to dst on every other rank (stream-ordered on c->stream)
     virtual int xfer(psim_ctx_impl* c, const XferOp* ops, int n) = 0;
+    // `bytes` bytes of every rank's send to slot r of recv on every OTHER rank (the own slot may or may not be written)
+    virtual int allgather(psim_ctx_impl* c, const void* send, void* recv, int64_t bytes) = 0;
 };
 
 struct Nccl {
@@ -218,10 +220,15 @@ struct NcclTransport : ShardTransport {
         for (int r = 0; r < world; r++) out[r] = all_h[r];
         return PSIM_OK;
     }
+    int allgather(psim_ctx_impl* c, const void* send, void* recv, int64_t bytes) override {
+        if (bytes <= 0) return PSIM_OK;
+        NCCL_TRY(g_nccl.AllGather(send, recv, (size_t)bytes, Nccl::kUint8, comm, c->stream));
+        return PSIM_OK;
+    }
     int xfer(psim_ctx_impl* c, const XferOp* ops, int n) override {
-        // one group of point-to-point transfers: the root of a part sends it to every other rank (tuning builds,
-        // PSIM_SHARD_BCAST=1: one ncclBroadcast per part instead)
-        static const int env_bcast = tuning_int("PSIM_SHARD_BCAST");
+        // one group of ncclBroadcast, a part each (tuning builds, PSIM_SHARD_SENDRECV=1: point-to-point transfers instead,
+        // the root of a part to every other rank - 4 % faster on 2 GPUs, 16 % slower on 8)
+        static const int env_bcast = tuning_int("PSIM_SHARD_SENDRECV") ? 0 : 1;
         NCCL_TRY(g_nccl.GroupStart());
         for (int k = 0; k < n; k++) {
             if (ops[k].bytes <= 0) continue;
@@ -260,6 +267,17 @@ struct LocalTransport : ShardTransport {
         g->value[rank] = v;
         if (int rc = barrier(c)) return rc;
         for (int r = 0; r < g->world; r++) out[r] = g->value[r];
+        return barrier(c);
+    }
+    int allgather(psim_ctx_impl* c, const void* send, void* recv, int64_t bytes) override {
+        CUDA_TRY(cudaStreamSynchronize(c->stream));   // what this rank sends is complete
+        g->device[rank] = c->cfg.device;
+        g->src[rank] = send;
+        if (int rc = barrier(c)) return rc;
+        for (int r = 0; r < g->world; r++)
+            if (r != rank && bytes > 0)
+                CUDA_TRY(cudaMemcpyPeerAsync((uint8_t*)recv + (size_t)r * bytes, c->cfg.device, g->src[r], g->device[r], (size_t)bytes, c->stream));
+        CUDA_TRY(cudaStreamSynchronize(c->stream));
         return barrier(c);
     }
     int xfer(psim_ctx_impl* c, const XferOp* ops, int n) override {
@@ -308,63 +326,93 @@ inline int64_t align8(int64_t x) { return (x + 7) / 8 * 8; }
 
 // The ranks hand each other the haplostructs of the listed individuals: lists[list_off[r] .. list_off[r + 1])
 // (device: lists_d, host: lists_h) is what rank r contributes and every other rank receives.
-// direct_from >= 0: every rank shares ALL it simulated in this generation (the block partition), and those segments
-// are the tail of its slab from direct_from on - they travel straight out of the slab (no pack pass, no scan), headed
-// by the homologs' descriptors relative to direct_from instead of offsets.
-int shard_exchange(psim_ctx_impl* c, ShardState* S, const int32_t* lists_d, const int32_t* lists_h, const int64_t* list_off, int64_t direct_from = -1) {
+// Every rank shares ALL it has just simulated (the block partition): the new segments are the tail of the rank's slab
+// from `from` on and travel straight out of it - no pack pass, no scan - as three all-gathers (the collective NCCL does
+// best: NVLS / ring over NVSwitch) of equal, padded parts: the homologs' descriptors relative to `from`, the founders
+// and the positions, the last two straight into the receivers' slabs (rank r's part at slot r; the own slot is a
+// duplicate that nobody reads, the price of the plain collective).
+int shard_exchange_all(psim_ctx_impl* c, ShardState* S, const int32_t* lists_d, const int32_t* lists_h, const int64_t* list_off, int64_t from) {
+    const int world = S->world, rank = S->rank, C = c->C, P = c->P;
+    const int64_t hp = (int64_t)C * P;
+    int64_t nh_max = 0;
+    for (int r = 0; r < world; r++) nh_max = std::max(nh_max, (list_off[r + 1] - list_off[r]) * hp);
+    if (nh_max == 0 || world == 1) return PSIM_OK;
+    const int64_t nh = (list_off[rank + 1] - list_off[rank]) * hp;
+    const int64_t mine = nh > 0 ? c->slab_used - from : 0;
+    if (int rc = ensure_buf(c, S->cnt, 2 * sizeof(int64_t))) return rc;
+    CUDA_TRY(cudaMemcpyAsync(S->cnt.p, &mine, sizeof(mine), cudaMemcpyHostToDevice, c->stream));   // (pageable: staged before it returns)
+    int64_t nseg[PSIM_SHARD_MAX_WORLD];
+    if (int rc = S->tr->sizes(c, (const int64_t*)S->cnt.p, nseg)) return rc;
+    S->stats.collectives++;
+    int64_t seg_max = 0, in_seg = 0;
+    for (int r = 0; r < world; r++) { seg_max = std::max(seg_max, nseg[r]); if (r != rank) in_seg += nseg[r]; }
+    // slots behind the widest possible send window, so that no rank's window overlaps what it receives
+    const int64_t slots_at = from + std::max(seg_max, c->slab_used - from);
+    if (int rc = ensure_slab(c, slots_at + (int64_t)world * seg_max)) return rc;
+    if (int rc = ensure_buf(c, S->send, (size_t)(8 * nh_max))) return rc;
+    if (int rc = ensure_buf(c, S->offs, (size_t)(8 * nh_max * world))) return rc;
+    if (nh > 0) {
+        k_pack_desc<<<grid_for(nh, 256), 256, 0, c->stream>>>(nh, lists_d + list_off[rank], C, c->N, P, c->desc_d, from, (uint64_t*)S->send.p);
+        c->stats.kernel_launches++;
+    }
+    if (int rc = S->tr->allgather(c, S->send.p, S->offs.p, 8 * nh_max)) return rc;
+    if (int rc = S->tr->allgather(c, c->seg_founder_d + from, c->seg_founder_d + slots_at, 4 * seg_max)) return rc;
+    if (int rc = S->tr->allgather(c, c->seg_pos_d + from, c->seg_pos_d + slots_at, 8 * seg_max)) return rc;
+    S->stats.collectives++;
+    for (int r = 0; r < world; r++) {
+        const int64_t nh_r = (list_off[r + 1] - list_off[r]) * hp;
+        if (r == rank || nh_r == 0) continue;
+        k_unpack_desc_rel<<<grid_for(nh_r, 256), 256, 0, c->stream>>>(nh_r, lists_d + list_off[r], C, c->N, P, (const uint64_t*)((uint8_t*)S->offs.p + (size_t)r * 8 * nh_max),
+                                                                      slots_at + (int64_t)r * seg_max, c->desc_d);
+        c->stats.kernel_launches++;
+        for (int64_t k = list_off[r]; k < list_off[r + 1]; k++) c->hs_reps[lists_h[k]] = c->R;
+    }
+    CUDA_TRY(cudaGetLastError());
+    c->slab_used = slots_at + (int64_t)world * seg_max;
+    c->stats.n_segments = c->slab_used;
+    c->runs_valid = false;
+    c->fresh = false;
+    S->stats.bytes_sent += nh > 0 ? 8 * nh + 12 * nseg[rank] : 0;
+    S->stats.segments_received += in_seg;
+    return PSIM_OK;
+}
+
+// The ranks hand each other the haplostructs of the listed individuals: lists[list_off[r] .. list_off[r + 1])
+// (device: lists_d, host: lists_h) is what rank r contributes and every other rank receives.
+int shard_exchange(psim_ctx_impl* c, ShardState* S, const int32_t* lists_d, const int32_t* lists_h, const int64_t* list_off) {
     const int world = S->world, rank = S->rank, C = c->C, P = c->P;
     const int64_t hp = (int64_t)C * P;
     int64_t any = 0;
     for (int r = 0; r < world; r++) any += list_off[r + 1] - list_off[r];
     if (any == 0 || world == 1) return PSIM_OK;
-    const bool direct = direct_from >= 0;
-    const int64_t head_unit = direct ? 8 : 4;   // bytes per homolog of a part's header (direct: + 0, else + 1 entries)
-    auto head_bytes = [&](int64_t nh_r) { return direct ? 8 * nh_r : align8(4 * (nh_r + 1)); };
-    (void)head_unit;
-    // ---- what this rank contributes
+    // ---- pack what this rank contributes
     const int64_t nh = (list_off[rank + 1] - list_off[rank]) * hp;
     if (int rc = ensure_buf(c, S->cnt, (size_t)(nh + 1) * 2 * sizeof(int64_t))) return rc;
     int64_t* const cnt = (int64_t*)S->cnt.p;
     int64_t* const off = cnt + nh + 1;
+    k_pack_counts<<<grid_for(nh + 1, 256), 256, 0, c->stream>>>(nh, lists_d + list_off[rank], C, c->N, P, c->desc_d, cnt);
+    c->stats.kernel_launches++;
+    if (int rc = exclusive_scan_i64(c, cnt, off, nh + 1)) return rc;
     int64_t nseg[PSIM_SHARD_MAX_WORLD];
-    if (direct) {
-        const int64_t mine = nh > 0 ? c->slab_used - direct_from : 0;
-        CUDA_TRY(cudaMemcpyAsync(off + nh, &mine, sizeof(mine), cudaMemcpyHostToDevice, c->stream));   // (pageable: staged before it returns)
-    } else {
-        k_pack_counts<<<grid_for(nh + 1, 256), 256, 0, c->stream>>>(nh, lists_d + list_off[rank], C, c->N, P, c->desc_d, cnt);
-        c->stats.kernel_launches++;
-        if (int rc = exclusive_scan_i64(c, cnt, off, nh + 1)) return rc;
-    }
     if (int rc = S->tr->sizes(c, off + nh, nseg)) return rc;
     S->stats.collectives++;
     if (nseg[rank] >= (1LL << 32)) return fail(c, PSIM_ECAPACITY, "more than 2^32 segments in one exchange");
-    const int64_t off_bytes = head_bytes(nh), fo_bytes = align8(4 * nseg[rank]);
-    if (int rc = ensure_buf(c, S->send, (size_t)(direct ? off_bytes : off_bytes + fo_bytes + 8 * nseg[rank]))) return rc;
+    const int64_t off_bytes = align8(4 * (nh + 1)), fo_bytes = align8(4 * nseg[rank]);
+    if (int rc = ensure_buf(c, S->send, (size_t)(off_bytes + fo_bytes + 8 * nseg[rank]))) return rc;
     uint8_t* const send = (uint8_t*)S->send.p;
-    const uint8_t* send_founder = send + off_bytes;
-    const uint8_t* send_pos = send + off_bytes + fo_bytes;
-    if (nh > 0 && direct) {
-        k_pack_desc<<<grid_for(nh, 256), 256, 0, c->stream>>>(nh, lists_d + list_off[rank], C, c->N, P, c->desc_d, direct_from, (uint64_t*)send);
-        c->stats.kernel_launches++;
-        send_founder = (const uint8_t*)(c->seg_founder_d + direct_from);
-        send_pos = (const uint8_t*)(c->seg_pos_d + direct_from);
-    } else if (nh > 0) {
+    if (nh > 0) {
         k_pack_segments<<<grid_for(nh + 1, 256), 256, 0, c->stream>>>(nh, lists_d + list_off[rank], C, c->N, P, c->desc_d, off, c->seg_pos_d, c->seg_founder_d,
                                                                       (uint32_t*)send, (int32_t*)(send + off_bytes), (double*)(send + off_bytes + fo_bytes));
         c->stats.kernel_launches++;
     }
-    // ---- where the others' parts go: headers into a receive buffer, segments straight into the slab
+    // ---- where the others' parts go: offsets into a receive buffer, segments straight into the slab
     int64_t in_seg = 0, in_off_bytes = 0;
     for (int r = 0; r < world; r++) {
         if (r == rank) continue;
         in_seg += nseg[r];
-        in_off_bytes += head_bytes((list_off[r + 1] - list_off[r]) * hp);
+        in_off_bytes += align8(4 * ((list_off[r + 1] - list_off[r]) * hp + 1));
     }
-    if (int rc = ensure_slab(c, c->slab_used + in_seg)) return rc;   // (may move the slab: the pointers are taken below)
-    if (direct && nh > 0) {
-        send_founder = (const uint8_t*)(c->seg_founder_d + direct_from);
-        send_pos = (const uint8_t*)(c->seg_pos_d + direct_from);
-    }
+    if (int rc = ensure_slab(c, c->slab_used + in_seg)) return rc;
     if (int rc = ensure_buf(c, S->offs, (size_t)in_off_bytes)) return rc;
     XferOp ops[3 * PSIM_SHARD_MAX_WORLD];
     int n_ops = 0;
@@ -373,11 +421,11 @@ int shard_exchange(psim_ctx_impl* c, ShardState* S, const int32_t* lists_d, cons
     for (int r = 0; r < world; r++) {
         const int64_t nh_r = (list_off[r + 1] - list_off[r]) * hp;
         if (nh_r == 0) continue;
-        const int64_t ob = head_bytes(nh_r);
+        const int64_t ob = align8(4 * (nh_r + 1));
         if (r == rank) {
             ops[n_ops++] = {r, send, nullptr, ob};
-            ops[n_ops++] = {r, send_founder, nullptr, 4 * nseg[r]};
-            ops[n_ops++] = {r, send_pos, nullptr, 8 * nseg[r]};
+            ops[n_ops++] = {r, send + off_bytes, nullptr, 4 * nseg[r]};
+            ops[n_ops++] = {r, send + off_bytes + fo_bytes, nullptr, 8 * nseg[r]};
             continue;
         }
         base[r] = slab_at; offs_pos[r] = offs_at;
@@ -391,12 +439,8 @@ int shard_exchange(psim_ctx_impl* c, ShardState* S, const int32_t* lists_d, cons
     for (int r = 0; r < world; r++) {
         const int64_t nh_r = (list_off[r + 1] - list_off[r]) * hp;
         if (r == rank || nh_r == 0) continue;
-        if (direct)
-            k_unpack_desc_rel<<<grid_for(nh_r, 256), 256, 0, c->stream>>>(nh_r, lists_d + list_off[r], C, c->N, P, (const uint64_t*)((uint8_t*)S->offs.p + offs_pos[r]),
-                                                                          base[r], c->desc_d);
-        else
-            k_unpack_desc<<<grid_for(nh_r, 256), 256, 0, c->stream>>>(nh_r, lists_d + list_off[r], C, c->N, P, (const uint32_t*)((uint8_t*)S->offs.p + offs_pos[r]),
-                                                                      base[r], c->desc_d);
+        k_unpack_desc<<<grid_for(nh_r, 256), 256, 0, c->stream>>>(nh_r, lists_d + list_off[r], C, c->N, P, (const uint32_t*)((uint8_t*)S->offs.p + offs_pos[r]),
+                                                                  base[r], c->desc_d);
         c->stats.kernel_launches++;
         for (int64_t k = list_off[r]; k < list_off[r + 1]; k++) c->hs_reps[lists_h[k]] = c->R;
     }
@@ -569,8 +613,11 @@ int psim_simulate_sharded(psim_ctx* ctx, int32_t max_founder_allele, int32_t par
             if (int rc = sim_start(c, S->mine, !S->mine.on_device, lv, lv, false)) return rc;
             if (int rc = sim_finish(c)) return rc;
         }
-        if (int rc = shard_exchange(c, S, (const int32_t*)S->lists_d.p, S->lists_h.data(), S->list_off.data() + (size_t)lv * world,
-                                    S->level_direct[(size_t)lv] ? slab_before : -1)) return rc;
+        if (S->level_direct[(size_t)lv]) {
+            if (int rc = shard_exchange_all(c, S, (const int32_t*)S->lists_d.p, S->lists_h.data(), S->list_off.data() + (size_t)lv * world, slab_before)) return rc;
+        } else {
+            if (int rc = shard_exchange(c, S, (const int32_t*)S->lists_d.p, S->lists_h.data(), S->list_off.data() + (size_t)lv * world)) return rc;
+        }
     }
     CUDA_TRY(cudaStreamSynchronize(c->stream));
     if (!S->owner_current) { S->owner = S->owner_after; S->owner_current = true; }   // (psim_shard_gather changes its copy)

@@ -102,6 +102,12 @@ def test_block_partition_leaves_the_whole_population_on_every_rank(ploidy, name,
     total = sum(g.shard_stats()["segments_received"] for g in ctxs)
     n_sim = int(s1[-1]) - int(s1[(p0 < 0).sum() * len(lengths) * ploidy])   # segments of the simulated individuals
     assert total == (world - 1) * n_sim                                     # everybody received everybody else's share, once
+    # the unsharded call on a context that has just run sharded (its device lists were this rank's share) and back
+    g = ctxs[0]
+    g.reset(31, 0)
+    g.simulate()
+    for a, b in zip(g.get_haplostructs(), g1.get_haplostructs()):
+        assert np.array_equal(a, b)
     for g in ctxs:
         g.close()
     group.close()
