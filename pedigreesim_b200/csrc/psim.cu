@@ -791,7 +791,7 @@ static int sim_start(psim_ctx_impl* c, psim_ctx_impl::SimPlan& plan, bool upload
 static int sim_begin(psim_ctx_impl* c, int32_t max_founder_allele, const int32_t* subset, int64_t n_subset) {
     if (c->N == 0) return fail(c, PSIM_ESTATE, "psim_set_pedigree must be called first");
     cudaSetDevice(c->cfg.device);
-    const int C = c->C, P = c->P, R = c->R;
+    const int P = c->P, R = c->R;
     const int64_t N = c->N;
     // A Monte Carlo loop (psim_reset, psim_simulate, ...) simulates the same pedigree from the same
     // empty state again and again: the founder list and the generation lists are then kept, on the

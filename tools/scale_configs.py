@@ -45,13 +45,15 @@ def run(name, P, p0, p1, lengths, centro, pref, fq, loci_per_chrom, emit_first, 
     out["setup_s"] = round(time.perf_counter() - t0, 3)
     ctx.simulate()          # cold: kernels are loaded on first use, scratch and slab are allocated
     ctx.reset(12345, 0)
+    before = ctx.stats()
     t0 = time.perf_counter()
     ctx.simulate()
     torch.cuda.synchronize()
     st = ctx.stats()
-    out.update(simulate_s=round(time.perf_counter() - t0, 3), simulate_device_ms=round(st["ms_simulate"], 2), meioses=int(st["n_meioses"]),
-               units=int(st["n_units"]), segments=int(st["n_segments"]),
-               meioses_per_s=round(st["n_meioses"] / (st["ms_simulate"] * 1e-3)))
+    n_mei, n_units = st["n_meioses"] - before["n_meioses"], st["n_units"] - before["n_units"]   # (the counters run on across calls)
+    out.update(simulate_s=round(time.perf_counter() - t0, 3), simulate_device_ms=round(st["ms_simulate"], 2), meioses=int(n_mei),
+               units=int(n_units), segments=int(st["n_segments"]),
+               meioses_per_s=round(n_mei / (st["ms_simulate"] * 1e-3)))
     off, pos = _cases.uniform_map(lengths, [loci_per_chrom] * C)
     ctx.set_map(off, pos)
     R = replicate_count
