@@ -436,6 +436,11 @@ def run_ours(args):
             a, b = k % NCTX, (k + 1) % NCTX
             if timed and k - (NCTX - 1) >= first:
                 collect(ctxs[b])                       # its emission of step k - 2 finished long ago: no wait
+            if args.order == "emit-first":
+                ctxs[a].emit_into(targets[a], 0, N, 0, L)  # the one host wait of the step: population k's simulation; then K0 + K2 are enqueued
+                ctxs[b].reset(SEED, replicate_id(k + 1))
+                ctxs[b].simulate_async()
+                continue
             ctxs[b].reset(SEED, replicate_id(k + 1))
             ctxs[b].simulate_async()
             ctxs[a].emit_into(targets[a], 0, N, 0, L)  # the one host wait of the step: population k's simulation; then K0 + K2 are enqueued
@@ -645,6 +650,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--order", default="simulate-first", choices=["simulate-first", "emit-first"],
+                    help="what a pipelined step enqueues first: the next population's meioses or this population's emission")
     ap.add_argument("--sharded-lines", type=int, default=1000000,
                     help="N > 1: F2 lines of the one-pedigree-over-all-GPUs block (configs[3]: 1 000 000); 0 skips it")
     args = ap.parse_args()

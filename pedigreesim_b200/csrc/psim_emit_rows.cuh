@@ -116,7 +116,7 @@ __global__ void k_rows_reset(uint8_t* plan, int64_t plan_stride, int n_units, in
 }
 
 #ifndef PSIM_ROWS_COMPUTE
-#define PSIM_ROWS_COMPUTE 512
+#define PSIM_ROWS_COMPUTE 384
 #endif
 constexpr int ROWS_COMPUTE = PSIM_ROWS_COMPUTE;   // threads that make the rows
 constexpr int ROWS_MAX_BAND = 255;     // the row of a run start inside its band is 8 bits
@@ -209,8 +209,17 @@ __device__ __forceinline__ void bucket_run_starts(const uint8_t* pu, int seg_cel
 //   2. with genotypes: barrier, then the dose row is recomputed from a 4-bit image of the row (kept
 //      twice, for even and odd rows, patched the same way) and goes from registers straight to global
 //      memory; without genotypes the dose row is patched like the founder row and leaves as a bulk store.
+// Sized to share an SM with the meiosis kernel: 384 compute threads + 3 issuing warps at 40 registers (the compiler
+// takes 87 when left alone, with no gain) leave room for three blocks of k_meiosis at 56 registers, and the pipelined
+// step - population k + 1 simulated while population k is emitted - is 0.40 ms instead of 0.45 (512 threads at 87
+// registers next to k_meiosis at 64: whichever kernel was resident first left the other next to nothing). The
+// kernel's own time does not change (configs[1]); profiles/README.md has the variants.
+#ifndef PSIM_ROWS_MAXREG
+#define PSIM_ROWS_MAXREG 40
+#endif
+#define ROWS_KERNEL_BOUNDS __maxnreg__(PSIM_ROWS_MAXREG)
 template <int DK>
-__global__ void __launch_bounds__(ROWS_THREADS, 1) k_emit_rows(const RowsArgs a) {
+__global__ void ROWS_KERNEL_BOUNDS k_emit_rows(const RowsArgs a) {
     extern __shared__ __align__(128) uint8_t smem[];
     const int tid = threadIdx.x;
     const int NT = ROWS_THREADS;
@@ -434,7 +443,7 @@ __global__ void __launch_bounds__(256) k_emit_rows_overflow(const RowsArgs a, co
 // the dose nibbles come straight out of the PRMT / IDP.4A lookup, and a table row leaves the SM as
 // half the bytes. Same plan, same issuing warps, same barriers as k_emit_rows.
 template <int DK>
-__global__ void __launch_bounds__(ROWS_THREADS, 1) k_emit_rows_packed(const RowsArgs a) {
+__global__ void ROWS_KERNEL_BOUNDS k_emit_rows_packed(const RowsArgs a) {
     extern __shared__ __align__(128) uint8_t smem[];
     const int tid = threadIdx.x;
     const int NT = ROWS_THREADS;

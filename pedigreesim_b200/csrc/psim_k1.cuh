@@ -151,8 +151,18 @@ __device__ __forceinline__ int trace_chromatid(const MeiosisArgs& a, const Chias
 
 // KOS / ANR: MAPFUNCTION=KOSAMBI and ALLOWNORECOMBINATION as compile-time constants, so that the code
 // of the other model (gamma sampler, pow, retry loop) is not in the kernel at all.
+// 56 registers (a few spills; 64 would be spill-free and 2 % faster alone): four blocks then leave a slice of the
+// register file free, and three fit next to the emission kernel (psim_emit_rows.cuh) when a caller pipelines the two.
+#ifndef PSIM_MEI_MAXREG
+#define PSIM_MEI_MAXREG 56
+#endif
+#if PSIM_MEI_MAXREG > 0
+#define MEI_KERNEL_BOUNDS __maxnreg__(PSIM_MEI_MAXREG)
+#else
+#define MEI_KERNEL_BOUNDS __launch_bounds__(MEI_THREADS, PSIM_MEI_MIN_BLOCKS)
+#endif
 template <bool KOS, bool ANR>
-__global__ void __launch_bounds__(MEI_THREADS, PSIM_MEI_MIN_BLOCKS) k_meiosis(const MeiosisArgs a) {
+__global__ void MEI_KERNEL_BOUNDS k_meiosis(const MeiosisArgs a) {
     typedef cub::BlockScan<int, MEI_THREADS> Scan;
     __shared__ typename Scan::TempStorage scan_tmp;
     __shared__ uint64_t s_seq[MEI_THREADS];
