@@ -917,6 +917,10 @@ static int sim_start(psim_ctx_impl* c, psim_ctx_impl::SimPlan& plan, bool upload
             most_blocks = std::max(most_blocks, (n * C * R * 2 + run.units_per_block - 1) / run.units_per_block);
         }
     }
+    if (run.batches.empty()) {   // nothing to simulate (e.g. the founders of a sharded run that all exist already): the
+        run.pending = false;     // device cursor is only valid behind a batch, so there is nothing to enqueue or settle
+        return PSIM_OK;
+    }
     if (founders && !plan.f_ind.empty()) {
         const size_t n_new = plan.f_ind.size();
         if (int rc = ensure_buf(c, c->b_find, n_new * sizeof(int32_t))) return rc;

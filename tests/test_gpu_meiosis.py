@@ -296,3 +296,21 @@ def test_subset_simulation_edge_cases():
     g.simulate_subset(np.concatenate([gen(1)[1::2], gen(0)[1::2]]))
     g.simulate()                                 # the rest
     assert_same_population(o, g)
+
+
+def test_simulate_with_nothing_left_to_simulate_keeps_the_population():
+    """Replay (HAPLOSTRUCT= covers everybody, Main.java:317-330): psim_simulate finds no individual without a haplostruct.
+    The recorded segments must survive the call (the slab cursor on the device is only valid behind a batch)."""
+    rng = np.random.default_rng(4)
+    p0, p1 = _cases.std_pedigree("F1", 40)
+    lengths = [1.0, 0.7]
+    rec = _cases.random_haplostructs(rng, len(p0), lengths, 4, 8)
+    g = _cases.make_engine("gpu", 4, seed=5)
+    g.set_chromosomes(lengths, [0.5, 0.3], [0.3, 0.3], [0.5, 0.5])
+    g.set_pedigree(p0, p1)
+    g.set_haplostructs(0, *rec)
+    g.simulate(7)
+    g.simulate_subset(np.zeros(0, np.int32), 7)
+    for a, b in zip(rec, g.get_haplostructs()):
+        assert np.array_equal(a, b)
+    g.close()

@@ -191,6 +191,93 @@ def test_sharded_calls_need_a_communicator_and_one_replicate():
     group.close()
 
 
+@pytest.mark.parametrize("partition", [ps.PARTITION_BLOCK, ps.PARTITION_LINEAGE])
+def test_more_ranks_than_individuals_and_other_models(partition):
+    """Ranks with nothing to simulate in a generation still take part in its exchange; hexaploid natural pairing with
+    interference goes through the same path."""
+    ploidy, world = 6, 4
+    p0, p1 = _cases.std_pedigree("F2", 3)           # P1 x P2 -> F1 -> three F2 plants: generations of 1 and 3 on 4 ranks
+    lengths, centro = [1.1, 0.6], [0.5, 0.3]
+    out = []
+    for kind in ("oracle-philox", "gpu"):
+        e = _cases.make_engine(kind, ploidy, seed=3, kosambi=True, natural_pairing=True)
+        _setup(e, ploidy, lengths, centro, p0, p1)
+        e.simulate()
+        out.append(e)
+    o, g1 = out
+    group = ps.ShardGroup(world)
+    ctxs = []
+    for r in range(world):
+        g = ps.PsimContext(ploidy, seed=3, kosambi=True, natural_pairing=True)
+        _setup(g, ploidy, lengths, centro, p0, p1)
+        g.shard_init_local(r, group)
+        ctxs.append(g)
+    errors = []
+
+    def work(g):
+        try:
+            g.simulate_sharded(partition=partition)
+            g.shard_gather(np.arange(len(p0), dtype=np.int32))
+        except Exception as e:   # noqa: BLE001
+            errors.append(e)
+
+    threads = [threading.Thread(target=work, args=(g,)) for g in ctxs]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    assert not errors, errors
+    for g in ctxs:
+        _assert_same(o, g)
+        g.close()
+    group.close()
+
+
+def test_sharded_extension_of_a_recorded_population():
+    """Mode 3 (Main.java:317-361): founders, F1 and the first selfed generation come from recorded haplostructs, the later
+    generations are simulated - sharded. The plan counts the recorded individuals as done on every rank."""
+    ploidy, world = 2, 2
+    lines = 11
+    p0, p1 = _cases.ril_pedigree(lines, 5)
+    lengths, centro = [1.3, 0.9], [0.6, 0.4]
+    n_rec = 3 + lines
+    first = _cases.make_engine("gpu", ploidy, seed=41)
+    _setup(first, ploidy, lengths, centro, p0[:n_rec], p1[:n_rec])
+    first.simulate()
+    rec = first.get_haplostructs()
+    ref = _cases.make_engine("gpu", ploidy, seed=99)
+    _setup(ref, ploidy, lengths, centro, p0, p1)
+    ref.set_haplostructs(0, *rec)
+    ref.simulate(int(rec[1].max()))
+    group = ps.ShardGroup(world)
+    ctxs = []
+    for r in range(world):
+        g = ps.PsimContext(ploidy, seed=99)
+        _setup(g, ploidy, lengths, centro, p0, p1)
+        g.set_haplostructs(0, *rec)
+        g.shard_init_local(r, group)
+        ctxs.append(g)
+    errors = []
+
+    def work(g):
+        try:
+            g.simulate_sharded(int(rec[1].max()), ps.PARTITION_BLOCK)
+        except Exception as e:   # noqa: BLE001
+            errors.append(e)
+
+    threads = [threading.Thread(target=work, args=(g,)) for g in ctxs]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    assert not errors, errors
+    for g in ctxs:
+        for a, b in zip(ref.get_haplostructs(), g.get_haplostructs()):
+            assert np.array_equal(a, b)
+        g.close()
+    group.close()
+
+
 def _free_port():
     s = socket.socket()
     s.bind(("127.0.0.1", 0))
