@@ -360,6 +360,11 @@ static int emit_rows_path(psim_ctx_impl* c, int64_t ind_first, int64_t ind_count
     ra.dose = dose; ra.dose_pitch = dose_pitch;
     ra.dose_which = dose_which; ra.mtab = c->mtab_d;
     ra.unit_counter = c->tile_counter_d;
+    {   // many run starts per unit: a global atomic each is what k_band_plan waits for, so they are counted per block first
+        // (costs a second walk over the runs; tuning builds: PSIM_PLAN_SHARED = 1 always, -1 never)
+        static const int env_shared = tuning_int("PSIM_PLAN_SHARED");
+        ra.plan_shared = env_shared ? env_shared > 0 : starts_per_cell * 256.0 * (double)std::min<int64_t>(band_cap, 64) >= 24.0;
+    }
     const size_t smem = (packed ? ROWS_NBUF * (size_t)seg_cells / 2 + (size_t)(DK >= 1 ? ROWS_NBUF : 0) * (seg_cells / P / 2)
                                 : ROWS_NBUF * (size_t)seg_cells + (DK >= 2 ? seg_cells : 0) + (size_t)(dose_rows ? ROWS_NBUF : 0) * (seg_cells / P)) +
                         (size_t)cap * 5 + 2 * (ROWS_MAX_BAND + 2) * 4;

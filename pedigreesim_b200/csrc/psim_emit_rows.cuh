@@ -38,70 +38,123 @@ struct RowsArgs {
     uint8_t* dose;    int64_t dose_pitch;
     int dose_which;               // without genotypes: founder allele to count
     const uint4* mtab;            // with genotypes: per-locus byte tables of the counted allele (k_match_codes)
+    int plan_shared;              // k_band_plan: count a block's run starts per band in shared memory, one global atomic per band
 };
-constexpr int ROWS_MAX_PLAN_BANDS = 4096;   // bands of one chromosome piece in one launch (more: the launch is cut)
+constexpr int ROWS_MAX_PLAN_BANDS = 2048;   // bands of one chromosome piece in one launch (more: the launch is cut)
 __device__ __forceinline__ void band_rows(const RowsArgs& a, int k, int j, int64_t& g0, int64_t& g1) {
     const int64_t len = a.chunk_l1[k] - a.chunk_l0[k];
     g0 = a.chunk_l0[k] + len * j / a.chunk_bands[k];
     g1 = a.chunk_l0[k] + len * (j + 1) / a.chunk_bands[k];
 }
 
-// One thread per (chromosome piece, emitted cell column): walks the homolog's runs once down the
-// piece and leaves the state byte of every band plus the run starts inside it. (The band bounds are computed once per
-// block, and the column arithmetic is 32-bit: 64-bit divisions per thread and band were most of this kernel's time.
-// One counter atomic per warp and band instead of one per run start was tried and is slower.)
+// One thread per (chromosome piece, emitted cell column): walks the homolog's runs down the piece and leaves the state
+// byte of every band plus the run starts inside it. The band bounds are computed once per block and the column
+// arithmetic is 32-bit (64-bit divisions per thread and band were a tenth of this kernel's time). Filing a run start
+// needs a place in its unit's list: a global atomic per run start was over half of the kernel's time (ncu: the threads
+// wait for the counter's old value), so a block counts its run starts per band in shared memory on a first walk,
+// reserves them with ONE global atomic per band and segment, and files them on a second walk (the loads hit L1 / L2).
+// Pieces of more than ROWS_PLAN_SHARED_BANDS bands keep the atomic per run start.
+constexpr int ROWS_PLAN_SHARED_BANDS = 512;
+struct PlanWalk {   // a homolog's runs from the first row of the piece on
+    uint64_t b; uint32_t n, kx, nxt, f;
+};
 __global__ void __launch_bounds__(256) k_band_plan(const RowsArgs a) {
-    __shared__ uint32_t s_tl[ROWS_MAX_PLAN_BANDS + 1];   // first row of every band, relative to the chromosome
+    __shared__ uint32_t s_tl[ROWS_MAX_PLAN_BANDS + 1];          // first row of every band, relative to the chromosome
+    __shared__ uint32_t s_cnt[2][ROWS_PLAN_SHARED_BANDS];        // [segment of the block][band]: run starts, then the cursor
+    __shared__ uint32_t s_base[2][ROWS_PLAN_SHARED_BANDS];       // first entry reserved in the unit's list
     const int k = blockIdx.y;
     const int n_bands = a.chunk_bands[k];
+    const bool shared_counts = a.plan_shared && n_bands <= ROWS_PLAN_SHARED_BANDS;
     const int64_t c_off = a.chunk_coff[k];
     for (int j = threadIdx.x; j <= n_bands; j += blockDim.x) {
         int64_t g0, g1;
         band_rows(a, k, min(j, n_bands - 1), g0, g1);
         s_tl[j] = (uint32_t)((j < n_bands ? g0 : g1) - c_off);
     }
+    if (shared_counts) for (int j = threadIdx.x; j < 2 * n_bands; j += blockDim.x) s_cnt[j / n_bands][j % n_bands] = 0;
     __syncthreads();
     const int64_t col = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     const uint32_t P = (uint32_t)a.P;
-    if (col >= a.n_cols_ind * P) return;
+    const bool live = col < a.n_cols_ind * P;   // (threads past the last column still reach the barriers)
     const int c = a.chunk_chrom[k];
-    const uint32_t col32 = (uint32_t)col;   // (the row-image path is taken for fewer than 2^31 cell columns)
+    const uint32_t col32 = live ? (uint32_t)col : 0u;   // (the row-image path is taken for fewer than 2^31 cell columns)
     const uint32_t q = col32 / P, h = col32 - q * P;
     const uint32_t r = q / (uint32_t)a.ind_count;
     const int64_t i = a.ind_first + (q - r * (uint32_t)a.ind_count);
     const int64_t hid = (((int64_t)c * a.R + r) * a.N + i) * P + h;
     const uint32_t s = col32 / (uint32_t)a.seg_cells;
     const uint32_t cs = col32 - s * (uint32_t)a.seg_cells;
-    const uint64_t d = __ldg(a.run_desc + hid);
-    const uint64_t b = desc_begin(d);   // (40 bits: the slab may hold more than 2^32 segments)
-    const uint32_t n = desc_count(d);
-    const uint32_t l_begin = s_tl[0];
-    uint32_t lo = 0, hi = n;   // last run with lb <= l_begin
-    while (hi - lo > 1) { const uint32_t mid = (lo + hi) >> 1; if (__ldg(a.run_lb + b + mid) <= l_begin) lo = mid; else hi = mid; }
-    uint32_t f = n ? __ldg(a.run_founder + b + lo) : 0;
-    uint32_t kx = lo + 1;
-    uint32_t nxt = kx < n ? __ldg(a.run_lb + b + kx) : NO_EVENT;
-    uint8_t* pu = a.plan + (int64_t)(a.chunk_unit_base[k] + s) * a.plan_stride;
+    const uint32_t s_first = (uint32_t)((blockIdx.x * (int64_t)blockDim.x) / a.seg_cells);   // (a block spans at most two segments)
+    const uint32_t sl = s - s_first;
+    PlanWalk w0{0, 0, 1, NO_EVENT, 0};
+    if (live) {
+        const uint64_t d = __ldg(a.run_desc + hid);
+        w0.b = desc_begin(d);   // (40 bits: the slab may hold more than 2^32 segments)
+        w0.n = desc_count(d);
+        const uint32_t l_begin = s_tl[0];
+        uint32_t lo = 0, hi = w0.n;   // last run with lb <= l_begin
+        while (hi - lo > 1) { const uint32_t mid = (lo + hi) >> 1; if (__ldg(a.run_lb + w0.b + mid) <= l_begin) lo = mid; else hi = mid; }
+        w0.f = w0.n ? __ldg(a.run_founder + w0.b + lo) : 0;
+        w0.kx = lo + 1;
+        w0.nxt = w0.kx < w0.n ? __ldg(a.run_lb + w0.b + w0.kx) : NO_EVENT;
+    }
+    auto advance = [&](PlanWalk& w) {
+        w.f = __ldg(a.run_founder + w.b + w.kx);
+        w.kx++;
+        w.nxt = w.kx < w.n ? __ldg(a.run_lb + w.b + w.kx) : NO_EVENT;
+    };
+    uint8_t* const pu0 = a.plan + (int64_t)(a.chunk_unit_base[k] + s) * a.plan_stride;
     const int64_t band_stride = (int64_t)a.n_seg * a.plan_stride;
-    for (int j = 0; j < n_bands; j++, pu += band_stride) {
-        const uint32_t tl0 = s_tl[j], tl1 = s_tl[j + 1];
-        while (nxt <= tl0) {   // a run starting exactly on the band's first row is its start state
-            f = __ldg(a.run_founder + b + kx);
-            kx++;
-            nxt = kx < n ? __ldg(a.run_lb + b + kx) : NO_EVENT;
+    auto file = [&](uint8_t* pu, uint32_t idx, uint32_t row, uint32_t f, uint32_t again) {
+        if (idx < (uint32_t)a.cap) {
+            reinterpret_cast<uint32_t*>(pu + 16 + a.seg_cells)[idx] = (row << 24) | (cs << 8) | f;
+            // rows until the same cell changes again (255: not soon): a row buffer that takes the run starts
+            // of several rows in one pass skips those that are overwritten inside its window
+            (pu + 16 + a.seg_cells + (size_t)a.cap * 4)[idx] = (uint8_t)min(again, 255u);
         }
-        pu[16 + cs] = (uint8_t)f;
-        while (nxt < tl1) {
-            f = __ldg(a.run_founder + b + kx);
-            const uint32_t idx = atomicAdd(reinterpret_cast<uint32_t*>(pu), 1u);
-            const uint32_t row = nxt - tl0;
-            kx++;
-            nxt = kx < n ? __ldg(a.run_lb + b + kx) : NO_EVENT;
-            if (idx < (uint32_t)a.cap) {
-                reinterpret_cast<uint32_t*>(pu + 16 + a.seg_cells)[idx] = (row << 24) | (cs << 8) | f;
-                // rows until the same cell changes again (255: not soon): a row buffer that takes the run starts
-                // of several rows in one pass skips those that are overwritten inside its window
-                (pu + 16 + a.seg_cells + (size_t)a.cap * 4)[idx] = (uint8_t)min(nxt - (row + tl0), 255u);
+    };
+    // ---- first walk: the state byte of every band; the run starts are counted (or filed, in a piece of many bands)
+    if (live) {
+        PlanWalk w = w0;
+        uint8_t* pu = pu0;
+        for (int j = 0; j < n_bands; j++, pu += band_stride) {
+            const uint32_t tl0 = s_tl[j], tl1 = s_tl[j + 1];
+            while (w.nxt <= tl0) advance(w);   // a run starting exactly on the band's first row is its start state
+            pu[16 + cs] = (uint8_t)w.f;
+            uint32_t cnt = 0;
+            while (w.nxt < tl1) {
+                const uint32_t row = w.nxt - tl0;
+                advance(w);
+                if (shared_counts) cnt++;
+                else file(pu, atomicAdd(reinterpret_cast<uint32_t*>(pu), 1u), row, w.f, w.nxt - (row + tl0));
+            }
+            if (cnt) atomicAdd(&s_cnt[sl][j], cnt);
+        }
+    }
+    if (!shared_counts) return;   // (the same for every thread of the block)
+    __syncthreads();
+    // ---- one reservation per band and segment of the block
+    for (int t = threadIdx.x; t < 2 * n_bands; t += blockDim.x) {
+        const int sg = t / n_bands, j = t % n_bands;
+        const uint32_t cnt = s_cnt[sg][j];
+        if (cnt) {
+            uint8_t* pu = a.plan + (int64_t)(a.chunk_unit_base[k] + j * a.n_seg + (int)s_first + sg) * a.plan_stride;
+            s_base[sg][j] = atomicAdd(reinterpret_cast<uint32_t*>(pu), cnt);
+            s_cnt[sg][j] = 0;
+        }
+    }
+    __syncthreads();
+    // ---- second walk: the run starts are filed
+    if (live) {
+        PlanWalk w = w0;
+        uint8_t* pu = pu0;
+        for (int j = 0; j < n_bands; j++, pu += band_stride) {
+            const uint32_t tl0 = s_tl[j], tl1 = s_tl[j + 1];
+            while (w.nxt <= tl0) advance(w);
+            while (w.nxt < tl1) {
+                const uint32_t row = w.nxt - tl0;
+                advance(w);
+                file(pu, s_base[sl][j] + atomicAdd(&s_cnt[sl][j], 1u), row, w.f, w.nxt - (row + tl0));
             }
         }
     }
