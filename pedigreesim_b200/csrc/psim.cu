@@ -100,6 +100,7 @@ struct psim_ctx_impl {
     std::vector<int64_t> locus_off_h;
     int64_t* locus_off_d = nullptr;
     double* locus_pos_d = nullptr;
+    int32_t* grid_d = nullptr; int64_t* grid_off_d = nullptr; double* grid_lo_d = nullptr; double* grid_inv_d = nullptr;   // MapGrid (k_index_runs)
     int64_t L = 0;
     // codes
     int A = 0;
@@ -551,6 +552,7 @@ void psim_destroy(psim_ctx* ctx) {
     cudaFree(c->chrom_d); cudaFree(c->seg_pos_d); cudaFree(c->seg_founder_d);
     cudaFree(c->run_lb_d); cudaFree(c->run_founder_d);
     cudaFree(c->locus_off_d); cudaFree(c->locus_pos_d); cudaFree(c->code_d); cudaFree(c->match_d);
+    cudaFree(c->grid_d); cudaFree(c->grid_off_d); cudaFree(c->grid_lo_d); cudaFree(c->grid_inv_d);
     cudaFree(c->code16_d); cudaFree(c->nibmask_d); cudaFree(c->mtab_d);
     cudaFree(c->status_d); cudaFree(c->cursor_d); cudaFree(c->tile_counter_d); cudaFree(c->cub_tmp); cudaFree(c->staging);
     cudaFree(c->exp_off_d); cudaFree(c->exp_founder_d); cudaFree(c->exp_pos_d);
@@ -1166,6 +1168,38 @@ int psim_set_map(psim_ctx* ctx, const int64_t* locus_off, const double* pos) {
     CUDA_TRY(dev_alloc(&c->locus_pos_d, (size_t)c->L));
     CUDA_TRY(cudaMemcpy(c->locus_off_d, locus_off, (c->C + 1) * sizeof(int64_t), cudaMemcpyHostToDevice));
     CUDA_TRY(cudaMemcpy(c->locus_pos_d, pos, c->L * sizeof(double), cudaMemcpyHostToDevice));
+    {   // the grid k_index_runs searches the map through: about four buckets per locus
+        std::vector<int64_t> goff((size_t)c->C + 1, 0);
+        std::vector<double> glo((size_t)c->C, 0.0), ginv((size_t)c->C, 0.0);
+        std::vector<int32_t> grid;
+        for (int k = 0; k < c->C; k++) {
+            const double* p0 = pos + locus_off[k];
+            const int64_t Lc = locus_off[k + 1] - locus_off[k];
+            const double span = Lc > 0 ? p0[Lc - 1] - p0[0] : 0.0;
+            const int64_t nb = span > 0.0 ? std::max<int64_t>(16, std::min<int64_t>(4 * Lc, 1 << 22)) : 1;
+            const double width = span > 0.0 ? span / (double)nb : 0.0;
+            glo[(size_t)k] = Lc > 0 ? p0[0] : 0.0;
+            ginv[(size_t)k] = width > 0.0 ? 1.0 / width : 0.0;
+            int64_t at = 0;   // (bucket starts and positions both ascend: one merge pass)
+            for (int64_t q = 0; q < nb; q++) {
+                const double start = glo[(size_t)k] + (double)q * width;
+                while (at < Lc && p0[at] < start) at++;
+                grid.push_back((int32_t)at);
+            }
+            grid.push_back((int32_t)Lc);
+            goff[(size_t)k + 1] = (int64_t)grid.size();
+        }
+        cudaFree(c->grid_d); cudaFree(c->grid_off_d); cudaFree(c->grid_lo_d); cudaFree(c->grid_inv_d);
+        c->grid_d = nullptr; c->grid_off_d = nullptr; c->grid_lo_d = nullptr; c->grid_inv_d = nullptr;
+        CUDA_TRY(dev_alloc(&c->grid_d, grid.size()));
+        CUDA_TRY(dev_alloc(&c->grid_off_d, goff.size()));
+        CUDA_TRY(dev_alloc(&c->grid_lo_d, glo.size()));
+        CUDA_TRY(dev_alloc(&c->grid_inv_d, ginv.size()));
+        CUDA_TRY(cudaMemcpy(c->grid_d, grid.data(), grid.size() * sizeof(int32_t), cudaMemcpyHostToDevice));
+        CUDA_TRY(cudaMemcpy(c->grid_off_d, goff.data(), goff.size() * sizeof(int64_t), cudaMemcpyHostToDevice));
+        CUDA_TRY(cudaMemcpy(c->grid_lo_d, glo.data(), glo.size() * sizeof(double), cudaMemcpyHostToDevice));
+        CUDA_TRY(cudaMemcpy(c->grid_inv_d, ginv.data(), ginv.size() * sizeof(double), cudaMemcpyHostToDevice));
+    }
     c->runs_valid = false;
     return PSIM_OK;
 }
@@ -1204,7 +1238,8 @@ static int ensure_runs(psim_ctx_impl* c) {
         c->run_cap = c->slab_cap;
     }
     k_index_runs<<<grid_for(c->n_hom, 128), 128, 0, c->stream>>>(c->n_hom, (int64_t)c->R * c->N * c->P, c->desc_d, c->seg_pos_d,
-                                                                 c->seg_founder_d, c->locus_off_d, c->locus_pos_d, c->run_desc_d,
+                                                                 c->seg_founder_d, c->locus_off_d, c->locus_pos_d,
+                                                                 MapGrid{c->grid_d, c->grid_off_d, c->grid_lo_d, c->grid_inv_d}, c->run_desc_d,
                                                                  c->run_lb_d, c->run_founder_d);
     c->stats.kernel_launches++;
     CUDA_TRY(cudaGetLastError());
@@ -1395,6 +1430,7 @@ static int emit_prepare(psim_ctx_impl* c, int64_t ind_first, int64_t ind_count, 
     if (locus_first < 0 || locus_count <= 0 || locus_first + locus_count > c->L) return fail(c, PSIM_EINVAL, "locus range out of bounds");
     for (int64_t i = ind_first; i < ind_first + ind_count; i++)
         if (c->hs_reps[i] != c->R) return fail(c, PSIM_ESTATE, "individual " + std::to_string(i) + " has no haplostruct yet");
+    CUDA_TRY(cudaEventRecord(c->ev0, c->stream));   // psim_emit's ms_emit_total counts K0 too (the other callers record their own start)
     return ensure_runs(c);
 }
 
@@ -1437,7 +1473,7 @@ int psim_emit(psim_ctx* ctx, int64_t ind_first, int64_t ind_count, int64_t locus
     }
     c->stats.emit_kernel_launches = 0;
     c->kev_used = 0;
-    CUDA_TRY(cudaEventRecord(c->ev0, c->stream));
+    // (ms_emit_total starts in emit_prepare, before the breakpoint -> locus-run index K0 of a new population)
     const int path = (t->flags >> 8) & 3;
     if (t->memory == PSIM_MEM_DEVICE) {
         if (int rc = emit_device(c, ind_first, ind_count, locus_first, locus_first + locus_count, locus_first, t->founder,

@@ -9,9 +9,20 @@
 // "last s with lb[s] <= l" (ties: a locus exactly on a breakpoint belongs to the segment starting
 // there). A suffix minimum makes lb monotone without changing that answer, empty runs are
 // dropped and neighbours with the same founder merged.
+// A map is searched through a grid over its positions (psim_set_map): bucket k of chromosome c starts at
+// lo + k * width and grid[k] = #loci left of that, so that a breakpoint's answer lies between the entries one bucket
+// below and two above its own - a bisection of one to three steps instead of log2(loci) (the search was half of this
+// kernel's instructions). The grid only narrows the interval; the answer is the plain lower bound.
+struct MapGrid {
+    const int32_t* grid;      // per chromosome: n_buckets + 1 entries from grid_off[c]
+    const int64_t* grid_off;  // [C + 1]
+    const double* lo;         // [C] position of the chromosome's first locus
+    const double* inv_width;  // [C] buckets per Morgan (0: all loci at one position)
+};
 __global__ void __launch_bounds__(128) k_index_runs(int64_t n_hom, int64_t hom_per_chrom, const uint64_t* __restrict__ desc,
                                                     const double* __restrict__ seg_pos, const int32_t* __restrict__ seg_founder,
                                                     const int64_t* __restrict__ locus_off, const double* __restrict__ locus_pos,
+                                                    const MapGrid mg,
                                                     uint64_t* __restrict__ run_desc, uint32_t* __restrict__ run_lb,
                                                     uint16_t* __restrict__ run_founder) {
     const int64_t hid = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
@@ -23,8 +34,13 @@ __global__ void __launch_bounds__(128) k_index_runs(int64_t n_hom, int64_t hom_p
     const int c = (int)(hid / hom_per_chrom);
     const double* lp = locus_pos + locus_off[c];
     const uint32_t Lc = (uint32_t)(locus_off[c + 1] - locus_off[c]);
+    const int32_t* const grid = mg.grid + mg.grid_off[c];
+    const int n_buckets = (int)(mg.grid_off[c + 1] - mg.grid_off[c]) - 1;
+    const double g_lo = mg.lo[c], g_inv = mg.inv_width[c];
     auto lower_bound = [&](double p) {   // #loci strictly left of p
-        uint32_t lo = 0, hi = Lc;
+        const double t = (p - g_lo) * g_inv;
+        const int k = t > 0.0 ? (t < (double)n_buckets ? (int)t : n_buckets - 1) : 0;
+        uint32_t lo = (uint32_t)__ldg(grid + max(k - 1, 0)), hi = (uint32_t)__ldg(grid + min(k + 2, n_buckets));
         while (lo < hi) { const uint32_t mid = (lo + hi) >> 1; if (__ldg(lp + mid) < p) lo = mid + 1; else hi = mid; }
         return lo;
     };
