@@ -331,19 +331,24 @@ inline int64_t align8(int64_t x) { return (x + 7) / 8 * 8; }
 // best: NVLS / ring over NVSwitch) of equal, padded parts: the homologs' descriptors relative to `from`, the founders
 // and the positions, the last two straight into the receivers' slabs (rank r's part at slot r; the own slot is a
 // duplicate that nobody reads, the price of the plain collective).
-int shard_exchange_all(psim_ctx_impl* c, ShardState* S, const int32_t* lists_d, const int32_t* lists_h, const int64_t* list_off, int64_t from) {
+// local_rc != 0: this rank failed in the generation; it still takes part in the size exchange (with -1) so that every
+// rank leaves the call with an error instead of waiting for it in a collective.
+int shard_exchange_all(psim_ctx_impl* c, ShardState* S, const int32_t* lists_d, const int32_t* lists_h, const int64_t* list_off, int64_t from, int local_rc) {
     const int world = S->world, rank = S->rank, C = c->C, P = c->P;
     const int64_t hp = (int64_t)C * P;
     int64_t nh_max = 0;
     for (int r = 0; r < world; r++) nh_max = std::max(nh_max, (list_off[r + 1] - list_off[r]) * hp);
     if (nh_max == 0 || world == 1) return PSIM_OK;
     const int64_t nh = (list_off[rank + 1] - list_off[rank]) * hp;
-    const int64_t mine = nh > 0 ? c->slab_used - from : 0;
+    const int64_t mine = local_rc ? -1 : nh > 0 ? c->slab_used - from : 0;
     if (int rc = ensure_buf(c, S->cnt, 2 * sizeof(int64_t))) return rc;
     CUDA_TRY(cudaMemcpyAsync(S->cnt.p, &mine, sizeof(mine), cudaMemcpyHostToDevice, c->stream));   // (pageable: staged before it returns)
     int64_t nseg[PSIM_SHARD_MAX_WORLD];
     if (int rc = S->tr->sizes(c, (const int64_t*)S->cnt.p, nseg)) return rc;
     S->stats.collectives++;
+    if (local_rc) return local_rc;
+    for (int r = 0; r < world; r++)
+        if (nseg[r] < 0) return fail(c, PSIM_ESTATE, "rank " + std::to_string(r) + " of the sharded pedigree failed in this generation");
     int64_t seg_max = 0, in_seg = 0;
     for (int r = 0; r < world; r++) { seg_max = std::max(seg_max, nseg[r]); if (r != rank) in_seg += nseg[r]; }
     // slots behind the widest possible send window, so that no rank's window overlaps what it receives
@@ -379,7 +384,7 @@ int shard_exchange_all(psim_ctx_impl* c, ShardState* S, const int32_t* lists_d, 
 
 // The ranks hand each other the haplostructs of the listed individuals: lists[list_off[r] .. list_off[r + 1])
 // (device: lists_d, host: lists_h) is what rank r contributes and every other rank receives.
-int shard_exchange(psim_ctx_impl* c, ShardState* S, const int32_t* lists_d, const int32_t* lists_h, const int64_t* list_off) {
+int shard_exchange(psim_ctx_impl* c, ShardState* S, const int32_t* lists_d, const int32_t* lists_h, const int64_t* list_off, int local_rc = 0) {
     const int world = S->world, rank = S->rank, C = c->C, P = c->P;
     const int64_t hp = (int64_t)C * P;
     int64_t any = 0;
@@ -393,9 +398,16 @@ int shard_exchange(psim_ctx_impl* c, ShardState* S, const int32_t* lists_d, cons
     k_pack_counts<<<grid_for(nh + 1, 256), 256, 0, c->stream>>>(nh, lists_d + list_off[rank], C, c->N, P, c->desc_d, cnt);
     c->stats.kernel_launches++;
     if (int rc = exclusive_scan_i64(c, cnt, off, nh + 1)) return rc;
+    if (local_rc) {
+        const int64_t minus = -1;
+        CUDA_TRY(cudaMemcpyAsync(off + nh, &minus, sizeof(minus), cudaMemcpyHostToDevice, c->stream));
+    }
     int64_t nseg[PSIM_SHARD_MAX_WORLD];
     if (int rc = S->tr->sizes(c, off + nh, nseg)) return rc;
     S->stats.collectives++;
+    if (local_rc) return local_rc;
+    for (int r = 0; r < world; r++)
+        if (nseg[r] < 0) return fail(c, PSIM_ESTATE, "rank " + std::to_string(r) + " of the sharded pedigree failed in this generation");
     if (nseg[rank] >= (1LL << 32)) return fail(c, PSIM_ECAPACITY, "more than 2^32 segments in one exchange");
     const int64_t off_bytes = align8(4 * (nh + 1)), fo_bytes = align8(4 * nseg[rank]);
     if (int rc = ensure_buf(c, S->send, (size_t)(off_bytes + fo_bytes + 8 * nseg[rank]))) return rc;
@@ -609,15 +621,19 @@ int psim_simulate_sharded(psim_ctx* ctx, int32_t max_founder_allele, int32_t par
     // generation costs its kernel, not a walk over its individuals on the host)
     for (int lv = 1; lv <= pl.max_level; lv++) {
         const int64_t slab_before = c->slab_used;
+        int rc_lv = PSIM_OK;
+        std::string err_lv;
         if (S->mine.level_off[lv + 1] > S->mine.level_off[lv]) {
-            if (int rc = sim_start(c, S->mine, !S->mine.on_device, lv, lv, false)) return rc;
-            if (int rc = sim_finish(c)) return rc;
+            rc_lv = sim_start(c, S->mine, !S->mine.on_device, lv, lv, false);
+            if (!rc_lv) rc_lv = sim_finish(c);
+            if (rc_lv) err_lv = c->err;
         }
-        if (S->level_direct[(size_t)lv]) {
-            if (int rc = shard_exchange_all(c, S, (const int32_t*)S->lists_d.p, S->lists_h.data(), S->list_off.data() + (size_t)lv * world, slab_before)) return rc;
-        } else {
-            if (int rc = shard_exchange(c, S, (const int32_t*)S->lists_d.p, S->lists_h.data(), S->list_off.data() + (size_t)lv * world)) return rc;
-        }
+        const int64_t* lo = S->list_off.data() + (size_t)lv * world;
+        int rc_x;
+        if (S->level_direct[(size_t)lv]) rc_x = shard_exchange_all(c, S, (const int32_t*)S->lists_d.p, S->lists_h.data(), lo, slab_before, rc_lv);
+        else rc_x = shard_exchange(c, S, (const int32_t*)S->lists_d.p, S->lists_h.data(), lo, rc_lv);
+        if (rc_lv) return fail(c, rc_lv, err_lv);   // (the other ranks have been told in the size exchange, if there was one)
+        if (rc_x) return rc_x;
     }
     CUDA_TRY(cudaStreamSynchronize(c->stream));
     if (!S->owner_current) { S->owner = S->owner_after; S->owner_current = true; }   // (psim_shard_gather changes its copy)
