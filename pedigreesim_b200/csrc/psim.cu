@@ -328,7 +328,7 @@ static int emit_rows_path(psim_ctx_impl* c, int64_t ind_first, int64_t ind_count
     // The list then takes the shared memory the narrower row buffers leave (5 bytes per run start): the segment is
     // the widest one whose band of `min_band` rows keeps its expected run starts within half of THAT list, because
     // what a short band costs is its start (state load, counting sort, buffer copies: ~5 us) against ~0.6 us per row.
-    const int min_band = 32;
+    const int min_band = 48;
     bool coarse = false;
     if (path != PSIM_PATH_ROWS && env_cap <= 0 && starts_per_cell * (double)seg_max * min_band > cap / 2) {
         const int64_t fit = (int64_t)((double)smem_lists / (per_cell + 10.0 * starts_per_cell * min_band)) / quantum * quantum;
