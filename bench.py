@@ -368,6 +368,44 @@ def sharded_block(ps, torch, dist, rank, world, local, lines, generations=8, chr
     return out
 
 
+def replicate_batch(ps, torch, local, rank, w, R=8):
+    """The bench workload with R replicate populations side by side in one context (replicate_count = R): what a Monte
+    Carlo sweep over configs[1] looks like to the library. One population's table row is 40 KB; R = 8 makes it 320 KB,
+    and the row-image kernel then runs at the pace of HBM instead of at the pace a 148-unit launch of short rows allows.
+    Not pipelined: simulate and emit alone, three passes."""
+    P, L, N = w["P"], w["L"], w["N"]
+    ctx = ps.PsimContext(P, seed=SEED, replicate_first=500000 + rank * R, replicate_count=R, device=local, **w["model"])
+    ctx.set_chromosomes(w["lengths"], w["centro"], w["pref"], w["fq"])
+    ctx.set_pedigree(w["p0"], w["p1"])
+    ctx.set_map(w["off"], w["pos"])
+    ctx.set_allele_codes(w["code"])
+    fp, dp = (R * N * P + 127) // 128 * 128, (R * N + 127) // 128 * 128
+    f = torch.empty((L, fp), dtype=torch.uint8, device="cuda")
+    d = torch.empty((L, dp), dtype=torch.uint8, device="cuda")
+    t = ps.EmitTargets()
+    t.founder, t.founder_pitch, t.founder_bytes = f.data_ptr(), fp, 1
+    t.dose, t.dose_pitch, t.dose_which = d.data_ptr(), dp, ps.DOSE_MAX_ALLELE
+    t.memory = ps.MEM_DEVICE
+    sim, ek, et, launches = [], [], [], 0
+    for k in range(4):
+        ctx.reset(SEED + k, 500000 + rank * R)
+        ctx.simulate()
+        ctx.emit_into(t, 0, N, 0, L)
+        st = ctx.stats()
+        if k:
+            sim.append(st["ms_simulate"]); ek.append(st["ms_emit_kernel"]); et.append(st["ms_emit_total"]); launches += st["emit_kernel_launches"]
+    ctx.close()
+    peak, _ = measured_peak()
+    bytes_ = R * N * L * (P + 1)
+    k_ms = float(np.sum(ek)) / max(1, launches)
+    ms_sim, ms_all = float(np.mean(sim)), float(np.mean(et))
+    return {"workload": "%d replicate populations of the bench workload side by side in one context (rows of %d KB)" % (R, R * N * P // 1000),
+            "simulate_ms": ms_sim, "emit_kernel_ms": k_ms, "emit_all_kernels_ms": ms_all, "bytes": bytes_,
+            "G_allele_loci_per_s_not_pipelined": R * N * L * P / ((ms_sim + ms_all) * 1e-3) / 1e9,
+            "roofline": {"bound": "hbm", "kernel": "k_emit_rows<2>, one launch", "achieved": bytes_ / (k_ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
+                         "frac": bytes_ / (k_ms * 1e-3) / 1e9 / peak}}
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
@@ -384,15 +422,16 @@ def run_ours(args):
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     w = workload()
     P, L, N, M = w["P"], w["L"], w["N"], w["M"]
-    fp = (N * P + 127) // 128 * 128
-    dp = (N + 127) // 128 * 128
+    R = max(1, args.replicates)   # replicate populations a context holds and a step simulates + emits (side by side in the tables)
+    fp = (R * N * P + 127) // 128 * 128
+    dp = (R * N + 127) // 128 * 128
 
     # three contexts = three device-resident populations in rotation: while population k is emitted, population k+1 is
     # simulated, and the context that takes population k+1 finished its last emission a whole step ago (no wait)
     NCTX = 3
     ctxs, streams, tgts, keep = [], [], [], []
     for k in range(NCTX):
-        ctx = ps.PsimContext(P, seed=SEED, replicate_first=rank, device=local, **w["model"])
+        ctx = ps.PsimContext(P, seed=SEED, replicate_first=rank * R, replicate_count=R, device=local, **w["model"])
         stream = torch.cuda.Stream()
         ctx.set_stream(stream.cuda_stream)
         ctx.set_chromosomes(w["lengths"], w["centro"], w["pref"], w["fq"])
@@ -425,7 +464,7 @@ def run_ours(args):
         acc["n"] += 1
 
     def replicate_id(k):
-        return rank + world * (k + 1)   # a fresh replicate every step: nothing is cached
+        return (rank + world * (k + 1)) * R   # fresh replicates every step: nothing is cached
 
     def run_steps(first, count, timed, targets=None):
         targets = targets or tgts
@@ -493,7 +532,7 @@ def run_ours(args):
     tgts[0].flags = ps.EMIT_ASYNC
 
     # ---- the same pipelined step with PSIM_EMIT_PACKED4 device tables (two 4-bit cells per byte: half the HBM stream)
-    pfp, pdp = ((N * P + 1) // 2 + 127) // 128 * 128, ((N + 1) // 2 + 127) // 128 * 128
+    pfp, pdp = ((R * N * P + 1) // 2 + 127) // 128 * 128, ((R * N + 1) // 2 + 127) // 128 * 128
     ptgts, pkeep = [], []
     for k in range(NCTX):
         pf = torch.empty((L, pfp), dtype=torch.uint8, device="cuda")
@@ -519,8 +558,11 @@ def run_ours(args):
     ms_packed = e0.elapsed_time(e1)
     del pkeep
 
-    # ---- end to end through the C ABI with host buffers
+    # ---- end to end through the C ABI with host buffers: one population per step, in a context of its own
     stream = streams[0]
+    ctx_e = ps.PsimContext(P, seed=SEED, replicate_first=rank, device=local, **w["model"])
+    ctx_e.set_stream(stream.cuda_stream)
+    ctx_e.set_chromosomes(w["lengths"], w["centro"], w["pref"], w["fq"])
     e2e_steps = max(1, min(args.steps, 5))
     trace = bool(os.environ.get("PSIM_BENCH_TRACE"))
 
@@ -536,15 +578,15 @@ def run_ours(args):
 
         def e2e_step(k):
             ts = [time.perf_counter()]
-            ctx.set_pedigree(w["p0"], w["p1"])  # drops the population and re-uploads the pedigree
+            ctx_e.set_pedigree(w["p0"], w["p1"])  # drops the population and re-uploads the pedigree
             ts.append(time.perf_counter())
-            ctx.reset(SEED, rank + world * (1000 + k))
-            ctx.set_map(w["off"], w["pos"])
-            ctx.set_allele_codes(w["code"])
+            ctx_e.reset(SEED, rank + world * (1000 + k))
+            ctx_e.set_map(w["off"], w["pos"])
+            ctx_e.set_allele_codes(w["code"])
             ts.append(time.perf_counter())
-            ctx.simulate()
+            ctx_e.simulate()
             ts.append(time.perf_counter())
-            ctx.emit_into(ht, 0, N, 0, L)
+            ctx_e.emit_into(ht, 0, N, 0, L)
             ts.append(time.perf_counter())
             if trace:
                 print("e2e step %d: set_pedigree %.2f inputs %.2f simulate %.2f emit %.2f ms" % (
@@ -575,12 +617,13 @@ def run_ours(args):
             sharded = sharded_block(ps, torch, dist, rank, world, local, args.sharded_lines)
         except Exception as e:   # (never let the extra block take the line down)
             sharded = {"error": str(e)}
-    cells = N * L * P
+    ctx_e.close()
+    cells = R * N * L * P
     value = world * cells * args.steps / (ms * 1e-3) / 1e9
-    e2e_value = world * cells * e2e_steps / (ms_e2e * 1e-3) / 1e9
+    e2e_value = world * N * L * P * e2e_steps / (ms_e2e * 1e-3) / 1e9
     peak, peak_src = measured_peak()
     k2_ms = solo["emit"] / max(1, solo["launches"])
-    algo_bytes = N * L * (P + 1)
+    algo_bytes = R * N * L * (P + 1)
     achieved = algo_bytes / (k2_ms * 1e-3) / 1e9 if k2_ms > 0 else 0.0
     h2d = int(w["p0"].nbytes * 2 + w["off"].nbytes + w["pos"].nbytes + w["code"].nbytes)
     if rank == 0:
@@ -588,14 +631,16 @@ def run_ours(args):
             "metric": "genotype calls/sec (G allele-loci/s)", "value": value, "unit": "G allele-loci/s",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
-            "config": {"workload": WORKLOAD_NAME, "per_gpu": "one replicate population per rank and step, no collective",
-                       "tables": "founder-allele u8 [L][N*P] + MAX-allele dose u8 [L][N]",
+            "config": {"workload": WORKLOAD_NAME, "per_gpu": "%d replicate population(s) of the workload per rank and step, side by side in one context "
+                                                                     "(replicate_count = %d) and in its tables; no collective" % (R, R),
+                       "replicates_per_step": R,
+                       "tables": "founder-allele u8 [L][R*N*P] + MAX-allele dose u8 [L][R*N]",
                        "pipeline": "three contexts per rank in rotation: population k+1 is simulated (psim_simulate_async) while population k is "
                                    "emitted (PSIM_EMIT_ASYNC); one host wait per step (K steps emit K populations and simulate K + 1)",
-                       "l2": "1.2 GB of output per step exceeds the 126 MB L2; a new replicate is simulated every step",
+                       "l2": "%.1f GB of output per step exceeds the 126 MB L2; new replicates are simulated every step" % (R * N * L * (P + 1) / 1e9),
                        "e2e_tables": "PSIM_EMIT_PACKED4: founder-allele and dose tables with two 4-bit cells per byte (e2e.u8: one byte per cell)",
                        "positions": "fp64 Morgan"},
-            "meioses_per_s": world * M * args.steps / (ms * 1e-3),
+            "meioses_per_s": world * R * M * args.steps / (ms * 1e-3),
             "kernel_ms": {"simulate_per_step_overlapped": acc["sim"] / max(1, acc["n"]),
                           "emit_all_kernels_per_step_overlapped": acc["emit_total"] / max(1, acc["n"]),
                           "simulate_alone": solo["sim"] / 3, "emit_all_kernels_alone": solo["total"] / 3,
@@ -608,16 +653,21 @@ def run_ours(args):
                          "peak_source": peak_src},
             "e2e": {"value": e2e_value, "unit": "G allele-loci/s", "steps": e2e_steps, "ms_per_step": ms_e2e / e2e_steps,
                     "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "tables": "PSIM_EMIT_PACKED4",
-                    "u8": {"value": world * cells * e2e_steps / (ms_e2e_u8 * 1e-3) / 1e9, "ms_per_step": ms_e2e_u8 / e2e_steps,
+                    "workload": "one population of the workload per step (host tables of one population)",
+                    "u8": {"value": world * N * L * P * e2e_steps / (ms_e2e_u8 * 1e-3) / 1e9, "ms_per_step": ms_e2e_u8 / e2e_steps,
                            "d2h_bytes_per_step": d2h_u8}},
             "packed_tables": {"value": world * cells * args.steps / (ms_packed * 1e-3) / 1e9, "unit": "G allele-loci/s", "ms_per_step": ms_packed / args.steps,
-                              "tables": "PSIM_EMIT_PACKED4 device tables (4 bits per cell): the same pipelined step, 0.6 GB per step instead of 1.2 GB"},
+                              "tables": "PSIM_EMIT_PACKED4 device tables (4 bits per cell): the same pipelined step, half the bytes per step"},
             "gpu_launches": int(launches),
             "clocks": clocks,
         }
         if sharded is not None:
             out["sharded"] = sharded
         if world == 1:
+            try:
+                out["replicate_batch"] = replicate_batch(ps, torch, local, rank, w)
+            except Exception as e:   # (never let the extra block take the line down)
+                out["replicate_batch"] = {"error": str(e)}
             try:
                 out["replicate_sweep"] = replicate_sweep(ps, torch, local, rank)
             except Exception as e:   # (never let the extra block take the line down)
@@ -650,6 +700,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--replicates", type=int, default=1,
+                    help="replicate populations of the workload a rank simulates and emits per step (one context, replicate_count)")
     ap.add_argument("--order", default="simulate-first", choices=["simulate-first", "emit-first"],
                     help="what a pipelined step enqueues first: the next population's meioses or this population's emission")
     ap.add_argument("--sharded-lines", type=int, default=1000000,
