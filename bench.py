@@ -4,20 +4,21 @@
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
 
-A step is one pass of the hot path over one batch of synthetic input: BASELINE.json configs[1]
-(autotetraploid F1 of 10 000, quadrivalent fraction 0.5, preferential pairing 0.3, 12 chromosomes
-x 2 000 loci, biallelic founder genotypes): all 20 000 meioses (K1), the breakpoint -> locus-run
-index (K0) and the dense emission of the founder-allele matrix plus the MAX-allele dose table (K2,
-the HBM-write-bound kernel; N*L*(P+1) algorithmic bytes). With N > 1 GPUs every rank simulates and
-emits its own replicate population of that size (weak scaling, no data-path collective).
+A step is one pass of the hot path over one batch of synthetic input: R (--replicates, default 8) replicate
+populations of BASELINE.json configs[1] (autotetraploid F1 of 10 000, quadrivalent fraction 0.5, preferential pairing
+0.3, 12 chromosomes x 2 000 loci, biallelic founder genotypes) side by side in one context - the batch of a Monte Carlo
+sweep, the job replicate sharding exists for: all R x 20 000 meioses (K1), the breakpoint -> locus-run index (K0) and
+the dense emission of the founder-allele matrix plus the MAX-allele dose table of all R populations in ONE launch (K2,
+the HBM-write-bound kernel; R*N*L*(P+1) algorithmic bytes). With N > 1 GPUs every rank simulates and emits its own
+replicate populations (weak scaling, no data-path collective). `single_population` reports R = 1 (one population on
+its own, not pipelined); --replicates 1 runs the whole line that way (round 1's configuration).
 
-Prints ONE JSON line (rank 0). `value` is measured with inputs resident in HBM and outputs written
-to HBM (u8 tables): two contexts alternate, the next replicate's meioses (psim_simulate_async) run
-while the current one is emitted (PSIM_EMIT_ASYNC), one host wait per step. `e2e` is the same metric
-through the C ABI with host buffers (pedigree / map / allele-code uploads and the device->host copy of
-both tables inside the timed region), with PSIM_EMIT_PACKED4 tables (two 4-bit cells per byte: the 8
-founder alleles and the doses 0..4 of this workload fit; SURVEY.md 8(d) counts a packed format at its
-packed size); `e2e.u8` is the same leg with one byte per cell.
+Prints ONE JSON line (rank 0). `value` is measured with inputs resident in HBM and outputs written to HBM (u8 tables):
+three contexts in rotation, the next batch's meioses (psim_simulate_async) run while the current one is emitted
+(PSIM_EMIT_ASYNC), one host wait per step. `e2e` is the same metric through the C ABI with host buffers, one population
+per step (pedigree / map / allele-code uploads and the device->host copy of both tables inside the timed region), with
+PSIM_EMIT_PACKED4 tables (two 4-bit cells per byte: the 8 founder alleles and the doses 0..4 of this workload fit;
+SURVEY.md 8(d) counts a packed format at its packed size); `e2e.u8` is the same leg with one byte per cell.
 """
 import argparse
 import json
@@ -369,10 +370,10 @@ def sharded_block(ps, torch, dist, rank, world, local, lines, generations=8, chr
 
 
 def replicate_batch(ps, torch, local, rank, w, R=8):
-    """The bench workload with R replicate populations side by side in one context (replicate_count = R): what a Monte
-    Carlo sweep over configs[1] looks like to the library. One population's table row is 40 KB; R = 8 makes it 320 KB,
-    and the row-image kernel then runs at the pace of HBM instead of at the pace a 148-unit launch of short rows allows.
-    Not pipelined: simulate and emit alone, three passes."""
+    """The bench workload with R replicate populations side by side in one context (replicate_count = R): R = 8 is what a
+    Monte Carlo sweep over configs[1] looks like to the library, R = 1 one population on its own. One population's table
+    row is 40 KB; R = 8 makes it 320 KB, and the row-image kernel then runs at the pace of HBM instead of at the pace a
+    launch of two units per SM allows. Not pipelined: simulate and emit alone, three passes."""
     P, L, N = w["P"], w["L"], w["N"]
     ctx = ps.PsimContext(P, seed=SEED, replicate_first=500000 + rank * R, replicate_count=R, device=local, **w["model"])
     ctx.set_chromosomes(w["lengths"], w["centro"], w["pref"], w["fq"])
@@ -646,8 +647,9 @@ def run_ours(args):
                           "simulate_alone": solo["sim"] / 3, "emit_all_kernels_alone": solo["total"] / 3,
                           "emit_kernel_per_launch": k2_ms,
                           "emit_kernel_share_of_step": k2_ms / (ms / args.steps) if ms > 0 else None},
-            "roofline": {"bound": "hbm", "kernel": "k_emit_rows<2> (row-image emission: shared-memory row + TMA bulk store per table row; "
-                                                   "timed alone on the device, 3 launches after the pipelined steps; the band-plan helper kernels are reported under kernel_ms)",
+            "roofline": {"bound": "hbm", "kernel": "k_emit_rows<2> (row-image emission: shared-memory row + TMA bulk store per table row; one launch emits the "
+                                                   "step's %d population(s); timed alone on the device, 3 launches after the pipelined steps; the band-plan helper "
+                                                   "kernels are reported under kernel_ms)" % R,
                          "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": None, "algorithmic_bytes_per_launch": algo_bytes,
                          "peak_source": peak_src},
@@ -664,10 +666,11 @@ def run_ours(args):
         if sharded is not None:
             out["sharded"] = sharded
         if world == 1:
-            try:
-                out["replicate_batch"] = replicate_batch(ps, torch, local, rank, w)
+            try:   # the other batch size, not pipelined: one population per step when the line is about eight, and the reverse
+                other = 1 if R > 1 else 8
+                out["single_population" if other == 1 else "replicate_batch"] = replicate_batch(ps, torch, local, rank, w, other)
             except Exception as e:   # (never let the extra block take the line down)
-                out["replicate_batch"] = {"error": str(e)}
+                out["single_population" if R > 1 else "replicate_batch"] = {"error": str(e)}
             try:
                 out["replicate_sweep"] = replicate_sweep(ps, torch, local, rank)
             except Exception as e:   # (never let the extra block take the line down)
@@ -682,8 +685,9 @@ def run_ours(args):
         if os.path.exists(prof):
             try:
                 tr = json.load(open(prof))
-                out["roofline"]["traffic"] = tr.get("dram_bytes_per_launch")
-                out["roofline"]["traffic_source"] = "not measured in this run: " + tr.get("source", "profiles/k2_traffic.json")
+                if tr.get("algorithmic_bytes_per_launch") == algo_bytes:   # (a capture of this very launch geometry)
+                    out["roofline"]["traffic"] = tr.get("dram_bytes_per_launch")
+                    out["roofline"]["traffic_source"] = "not measured in this run: " + tr.get("source", "profiles/k2_traffic.json")
             except Exception:
                 pass
         print(json.dumps(out))
@@ -700,8 +704,9 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
-    ap.add_argument("--replicates", type=int, default=1,
-                    help="replicate populations of the workload a rank simulates and emits per step (one context, replicate_count)")
+    ap.add_argument("--replicates", type=int, default=8,
+                    help="replicate populations of the workload a rank simulates and emits per step, side by side in one context "
+                         "(replicate_count): a Monte Carlo sweep over the workload, the job replicate sharding is for. 1: one population per step")
     ap.add_argument("--order", default="simulate-first", choices=["simulate-first", "emit-first"],
                     help="what a pipelined step enqueues first: the next population's meioses or this population's emission")
     ap.add_argument("--sharded-lines", type=int, default=1000000,

@@ -24,20 +24,22 @@ def main():
     ap.add_argument("--no-founder", action="store_true")
     ap.add_argument("--no-codes", action="store_true", help="no founder genotypes: dose of founder allele 0")
     ap.add_argument("--packed", action="store_true", help="PSIM_EMIT_PACKED4 tables")
+    ap.add_argument("--replicates", type=int, default=1, help="replicate populations side by side in the context and its tables")
     ap.add_argument("--scale", type=float, default=1.0, help="scale chromosome lengths (1e-4: no crossovers at all)")
     args = ap.parse_args()
     w = bench.workload(args.popsize)
     for k in ("lengths", "centro", "pos"):
         w[k] = w[k] * args.scale
     P, L, N = w["P"], w["L"], w["N"]
-    ctx = ps.PsimContext(P, seed=bench.SEED, **w["model"])
+    R = args.replicates
+    ctx = ps.PsimContext(P, seed=bench.SEED, replicate_count=R, **w["model"])
     ctx.set_chromosomes(w["lengths"], w["centro"], w["pref"], w["fq"])
     ctx.set_pedigree(w["p0"], w["p1"])
     ctx.set_map(w["off"], w["pos"])
     if not args.no_codes:
         ctx.set_allele_codes(w["code"])
-    fp = (N * P // (2 if args.packed else 1) + 127) // 128 * 128
-    dp = ((N + 1) // (2 if args.packed else 1) + 127) // 128 * 128
+    fp = (R * N * P // (2 if args.packed else 1) + 127) // 128 * 128
+    dp = ((R * N + 1) // (2 if args.packed else 1) + 127) // 128 * 128
     d_founder = torch.empty((L, fp), dtype=torch.uint8, device="cuda")
     d_dose = torch.empty((L, dp), dtype=torch.uint8, device="cuda")
     d_allele = torch.empty((L, fp), dtype=torch.uint8, device="cuda") if args.alleles else None
@@ -63,7 +65,7 @@ def main():
         st = ctx.stats()
         print("step %d: reset %.2f ms, simulate %.2f ms (device %.2f), emit %.2f ms (kernel %.3f ms = %.0f GB/s)" % (
             k, (t1 - t0) * 1e3, (t2 - t1) * 1e3, st["ms_simulate"], (t3 - t2) * 1e3, st["ms_emit_kernel"],
-            N * L * ((0 if args.no_founder else P) + (0 if args.no_dose else 1) + (P if args.alleles else 0)) / div / st["ms_emit_kernel"] / 1e6))
+            R * N * L * ((0 if args.no_founder else P) + (0 if args.no_dose else 1) + (P if args.alleles else 0)) / div / st["ms_emit_kernel"] / 1e6))
     ctx.close()
 
 
