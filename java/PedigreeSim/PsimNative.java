@@ -75,7 +75,19 @@ final class PsimNative implements AutoCloseable {
     private static final MethodHandle EMIT = fn("psim_emit",
             FunctionDescriptor.of(JAVA_INT, ADDRESS, JAVA_LONG, JAVA_LONG, JAVA_LONG, JAVA_LONG, ADDRESS));
 
-    private final Arena arena = Arena.ofConfined();
+    // several GPUs in one JVM: one PsimNative (context) and one Java thread per GPU (include/psim.h "psim_simulate_sharded")
+    private static final MethodHandle SHARD_GROUP_CREATE = fn("psim_shard_group_create", FunctionDescriptor.of(JAVA_INT, JAVA_INT, ADDRESS));
+    private static final MethodHandle SHARD_GROUP_DESTROY = fn("psim_shard_group_destroy", FunctionDescriptor.ofVoid(ADDRESS));
+    private static final MethodHandle SHARD_INIT_LOCAL = fn("psim_shard_init_local", FunctionDescriptor.of(JAVA_INT, ADDRESS, JAVA_INT, ADDRESS));
+    private static final MethodHandle SIMULATE_SHARDED = fn("psim_simulate_sharded", FunctionDescriptor.of(JAVA_INT, ADDRESS, JAVA_INT, JAVA_INT));
+    private static final MethodHandle SHARD_OWNER = fn("psim_shard_owner", FunctionDescriptor.of(JAVA_INT, ADDRESS, ADDRESS));
+    private static final MethodHandle SHARD_GATHER = fn("psim_shard_gather", FunctionDescriptor.of(JAVA_INT, ADDRESS, ADDRESS, JAVA_LONG));
+    // a host thread that keeps several contexts busy (psim_simulate_async returns once the work is enqueued)
+    private static final MethodHandle SIMULATE_ASYNC = fn("psim_simulate_async", FunctionDescriptor.of(JAVA_INT, ADDRESS, JAVA_INT));
+    private static final MethodHandle WAIT = fn("psim_wait", FunctionDescriptor.of(JAVA_INT, ADDRESS));
+    static final int PARTITION_BLOCK = 0, PARTITION_LINEAGE = 1;
+
+    private final Arena arena = Arena.ofShared();   // (a sharded run touches the context from its own thread)
     private final MemorySegment ctx;
     private final PopulationData popdata;
 
@@ -138,6 +150,54 @@ final class PsimNative implements AutoCloseable {
         for (int i = 0; i < n; i++) if (inds.get(i).getAllHaploStruct() != null) uploadHaploStruct(i, inds.get(i));
         check((int) invoke(SIMULATE, ctx, maxfounderallele));
         for (int i = 0; i < n; i++) if (inds.get(i).getAllHaploStruct() == null) downloadIndividual(i, inds.get(i));
+    }
+
+    /** Seam A over the GPUs of the box: `ranks[r]` is a PsimNative on device r, all made from the same PopulationData.
+     *  Every rank runs on its own thread and makes the same calls; with PARTITION_BLOCK every rank ends with the whole
+     *  population and rank 0 fills in the Individuals, with PARTITION_LINEAGE the last generations are gathered first. */
+    static void simulateIndividualsSharded(PsimNative[] ranks, int maxfounderallele, int partition) throws Exception {
+        MemorySegment out = ranks[0].arena.allocate(ADDRESS);
+        if ((int) invoke(SHARD_GROUP_CREATE, ranks.length, out) != 0) throw new Exception("psim_shard_group_create failed");
+        MemorySegment group = out.get(ADDRESS, 0);
+        Exception[] failed = new Exception[ranks.length];
+        Thread[] th = new Thread[ranks.length];
+        for (int r = 0; r < ranks.length; r++) {
+            final int rank = r;
+            th[r] = new Thread(() -> {
+                try {
+                    PsimNative g = ranks[rank];
+                    g.setPedigreeAndPresets();
+                    g.check((int) invoke(SHARD_INIT_LOCAL, g.ctx, rank, group));
+                    g.check((int) invoke(SIMULATE_SHARDED, g.ctx, maxfounderallele, partition));
+                    if (partition == PARTITION_LINEAGE) {   // bring everybody to every rank (or emit per rank instead: psim_shard_owner)
+                        int n = g.popdata.getIndividual().size();
+                        int[] all = new int[n];
+                        for (int i = 0; i < n; i++) all[i] = i;
+                        g.check((int) invoke(SHARD_GATHER, g.ctx, g.arena.allocateFrom(JAVA_INT, all), (long) n));
+                    }
+                } catch (Exception e) { failed[rank] = e; }
+            });
+            th[r].start();
+        }
+        for (Thread t : th) t.join();
+        for (Exception e : failed) if (e != null) throw e;
+        ArrayList<Individual> inds = ranks[0].popdata.getIndividual();
+        for (int i = 0; i < inds.size(); i++) if (inds.get(i).getAllHaploStruct() == null) ranks[0].downloadIndividual(i, inds.get(i));
+        invoke(SHARD_GROUP_DESTROY, group);
+    }
+
+    /** The first half of simulateIndividuals: pedigree and recorded haplostructs into the context. */
+    private void setPedigreeAndPresets() throws Exception {
+        ArrayList<Individual> inds = popdata.getIndividual();
+        int n = inds.size();
+        int[] p0 = new int[n], p1 = new int[n];
+        for (int i = 0; i < n; i++) {
+            Individual ind = inds.get(i);
+            p0[i] = ind.isFounder() ? -1 : inds.indexOf(ind.getParents()[0]);
+            p1[i] = ind.isFounder() ? -1 : inds.indexOf(ind.getParents()[1]);
+        }
+        check((int) invoke(SET_PEDIGREE, ctx, (long) n, arena.allocateFrom(JAVA_INT, p0), arena.allocateFrom(JAVA_INT, p1)));
+        for (int i = 0; i < n; i++) if (inds.get(i).getAllHaploStruct() != null) uploadHaploStruct(i, inds.get(i));
     }
 
     private void uploadHaploStruct(int i, Individual ind) throws Exception {
