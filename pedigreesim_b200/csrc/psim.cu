@@ -134,6 +134,9 @@ struct psim_ctx_impl {
     struct Buf { void* p = nullptr; size_t cap = 0; };
     Buf b_lev, b_xpos, b_xab, b_mark, b_find, b_fal;
     Buf b_plan, b_dense_list, b_text, b_text2, b_rowlen, b_rowoff;
+    // map and allele-code arrays (psim_set_map / psim_set_allele_codes in a loop: no cudaFree / cudaMalloc per call - they
+    // cost 2 - 17 ms of an end-to-end step; the *_d pointers above point into these, or are null when nothing is set)
+    Buf b_locoff, b_locpos, b_grid, b_gridoff, b_gridlo, b_gridinv, b_code, b_match, b_code16, b_nibmask, b_mtab;
     // export buffers
     int64_t* exp_off_d = nullptr; int32_t* exp_founder_d = nullptr; double* exp_pos_d = nullptr;
     int64_t exp_off_cap = 0, exp_seg_cap = 0;
@@ -551,14 +554,13 @@ void psim_destroy(psim_ctx* ctx) {
     free_population(c);
     cudaFree(c->chrom_d); cudaFree(c->seg_pos_d); cudaFree(c->seg_founder_d);
     cudaFree(c->run_lb_d); cudaFree(c->run_founder_d);
-    cudaFree(c->locus_off_d); cudaFree(c->locus_pos_d); cudaFree(c->code_d); cudaFree(c->match_d);
-    cudaFree(c->grid_d); cudaFree(c->grid_off_d); cudaFree(c->grid_lo_d); cudaFree(c->grid_inv_d);
-    cudaFree(c->code16_d); cudaFree(c->nibmask_d); cudaFree(c->mtab_d);
     cudaFree(c->status_d); cudaFree(c->cursor_d); cudaFree(c->tile_counter_d); cudaFree(c->cub_tmp); cudaFree(c->staging);
     cudaFree(c->exp_off_d); cudaFree(c->exp_founder_d); cudaFree(c->exp_pos_d);
     for (cudaEvent_t e : c->kev) cudaEventDestroy(e);
     for (psim_ctx_impl::Buf* b : {&c->b_lev, &c->b_xpos, &c->b_xab, &c->b_mark, &c->b_find, &c->b_fal,
-                                 &c->b_plan, &c->b_dense_list, &c->b_text, &c->b_text2, &c->b_rowlen, &c->b_rowoff}) cudaFree(b->p);
+                                 &c->b_plan, &c->b_dense_list, &c->b_text, &c->b_text2, &c->b_rowlen, &c->b_rowoff,
+                                 &c->b_locoff, &c->b_locpos, &c->b_grid, &c->b_gridoff, &c->b_gridlo, &c->b_gridinv,
+                                 &c->b_code, &c->b_match, &c->b_code16, &c->b_nibmask, &c->b_mtab}) cudaFree(b->p);
     cudaFree(c->label_off_d); cudaFree(c->labels_d); cudaFree(c->code_off_d); cudaFree(c->aname_off_d); cudaFree(c->anames_d);
     if (c->ev0) cudaEventDestroy(c->ev0);
     if (c->ev1) cudaEventDestroy(c->ev1);
@@ -1159,15 +1161,14 @@ int psim_set_map(psim_ctx* ctx, const int64_t* locus_off, const double* pos) {
     }
     c->L = locus_off[c->C];
     c->locus_off_h.assign(locus_off, locus_off + c->C + 1);
-    cudaFree(c->locus_off_d); cudaFree(c->locus_pos_d); cudaFree(c->code_d); cudaFree(c->match_d);
-    cudaFree(c->code16_d); cudaFree(c->nibmask_d); cudaFree(c->mtab_d);
     c->locus_off_d = nullptr; c->locus_pos_d = nullptr; c->code_d = nullptr; c->match_d = nullptr;
     c->code16_d = nullptr; c->nibmask_d = nullptr; c->mtab_d = nullptr;
     c->A = 0; c->code_h.clear();
-    CUDA_TRY(dev_alloc(&c->locus_off_d, (size_t)c->C + 1));
-    CUDA_TRY(dev_alloc(&c->locus_pos_d, (size_t)c->L));
-    CUDA_TRY(cudaMemcpy(c->locus_off_d, locus_off, (c->C + 1) * sizeof(int64_t), cudaMemcpyHostToDevice));
-    CUDA_TRY(cudaMemcpy(c->locus_pos_d, pos, c->L * sizeof(double), cudaMemcpyHostToDevice));
+    if (int rc = ensure_buf(c, c->b_locoff, ((size_t)c->C + 1) * sizeof(int64_t))) return rc;
+    if (int rc = ensure_buf(c, c->b_locpos, std::max<size_t>(1, (size_t)c->L) * sizeof(double))) return rc;
+    c->locus_off_d = (int64_t*)c->b_locoff.p; c->locus_pos_d = (double*)c->b_locpos.p;
+    CUDA_TRY(cudaMemcpyAsync(c->locus_off_d, locus_off, (c->C + 1) * sizeof(int64_t), cudaMemcpyHostToDevice, c->stream));
+    CUDA_TRY(cudaMemcpyAsync(c->locus_pos_d, pos, c->L * sizeof(double), cudaMemcpyHostToDevice, c->stream));
     {   // the grid k_index_runs searches the map through: about four buckets per locus
         std::vector<int64_t> goff((size_t)c->C + 1, 0);
         std::vector<double> glo((size_t)c->C, 0.0), ginv((size_t)c->C, 0.0);
@@ -1189,16 +1190,17 @@ int psim_set_map(psim_ctx* ctx, const int64_t* locus_off, const double* pos) {
             grid.push_back((int32_t)Lc);
             goff[(size_t)k + 1] = (int64_t)grid.size();
         }
-        cudaFree(c->grid_d); cudaFree(c->grid_off_d); cudaFree(c->grid_lo_d); cudaFree(c->grid_inv_d);
-        c->grid_d = nullptr; c->grid_off_d = nullptr; c->grid_lo_d = nullptr; c->grid_inv_d = nullptr;
-        CUDA_TRY(dev_alloc(&c->grid_d, grid.size()));
-        CUDA_TRY(dev_alloc(&c->grid_off_d, goff.size()));
-        CUDA_TRY(dev_alloc(&c->grid_lo_d, glo.size()));
-        CUDA_TRY(dev_alloc(&c->grid_inv_d, ginv.size()));
-        CUDA_TRY(cudaMemcpy(c->grid_d, grid.data(), grid.size() * sizeof(int32_t), cudaMemcpyHostToDevice));
-        CUDA_TRY(cudaMemcpy(c->grid_off_d, goff.data(), goff.size() * sizeof(int64_t), cudaMemcpyHostToDevice));
-        CUDA_TRY(cudaMemcpy(c->grid_lo_d, glo.data(), glo.size() * sizeof(double), cudaMemcpyHostToDevice));
-        CUDA_TRY(cudaMemcpy(c->grid_inv_d, ginv.data(), ginv.size() * sizeof(double), cudaMemcpyHostToDevice));
+        if (int rc = ensure_buf(c, c->b_grid, grid.size() * sizeof(int32_t))) return rc;
+        if (int rc = ensure_buf(c, c->b_gridoff, goff.size() * sizeof(int64_t))) return rc;
+        if (int rc = ensure_buf(c, c->b_gridlo, glo.size() * sizeof(double))) return rc;
+        if (int rc = ensure_buf(c, c->b_gridinv, ginv.size() * sizeof(double))) return rc;
+        c->grid_d = (int32_t*)c->b_grid.p; c->grid_off_d = (int64_t*)c->b_gridoff.p;
+        c->grid_lo_d = (double*)c->b_gridlo.p; c->grid_inv_d = (double*)c->b_gridinv.p;
+        CUDA_TRY(cudaMemcpyAsync(c->grid_d, grid.data(), grid.size() * sizeof(int32_t), cudaMemcpyHostToDevice, c->stream));
+        CUDA_TRY(cudaMemcpyAsync(c->grid_off_d, goff.data(), goff.size() * sizeof(int64_t), cudaMemcpyHostToDevice, c->stream));
+        CUDA_TRY(cudaMemcpyAsync(c->grid_lo_d, glo.data(), glo.size() * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+        CUDA_TRY(cudaMemcpyAsync(c->grid_inv_d, ginv.data(), ginv.size() * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+        CUDA_TRY(cudaStreamSynchronize(c->stream));   // (the sources are this call's and the caller's arrays)
     }
     c->runs_valid = false;
     return PSIM_OK;
@@ -1210,7 +1212,6 @@ int psim_set_allele_codes(psim_ctx* ctx, int32_t n_alleles, const uint8_t* code)
     if (c->L == 0) return fail(c, PSIM_ESTATE, "psim_set_map must be called first");
     cudaSetDevice(c->cfg.device);
     if (int rc = settle(c)) return rc;
-    cudaFree(c->code_d); cudaFree(c->match_d); cudaFree(c->code16_d); cudaFree(c->nibmask_d); cudaFree(c->mtab_d);
     c->code_d = nullptr; c->match_d = nullptr; c->code16_d = nullptr; c->nibmask_d = nullptr; c->mtab_d = nullptr;
     c->A = 0; c->code_h.clear(); c->match_which = 12345678;
     if (!code) return PSIM_OK;
@@ -1219,12 +1220,15 @@ int psim_set_allele_codes(psim_ctx* ctx, int32_t n_alleles, const uint8_t* code)
     if (n_alleles <= 0 || n_alleles > 65536) return fail(c, PSIM_EINVAL, "allele codes need 1..65536 founder alleles");
     c->A = n_alleles;
     c->code_h.assign(code, code + (size_t)c->L * n_alleles);
-    CUDA_TRY(dev_alloc(&c->code_d, (size_t)c->L * n_alleles));
-    CUDA_TRY(dev_alloc(&c->match_d, (size_t)c->L));
-    CUDA_TRY(dev_alloc(&c->code16_d, (size_t)c->L * 4));
-    CUDA_TRY(dev_alloc(&c->nibmask_d, (size_t)c->L * 2));
-    CUDA_TRY(dev_alloc(&c->mtab_d, (size_t)c->L));
-    CUDA_TRY(cudaMemcpy(c->code_d, code, (size_t)c->L * n_alleles, cudaMemcpyHostToDevice));
+    if (int rc = ensure_buf(c, c->b_code, (size_t)c->L * n_alleles)) return rc;
+    if (int rc = ensure_buf(c, c->b_match, (size_t)c->L)) return rc;
+    if (int rc = ensure_buf(c, c->b_code16, (size_t)c->L * 4 * sizeof(uint32_t))) return rc;
+    if (int rc = ensure_buf(c, c->b_nibmask, (size_t)c->L * 2 * sizeof(uint32_t))) return rc;
+    if (int rc = ensure_buf(c, c->b_mtab, (size_t)c->L * sizeof(uint4))) return rc;
+    c->code_d = (uint8_t*)c->b_code.p; c->match_d = (uint8_t*)c->b_match.p; c->code16_d = (uint32_t*)c->b_code16.p;
+    c->nibmask_d = (uint32_t*)c->b_nibmask.p; c->mtab_d = (uint4*)c->b_mtab.p;
+    CUDA_TRY(cudaMemcpyAsync(c->code_d, code, (size_t)c->L * n_alleles, cudaMemcpyHostToDevice, c->stream));
+    CUDA_TRY(cudaStreamSynchronize(c->stream));   // (c->code_h holds a copy, but the contract is that `code` is free on return)
     return PSIM_OK;
 }
 
