@@ -137,12 +137,14 @@ def test_levelize_and_partition():
         sharded.levelize([-1, 2, 0], [-1, 2, 0])
 
 
-def test_replicate_ids_partition_without_overlap():
-    # bench.py: rank r of `world` simulates replicate ids r + world * (k + 1) in step k
+@pytest.mark.parametrize("per_step", [1, 8])
+def test_replicate_ids_partition_without_overlap(per_step):
+    # bench.py: in step k, rank r of `world` simulates the `per_step` replicate ids from (r + world * (k + 1)) * per_step on
+    # (one context with replicate_count = per_step)
     world, steps = 4, 5
-    seen = [r + world * (k + 1) for r in range(world) for k in range(steps)]
-    assert len(set(seen)) == world * steps
-    assert sorted(seen) == list(range(world, world * (steps + 1)))
+    seen = [(r + world * (k + 1)) * per_step + j for r in range(world) for k in range(steps) for j in range(per_step)]
+    assert len(set(seen)) == world * steps * per_step
+    assert sorted(seen) == list(range(world * per_step, world * (steps + 1) * per_step))
 
 
 @pytest.mark.parametrize("name", ["f1", "ril", "random"])
