@@ -258,14 +258,15 @@ int psim_free_host(psim_ctx* ctx, void* p);
 
 /* Introspection for benchmarks and sharded drivers. */
 typedef struct psim_stats {
-    int64_t n_meioses;          /* Individual.doMeiosis() equivalents run by psim_simulate */
-    int64_t n_units;            /* (meiosis, chromosome) units */
+    int64_t n_meioses;          /* Individual.doMeiosis() equivalents run by psim_simulate (running total since create) */
+    int64_t n_units;            /* (meiosis, chromosome) units (running total) */
     int64_t n_segments;         /* segments resident on the device */
     int64_t kernel_launches;    /* libpsim kernels launched since create */
     double  ms_simulate;        /* device time of the last psim_simulate (CUDA events) */
-    double  ms_emit_kernel;     /* device time of the streaming emission kernel (k_emit_tiles / k_emit_generic)
+    double  ms_emit_kernel;     /* device time of the streaming emission kernel (k_emit_rows / k_emit_tiles / k_emit_generic)
                                    launches of the last psim_emit*, CUDA events on the launching stream */
-    double  ms_emit_total;      /* device time of the last psim_emit* including plan kernels and copies */
+    double  ms_emit_total;      /* device time of the last psim_emit*: the breakpoint -> locus-run index of a new population
+                                   (k_index_runs), plan kernels, streaming kernels and copies */
     int64_t emit_kernel_launches; /* streaming-kernel launches of the last psim_emit* */
     double  ms_emit_plan;       /* device time of the tile-plan / dense helper kernels of the last psim_emit* */
 } psim_stats;
